@@ -1,0 +1,380 @@
+#!/usr/bin/env python3
+"""Benchmark of the PIQL hot path on B200: sampled transitions/s (+ soft-VI sweeps/s).
+
+    python bench.py --gpus N --steps K --warmup W              # this build (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU restatement (oracle)
+
+A step is one iteration of the Monte-Carlo hot path on one batch of synthetic trajectories:
+reset the per-(cell, action) accumulators, roll out the rank's block of path ids under the soft
+policy of V, reduce the per-path records with log-sum-exp, and (N > 1) all-reduce the accumulators.
+Workloads (BASELINE.json configs 4 and 5): synthetic gridworld of 1024^2 (N = 1) or 4096^2 (N > 1)
+interior cells, wall density 0.2, randomness 0.01, gamma 0.99, beta 1; V is 1000 Jacobi sweeps of
+the soft Bellman backup with rewards x 0.1 (the experiment protocol's starting V_lo); paths start
+at the free cells in cyclic order; estimator A (sampled stop).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (interior size, numpy Philox seed, paths per step [whole job])
+    "grid1024": dict(size=1024, seed=1234, paths=1 << 27),
+    "grid4096": dict(size=4096, seed=5678, paths=1 << 27),
+    "grid256": dict(size=256, seed=99, paths=1 << 22),   # quick functional check
+}
+RANDOMNESS, GAMMA, BETA, DENSITY = 0.01, 0.99, 1.0, 0.2
+REWARD_SCALE = 0.2
+VLO_SCALE, VLO_SWEEPS = 0.1, 1000
+MC_SEED = 20261019
+
+
+def make_world(name):
+    import piql_jl_b200 as piql
+    w = WORKLOADS[name]
+    gw = piql.make_gridworld((w["size"], w["size"]), density=DENSITY, rng=np.random.Generator(np.random.Philox(w["seed"])))
+    walls = np.asfortranarray(gw.walls, dtype=np.uint8)
+    params = dict(randomness=RANDOMNESS, step_cost=0.1 * REWARD_SCALE, reward=1 * REWARD_SCALE, gamma=GAMMA)
+    return walls, tuple(int(v) for v in gw.goal), params
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx = float(f[1])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def pinned(shape, dtype, order="C"):
+    import torch
+    n = int(np.prod(shape))
+    t = torch.empty(n * np.dtype(dtype).itemsize, dtype=torch.uint8, pin_memory=True)
+    a = t.numpy().view(dtype)
+    return a.reshape(shape, order=order), t   # keep t alive as long as the view is used
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's algorithm on the host cores: the C restatement (oracle/), all threads."""
+    if rank != 0:
+        return
+    import oracle
+    name = args.workload
+    walls, goal, params = make_world(name)
+    org = oracle.Grid(walls, goal, **params)
+    threads = oracle.num_threads()
+    V, _ = org.nu_jacobi_dense(VLO_SWEEPS, reward_scale=VLO_SCALE, nthreads=threads)
+    V = np.nan_to_num(V)
+    table = org.policy_table(V, beta=BETA)
+    free = org.free_cells()
+    sample = args.ref_paths
+    vgoal = V[goal]
+    done = 0
+
+    def step():
+        nonlocal done
+        lw, meta = org.rollout(table, vgoal, free, sample, path0=done, seed=MC_SEED, nthreads=threads)
+        mx, sm, cnt, tr = oracle.reduce_paths(lw, meta, len(free), path0=done)
+        done += sample
+        return tr
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    transitions = sum(step() for _ in range(args.steps))
+    dt = time.perf_counter() - t0
+    value = transitions / dt
+    line = {
+        "impl": "reference", "metric": "sampled transitions/sec", "value": value, "unit": "transitions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(name, args, world),
+        "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": threads, "kind": "port",
+                         "sample": "%d paths per step (of the %d-path step), oracle/piql_oracle.c with OpenMP over paths; "
+                                   "Julia is not installed, so the reference itself cannot run" % (sample, WORKLOADS[name]["paths"])},
+        "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, args, world):
+    w = WORKLOADS[name]
+    return {"workload": "synthetic %dx%d gridworld (BASELINE config %s), density %.1f, randomness %.2f, gamma %.2f, beta %.0f, "
+                        "V = %d Jacobi sweeps at reward x %.1f, estimator A, starts cycle over free cells"
+                        % (w["size"], w["size"], "4" if name == "grid1024" else "5" if name == "grid4096" else "-", DENSITY,
+                           RANDOMNESS, GAMMA, BETA, VLO_SWEEPS, VLO_SCALE),
+            "paths_per_step": int(args.paths or w["paths"]), "sharding": "path ids split in %d contiguous blocks" % world,
+            "l2": "each step writes 8 B x paths of records (> L2) between reads of the policy table; the table is "
+                  "%.0f MB" % (32 * (w["size"] + 2) ** 2 / 1e6)}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import piql_jl_b200 as piql
+    from piql_jl_b200 import distributed as pd
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    name = args.workload
+    w = WORKLOADS[name]
+    P = int(args.paths or w["paths"])
+    walls, goal, params = make_world(name)
+    eng = piql.Engine(local_rank)
+    eng.load_grid(walls, goal, **params)
+    H, W = eng.H, eng.W
+    n = H * W
+    stream = torch.cuda.ExternalStream(eng.stream, device="cuda:%d" % local_rank)
+
+    # V_lo on the GPU: exactly VLO_SWEEPS Jacobi sweeps in float64 (setup, untimed)
+    V, vst = eng.solve_nu(reward_scale=VLO_SCALE, tol=0.0, max_sweeps=VLO_SWEEPS)
+    V = np.nan_to_num(V)
+    eng.policy_table(V, beta=BETA, download=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step_no = [0]
+
+    def step():
+        p0, cnt = pd.shard_range(P, rank, world)
+        eng.mc_reset()
+        eng.mc_rollout(cnt, path0=step_no[0] * P + p0, seed=MC_SEED)
+        if world > 1:
+            pd.allreduce_engine_stats(eng)
+        step_no[0] += 1
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        eng.mc_timing()            # drop warm-up launches from the kernel timers
+        tr0 = eng.mc_transitions_total()
+        l0 = eng.launches
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms = e0.elapsed_time(e1)
+        launches = eng.launches - l0
+        roll_s, red_s, nl = eng.mc_timing()
+        tr_local = eng.mc_transitions_total() - tr0
+        stat = torch.tensor([ms, float(tr_local)], dtype=torch.float64, device="cuda:%d" % local_rank)
+        if world > 1:
+            mx = stat.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = stat.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms, transitions = float(mx[0]), float(sm[1])
+        else:
+            transitions = float(tr_local)
+    value = transitions / (ms * 1e-3)
+
+    # roofline of the dominant kernel (rollout) on this rank: 32 B policy record per sampled transition
+    # + 8 B record per finished path, over the CUDA-event time of the rollout launches
+    peak, peak_src = measured_peak()
+    p0, cnt = pd.shard_range(P, rank, world)
+    alg_bytes = 32.0 * tr_local + 8.0 * cnt * args.steps
+    achieved = alg_bytes / roll_s / 1e9 if roll_s > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "rollout_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(name)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "rollout_kernel<0,false,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_transition": 32, "bytes_per_path": 8, "launches": nl,
+                "avg_launch_ms": 1e3 * roll_s / max(nl, 1), "reduce_share": red_s / max(roll_s + red_s, 1e-12),
+                "transitions_per_s_kernel": tr_local / roll_s if roll_s > 0 else 0.0}
+
+    # ---- end to end through the public call, host buffers in pinned memory --------------------
+    e2e = None
+    if not args.no_e2e:
+        Vp, _k1 = pinned((H, W), np.float64, order="F")
+        Vp[...] = V
+        sa, _k2 = pinned((n, 4), np.float64)
+        cn, _k3 = pinned((n, 4), np.uint64)
+        ls, _k4 = pinned((H, W), np.float64, order="F")
+        reps = max(1, min(args.steps, 3))
+        tot = 0.0
+        pd.mc_logz_sharded(eng, Vp, BETA, P, rank, world, seed=MC_SEED + 1, out=(sa, cn, ls))   # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(reps):
+            _sa, _cn, _ls, st = pd.mc_logz_sharded(eng, Vp, BETA, P, rank, world, seed=MC_SEED + 2 + i, out=(sa, cn, ls))
+            tot += float(st.transitions)
+        barrier()
+        dt = time.perf_counter() - t0
+        stat = torch.tensor([dt, tot], dtype=torch.float64, device="cuda:%d" % local_rank)
+        if world > 1:
+            mx = stat.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = stat.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            dt, tot = float(mx[0]), float(sm[1])
+        e2e = {"value": tot / dt, "unit": "transitions/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 72 * n,
+               "steps": reps, "ms_per_step": 1e3 * dt / reps,
+               "call": "piql_policy_table + piql_mc_reset_dev + piql_mc_rollout_dev (+ all-reduce) + piql_mc_finalize "
+                       "with pinned host V in, logz_sa / count_sa / logz_s out"}
+
+    # ---- soft-VI sweeps on the same grid (rank 0) ----------------------------------------------
+    vi = None
+    if rank == 0 and not args.no_vi:
+        vi = {}
+        for prec, nbytes in (("f32", 8), ("f64", 16)):
+            eng.vi_prepare("nu", reward_scale=1.0, precision=prec)
+            with torch.cuda.stream(stream):
+                eng.vi_sweeps(20)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                eng.vi_sweeps(args.vi_sweeps)
+                b.record(stream)
+                torch.cuda.synchronize()
+            sec = a.elapsed_time(b) * 1e-3
+            sps = args.vi_sweeps / sec
+            gbs = nbytes * eng.nfree * sps / 1e9
+            vi[prec] = {"sweeps_per_s": sps, "state_backups_per_s": sps * eng.nfree, "us_per_sweep": 1e6 / sps,
+                        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                     "bytes_per_state": nbytes, "traffic": None}}
+        vi["kernel"] = "sweep_kernel<T,KIND_NU>, one launch per Jacobi sweep (includes the residual reduction on the last)"
+        vi["setup_vlo"] = {"sweeps": int(vst.sweeps), "device_seconds": float(vst.device_seconds)}
+
+    # ---- CPU baseline beside it (rank 0, N = 1) ------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle
+        org = oracle.Grid(walls, goal, **params)
+        threads = oracle.num_threads()
+        table = eng.policy_table(V, beta=BETA)        # same fp32 table the GPU read
+        free = org.free_cells()
+        sample = args.ref_paths
+        org.rollout(table, V[goal], free, 1 << 14, seed=MC_SEED, nthreads=threads)
+        t0 = time.perf_counter()
+        lw, meta = org.rollout(table, V[goal], free, sample, path0=0, seed=MC_SEED, nthreads=threads)
+        mxo, smo, cno, tr = oracle.reduce_paths(lw, meta, len(free), path0=0)
+        dt = time.perf_counter() - t0
+        cpu = {"value": tr / dt, "unit": "transitions/s", "cores": threads, "kind": "port",
+               "sample": "first %d paths of the step (%.2e transitions), oracle/piql_oracle.c with OpenMP over paths"
+                         % (sample, tr)}
+        if vi is not None:
+            t0 = time.perf_counter()
+            org.nu_jacobi_dense(3, nthreads=threads)
+            vi["cpu_baseline"] = {"sweeps_per_s": 3 / (time.perf_counter() - t0), "cores": threads, "kind": "port",
+                                  "sample": "3 dense OpenMP Jacobi sweeps (f64)"}
+
+    if rank == 0:
+        line = {"metric": "sampled transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(name, args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu, "vi": vi,
+                "transitions_per_step": transitions / args.steps}
+        print(json.dumps(line), flush=True)
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
+    ap.add_argument("--paths", type=int, default=0, help="paths per step over all ranks (default: workload's)")
+    ap.add_argument("--ref-paths", type=int, default=1 << 20, help="CPU sample: paths per reference step")
+    ap.add_argument("--vi-sweeps", type=int, default=200)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-vi", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.workload == "auto":
+        args.workload = "grid1024" if args.gpus <= 1 else "grid4096"
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

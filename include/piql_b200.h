@@ -1,0 +1,201 @@
+/*
+ * piql_b200.h -- C ABI of the B200 (sm_100a) accelerator for PIQL.jl's data-parallel hot path.
+ *
+ * This is the drop-in boundary: a Julia host keeps PIQL's public API (generate_ν, generate_logz,
+ * logz_updateV, generate_optimality_gap, plus a Monte-Carlo log Z estimator) and reaches these
+ * entry points through `ccall`; see INTEGRATION.md for the Julia shim and julia/PIQLB200.jl.
+ * Each entry point names the reference code it replaces (paths relative to the reference repo,
+ * chelate/PIQL.jl).
+ *
+ * Conventions
+ *   - Every function returns an int32 status, 0 = PIQL_OK.  On failure piql_last_error(ctx)
+ *     returns a message owned by the library (valid until the next call on that context).
+ *     No exceptions, no abort, nothing printed.
+ *   - Per-cell arrays are column-major H x W like the Julia wall array (border included);
+ *     cell (i, j), 0-based, has linear index i + H*j.  Wall cells are NaN in every output.
+ *   - Per-(cell, action) arrays have the action fastest: Q[a + 4*(i + H*j)] (Julia Q[a,i,j]).
+ *   - Host pointers are read/written only during the call; the library never keeps or frees
+ *     them.  Calls block until the result is in the caller's buffers.  One caller at a time
+ *     per context.
+ *   - Actions 0..3 move by (+1,0) (-1,0) (0,+1) (0,-1) on (i,j)   src/Problems/GridWorld.jl:24-26
+ *   - There is no CPU fallback: without a CUDA device piql_create fails.
+ */
+#ifndef PIQL_B200_H
+#define PIQL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIQL_VERSION 100 /* 0.1.0 */
+
+enum {
+  PIQL_OK = 0,
+  PIQL_ERR_ARG = 1,      /* bad argument (null pointer, size, range) */
+  PIQL_ERR_STATE = 2,    /* call order: no grid loaded, no policy table, ... */
+  PIQL_ERR_CUDA = 3,     /* CUDA runtime error; text in piql_last_error */
+  PIQL_ERR_NO_DEVICE = 4,
+  PIQL_ERR_UNSUPPORTED = 5,
+  PIQL_ERR_NOT_CONVERGED = 6 /* max_sweeps reached; outputs hold the last iterate */
+};
+
+enum { PIQL_F64 = 0, PIQL_F32 = 1 };
+
+typedef struct piql_ctx piql_ctx;
+
+/* keyword arguments of gridworld_ctrl   src/Problems/GridWorld.jl:90-95 */
+typedef struct {
+  double randomness; /* likelihood of a random action */
+  double step_cost;  /* entropic cost of a step   (0.1 * reward_scale) */
+  double reward;     /* reward of reaching the goal (1 * reward_scale) */
+  double gamma;      /* discount */
+} piql_grid_params;
+
+/* Stop rule of the reference: sum_s |new(s) - old(s)| < tol   src/value_iteration.jl:74,82,112,149
+ * (reference tol = 1e-12; sweeps are Jacobi here -- same fixed point). */
+typedef struct {
+  double tol;          /* <= 0: run exactly max_sweeps */
+  int64_t max_sweeps;  /* hard cap */
+  int32_t precision;   /* PIQL_F64 | PIQL_F32: arithmetic and storage type of the sweep */
+  int32_t check_every; /* residual is evaluated every this many sweeps; <= 0: library default */
+} piql_solve_opts;
+
+typedef struct {
+  int64_t sweeps;
+  double residual;       /* sum |delta| of the last checked sweep */
+  double device_seconds; /* CUDA-event time of the sweeps */
+  int64_t backups;       /* state backups performed = sweeps * free cells */
+  int32_t converged;
+  int32_t kernel;        /* 0 = one launch per sweep, 1 = single-CTA resident solver */
+} piql_solve_stats;
+
+enum { PIQL_EST_SAMPLED_STOP = 0 /* estimator A */, PIQL_EST_DISCOUNTED = 1 /* estimator B */ };
+enum { PIQL_START_ALL_FREE = 0 /* path p starts at free cell p mod nfree */, PIQL_START_LIST = 1 };
+
+typedef struct {
+  int64_t npaths;        /* paths in this call */
+  int64_t path0;         /* global id of the first path (shards: rank r takes [path0, path0+npaths)) */
+  uint64_t seed;         /* Philox4x32-10 key; counter = (step, 0, path id lo, path id hi) */
+  int32_t estimator;     /* PIQL_EST_* */
+  int32_t start_mode;    /* PIQL_START_* */
+  int64_t horizon;       /* step cap per path (estimator B: the truncation horizon) */
+  const int32_t* starts; /* PIQL_START_LIST: cell indices; path p starts at starts[p mod nstarts] */
+  int64_t nstarts;
+  const float* injected; /* optional [npaths][injected_steps][4] uniforms replacing Philox */
+  int64_t injected_steps;
+} piql_mc_opts;
+
+typedef struct {
+  uint64_t transitions;  /* sampled (s,a,s') transitions */
+  uint64_t paths;
+  double device_seconds; /* rollout + reduction kernels, CUDA events */
+  double rollout_seconds; /* rollout kernels only */
+} piql_mc_stats;
+
+/* ---- context -------------------------------------------------------------------------------
+ * Replaces the reference's worker pool (addprocs/pmap/@spawn, scripts/distributed_experiments.jl
+ * :3,26,28,43-46): one context drives one GPU; multi-GPU runs use one context per device (one
+ * process or thread each) and combine statistics with the *_dev entry points below. */
+int32_t piql_version(void);
+int32_t piql_device_count(int32_t* n_out);
+int32_t piql_create(piql_ctx** ctx_out, int32_t device_id);
+int32_t piql_destroy(piql_ctx* ctx);
+const char* piql_last_error(const piql_ctx* ctx);
+/* cudaStream_t all of this context's work is launched on (for event timing / interop) */
+int32_t piql_stream(piql_ctx* ctx, void** stream_out);
+
+/* ---- problem --------------------------------------------------------------------------------
+ * Tabulated gridworld_ctrl(gw; randomness, step_cost, reward, γ)   src/Problems/GridWorld.jl:90-121
+ * walls: the Gridworld.walls Bool array (:35-38), 1 = wall, border included; goal 0-based. */
+int32_t piql_grid_load(piql_ctx* ctx, const uint8_t* walls_colmajor, int64_t H, int64_t W,
+                       int64_t goal_i, int64_t goal_j, const piql_grid_params* params);
+int32_t piql_grid_free_count(piql_ctx* ctx, int64_t* nfree_out);
+
+/* ---- soft value iteration -------------------------------------------------------------------
+ * generate_ν(ctrl)   src/value_iteration.jl:62-87, truevalue_recursion src/PIQL.jl:95-101.
+ * reward_scale multiplies the reward function (modify(ctrl, reward_function = c*r),
+ * scripts/experiments.jl:26, test/runtests.jl:7-8). */
+int32_t piql_solve_nu(piql_ctx* ctx, double reward_scale, const piql_solve_opts* opts, double* nu_out,
+                      piql_solve_stats* stats_out);
+/* generate_logz(ctrl, V; β)   src/value_iteration.jl:89-117, logz_recursion src/PIQL.jl:125-130.
+ * Q: optional per-(cell,action) table; NULL = the V-determined Q, (s,a)->controlV(ctrl,V,s,a). */
+int32_t piql_solve_logz(piql_ctx* ctx, const double* V, const double* Q, double beta,
+                        const piql_solve_opts* opts, double* logz_out, piql_solve_stats* stats_out);
+/* logz_updateV(ctrl, V; β) = V + logz/β   src/value_iteration.jl:119-124.  logz_out optional. */
+int32_t piql_update_v(piql_ctx* ctx, const double* V, double beta, const piql_solve_opts* opts,
+                      double* vnew_out, double* logz_out, piql_solve_stats* stats_out);
+/* generate_optimality_gap(ctrl, V; ν)   src/value_iteration.jl:129-169 */
+int32_t piql_solve_gap(piql_ctx* ctx, const double* V, const double* Q, const double* nu,
+                       const piql_solve_opts* opts, double* gap_out, piql_solve_stats* stats_out);
+/* One Jacobi sweep from x_in (kind: 0 nu, 1 logz, 2 gap), for parity tests of the backup itself. */
+int32_t piql_sweep_once(piql_ctx* ctx, int32_t kind, const double* V, const double* Q, const double* nu,
+                        double beta, double reward_scale, int32_t precision, const double* x_in,
+                        double* x_out, double* residual_out);
+
+/* ---- Monte-Carlo path sampling --------------------------------------------------------------
+ * Replaces choose_action / path_transitions / fitness_reward_estimate   src/path_functions.jl:12-41
+ * and the propagator closure src/Problems/GridWorld.jl:113-115.
+ *
+ * piql_policy_table builds, on the device, the per-cell record the sampler reads (32 bytes):
+ *   float c[3]   running sums of action_probability(ctrl,Q,s,a)/sum  (StatsBase walk cw < u)
+ *   uint32 mask  bit a set <=> take_step(s,a) is blocked by a wall
+ *   float bf[4]  beta * fitness(ctrl,V,Q,s,a)                         src/PIQL.jl:87-89
+ * table_out (optional) receives H*W*8 floats.  piql_policy_table_set uploads a caller's table. */
+int32_t piql_policy_table(piql_ctx* ctx, const double* V, const double* Q, double beta, float* table_out);
+int32_t piql_policy_table_set(piql_ctx* ctx, const float* table, double v_goal);
+
+/* Monte-Carlo estimate of log Z (the fixed point of logz_recursion, src/PIQL.jl:125-130) from
+ * npaths rollouts under pi_Q, bucketed by (start cell, first action):
+ *   logz_sa_out[a + 4*cell]  log mean path weight of the bucket (NaN when empty)   H*W*4
+ *   count_sa_out[a + 4*cell] paths in the bucket                                   H*W*4
+ *   logz_s_out[cell]         log mean path weight over the cell's four buckets     H*W
+ * Any output pointer may be NULL.  Builds the policy table from V (and Q) first. */
+int32_t piql_mc_logz(piql_ctx* ctx, const double* V, const double* Q, double beta, const piql_mc_opts* opts,
+                     double* logz_sa_out, uint64_t* count_sa_out, double* logz_s_out,
+                     piql_mc_stats* stats_out);
+
+/* Debug export for bit-exact trajectory parity: the (s, a, s') triples of each path (int32 cell
+ * indices, -1 padded, [npaths][max_steps][3]) and the per-path record: logw (float) and
+ * meta = a0 | (len << 2).  Uses the current policy table. */
+int32_t piql_trace_paths(piql_ctx* ctx, const piql_mc_opts* opts, int64_t max_steps, int32_t* triples_out,
+                         float* logw_out, uint32_t* meta_out);
+
+/* ---- device-resident entry points (bench + multi-GPU) ---------------------------------------
+ * The per-(start slot, action) accumulators (lse_max float, lse_sum float, count uint32, each
+ * nslots*4 long, slot = index into the start list / free-cell list) stay on the device so that
+ * shards can be combined by an all-reduce before they are finalised:
+ *     piql_mc_reset_dev -> piql_mc_rollout_dev (xN) -> [allreduce MAX on lse_max into gmax ->
+ *     piql_mc_rescale_dev(gmax) -> allreduce SUM on lse_sum and count] -> piql_mc_finalize
+ * All of them are asynchronous on the context's stream except finalize. */
+int32_t piql_mc_reset_dev(piql_ctx* ctx, const piql_mc_opts* opts);
+int32_t piql_mc_rollout_dev(piql_ctx* ctx, const piql_mc_opts* opts);
+int32_t piql_mc_stats_dev(piql_ctx* ctx, void** lse_max_dev, void** lse_sum_dev, void** count_dev,
+                          int64_t* n_out);
+int32_t piql_mc_rescale_dev(piql_ctx* ctx, const void* global_max_dev);
+int32_t piql_mc_finalize(piql_ctx* ctx, double* logz_sa_out, uint64_t* count_sa_out, double* logz_s_out,
+                         piql_mc_stats* stats_out);
+/* CUDA-event durations of the rollout and reduction kernels launched since the previous call of
+ * this function (or since context creation), summed over launches.  Synchronises the stream. */
+int32_t piql_mc_timing(piql_ctx* ctx, double* rollout_seconds, double* reduce_seconds, int64_t* launches);
+/* Sampled transitions of every rollout on this context since creation (synchronises the stream). */
+int32_t piql_mc_transitions_total(piql_ctx* ctx, uint64_t* total_out);
+/* Per-path records of the last piql_mc_rollout_dev call, copied to the host (tests). */
+int32_t piql_mc_records(piql_ctx* ctx, float* logw_out, uint32_t* meta_out, int64_t n);
+
+/* Device-resident soft-VI for timing: runs `sweeps` Jacobi sweeps of kind (0 nu, 1 logz, 2 gap)
+ * on the context's stream from the current device state without touching the host.
+ * piql_vi_prepare_dev uploads V/Q/nu (as needed) and resets the iterate. */
+int32_t piql_vi_prepare_dev(piql_ctx* ctx, int32_t kind, const double* V, const double* Q, const double* nu,
+                            double beta, double reward_scale, int32_t precision);
+int32_t piql_vi_sweeps_dev(piql_ctx* ctx, int64_t sweeps);
+int32_t piql_vi_fetch(piql_ctx* ctx, double* x_out, double* residual_out);
+
+/* Kernels launched by this context since creation (for the bench's gpu_launches count). */
+int32_t piql_launch_count(piql_ctx* ctx, int64_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIQL_B200_H */

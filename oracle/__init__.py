@@ -103,6 +103,14 @@ class Grid:
                         C.byref(diff))
         return out, diff.value
 
+    def nu_jacobi_dense(self, sweeps, reward_scale=1.0, nthreads=1):
+        """Exactly `sweeps` dense OpenMP Jacobi sweeps of the nu backup from zero (the optimised CPU variant)."""
+        out = np.empty((self.H, self.W), dtype=np.float64, order="F")
+        f = lib().orc_nu_jacobi_dense
+        f.restype = C.c_double
+        diff = f(*self._args(reward_scale), C.c_int64(sweeps), C.c_int(nthreads), _p(out, C.c_double))
+        return out, diff
+
     def generate_nu(self, reward_scale=1.0, **kw):
         return self.solve("nu", reward_scale=reward_scale, **kw)[0]
 

@@ -1,0 +1,23 @@
+"""piql.jl_b200 -- B200 (sm_100a) accelerator for PIQL.jl's Monte-Carlo path sampling and soft
+value-iteration hot path, behind the reference's own problem/solver interface.
+
+The directory name carries a dot, so import it through the `piql_jl_b200` shim at the repo root:
+
+    import piql_jl_b200 as piql
+    gw = piql.make_gridworld((18, 18), density=0.2)
+    ctrl = piql.gridworld_ctrl(gw, randomness=0.01, gamma=0.99)
+    nu = piql.generate_nu(ctrl)
+
+Layout: csrc/ (CUDA kernels + the C ABI of include/piql_b200.h), lib/ (the built shared library),
+_capi.py (ctypes binding), engine.py (one context per GPU), gridworld.py and solvers.py (the
+host-side mirror of the reference interface), build.py.
+"""
+from . import _capi
+from ._capi import PiqlError
+from .engine import Engine
+from .gridworld import (ControlProblem, Gridworld, gridworld_ctrl, make_gridworld, make_walls, modify,
+                        state_iterator, tabulate, take_step)
+from .solvers import (Growable, McResult, Qnormalization, action_probability, average_reward, choose_action,
+                      controlQ, controlV, engine_for, fitness, fitness_reward_estimate, generate_logz, generate_nu,
+                      generate_optimality_gap, generate_ν, kl_cost, learning_traj, logz_updateV, mc_logz,
+                      path_transitions, run_experiment)

@@ -1,0 +1,801 @@
+// api.cu -- the C ABI (include/piql_b200.h): context, device buffers, call sequencing.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/piql_b200.h"
+#include "internal.h"
+
+using namespace piql;
+
+struct piql_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  long long launches = 0;
+
+  // problem
+  bool has_grid = false;
+  GridDev g{};
+  long long nfree = 0;
+  uint8_t* d_walls = nullptr;
+  uint8_t* d_cell = nullptr;
+  int* d_free = nullptr;  // free cells in index order
+
+  // soft VI
+  long long vi_cap = 0;  // cells the buffers below were sized for
+  ViState vs{};
+  bool vs_ready = false;
+  double *d_in0 = nullptr, *d_in1 = nullptr, *d_in4 = nullptr, *d_out = nullptr;  // double staging
+  void* d_Q = nullptr;
+  void* d_nu = nullptr;
+  double* d_scalars = nullptr;  // [0] residual, [1..2] resident solver output
+  double* h_scalars = nullptr;  // pinned mirror
+  long long vi_sweeps_done = 0;
+
+  // Monte-Carlo
+  float4* d_table = nullptr;
+  bool has_table = false;
+  double v_goal = 0.0;
+  float* d_logw = nullptr;
+  uint32_t* d_meta = nullptr;
+  long long rec_cap = 0;
+  int* d_starts = nullptr;       // current slot list (points at d_free or d_starts_own)
+  int* d_starts_own = nullptr;
+  long long starts_own_cap = 0;
+  long long nstarts = 0;
+  float *acc_max = nullptr, *acc_sum = nullptr;
+  uint32_t* acc_cnt = nullptr;
+  long long acc_cap = 0;
+  float* d_scratch = nullptr;
+  size_t scratch_cap = 0;
+  unsigned long long* d_transitions = nullptr;
+  unsigned long long* h_transitions = nullptr;
+  float* d_inj = nullptr;
+  size_t inj_cap = 0;
+  unsigned long long paths_done = 0;
+  // per-launch timing: triples (before rollout, after rollout, after reduce) since the last reset
+  std::vector<cudaEvent_t> tev;
+  size_t tev_used = 0;
+};
+
+namespace {
+
+constexpr long long MAX_RECORDS_PER_LAUNCH = 1LL << 28;  // 2 GiB of per-path records
+constexpr size_t MAX_TIMING_EVENTS = 3 * 4096;
+
+struct LaunchScope {
+  piql_ctx* c;
+  long long l0;
+  explicit LaunchScope(piql_ctx* ctx) : c(ctx), l0(g_launches) {}
+  ~LaunchScope() { c->launches += g_launches - l0; }
+};
+
+int fail(piql_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(ctx, PIQL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));      \
+  } while (0)
+#define CK_LAST() CK(cudaGetLastError())
+#define NEED(cond, code, msg) \
+  do { if (!(cond)) return fail(ctx, code, msg); } while (0)
+
+template <typename T> cudaError_t grow(T*& p, long long& cap, long long want) {
+  if (want <= cap) return cudaSuccess;
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+  cudaError_t e = cudaMalloc((void**)&p, sizeof(T) * (size_t)want);
+  if (e == cudaSuccess) cap = want;
+  return e;
+}
+template <typename T> cudaError_t grow(T*& p, size_t& cap, size_t want) {
+  long long c = (long long)cap;
+  cudaError_t e = grow(p, c, (long long)want);
+  cap = (size_t)c;
+  return e;
+}
+
+void free_vi(piql_ctx* c) {
+  for (void* p : {c->vs.x[0], c->vs.x[1], c->vs.V, c->vs.aux4, c->vs.aux1, (void*)c->vs.partial, (void*)c->d_in0,
+                  (void*)c->d_in1, (void*)c->d_in4, (void*)c->d_out, c->d_Q, c->d_nu})
+    if (p) cudaFree(p);
+  c->vs = ViState{};
+  c->d_in0 = c->d_in1 = c->d_in4 = c->d_out = nullptr;
+  c->d_Q = c->d_nu = nullptr;
+  c->vi_cap = 0;
+  c->vs_ready = false;
+}
+
+int ensure_vi(piql_ctx* ctx) {
+  const long long n = ctx->g.n;
+  if (ctx->vi_cap >= n) return PIQL_OK;
+  free_vi(ctx);
+  const size_t e8 = 8 * (size_t)n;  // sized for double; float runs use half
+  CK(cudaMalloc(&ctx->vs.x[0], e8));
+  CK(cudaMalloc(&ctx->vs.x[1], e8));
+  CK(cudaMalloc(&ctx->vs.V, e8));
+  CK(cudaMalloc(&ctx->vs.aux4, 4 * e8));
+  CK(cudaMalloc(&ctx->vs.aux1, e8));
+  CK(cudaMalloc(&ctx->d_Q, 4 * e8));
+  CK(cudaMalloc(&ctx->d_nu, e8));
+  CK(cudaMalloc((void**)&ctx->d_in0, e8));
+  CK(cudaMalloc((void**)&ctx->d_in1, e8));
+  CK(cudaMalloc((void**)&ctx->d_in4, 4 * e8));
+  CK(cudaMalloc((void**)&ctx->d_out, e8));
+  const int nb = (int)((n + SWEEP_THREADS - 1) / SWEEP_THREADS);
+  CK(cudaMalloc((void**)&ctx->vs.partial, sizeof(double) * nb));
+  ctx->vs.nblocks = nb;
+  ctx->vs.residual = ctx->d_scalars;
+  ctx->vi_cap = n;
+  return PIQL_OK;
+}
+
+// Upload V/Q/nu, convert to the sweep precision, reset the iterate, precompute per-cell constants.
+int vi_prepare(piql_ctx* ctx, int kind, const double* V, const double* Q, const double* nu, double beta,
+               double reward_scale, int precision) {
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded (call piql_grid_load first)");
+  NEED(kind >= 0 && kind <= 2, PIQL_ERR_ARG, "kind must be 0 (nu), 1 (logz) or 2 (gap)");
+  NEED(precision == PIQL_F64 || precision == PIQL_F32, PIQL_ERR_ARG, "precision must be PIQL_F64 or PIQL_F32");
+  NEED(kind == KIND_NU || V != nullptr, PIQL_ERR_ARG, "V is required for logz / gap");
+  NEED(kind != KIND_GAP || nu != nullptr, PIQL_ERR_ARG, "nu is required for the optimality gap");
+  NEED(kind == KIND_NU || (beta == beta), PIQL_ERR_ARG, "beta is NaN");
+  int rc = ensure_vi(ctx);
+  if (rc) return rc;
+  const int n = ctx->g.n;
+  cudaStream_t st = ctx->stream;
+  ViState& vs = ctx->vs;
+  vs.precision = precision; vs.kind = kind; vs.beta = beta; vs.reward_scale = reward_scale; vs.cur = 0;
+  vs.nblocks = (n + SWEEP_THREADS - 1) / SWEEP_THREADS;
+  vs.v_goal = 0.0;
+  vs.residual = ctx->d_scalars;
+  if (V) {
+    const double vg = V[ctx->g.goal];
+    NEED(vg == vg, PIQL_ERR_ARG, "V(goal) is NaN");
+    vs.v_goal = vg;
+    CK(cudaMemcpyAsync(ctx->d_in0, V, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+    launch_convert_in(ctx->d_in0, vs.V, n, precision, st);
+  }
+  const void* dQ = nullptr;
+  if (Q && kind != KIND_NU) {
+    CK(cudaMemcpyAsync(ctx->d_in4, Q, 32 * (size_t)n, cudaMemcpyHostToDevice, st));
+    launch_convert_in(ctx->d_in4, ctx->d_Q, 4 * n, precision, st);
+    dQ = ctx->d_Q;
+  }
+  if (nu && kind == KIND_GAP) {
+    CK(cudaMemcpyAsync(ctx->d_in1, nu, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+    launch_convert_in(ctx->d_in1, ctx->d_nu, n, precision, st);
+  }
+  launch_fill(vs.x[0], 0.0, n, precision, st);  // Growable default x -> 0.0   value_iteration.jl:79,109,146
+  launch_fill(vs.x[1], 0.0, n, precision, st);
+  launch_prep(ctx->g, ctx->d_cell, vs, dQ, ctx->d_nu, st);
+  CK_LAST();
+  ctx->vs_ready = true;
+  ctx->vi_sweeps_done = 0;
+  return PIQL_OK;
+}
+
+int vi_solve(piql_ctx* ctx, const piql_solve_opts* opts, double* out, piql_solve_stats* stats) {
+  NEED(opts != nullptr, PIQL_ERR_ARG, "opts is null");
+  NEED(opts->max_sweeps > 0, PIQL_ERR_ARG, "max_sweeps must be positive");
+  const int n = ctx->g.n;
+  cudaStream_t st = ctx->stream;
+  ViState& vs = ctx->vs;
+  const double tol = opts->tol;
+  long long sweeps = 0;
+  double residual = INFINITY;
+  int kernel = 0;
+  CK(cudaEventRecord(ctx->ev0, st));
+  if (n <= RESIDENT_MAX_CELLS) {
+    kernel = 1;
+    launch_resident_solve(ctx->g, ctx->d_cell, vs, tol > 0 ? tol : -1.0, opts->max_sweeps, ctx->d_scalars + 1, st);
+    CK_LAST();
+    CK(cudaMemcpyAsync(ctx->h_scalars + 1, ctx->d_scalars + 1, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    sweeps = (long long)ctx->h_scalars[1];
+    residual = ctx->h_scalars[2];
+  } else {
+    const long long every = opts->check_every > 0 ? opts->check_every : 64;
+    while (sweeps < opts->max_sweeps) {
+      long long batch = opts->max_sweeps - sweeps < every ? opts->max_sweeps - sweeps : every;
+      for (long long i = 0; i < batch; i++) launch_sweep(ctx->g, ctx->d_cell, vs, i == batch - 1, st);
+      CK_LAST();
+      sweeps += batch;
+      CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      residual = ctx->h_scalars[0];
+      if (!(residual == residual)) return fail(ctx, PIQL_ERR_CUDA, "soft-VI residual is NaN (diverged)");
+      if (tol > 0 && residual < tol) break;
+    }
+  }
+  CK(cudaEventRecord(ctx->ev1, st));
+  if (out) {
+    launch_convert_out(vs.x[vs.cur], ctx->d_cell, ctx->d_out, n, vs.precision, st);
+    CK_LAST();
+    CK(cudaMemcpyAsync(out, ctx->d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  const bool conv = tol > 0 ? residual < tol : true;
+  if (stats) {
+    stats->sweeps = sweeps; stats->residual = residual; stats->device_seconds = ms * 1e-3;
+    stats->backups = sweeps * ctx->nfree; stats->converged = conv ? 1 : 0; stats->kernel = kernel;
+  }
+  ctx->vi_sweeps_done += sweeps;
+  if (!conv) return fail(ctx, PIQL_ERR_NOT_CONVERGED, "max_sweeps reached before the residual fell below tol");
+  return PIQL_OK;
+}
+
+int mc_check_opts(piql_ctx* ctx, const piql_mc_opts* o) {
+  NEED(o != nullptr, PIQL_ERR_ARG, "mc opts is null");
+  NEED(o->npaths >= 0 && o->path0 >= 0, PIQL_ERR_ARG, "npaths and path0 must be non-negative");
+  NEED(o->estimator == 0 || o->estimator == 1, PIQL_ERR_ARG, "estimator must be 0 (sampled stop) or 1 (discounted)");
+  NEED(o->horizon > 0, PIQL_ERR_ARG, "horizon must be positive");
+  NEED(o->start_mode == PIQL_START_ALL_FREE || o->start_mode == PIQL_START_LIST, PIQL_ERR_ARG, "bad start_mode");
+  if (o->start_mode == PIQL_START_LIST) {
+    NEED(o->starts != nullptr && o->nstarts > 0, PIQL_ERR_ARG, "start list is empty");
+    for (long long i = 0; i < o->nstarts; i++)
+      NEED(o->starts[i] >= 0 && o->starts[i] < ctx->g.n, PIQL_ERR_ARG, "start cell out of range");
+  }
+  if (o->injected) NEED(o->injected_steps > 0, PIQL_ERR_ARG, "injected_steps must be positive");
+  return PIQL_OK;
+}
+
+// Select the slot list and make sure the accumulators can hold it.
+int mc_setup_slots(piql_ctx* ctx, const piql_mc_opts* o) {
+  cudaStream_t st = ctx->stream;
+  if (o->start_mode == PIQL_START_ALL_FREE) {
+    ctx->d_starts = ctx->d_free;
+    ctx->nstarts = ctx->nfree;
+  } else {
+    CK(grow(ctx->d_starts_own, ctx->starts_own_cap, o->nstarts));
+    // reject wall cells: a path cannot start inside a wall
+    CK(cudaMemcpyAsync(ctx->d_starts_own, o->starts, 4 * (size_t)o->nstarts, cudaMemcpyHostToDevice, st));
+    ctx->d_starts = ctx->d_starts_own;
+    ctx->nstarts = o->nstarts;
+  }
+  const long long need = ctx->nstarts * NA;
+  if (need > ctx->acc_cap) {
+    for (void* p : {(void*)ctx->acc_max, (void*)ctx->acc_sum, (void*)ctx->acc_cnt}) if (p) cudaFree(p);
+    ctx->acc_max = ctx->acc_sum = nullptr; ctx->acc_cnt = nullptr; ctx->acc_cap = 0;
+    CK(cudaMalloc((void**)&ctx->acc_max, 4 * (size_t)need));
+    CK(cudaMalloc((void**)&ctx->acc_sum, 4 * (size_t)need));
+    CK(cudaMalloc((void**)&ctx->acc_cnt, 4 * (size_t)need));
+    ctx->acc_cap = need;
+  }
+  return PIQL_OK;
+}
+
+int mc_reset(piql_ctx* ctx, const piql_mc_opts* o) {
+  int rc = mc_setup_slots(ctx, o);
+  if (rc) return rc;
+  launch_mc_reset(ctx->acc_max, ctx->acc_sum, ctx->acc_cnt, ctx->nstarts * NA, ctx->stream);
+  launch_fold_counter(ctx->d_transitions, ctx->stream);  // this run's count moves into the running total
+  CK_LAST();
+  ctx->paths_done = 0;
+  return PIQL_OK;
+}
+
+RolloutArgs make_rollout_args(piql_ctx* ctx, const piql_mc_opts* o) {
+  RolloutArgs a{};
+  a.table = ctx->d_table;
+  a.goal = ctx->g.goal; a.H = ctx->g.H;
+  a.gamma = (float)ctx->g.gamma; a.rho = (float)ctx->g.randomness; a.vgoal = (float)ctx->v_goal;
+  a.lgam = (float)std::log(ctx->g.gamma); a.l1mg = (float)std::log(1.0 - ctx->g.gamma);
+  a.estimator = o->estimator; a.horizon = o->horizon;
+  a.starts = ctx->d_starts; a.nstarts = ctx->nstarts;
+  a.seed_lo = (uint32_t)o->seed; a.seed_hi = (uint32_t)(o->seed >> 32);
+  return a;
+}
+
+// Rollout + reduction of opts->npaths paths in launches of at most MAX_RECORDS_PER_LAUNCH.
+int mc_rollout(piql_ctx* ctx, const piql_mc_opts* o, int* trace_dev, long long trace_steps) {
+  NEED(ctx->has_table, PIQL_ERR_STATE, "no policy table (call piql_policy_table or piql_mc_logz first)");
+  cudaStream_t st = ctx->stream;
+  const long long chunk = o->npaths < MAX_RECORDS_PER_LAUNCH ? o->npaths : MAX_RECORDS_PER_LAUNCH;
+  if (chunk > ctx->rec_cap) {
+    if (ctx->d_logw) cudaFree(ctx->d_logw);
+    if (ctx->d_meta) cudaFree(ctx->d_meta);
+    ctx->d_logw = nullptr; ctx->d_meta = nullptr; ctx->rec_cap = 0;
+    CK(cudaMalloc((void**)&ctx->d_logw, 4 * (size_t)chunk));
+    CK(cudaMalloc((void**)&ctx->d_meta, 4 * (size_t)chunk));
+    ctx->rec_cap = chunk;
+  }
+  const size_t sf = reduce_scratch_floats(chunk, ctx->nstarts);
+  CK(grow(ctx->d_scratch, ctx->scratch_cap, sf ? sf : 1));
+  const float* inj_dev = nullptr;
+  if (o->injected) {
+    NEED(o->npaths <= MAX_RECORDS_PER_LAUNCH, PIQL_ERR_ARG, "too many paths for injected uniforms");
+    const size_t nf = (size_t)o->npaths * (size_t)o->injected_steps * 4;
+    CK(grow(ctx->d_inj, ctx->inj_cap, nf));
+    CK(cudaMemcpyAsync(ctx->d_inj, o->injected, 4 * nf, cudaMemcpyHostToDevice, st));
+    inj_dev = ctx->d_inj;
+  }
+  RolloutArgs a = make_rollout_args(ctx, o);
+  a.injected = inj_dev; a.injected_steps = o->injected_steps;
+  a.logw = ctx->d_logw; a.meta = ctx->d_meta;
+  a.trace = trace_dev; a.trace_steps = trace_steps;
+  for (long long done = 0; done < o->npaths; done += chunk) {
+    a.path0 = o->path0 + done;
+    a.npaths = o->npaths - done < chunk ? o->npaths - done : chunk;
+    const bool timed = ctx->tev_used + 3 <= MAX_TIMING_EVENTS;
+    if (timed) {
+      while (ctx->tev.size() < ctx->tev_used + 3) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        ctx->tev.push_back(e);
+      }
+      CK(cudaEventRecord(ctx->tev[ctx->tev_used], st));
+    }
+    launch_rollout(a, ctx->num_sms, st);
+    if (timed) CK(cudaEventRecord(ctx->tev[ctx->tev_used + 1], st));
+    launch_reduce(ctx->d_logw, ctx->d_meta, a.path0, a.npaths, ctx->nstarts, ctx->acc_max, ctx->acc_sum, ctx->acc_cnt,
+                  ctx->d_scratch, ctx->scratch_cap, ctx->d_transitions, ctx->num_sms, st);
+    if (timed) {
+      CK(cudaEventRecord(ctx->tev[ctx->tev_used + 2], st));
+      ctx->tev_used += 3;
+    }
+  }
+  CK_LAST();
+  ctx->paths_done += (unsigned long long)o->npaths;
+  return PIQL_OK;
+}
+
+// Sum of the rollout / reduction kernel durations recorded since the last reset (stream must be idle).
+int mc_timing(piql_ctx* ctx, double* rollout_s, double* reduce_s, int64_t* launches, bool consume) {
+  double ro = 0.0, re = 0.0;
+  for (size_t i = 0; i + 3 <= ctx->tev_used; i += 3) {
+    float a = 0.f, b = 0.f;
+    CK(cudaEventElapsedTime(&a, ctx->tev[i], ctx->tev[i + 1]));
+    CK(cudaEventElapsedTime(&b, ctx->tev[i + 1], ctx->tev[i + 2]));
+    ro += a * 1e-3; re += b * 1e-3;
+  }
+  if (rollout_s) *rollout_s = ro;
+  if (reduce_s) *reduce_s = re;
+  if (launches) *launches = (int64_t)(ctx->tev_used / 3);
+  if (consume) ctx->tev_used = 0;
+  return PIQL_OK;
+}
+
+int mc_finalize(piql_ctx* ctx, double* logz_sa, uint64_t* count_sa, double* logz_s, piql_mc_stats* stats) {
+  cudaStream_t st = ctx->stream;
+  const long long n = ctx->g.n;
+  NEED(ctx->nstarts > 0, PIQL_ERR_STATE, "no Monte-Carlo run to finalise");
+  // device staging: reuse the VI double buffers (d_in4: 4n doubles, d_out: n doubles)
+  int rc = ensure_vi(ctx);
+  if (rc) return rc;
+  double* d_sa = logz_sa ? ctx->d_in4 : nullptr;
+  double* d_s = logz_s ? ctx->d_out : nullptr;
+  unsigned long long* d_cnt = count_sa ? reinterpret_cast<unsigned long long*>(ctx->vs.aux4) : nullptr;
+  ctx->vs_ready = false;  // aux4 is clobbered
+  if (d_sa) launch_fill_f64(d_sa, NAN, 4 * n, st);
+  if (d_s) launch_fill_f64(d_s, NAN, n, st);
+  if (d_cnt) CK(cudaMemsetAsync(d_cnt, 0, 32 * (size_t)n, st));
+  launch_mc_finalize(ctx->acc_max, ctx->acc_sum, ctx->acc_cnt, ctx->d_starts, ctx->nstarts, d_sa, d_cnt, d_s, st);
+  CK_LAST();
+  if (d_sa) CK(cudaMemcpyAsync(logz_sa, d_sa, 32 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (d_cnt) CK(cudaMemcpyAsync(count_sa, d_cnt, 32 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (d_s) CK(cudaMemcpyAsync(logz_s, d_s, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->h_transitions, ctx->d_transitions, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (stats) {
+    stats->transitions = *ctx->h_transitions;
+    stats->paths = ctx->paths_done;
+    double ro = 0.0, re = 0.0;
+    int rc2 = mc_timing(ctx, &ro, &re, nullptr, false);
+    if (rc2) return rc2;
+    stats->rollout_seconds = ro;
+    stats->device_seconds = ro + re;
+  }
+  return PIQL_OK;
+}
+
+int build_table(piql_ctx* ctx, const double* V, const double* Q, double beta) {
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded (call piql_grid_load first)");
+  NEED(V != nullptr, PIQL_ERR_ARG, "V is null");
+  NEED(beta == beta, PIQL_ERR_ARG, "beta is NaN");
+  int rc = ensure_vi(ctx);
+  if (rc) return rc;
+  const int n = ctx->g.n;
+  cudaStream_t st = ctx->stream;
+  const double vg = V[ctx->g.goal];
+  NEED(vg == vg, PIQL_ERR_ARG, "V(goal) is NaN");
+  CK(cudaMemcpyAsync(ctx->d_in0, V, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+  if (Q) CK(cudaMemcpyAsync(ctx->d_in4, Q, 32 * (size_t)n, cudaMemcpyHostToDevice, st));
+  launch_policy_table(ctx->g, ctx->d_cell, ctx->d_in0, Q ? ctx->d_in4 : nullptr, beta, 1.0, ctx->d_table, st);
+  CK_LAST();
+  ctx->v_goal = vg;
+  ctx->has_table = true;
+  return PIQL_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int32_t piql_version(void) { return PIQL_VERSION; }
+
+int32_t piql_device_count(int32_t* n_out) {
+  if (!n_out) return PIQL_ERR_ARG;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { *n_out = 0; return PIQL_ERR_NO_DEVICE; }
+  *n_out = n;
+  return PIQL_OK;
+}
+
+int32_t piql_create(piql_ctx** ctx_out, int32_t device_id) {
+  if (!ctx_out) return PIQL_ERR_ARG;
+  *ctx_out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return PIQL_ERR_NO_DEVICE;  // no CPU fallback
+  if (device_id < 0 || device_id >= n) return PIQL_ERR_ARG;
+  piql_ctx* ctx = new (std::nothrow) piql_ctx();
+  if (!ctx) return PIQL_ERR_ARG;
+  ctx->device = device_id;
+  cudaDeviceProp prop;
+  bool ok = cudaSetDevice(device_id) == cudaSuccess && cudaGetDeviceProperties(&prop, device_id) == cudaSuccess;
+  if (ok && prop.major != 10) {  // built for sm_100a only
+    delete ctx;
+    return PIQL_ERR_UNSUPPORTED;
+  }
+  ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+       cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
+       cudaMalloc((void**)&ctx->d_scalars, 64) == cudaSuccess &&
+       cudaMallocHost((void**)&ctx->h_scalars, 64) == cudaSuccess &&
+       cudaMalloc((void**)&ctx->d_transitions, 16) == cudaSuccess &&
+       cudaMemset(ctx->d_transitions, 0, 16) == cudaSuccess &&
+       cudaMallocHost((void**)&ctx->h_transitions, 16) == cudaSuccess && configure_backup_kernels() == 0 &&
+       configure_rollout_kernels() == 0;
+  if (!ok) {
+    cudaGetLastError();
+    delete ctx;
+    return PIQL_ERR_CUDA;
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  *ctx_out = ctx;
+  return PIQL_OK;
+}
+
+int32_t piql_destroy(piql_ctx* ctx) {
+  if (!ctx) return PIQL_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  free_vi(ctx);
+  for (void* p : {(void*)ctx->d_walls, (void*)ctx->d_cell, (void*)ctx->d_free, (void*)ctx->d_table, (void*)ctx->d_logw,
+                  (void*)ctx->d_meta, (void*)ctx->d_starts_own, (void*)ctx->acc_max, (void*)ctx->acc_sum,
+                  (void*)ctx->acc_cnt, (void*)ctx->d_scratch, (void*)ctx->d_transitions, (void*)ctx->d_inj,
+                  (void*)ctx->d_scalars})
+    if (p) cudaFree(p);
+  if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+  if (ctx->h_transitions) cudaFreeHost(ctx->h_transitions);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (cudaEvent_t e : ctx->tev) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return PIQL_OK;
+}
+
+const char* piql_last_error(const piql_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int32_t piql_stream(piql_ctx* ctx, void** stream_out) {
+  if (!ctx || !stream_out) return PIQL_ERR_ARG;
+  *stream_out = (void*)ctx->stream;
+  return PIQL_OK;
+}
+
+int32_t piql_launch_count(piql_ctx* ctx, int64_t* n_out) {
+  if (!ctx || !n_out) return PIQL_ERR_ARG;
+  *n_out = ctx->launches;
+  return PIQL_OK;
+}
+
+int32_t piql_grid_load(piql_ctx* ctx, const uint8_t* walls, int64_t H, int64_t W, int64_t goal_i, int64_t goal_j,
+                       const piql_grid_params* p) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  NEED(walls && p, PIQL_ERR_ARG, "walls / params is null");
+  NEED(H >= 3 && W >= 3 && H * W < (1LL << 31) / 8, PIQL_ERR_ARG, "grid must be at least 3x3 and below 2^28 cells");
+  NEED(goal_i >= 0 && goal_i < H && goal_j >= 0 && goal_j < W, PIQL_ERR_ARG, "goal outside the grid");
+  NEED(p->gamma > 0.0 && p->gamma < 1.0, PIQL_ERR_ARG, "gamma must lie in (0, 1)");
+  NEED(p->randomness >= 0.0 && p->randomness <= 1.0, PIQL_ERR_ARG, "randomness must lie in [0, 1]");
+  const long long n = H * W;
+  NEED(!walls[goal_i + H * goal_j], PIQL_ERR_ARG, "goal is a wall");
+  // The border must be wall (make_walls, GridWorld.jl:40-45): take_step never leaves the array.
+  for (int64_t i = 0; i < H; i++) NEED(walls[i] && walls[i + H * (W - 1)], PIQL_ERR_ARG, "border cells must be walls");
+  for (int64_t j = 0; j < W; j++) NEED(walls[H * j] && walls[H - 1 + H * j], PIQL_ERR_ARG, "border cells must be walls");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CK(cudaStreamSynchronize(st));
+  for (void* q : {(void*)ctx->d_walls, (void*)ctx->d_cell, (void*)ctx->d_free, (void*)ctx->d_table})
+    if (q) cudaFree(q);
+  ctx->d_walls = ctx->d_cell = nullptr; ctx->d_free = nullptr; ctx->d_table = nullptr;
+  ctx->has_grid = ctx->has_table = false; ctx->vs_ready = false;
+  // free-cell list, in index order (host: it is the tabulation step of the boundary)
+  long long nfree = 0;
+  for (long long s = 0; s < n; s++) nfree += walls[s] == 0;
+  int* h_free = (int*)malloc(sizeof(int) * (size_t)(nfree ? nfree : 1));
+  NEED(h_free != nullptr, PIQL_ERR_ARG, "out of host memory");
+  long long k = 0;
+  for (long long s = 0; s < n; s++) if (!walls[s]) h_free[k++] = (int)s;
+  cudaError_t e = cudaMalloc((void**)&ctx->d_walls, (size_t)n);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_cell, (size_t)n);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_free, sizeof(int) * (size_t)(nfree ? nfree : 1));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_table, 32 * (size_t)n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_walls, walls, (size_t)n, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_free, h_free, sizeof(int) * (size_t)nfree, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    ctx->g.H = (int)H; ctx->g.W = (int)W; ctx->g.n = (int)n; ctx->g.goal = (int)(goal_i + H * goal_j);
+    ctx->g.randomness = p->randomness; ctx->g.step_cost = p->step_cost; ctx->g.reward = p->reward; ctx->g.gamma = p->gamma;
+    launch_cellinfo(ctx->d_walls, ctx->g, ctx->d_cell, st);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  free(h_free);
+  if (e != cudaSuccess) return fail(ctx, PIQL_ERR_CUDA, std::string("piql_grid_load: ") + cudaGetErrorString(e));
+  ctx->nfree = nfree;
+  ctx->has_grid = true;
+  return PIQL_OK;
+}
+
+int32_t piql_grid_free_count(piql_ctx* ctx, int64_t* nfree_out) {
+  if (!ctx || !nfree_out) return PIQL_ERR_ARG;
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded");
+  *nfree_out = ctx->nfree;
+  return PIQL_OK;
+}
+
+static int solve_entry(piql_ctx* ctx, int kind, const double* V, const double* Q, const double* nu, double beta,
+                       double reward_scale, const piql_solve_opts* opts, double* out, piql_solve_stats* stats) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  NEED(opts != nullptr, PIQL_ERR_ARG, "opts is null");
+  NEED(out != nullptr, PIQL_ERR_ARG, "output pointer is null");
+  CK(cudaSetDevice(ctx->device));
+  int rc = vi_prepare(ctx, kind, V, Q, nu, beta, reward_scale, opts->precision);
+  if (rc) return rc;
+  return vi_solve(ctx, opts, out, stats);
+}
+
+int32_t piql_solve_nu(piql_ctx* ctx, double reward_scale, const piql_solve_opts* opts, double* nu_out,
+                      piql_solve_stats* stats) {
+  return solve_entry(ctx, KIND_NU, nullptr, nullptr, nullptr, 1.0, reward_scale, opts, nu_out, stats);
+}
+int32_t piql_solve_logz(piql_ctx* ctx, const double* V, const double* Q, double beta, const piql_solve_opts* opts,
+                        double* logz_out, piql_solve_stats* stats) {
+  return solve_entry(ctx, KIND_LOGZ, V, Q, nullptr, beta, 1.0, opts, logz_out, stats);
+}
+int32_t piql_solve_gap(piql_ctx* ctx, const double* V, const double* Q, const double* nu, const piql_solve_opts* opts,
+                       double* gap_out, piql_solve_stats* stats) {
+  return solve_entry(ctx, KIND_GAP, V, Q, nu, 1.0, 1.0, opts, gap_out, stats);
+}
+
+int32_t piql_update_v(piql_ctx* ctx, const double* V, double beta, const piql_solve_opts* opts, double* vnew_out,
+                      double* logz_out, piql_solve_stats* stats) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  NEED(opts != nullptr && vnew_out != nullptr, PIQL_ERR_ARG, "opts / output pointer is null");
+  NEED(beta != 0.0, PIQL_ERR_ARG, "beta must be non-zero");
+  CK(cudaSetDevice(ctx->device));
+  int rc = vi_prepare(ctx, KIND_LOGZ, V, nullptr, nullptr, beta, 1.0, opts->precision);
+  if (rc) return rc;
+  rc = vi_solve(ctx, opts, logz_out, stats);
+  if (rc && rc != PIQL_ERR_NOT_CONVERGED) return rc;
+  // V + logz/beta   value_iteration.jl:119-124 (d_in0 still holds the caller's V in double)
+  cudaStream_t st = ctx->stream;
+  launch_update_v(ctx->d_in0, ctx->vs.x[ctx->vs.cur], ctx->d_cell, beta, ctx->d_out, ctx->g.n, ctx->vs.precision, st);
+  CK_LAST();
+  CK(cudaMemcpyAsync(vnew_out, ctx->d_out, 8 * (size_t)ctx->g.n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return rc;
+}
+
+int32_t piql_sweep_once(piql_ctx* ctx, int32_t kind, const double* V, const double* Q, const double* nu, double beta,
+                        double reward_scale, int32_t precision, const double* x_in, double* x_out, double* residual_out) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  NEED(x_in && x_out, PIQL_ERR_ARG, "x_in / x_out is null");
+  CK(cudaSetDevice(ctx->device));
+  int rc = vi_prepare(ctx, kind, V, Q, nu, beta, reward_scale, precision);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  const int n = ctx->g.n;
+  CK(cudaMemcpyAsync(ctx->d_out, x_in, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+  launch_convert_in(ctx->d_out, ctx->vs.x[0], n, precision, st);
+  launch_sweep(ctx->g, ctx->d_cell, ctx->vs, true, st);
+  launch_convert_out(ctx->vs.x[ctx->vs.cur], ctx->d_cell, ctx->d_out, n, precision, st);
+  CK_LAST();
+  CK(cudaMemcpyAsync(x_out, ctx->d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (residual_out) *residual_out = ctx->h_scalars[0];
+  return PIQL_OK;
+}
+
+int32_t piql_vi_prepare_dev(piql_ctx* ctx, int32_t kind, const double* V, const double* Q, const double* nu, double beta,
+                            double reward_scale, int32_t precision) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  CK(cudaSetDevice(ctx->device));
+  return vi_prepare(ctx, kind, V, Q, nu, beta, reward_scale, precision);
+}
+int32_t piql_vi_sweeps_dev(piql_ctx* ctx, int64_t sweeps) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  NEED(ctx->vs_ready, PIQL_ERR_STATE, "call piql_vi_prepare_dev first");
+  NEED(sweeps > 0, PIQL_ERR_ARG, "sweeps must be positive");
+  CK(cudaSetDevice(ctx->device));
+  for (int64_t i = 0; i < sweeps; i++) launch_sweep(ctx->g, ctx->d_cell, ctx->vs, i == sweeps - 1, ctx->stream);
+  CK_LAST();
+  ctx->vi_sweeps_done += sweeps;
+  return PIQL_OK;
+}
+int32_t piql_vi_fetch(piql_ctx* ctx, double* x_out, double* residual_out) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  NEED(ctx->vs_ready, PIQL_ERR_STATE, "call piql_vi_prepare_dev first");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int n = ctx->g.n;
+  if (x_out) {
+    launch_convert_out(ctx->vs.x[ctx->vs.cur], ctx->d_cell, ctx->d_out, n, ctx->vs.precision, st);
+    CK_LAST();
+    CK(cudaMemcpyAsync(x_out, ctx->d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (residual_out) *residual_out = ctx->h_scalars[0];
+  return PIQL_OK;
+}
+
+int32_t piql_policy_table(piql_ctx* ctx, const double* V, const double* Q, double beta, float* table_out) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  CK(cudaSetDevice(ctx->device));
+  int rc = build_table(ctx, V, Q, beta);
+  if (rc) return rc;
+  if (table_out) CK(cudaMemcpyAsync(table_out, ctx->d_table, 32 * (size_t)ctx->g.n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PIQL_OK;
+}
+
+int32_t piql_policy_table_set(piql_ctx* ctx, const float* table, double v_goal) {
+  if (!ctx) return PIQL_ERR_ARG;
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded");
+  NEED(table != nullptr, PIQL_ERR_ARG, "table is null");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->d_table, table, 32 * (size_t)ctx->g.n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->v_goal = v_goal;
+  ctx->has_table = true;
+  return PIQL_OK;
+}
+
+int32_t piql_mc_logz(piql_ctx* ctx, const double* V, const double* Q, double beta, const piql_mc_opts* opts,
+                     double* logz_sa_out, uint64_t* count_sa_out, double* logz_s_out, piql_mc_stats* stats) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded (call piql_grid_load first)");
+  int rc = mc_check_opts(ctx, opts);
+  if (rc) return rc;
+  rc = build_table(ctx, V, Q, beta);
+  if (rc) return rc;
+  ctx->tev_used = 0;
+  rc = mc_reset(ctx, opts);
+  if (rc) return rc;
+  rc = mc_rollout(ctx, opts, nullptr, 0);
+  if (rc) return rc;
+  return mc_finalize(ctx, logz_sa_out, count_sa_out, logz_s_out, stats);
+}
+
+int32_t piql_trace_paths(piql_ctx* ctx, const piql_mc_opts* opts, int64_t max_steps, int32_t* triples_out,
+                         float* logw_out, uint32_t* meta_out) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded");
+  int rc = mc_check_opts(ctx, opts);
+  if (rc) return rc;
+  NEED(max_steps > 0 && triples_out, PIQL_ERR_ARG, "max_steps must be positive and triples_out non-null");
+  NEED(opts->npaths * max_steps < (1LL << 28), PIQL_ERR_ARG, "trace too large (npaths*max_steps must be < 2^28)");
+  rc = mc_reset(ctx, opts);
+  if (rc) return rc;
+  int* d_trace = nullptr;
+  const size_t nt = (size_t)opts->npaths * (size_t)max_steps * 3;
+  CK(cudaMalloc((void**)&d_trace, 4 * (nt ? nt : 1)));
+  cudaError_t e = cudaMemsetAsync(d_trace, 0xff, 4 * nt, ctx->stream);  // -1 padding
+  rc = e == cudaSuccess ? mc_rollout(ctx, opts, d_trace, max_steps) : fail(ctx, PIQL_ERR_CUDA, cudaGetErrorString(e));
+  if (rc == PIQL_OK) {
+    e = cudaMemcpyAsync(triples_out, d_trace, 4 * nt, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && logw_out) e = cudaMemcpyAsync(logw_out, ctx->d_logw, 4 * (size_t)opts->npaths, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && meta_out) e = cudaMemcpyAsync(meta_out, ctx->d_meta, 4 * (size_t)opts->npaths, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, PIQL_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaFree(d_trace);
+  return rc;
+}
+
+int32_t piql_mc_reset_dev(piql_ctx* ctx, const piql_mc_opts* opts) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded");
+  int rc = mc_check_opts(ctx, opts);
+  if (rc) return rc;
+  return mc_reset(ctx, opts);
+}
+int32_t piql_mc_rollout_dev(piql_ctx* ctx, const piql_mc_opts* opts) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded");
+  NEED(ctx->nstarts > 0, PIQL_ERR_STATE, "call piql_mc_reset_dev first");
+  int rc = mc_check_opts(ctx, opts);
+  if (rc) return rc;
+  return mc_rollout(ctx, opts, nullptr, 0);
+}
+int32_t piql_mc_stats_dev(piql_ctx* ctx, void** lse_max_dev, void** lse_sum_dev, void** count_dev, int64_t* n_out) {
+  if (!ctx) return PIQL_ERR_ARG;
+  NEED(ctx->nstarts > 0 && ctx->acc_max, PIQL_ERR_STATE, "call piql_mc_reset_dev first");
+  if (lse_max_dev) *lse_max_dev = ctx->acc_max;
+  if (lse_sum_dev) *lse_sum_dev = ctx->acc_sum;
+  if (count_dev) *count_dev = ctx->acc_cnt;
+  if (n_out) *n_out = ctx->nstarts * NA;
+  return PIQL_OK;
+}
+int32_t piql_mc_rescale_dev(piql_ctx* ctx, const void* global_max_dev) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  NEED(ctx->nstarts > 0 && ctx->acc_max, PIQL_ERR_STATE, "call piql_mc_reset_dev first");
+  NEED(global_max_dev != nullptr, PIQL_ERR_ARG, "global_max_dev is null");
+  CK(cudaSetDevice(ctx->device));
+  launch_mc_rescale(ctx->acc_max, ctx->acc_sum, (const float*)global_max_dev, ctx->nstarts * NA, ctx->stream);
+  CK_LAST();
+  return PIQL_OK;
+}
+int32_t piql_mc_finalize(piql_ctx* ctx, double* logz_sa_out, uint64_t* count_sa_out, double* logz_s_out,
+                         piql_mc_stats* stats) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded");
+  return mc_finalize(ctx, logz_sa_out, count_sa_out, logz_s_out, stats);
+}
+int32_t piql_mc_timing(piql_ctx* ctx, double* rollout_seconds, double* reduce_seconds, int64_t* launches) {
+  if (!ctx) return PIQL_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return mc_timing(ctx, rollout_seconds, reduce_seconds, launches, true);
+}
+int32_t piql_mc_transitions_total(piql_ctx* ctx, uint64_t* total_out) {
+  if (!ctx || !total_out) return PIQL_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->h_transitions, ctx->d_transitions, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *total_out = ctx->h_transitions[0] + ctx->h_transitions[1];
+  return PIQL_OK;
+}
+int32_t piql_mc_records(piql_ctx* ctx, float* logw_out, uint32_t* meta_out, int64_t n) {
+  if (!ctx) return PIQL_ERR_ARG;
+  NEED(n >= 0 && n <= ctx->rec_cap, PIQL_ERR_ARG, "more records requested than the last rollout produced");
+  CK(cudaSetDevice(ctx->device));
+  if (logw_out) CK(cudaMemcpyAsync(logw_out, ctx->d_logw, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (meta_out) CK(cudaMemcpyAsync(meta_out, ctx->d_meta, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PIQL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,433 @@
+// backup.cu -- soft value-iteration Bellman backups on the implicit gridworld (sm_100a).
+//
+// Restates, per cell, the recursions the reference evaluates through closures and a Dict:
+//   nu    truevalue_recursion        src/PIQL.jl:95-101      driven by update_ν!   src/value_iteration.jl:62-75
+//   logz  logz_recursion             src/PIQL.jl:125-130     driven by update_logz! src/value_iteration.jl:89-105
+//   gap   optimality_gap_recursion   src/value_iteration.jl:160-169, update_optimality_gap! :129-142
+// with the gridworld closures pa / log_pa / reward (src/Problems/GridWorld.jl:98-116).
+//
+// Layout: one value per cell of the H x W wall array (border included), column-major, so a
+// thread per cell reads its own value and the 4 neighbours at s+-1, s+-H: loads are coalesced
+// along i and the +-H neighbours are whole coalesced lines served from L1/L2.  Sweeps are Jacobi
+// (ping-pong): every cell's new value depends only on the previous iterate, so the result is
+// independent of grid/block shape and of how many GPUs a caller splits the grid over.
+#include "internal.h"
+
+namespace piql {
+
+thread_local long long g_launches = 0;
+
+// Constants of one sweep in the sweep's precision.
+template <typename T> struct K {
+  int H, n, goal;
+  T w_on, w_off;        // (a==aa)*(1-randomness) + randomness/len      GridWorld.jl:101
+  T lw_on, lw_off;      // their logs (log_pa, GridWorld.jl:106)
+  T gamma, lgamma, l1mgamma;
+  T rwd_goal, rwd_step; // reward_function values times the modify() scale   GridWorld.jl:116
+  T log_prior;          // log(1/len)                                       GridWorld.jl:112
+  T beta;
+};
+template <typename T> static K<T> make_k(const GridDev& g, double reward_scale, double beta) {
+  K<T> k;
+  k.H = g.H; k.n = g.n; k.goal = g.goal;
+  const double w_on = 1.0 * (1.0 - g.randomness) + g.randomness / NA;
+  const double w_off = 0.0 * (1.0 - g.randomness) + g.randomness / NA;
+  k.w_on = (T)w_on; k.w_off = (T)w_off;
+  k.lw_on = (T)log(w_on); k.lw_off = (T)log(w_off);
+  k.gamma = (T)g.gamma; k.lgamma = (T)log(g.gamma); k.l1mgamma = (T)log(1.0 - g.gamma);
+  k.rwd_goal = (T)(reward_scale * g.reward); k.rwd_step = (T)(reward_scale * -g.step_cost);
+  k.log_prior = (T)log(1.0 / NA);
+  k.beta = (T)beta;
+  return k;
+}
+
+// ---- per-cell algebra on a gathered 5-point stencil ----------------------------------------------
+template <typename T>
+__device__ __forceinline__ void gather(const T* __restrict__ X, int s, int H, unsigned ci, T& c, T (&nb)[NA]) {
+  // f(take_step(s,aa)): the neighbour, or the cell itself when a wall blocks the move  GridWorld.jl:29-32
+  c = X[s];
+  nb[0] = (ci & 1u) ? c : X[s + 1];
+  nb[1] = (ci & 2u) ? c : X[s - 1];
+  nb[2] = (ci & 4u) ? c : X[s + H];
+  nb[3] = (ci & 8u) ? c : X[s - H];
+}
+template <typename T> __device__ __forceinline__ T pa(const K<T>& k, int a, const T (&f)[NA]) {
+  T out = 0;  // propagator_average, same accumulation order as GridWorld.jl:98-104
+#pragma unroll
+  for (int aa = 0; aa < NA; aa++) out += (a == aa ? k.w_on : k.w_off) * f[aa];
+  return out;
+}
+template <typename T>
+__device__ __forceinline__ void avg_rewards(const K<T>& k, int s, unsigned ci, T (&rbar)[NA]) {
+  // average_reward(ctrl,s,a) = pa(s,a, s1 -> reward_function(s,a,s1))   PIQL.jl:55-57
+  T r[NA];
+  r[0] = (!(ci & 1u) && s + 1 == k.goal) ? k.rwd_goal : k.rwd_step;
+  r[1] = (!(ci & 2u) && s - 1 == k.goal) ? k.rwd_goal : k.rwd_step;
+  r[2] = (!(ci & 4u) && s + k.H == k.goal) ? k.rwd_goal : k.rwd_step;
+  r[3] = (!(ci & 8u) && s - k.H == k.goal) ? k.rwd_goal : k.rwd_step;
+#pragma unroll
+  for (int a = 0; a < NA; a++) rbar[a] = pa(k, a, r);
+}
+template <typename T>
+__device__ __forceinline__ void control_v(const K<T>& k, T c, const T (&nb)[NA], const T (&rbar)[NA], T (&cv)[NA]) {
+#pragma unroll
+  for (int a = 0; a < NA; a++) cv[a] = k.gamma * pa(k, a, nb) - c + rbar[a];  // PIQL.jl:63-66
+}
+
+template <typename T>
+__device__ __forceinline__ T backup_nu(const K<T>& k, int s, unsigned ci, const T (&nb)[NA]) {
+  T rbar[NA], x[NA];
+  avg_rewards(k, s, ci, rbar);
+#pragma unroll
+  for (int a = 0; a < NA; a++) x[a] = k.log_prior + k.gamma * pa(k, a, nb) + rbar[a];
+  return lse4(x);
+}
+// A[a] = log prior + beta*controlV + (1-beta)*controlQ (fixed during the solve, from prep_kernel)
+template <typename T>
+__device__ __forceinline__ T backup_logz(const K<T>& k, const T (&A)[NA], const T (&nb)[NA]) {
+  // log_pa(s,a,logz) = logsumexp_aa(log P(aa|a) + logz(step(s,aa))), with the four exponentials
+  // shared between the actions: P(aa|a) takes two values only.
+  const T m = fmax(fmax(nb[0], nb[1]), fmax(nb[2], nb[3]));
+  T e[NA], esum = 0;
+#pragma unroll
+  for (int aa = 0; aa < NA; aa++) { e[aa] = xexp(nb[aa] - m); esum += e[aa]; }
+  T x[NA];
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+    const T inner = m + xlog(k.w_on * e[a] + k.w_off * (esum - e[a]));
+    x[a] = A[a] + logaddexp(k.lgamma + inner, k.l1mgamma);
+  }
+  return lse4(x);
+}
+template <typename T>
+__device__ __forceinline__ T backup_gap(const K<T>& k, const T (&P)[NA], T D, const T (&nb)[NA]) {
+  T out = D;  // D = sum_a pi_a (controlQ - controlV(nu)); gap term has no gamma (value_iteration.jl:165)
+#pragma unroll
+  for (int a = 0; a < NA; a++) out += P[a] * pa(k, a, nb);
+  return out;
+}
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<double> { using type = double4; };
+template <typename T> __device__ __forceinline__ void load4(const T* p, int s, T (&o)[NA]);
+template <> __device__ __forceinline__ void load4<float>(const float* p, int s, float (&o)[NA]) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p) + s);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <> __device__ __forceinline__ void load4<double>(const double* p, int s, double (&o)[NA]) {
+  const double2 v0 = __ldg(reinterpret_cast<const double2*>(p) + 2 * s);
+  const double2 v1 = __ldg(reinterpret_cast<const double2*>(p) + 2 * s + 1);
+  o[0] = v0.x; o[1] = v0.y; o[2] = v1.x; o[3] = v1.y;
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, int s, const T (&v)[NA]);
+template <> __device__ __forceinline__ void store4<float>(float* p, int s, const float (&v)[NA]) {
+  reinterpret_cast<float4*>(p)[s] = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void store4<double>(double* p, int s, const double (&v)[NA]) {
+  reinterpret_cast<double2*>(p)[2 * s] = make_double2(v[0], v[1]);
+  reinterpret_cast<double2*>(p)[2 * s + 1] = make_double2(v[2], v[3]);
+}
+
+// One backup of cell s reading the iterate through X (global or shared memory).
+template <typename T, int KIND>
+__device__ __forceinline__ void backup_cell(const K<T>& k, int s, unsigned ci, const T* X, const T* __restrict__ aux4,
+                                            const T* __restrict__ aux1, T term_value, T& stored, double& absdiff) {
+  T c, nb[NA];
+  gather(X, s, k.H, ci, c, nb);
+  T nw;
+  if (ci & CELL_GOAL) {
+    nw = term_value;  // terminal_condition: nu, gap -> 0; logz -> 0 - V(goal)
+  } else if (KIND == KIND_NU) {
+    nw = backup_nu(k, s, ci, nb);
+  } else if (KIND == KIND_LOGZ) {
+    T A[NA];
+    load4(aux4, s, A);
+    nw = backup_logz(k, A, nb);
+  } else {
+    T P[NA];
+    load4(aux4, s, P);
+    nw = backup_gap(k, P, __ldg(aux1 + s), nb);
+  }
+  absdiff = fabs((double)nw - (double)c);
+  // eta = 0.5 damping of update_logz!: logaddexp(log(eta)+new, log(1-eta)+old)   value_iteration.jl:101-102
+  stored = (KIND == KIND_LOGZ) ? logaddexp((T)(-0.6931471805599453) + nw, (T)(-0.6931471805599453) + c) : nw;
+}
+
+// ---- kernels -----------------------------------------------------------------------------------
+__global__ void cellinfo_kernel(const uint8_t* __restrict__ walls, int H, int W, int goal, uint8_t* __restrict__ cell) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= H * W) return;
+  const int i = s % H, j = s / H;
+  unsigned ci = 0;
+  if (walls[s]) {
+    ci = CELL_WALL | CELL_BLOCK_MASK;
+  } else {
+    // the border is wall by construction (make_walls, GridWorld.jl:40-45); guard anyway
+    if (i + 1 >= H || walls[s + 1]) ci |= 1u;
+    if (i - 1 < 0 || walls[s - 1]) ci |= 2u;
+    if (j + 1 >= W || walls[s + H]) ci |= 4u;
+    if (j - 1 < 0 || walls[s - H]) ci |= 8u;
+    if (s == goal) ci |= CELL_GOAL;
+  }
+  cell[s] = (uint8_t)ci;
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(SWEEP_THREADS)
+sweep_kernel(K<T> k, const uint8_t* __restrict__ cell, const T* __restrict__ X, T* __restrict__ Y,
+             const T* __restrict__ aux4, const T* __restrict__ aux1, T term_value, double* __restrict__ partial) {
+  __shared__ double red[32];
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  double d = 0.0;
+  if (s < k.n) {
+    const unsigned ci = cell[s];
+    if (!(ci & CELL_WALL)) {
+      T stored;
+      backup_cell<T, KIND>(k, s, ci, X, aux4, aux1, term_value, stored, d);
+      Y[s] = stored;
+    }
+  }
+  if (partial) {  // uniform branch
+    const double r = block_sum(d, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+  }
+}
+
+__global__ void __launch_bounds__(1024) residual_final_kernel(const double* __restrict__ partial, int nblocks, double* out) {
+  __shared__ double red[32];
+  double d = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) d += partial[b];
+  const double r = block_sum(d, red);
+  if (threadIdx.x == 0) *out = r;
+}
+
+// Whole solve in one CTA with the iterate resident in shared memory: the reference-scale
+// problems (251 states) need 10^3..10^4 sweeps, which one launch per sweep would turn into
+// pure launch latency.
+template <typename T, int KIND>
+__global__ void __launch_bounds__(1024)
+resident_solve_kernel(K<T> k, const uint8_t* __restrict__ cell, const T* __restrict__ x0, T* __restrict__ xout,
+                      const T* __restrict__ aux4, const T* __restrict__ aux1, T term_value, double tol,
+                      long long max_sweeps, double* __restrict__ out2) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[32];
+  __shared__ double s_res;
+  T* A = reinterpret_cast<T*>(smem_raw);
+  T* B = A + k.n;
+  uint8_t* cs = reinterpret_cast<uint8_t*>(B + k.n);
+  for (int s = threadIdx.x; s < k.n; s += blockDim.x) { A[s] = x0[s]; B[s] = x0[s]; cs[s] = cell[s]; }
+  __syncthreads();
+  long long sweeps = 0;
+  double res = CUDART_INF;
+  while (sweeps < max_sweeps) {
+    double d = 0.0;
+    for (int s = threadIdx.x; s < k.n; s += blockDim.x) {
+      const unsigned ci = cs[s];
+      if (ci & CELL_WALL) continue;
+      T stored; double dd;
+      backup_cell<T, KIND>(k, s, ci, A, aux4, aux1, term_value, stored, dd);
+      B[s] = stored;
+      d += dd;
+    }
+    const double r = block_sum(d, red);  // contains the barriers that order A reads / B writes
+    if (threadIdx.x == 0) s_res = r;
+    __syncthreads();
+    res = s_res;
+    T* t = A; A = B; B = t;
+    sweeps++;
+    if (res < tol) break;
+  }
+  for (int s = threadIdx.x; s < k.n; s += blockDim.x) xout[s] = A[s];
+  if (threadIdx.x == 0) { out2[0] = (double)sweeps; out2[1] = res; }
+}
+
+// Per-cell constants of the logz / gap sweeps.
+template <typename T, int KIND>
+__global__ void __launch_bounds__(SWEEP_THREADS)
+prep_kernel(K<T> k, const uint8_t* __restrict__ cell, const T* __restrict__ V, const T* __restrict__ Q,
+            const T* __restrict__ nu, T* __restrict__ aux4, T* __restrict__ aux1) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= k.n) return;
+  const unsigned ci = cell[s];
+  T out4[NA] = {0, 0, 0, 0};
+  T out1 = 0;
+  if (!(ci & (CELL_WALL | CELL_GOAL))) {
+    T c, nb[NA], rbar[NA], cv[NA], q[NA], x[NA];
+    gather(V, s, k.H, ci, c, nb);
+    avg_rewards(k, s, ci, rbar);
+    control_v(k, c, nb, rbar, cv);
+    if (Q) load4(Q, s, q);
+    else {
+#pragma unroll
+      for (int a = 0; a < NA; a++) q[a] = cv[a];  // (s,a) -> controlV(ctrl,V,s,a)   value_iteration.jl:97,157
+    }
+#pragma unroll
+    for (int a = 0; a < NA; a++) x[a] = k.log_prior + q[a];
+    const T norm = lse4(x);  // Qnormalization   PIQL.jl:72-75
+    if (KIND == KIND_LOGZ) {
+#pragma unroll
+      for (int a = 0; a < NA; a++) out4[a] = k.log_prior + k.beta * cv[a] + ((T)1 - k.beta) * (q[a] - norm);
+    } else {
+      T nc, nnb[NA], cvn[NA];
+      gather(nu, s, k.H, ci, nc, nnb);
+      control_v(k, nc, nnb, rbar, cvn);
+#pragma unroll
+      for (int a = 0; a < NA; a++) {
+        const T cq = q[a] - norm;                 // controlQ            PIQL.jl:79-81
+        out4[a] = (T)0.25 * xexp(cq);             // action_probability  PIQL.jl:83-85
+        out1 += out4[a] * (cq - cvn[a]);
+      }
+    }
+  }
+  store4(aux4, s, out4);
+  if (KIND == KIND_GAP) aux1[s] = out1;
+}
+
+template <typename T>
+__global__ void convert_in_kernel(const double* __restrict__ src, T* __restrict__ dst, int n) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) {
+    const double v = src[s];
+    dst[s] = (v == v) ? (T)v : (T)0;  // callers pass NaN at walls; never read, but keep them finite
+  }
+}
+template <typename T>
+__global__ void convert_out_kernel(const T* __restrict__ src, const uint8_t* __restrict__ cell, double* __restrict__ dst, int n) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) dst[s] = (cell[s] & CELL_WALL) ? CUDART_NAN : (double)src[s];
+}
+template <typename T> __global__ void fill_kernel(T* dst, T v, int n) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) dst[s] = v;
+}
+template <typename T>
+__global__ void update_v_kernel(const double* __restrict__ V, const T* __restrict__ logz, const uint8_t* __restrict__ cell,
+                                double beta, double* __restrict__ out, int n) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;  // V(k) + logz(k)/beta   value_iteration.jl:121-122
+  if (s < n) out[s] = (cell[s] & CELL_WALL) ? CUDART_NAN : V[s] + (double)logz[s] / beta;
+}
+
+// ---- host launchers ------------------------------------------------------------------------------
+static inline int nblk(int n, int t) { return (n + t - 1) / t; }
+
+void launch_cellinfo(const uint8_t* walls, const GridDev& g, uint8_t* cell, cudaStream_t st) {
+  cellinfo_kernel<<<nblk(g.n, 256), 256, 0, st>>>(walls, g.H, g.W, g.goal, cell);
+  g_launches++;
+}
+void launch_convert_in(const double* src, void* dst, int n, int precision, cudaStream_t st) {
+  if (precision == 0) convert_in_kernel<double><<<nblk(n, 256), 256, 0, st>>>(src, (double*)dst, n);
+  else convert_in_kernel<float><<<nblk(n, 256), 256, 0, st>>>(src, (float*)dst, n);
+  g_launches++;
+}
+void launch_convert_out(const void* src, const uint8_t* cell, double* dst, int n, int precision, cudaStream_t st) {
+  if (precision == 0) convert_out_kernel<double><<<nblk(n, 256), 256, 0, st>>>((const double*)src, cell, dst, n);
+  else convert_out_kernel<float><<<nblk(n, 256), 256, 0, st>>>((const float*)src, cell, dst, n);
+  g_launches++;
+}
+void launch_fill(void* dst, double value, int n, int precision, cudaStream_t st) {
+  if (precision == 0) fill_kernel<double><<<nblk(n, 256), 256, 0, st>>>((double*)dst, value, n);
+  else fill_kernel<float><<<nblk(n, 256), 256, 0, st>>>((float*)dst, (float)value, n);
+  g_launches++;
+}
+void launch_update_v(const double* V, const void* logz, const uint8_t* cell, double beta, double* out, int n,
+                     int precision, cudaStream_t st) {
+  if (precision == 0) update_v_kernel<double><<<nblk(n, 256), 256, 0, st>>>(V, (const double*)logz, cell, beta, out, n);
+  else update_v_kernel<float><<<nblk(n, 256), 256, 0, st>>>(V, (const float*)logz, cell, beta, out, n);
+  g_launches++;
+}
+
+template <typename T>
+static void prep_t(const GridDev& g, const uint8_t* cell, ViState& vs, const void* Q, const void* nu, cudaStream_t st) {
+  const K<T> k = make_k<T>(g, vs.reward_scale, vs.beta);
+  const int nb = nblk(g.n, SWEEP_THREADS);
+  if (vs.kind == KIND_LOGZ)
+    prep_kernel<T, KIND_LOGZ><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, (const T*)vs.V, (const T*)Q, nullptr, (T*)vs.aux4, nullptr);
+  else
+    prep_kernel<T, KIND_GAP><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, (const T*)vs.V, (const T*)Q, (const T*)nu, (T*)vs.aux4, (T*)vs.aux1);
+  g_launches++;
+}
+void launch_prep(const GridDev& g, const uint8_t* cell, ViState& vs, const void* Q, const void* nu, cudaStream_t st) {
+  if (vs.kind == KIND_NU) return;
+  if (vs.precision == 0) prep_t<double>(g, cell, vs, Q, nu, st);
+  else prep_t<float>(g, cell, vs, Q, nu, st);
+}
+
+// terminal cells: nu, gap -> 0; logz -> 0 - V(goal)   value_iteration.jl:66-67,93-94,133-134
+template <typename T> static T term_value_of(const ViState& vs) {
+  return vs.kind == KIND_LOGZ ? (T)(0.0 - vs.v_goal) : (T)0;
+}
+
+template <typename T>
+static void sweep_t(const GridDev& g, const uint8_t* cell, ViState& vs, bool with_residual, cudaStream_t st) {
+  const K<T> k = make_k<T>(g, vs.reward_scale, vs.beta);
+  const int nb = vs.nblocks;
+  const T* X = (const T*)vs.x[vs.cur];
+  T* Y = (T*)vs.x[vs.cur ^ 1];
+  double* partial = with_residual ? vs.partial : nullptr;
+  const T tv = term_value_of<T>(vs);
+  switch (vs.kind) {
+    case KIND_NU:
+      sweep_kernel<T, KIND_NU><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, X, Y, nullptr, nullptr, tv, partial); break;
+    case KIND_LOGZ:
+      sweep_kernel<T, KIND_LOGZ><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, X, Y, (const T*)vs.aux4, nullptr, tv, partial); break;
+    default:
+      sweep_kernel<T, KIND_GAP><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, X, Y, (const T*)vs.aux4, (const T*)vs.aux1, tv, partial); break;
+  }
+  g_launches++;
+  if (with_residual) {
+    residual_final_kernel<<<1, 1024, 0, st>>>(vs.partial, nb, vs.residual);
+    g_launches++;
+  }
+  vs.cur ^= 1;
+}
+
+void launch_sweep(const GridDev& g, const uint8_t* cell, ViState& vs, bool with_residual, cudaStream_t st) {
+  if (vs.precision == 0) sweep_t<double>(g, cell, vs, with_residual, st);
+  else sweep_t<float>(g, cell, vs, with_residual, st);
+}
+
+size_t resident_smem_bytes(int n, int precision) {
+  const size_t e = precision == 0 ? 8 : 4;
+  return 2 * e * (size_t)n + (((size_t)n + 15) / 16) * 16;
+}
+
+template <typename T>
+static void resident_t(const GridDev& g, const uint8_t* cell, ViState& vs, double tol, long long max_sweeps,
+                       double* dev_out, cudaStream_t st) {
+  const K<T> k = make_k<T>(g, vs.reward_scale, vs.beta);
+  const size_t smem = resident_smem_bytes(g.n, vs.precision);
+  const T* x0 = (const T*)vs.x[vs.cur];
+  T* xout = (T*)vs.x[vs.cur ^ 1];
+  const T tv = term_value_of<T>(vs);
+  const int threads = g.n >= 1024 ? 1024 : ((g.n + 31) / 32) * 32;
+  switch (vs.kind) {
+    case KIND_NU:
+      resident_solve_kernel<T, KIND_NU><<<1, threads, smem, st>>>(k, cell, x0, xout, nullptr, nullptr, tv, tol, max_sweeps, dev_out); break;
+    case KIND_LOGZ:
+      resident_solve_kernel<T, KIND_LOGZ><<<1, threads, smem, st>>>(k, cell, x0, xout, (const T*)vs.aux4, nullptr, tv, tol, max_sweeps, dev_out); break;
+    default:
+      resident_solve_kernel<T, KIND_GAP><<<1, threads, smem, st>>>(k, cell, x0, xout, (const T*)vs.aux4, (const T*)vs.aux1, tv, tol, max_sweeps, dev_out); break;
+  }
+  g_launches++;
+  vs.cur ^= 1;
+}
+void launch_resident_solve(const GridDev& g, const uint8_t* cell, ViState& vs, double tol, long long max_sweeps,
+                           double* dev_out, cudaStream_t st) {
+  if (vs.precision == 0) resident_t<double>(g, cell, vs, tol, max_sweeps, dev_out, st);
+  else resident_t<float>(g, cell, vs, tol, max_sweeps, dev_out, st);
+}
+
+int configure_backup_kernels() {
+  // opt in to > 48 KB dynamic shared memory for the resident solver
+  const int maxb = (int)resident_smem_bytes(RESIDENT_MAX_CELLS, 0);
+  cudaError_t e = cudaSuccess;
+#define PIQL_SET(T, KND) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(resident_solve_kernel<T, KND>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
+  PIQL_SET(double, KIND_NU) PIQL_SET(double, KIND_LOGZ) PIQL_SET(double, KIND_GAP)
+  PIQL_SET(float, KIND_NU) PIQL_SET(float, KIND_LOGZ) PIQL_SET(float, KIND_GAP)
+#undef PIQL_SET
+  return (int)e;
+}
+
+}  // namespace piql

@@ -1,0 +1,88 @@
+// common.cuh -- shared device helpers for the PIQL B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace piql {
+
+constexpr int NA = 4;                  // actions of the 2-D gridworld (step_choices, GridWorld.jl:20-22)
+constexpr uint8_t CELL_BLOCK_MASK = 0x0f;  // bit a: take_step(s,a) is blocked by a wall
+constexpr uint8_t CELL_WALL = 0x10;
+constexpr uint8_t CELL_GOAL = 0x20;
+constexpr unsigned FULL = 0xffffffffu;
+
+// Problem constants, passed by value to every kernel.
+struct GridDev {
+  int H, W;
+  int n;       // H*W
+  int goal;    // linear index of the goal cell
+  double randomness, step_cost, reward, gamma;
+};
+
+// ---- precision-generic math ------------------------------------------------------------------
+__device__ __forceinline__ float xexp(float x) { return expf(x); }
+__device__ __forceinline__ double xexp(double x) { return exp(x); }
+__device__ __forceinline__ float xlog(float x) { return logf(x); }
+__device__ __forceinline__ double xlog(double x) { return log(x); }
+__device__ __forceinline__ float xlog1p(float x) { return log1pf(x); }
+__device__ __forceinline__ double xlog1p(double x) { return log1p(x); }
+template <typename T> __device__ __forceinline__ T neg_inf();
+template <> __device__ __forceinline__ float neg_inf<float>() { return -CUDART_INF_F; }
+template <> __device__ __forceinline__ double neg_inf<double>() { return -CUDART_INF; }
+
+// LogExpFunctions.logsumexp over the four actions (max-shifted).
+template <typename T> __device__ __forceinline__ T lse4(const T (&x)[NA]) {
+  T m = fmax(fmax(x[0], x[1]), fmax(x[2], x[3]));
+  if (m == neg_inf<T>()) return m;
+  T s = xexp(x[0] - m) + xexp(x[1] - m) + xexp(x[2] - m) + xexp(x[3] - m);
+  return m + xlog(s);
+}
+// LogExpFunctions.logaddexp
+template <typename T> __device__ __forceinline__ T logaddexp(T x, T y) {
+  if (x == neg_inf<T>()) return y;
+  if (y == neg_inf<T>()) return x;
+  return fmax(x, y) + xlog1p(xexp(-fabs(x - y)));
+}
+
+// ---- reductions --------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+// Sum over the block in a fixed order (deterministic); result valid in thread 0.
+template <typename T> __device__ __forceinline__ T block_sum(T v, T* smem /* >= 32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  T r = 0;
+  if (warp == 0) {
+    r = lane < nw ? smem[lane] : T(0);
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+// ---- Philox4x32-10 (Salmon, Moraes, Dror, Shaw; SC'11) -------------------------------------------
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+      const uint32_t lo0 = 0xD2511F53u * c0, hi0 = __umulhi(0xD2511F53u, c0);
+      const uint32_t lo1 = 0xCD9E8D57u * c2, hi1 = __umulhi(0xCD9E8D57u, c2);
+      const uint32_t n0 = hi1 ^ c1 ^ a, n2 = hi0 ^ c3 ^ b;
+      c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+// 24-bit uniform in [0,1): exactly representable, identical on host and device.
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
+
+}  // namespace piql

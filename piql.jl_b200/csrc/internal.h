@@ -1,0 +1,92 @@
+// internal.h -- host-side interfaces between api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace piql {
+
+enum Kind { KIND_NU = 0, KIND_LOGZ = 1, KIND_GAP = 2 };
+
+// Device state of one soft-VI solve.  All value arrays hold n = H*W elements of the sweep
+// precision (float or double), column-major like the wall array.
+struct ViState {
+  int precision;      // PIQL_F64 / PIQL_F32
+  int kind;
+  double beta, reward_scale;
+  double v_goal;      // V(goal): logz at the terminal cell is 0 - V(goal)
+  void* x[2];         // Jacobi ping-pong iterate; x[cur] is current
+  int cur;
+  void* V;            // fixed V (logz, gap)
+  void* aux4;         // logz: A[4] per cell; gap: pi[4] per cell
+  void* aux1;         // gap: D per cell
+  double* partial;    // per-block residual partials
+  double* residual;   // device scalar
+  int nblocks;
+};
+
+constexpr int SWEEP_THREADS = 256;
+constexpr int RESIDENT_MAX_CELLS = 8192;  // single-CTA resident solver limit
+
+// backup.cu ---------------------------------------------------------------------------------
+void launch_cellinfo(const uint8_t* walls, const GridDev& g, uint8_t* cell, cudaStream_t st);
+// Converts double input to the sweep precision (or copies).
+void launch_convert_in(const double* src, void* dst, int n, int precision, cudaStream_t st);
+// Writes double output with NaN at walls.
+void launch_convert_out(const void* src, const uint8_t* cell, double* dst, int n, int precision, cudaStream_t st);
+void launch_fill(void* dst, double value, int n, int precision, cudaStream_t st);
+// Precompute the per-cell constants of the logz / gap sweeps from V (and Q, nu).
+void launch_prep(const GridDev& g, const uint8_t* cell, ViState& vs, const void* Q, const void* nu, cudaStream_t st);
+// One Jacobi sweep x[cur] -> x[cur^1]; with_residual: also per-block partials + final sum.
+void launch_sweep(const GridDev& g, const uint8_t* cell, ViState& vs, bool with_residual, cudaStream_t st);
+// Whole solve in one CTA (n <= RESIDENT_MAX_CELLS): returns through dev_out {sweeps, residual}.
+void launch_resident_solve(const GridDev& g, const uint8_t* cell, ViState& vs, double tol, long long max_sweeps,
+                           double* dev_out /*2 doubles*/, cudaStream_t st);
+void launch_update_v(const double* V, const void* logz, const uint8_t* cell, double beta, double* out, int n,
+                     int precision, cudaStream_t st);
+size_t resident_smem_bytes(int n, int precision);
+int configure_backup_kernels();
+
+// rollout.cu --------------------------------------------------------------------------------
+struct RolloutArgs {
+  const float4* table;   // 2 x float4 per cell
+  int goal;
+  int H;
+  float gamma, rho, vgoal, lgam, l1mg;
+  int estimator;
+  long long horizon;
+  long long path0, npaths;
+  const int* starts;
+  long long nstarts;
+  uint32_t seed_lo, seed_hi;
+  const float* injected;
+  long long injected_steps;
+  float* logw;           // [npaths]
+  uint32_t* meta;        // [npaths]
+  int* trace;            // optional [npaths][trace_steps][3]
+  long long trace_steps;
+};
+void launch_policy_table(const GridDev& g, const uint8_t* cell, const double* V, const double* Q, double beta,
+                         double reward_scale, float4* table, cudaStream_t st);
+void launch_rollout(const RolloutArgs& a, int num_sms, cudaStream_t st);
+// Reduce records into (max, sum, count)[nstarts*4], merged into the accumulators; adds the
+// transition count to *transitions.
+void launch_reduce(const float* logw, const uint32_t* meta, long long path0, long long npaths, long long nstarts,
+                   float* acc_max, float* acc_sum, uint32_t* acc_cnt, float* scratch, size_t scratch_floats,
+                   unsigned long long* transitions, int num_sms, cudaStream_t st);
+size_t reduce_scratch_floats(long long npaths, long long nstarts);
+void launch_mc_reset(float* acc_max, float* acc_sum, uint32_t* acc_cnt, long long n, cudaStream_t st);
+void launch_fold_counter(unsigned long long* counters, cudaStream_t st);
+void launch_mc_rescale(float* acc_max, float* acc_sum, const float* gmax, long long n, cudaStream_t st);
+// Scatter accumulators into per-cell outputs (NaN / 0 elsewhere already set by the caller).
+void launch_mc_finalize(const float* acc_max, const float* acc_sum, const uint32_t* acc_cnt, const int* starts,
+                        long long nstarts, double* logz_sa, unsigned long long* count_sa, double* logz_s,
+                        cudaStream_t st);
+void launch_fill_f64(double* dst, double v, long long n, cudaStream_t st);
+int configure_rollout_kernels();
+
+// counts kernel launches made through the launch_* wrappers
+extern thread_local long long g_launches;
+
+}  // namespace piql

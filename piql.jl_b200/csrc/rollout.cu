@@ -1,0 +1,438 @@
+// rollout.cu -- Monte-Carlo path sampling under the soft policy pi_Q, with per-path log-weight
+// accumulation and the log-sum-exp reduction into per-(start cell, first action) statistics.
+//
+// Replaces choose_action / path_transitions / fitness_reward_estimate (src/path_functions.jl:12-41),
+// the propagator closure (src/Problems/GridWorld.jl:113-115) and StatsBase's sample(a, Weights).
+// The estimator is the Monte-Carlo form of z_recursion (src/PIQL.jl:109-115): with
+// pi_0 exp(beta cV + (1-beta) cQ) = pi_Q exp(beta fitness),
+//     Z(s) = E_{a~pi_Q}[ exp(beta fitness(s,a)) (gamma E_{s'} Z(s') + 1 - gamma) ],  Z(goal) = exp(-V(goal)).
+//
+// Data layout: one 32-byte record per cell {c0,c1,c2,mask | bf0..bf3} = exactly one DRAM/L2
+// sector per sampled transition; one 8-byte record per finished path {logw, a0|len<<2}.
+// One trajectory per thread; a warp owns a contiguous range of path ids and refills finished
+// lanes warp-synchronously (ballot + popc), so path -> lane assignment is deterministic.
+#include "internal.h"
+
+namespace piql {
+
+// ---- policy table ----------------------------------------------------------------------------------
+// Computed in double from the caller's V (and Q) and rounded once to float, like the oracle.
+__global__ void __launch_bounds__(256)
+policy_table_kernel(GridDev g, double reward_scale, double beta, const uint8_t* __restrict__ cell,
+                    const double* __restrict__ V, const double* __restrict__ Q, float4* __restrict__ table) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= g.n) return;
+  const unsigned ci = cell[s];
+  float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+  if (!(ci & CELL_WALL)) {
+    const double w_on = 1.0 * (1.0 - g.randomness) + g.randomness / NA;
+    const double w_off = 0.0 * (1.0 - g.randomness) + g.randomness / NA;
+    const double c = V[s];
+    double nb[NA], rw[NA];
+    const int off[NA] = {1, -1, g.H, -g.H};
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+      const bool blocked = (ci >> a) & 1u;
+      nb[a] = blocked ? c : V[s + off[a]];
+      rw[a] = reward_scale * ((!blocked && s + off[a] == g.goal) ? g.reward : -g.step_cost);
+    }
+    double cv[NA], q[NA], x[NA];
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+      double pv = 0.0, pr = 0.0;
+#pragma unroll
+      for (int aa = 0; aa < NA; aa++) {
+        const double w = (a == aa) ? w_on : w_off;
+        pv += w * nb[aa];
+        pr += w * rw[aa];
+      }
+      cv[a] = g.gamma * pv - c + pr;                       // controlV   PIQL.jl:63-66
+      q[a] = Q ? Q[(size_t)s * NA + a] : cv[a];
+      x[a] = log(1.0 / NA) + q[a];
+    }
+    const double norm = lse4(x);                            // Qnormalization   PIQL.jl:72-75
+    double w[NA], sum = 0.0, cw = 0.0;
+#pragma unroll
+    for (int a = 0; a < NA; a++) { w[a] = 0.25 * exp(q[a] - norm); sum += w[a]; }  // action_probability :83-85
+    float cdf[3], bf[NA];
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+      cw += w[a];
+      if (a < 3) cdf[a] = (float)(cw / sum);
+      bf[a] = (float)(beta * (cv[a] - (q[a] - norm)));      // beta * fitness   PIQL.jl:87-89
+    }
+    r0 = make_float4(cdf[0], cdf[1], cdf[2], __uint_as_float(ci & CELL_BLOCK_MASK));
+    r1 = make_float4(bf[0], bf[1], bf[2], bf[3]);
+  }
+  table[2 * (size_t)s] = r0;
+  table[2 * (size_t)s + 1] = r1;
+}
+
+void launch_policy_table(const GridDev& g, const uint8_t* cell, const double* V, const double* Q, double beta,
+                         double reward_scale, float4* table, cudaStream_t st) {
+  policy_table_kernel<<<(g.n + 255) / 256, 256, 0, st>>>(g, reward_scale, beta, cell, V, Q, table);
+  g_launches++;
+}
+
+// ---- rollout ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float logaddexpf_dev(float x, float y) {
+  if (x == -CUDART_INF_F) return y;
+  if (y == -CUDART_INF_F) return x;
+  return fmaxf(x, y) + log1pf(expf(-fabsf(x - y)));
+}
+
+constexpr int ROLL_THREADS = 256;
+
+template <int EST, bool INJ, bool TRACE>
+__global__ void __launch_bounds__(ROLL_THREADS)
+rollout_kernel(const RolloutArgs p) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const long long nwarps = (long long)gridDim.x * (ROLL_THREADS / 32);
+  const long long wid = (long long)blockIdx.x * (ROLL_THREADS / 32) + (threadIdx.x >> 5);
+  // contiguous range of local path indices for this warp
+  const long long per = (p.npaths + nwarps - 1) / nwarps;
+  long long next = wid * per;
+  const long long wend = min(p.npaths, next + per);
+  const Philox rng{p.seed_lo, p.seed_hi};
+
+  bool active = false;
+  long long q = 0;          // local path index
+  uint32_t plo = 0, phi = 0;  // global path id
+  int s = 0;
+  uint32_t t = 0, len = 0, a0 = 0;
+  float logw = 0.f, acc = -CUDART_INF_F;
+
+  for (;;) {
+    const unsigned need = __ballot_sync(FULL, !active);
+    if (need) {
+      if (!active) {
+        const long long qq = next + __popc(need & lt_mask);
+        if (qq < wend) {
+          q = qq;
+          const unsigned long long gp = (unsigned long long)(p.path0 + qq);
+          plo = (uint32_t)gp; phi = (uint32_t)(gp >> 32);
+          s = p.starts[gp % (unsigned long long)p.nstarts];
+          t = 0; len = 0; a0 = 0; logw = 0.f; acc = -CUDART_INF_F;
+          active = true;
+        }
+      }
+      next += __popc(need);
+      if (!__any_sync(FULL, active)) break;
+    }
+    if (active) {
+      bool done = false;
+      if (s == p.goal) {
+        // Z(goal) = exp(0 - V(goal))   value_iteration.jl:93-94
+        if (EST == 0) logw = __fsub_rn(logw, p.vgoal);
+        else acc = logaddexpf_dev(acc, __fadd_rn(__fmul_rn((float)t, p.lgam), __fsub_rn(logw, p.vgoal)));
+        done = true;
+      } else if ((long long)t >= p.horizon || (INJ && (long long)t >= p.injected_steps)) {
+        done = true;
+      } else {
+        float u0, u1, u2, u3;
+        int aslip;
+        if (INJ) {
+          const float4 u = *reinterpret_cast<const float4*>(p.injected + ((size_t)q * p.injected_steps + t) * 4);
+          u0 = u.x; u1 = u.y; u2 = u.z; u3 = u.w;
+          aslip = min((int)(4.0f * u3), 3);
+        } else {
+          const uint4 r = rng(t, 0u, plo, phi);
+          u0 = u01(r.x); u1 = u01(r.y); u2 = u01(r.z);
+          aslip = (int)(r.w >> 30);
+        }
+        const float4 r0 = __ldg(p.table + 2 * (size_t)s);
+        const float4 r1 = __ldg(p.table + 2 * (size_t)s + 1);
+        // StatsBase sample(a, Weights): i = 1; cw = w[1]; while cw < t && i < n: i += 1; cw += w[i]
+        const int a = (int)(r0.x < u0) + (int)(r0.y < u0) + (int)(r0.z < u0);
+        const float bf = a == 0 ? r1.x : a == 1 ? r1.y : a == 2 ? r1.z : r1.w;
+        logw = __fadd_rn(logw, bf);
+        if (t == 0) a0 = (uint32_t)a;
+        bool stop = false;
+        if (EST == 0) stop = (u1 >= p.gamma);  // continue w.p. gamma, else the (1 - gamma) * 1 branch
+        else acc = logaddexpf_dev(acc, __fadd_rn(__fadd_rn(__fmul_rn((float)t, p.lgam), p.l1mg), logw));
+        if (stop) {
+          done = true;
+        } else {
+          // propagator: take_step(s, ifelse(rand() < randomness, sample(0:3), a))   GridWorld.jl:113-115
+          const int aa = (u2 < p.rho) ? aslip : a;
+          const unsigned mask = __float_as_uint(r0.w);
+          const int delta = (aa & 2) ? p.H : 1;
+          const int s1 = ((mask >> aa) & 1u) ? s : s + ((aa & 1) ? -delta : delta);
+          if (TRACE) {
+            if ((long long)t < p.trace_steps) {
+              int* tr = p.trace + ((size_t)q * p.trace_steps + t) * 3;
+              tr[0] = s; tr[1] = a; tr[2] = s1;
+            }
+          }
+          s = s1;
+          len++;
+          t++;
+        }
+      }
+      if (done) {
+        p.logw[q] = (EST == 0) ? logw : acc;
+        p.meta[q] = a0 | (len << 2);
+        active = false;
+      }
+    }
+  }
+}
+
+void launch_rollout(const RolloutArgs& a, int num_sms, cudaStream_t st) {
+  if (a.npaths <= 0) return;
+  // persistent grid: 8 CTAs of 256 threads per SM (2048 resident threads), fewer for small jobs
+  long long want = (a.npaths + ROLL_THREADS - 1) / ROLL_THREADS;
+  long long cap = (long long)num_sms * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  const bool inj = a.injected != nullptr, tr = a.trace != nullptr;
+#define PIQL_ROLL(E, I, T) rollout_kernel<E, I, T><<<grid, ROLL_THREADS, 0, st>>>(a)
+  if (a.estimator == 0) {
+    if (inj) { if (tr) PIQL_ROLL(0, true, true); else PIQL_ROLL(0, true, false); }
+    else { if (tr) PIQL_ROLL(0, false, true); else PIQL_ROLL(0, false, false); }
+  } else {
+    if (inj) { if (tr) PIQL_ROLL(1, true, true); else PIQL_ROLL(1, true, false); }
+    else { if (tr) PIQL_ROLL(1, false, true); else PIQL_ROLL(1, false, false); }
+  }
+#undef PIQL_ROLL
+  g_launches++;
+}
+
+// ---- log-sum-exp reduction of path records ----------------------------------------------------------
+// Online (max, sum) update with one exponential per record.
+// The exponentials are fp32 (one MUFU each); the running sum is kept in double so that a bucket
+// of 10^7 records loses nothing to accumulation order.
+struct Lse {
+  float m;
+  double s;
+  uint32_t c;
+  __device__ __forceinline__ void init() { m = -CUDART_INF_F; s = 0.0; c = 0u; }
+  __device__ __forceinline__ void add(float x) {
+    if (x > m) { s = s * (double)expf(m - x) + 1.0; m = x; }
+    else if (x != -CUDART_INF_F) s += (double)expf(x - m);
+    c++;
+  }
+  __device__ __forceinline__ void merge(float m2, double s2, uint32_t c2) {
+    if (m2 > m) { s = s * (double)expf(m - m2) + s2; m = m2; }
+    else if (m2 != -CUDART_INF_F) s += s2 * (double)expf(m2 - m);
+    c += c2;
+  }
+};
+
+// Regime "many start slots": one thread per slot walks that slot's records (stride nstarts), so
+// consecutive threads read consecutive records; no cross-thread combine is needed at all.
+__global__ void __launch_bounds__(256)
+reduce_by_slot_kernel(const float* __restrict__ logw, const uint32_t* __restrict__ meta, long long path0,
+                      long long npaths, long long nstarts, float* __restrict__ acc_max, float* __restrict__ acc_sum,
+                      uint32_t* __restrict__ acc_cnt, unsigned long long* __restrict__ transitions) {
+  __shared__ unsigned long long red[32];
+  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long tr = 0;
+  if (slot < nstarts) {
+    Lse b[NA];
+#pragma unroll
+    for (int a = 0; a < NA; a++) b[a].init();
+    // first local index q with (path0 + q) % nstarts == slot
+    long long q = (slot - path0 % nstarts + nstarts) % nstarts;
+    for (; q < npaths; q += nstarts) {
+      const float x = logw[q];
+      const uint32_t me = meta[q];
+      tr += me >> 2;
+      const uint32_t a = me & 3u;
+#pragma unroll
+      for (int k = 0; k < NA; k++) if (a == (uint32_t)k) b[k].add(x);
+    }
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+      if (b[a].c == 0) continue;
+      const size_t i = (size_t)slot * NA + a;
+      Lse g; g.m = acc_max[i]; g.s = acc_sum[i]; g.c = acc_cnt[i];
+      g.merge(b[a].m, b[a].s, b[a].c);
+      acc_max[i] = g.m; acc_sum[i] = (float)g.s; acc_cnt[i] = g.c;
+    }
+  }
+  const unsigned long long r = block_sum(tr, red);
+  if (threadIdx.x == 0 && r) atomicAdd(transitions, r);
+}
+
+// Regime "few start slots": grid.y = slot, grid.x = chunks of that slot's records; warp-shuffle
+// then block-level combine of (max, sum, count) per action, one partial per block, merged in a
+// fixed order by reduce_merge_kernel.
+__global__ void __launch_bounds__(256)
+reduce_block_kernel(const float* __restrict__ logw, const uint32_t* __restrict__ meta, long long path0,
+                    long long npaths, long long nstarts, float* __restrict__ part /*[slot][chunk][a][3]*/,
+                    unsigned long long* __restrict__ transitions) {
+  __shared__ float sm_m[NA][8];
+  __shared__ double sm_s[NA][8];
+  __shared__ uint32_t sm_c[NA][8];
+  __shared__ unsigned long long red[32];
+  const long long slot = blockIdx.y;
+  const long long q0 = (slot - path0 % nstarts + nstarts) % nstarts;
+  const long long nrec = q0 < npaths ? (npaths - q0 + nstarts - 1) / nstarts : 0;  // records of this slot
+  const long long per = (nrec + gridDim.x - 1) / gridDim.x;
+  const long long jb = (long long)blockIdx.x * per, je = min(nrec, jb + per);
+  Lse b[NA];
+#pragma unroll
+  for (int a = 0; a < NA; a++) b[a].init();
+  unsigned long long tr = 0;
+  for (long long j = jb + threadIdx.x; j < je; j += blockDim.x) {
+    const long long q = q0 + j * nstarts;
+    const float x = logw[q];
+    const uint32_t me = meta[q];
+    tr += me >> 2;
+    const uint32_t a = me & 3u;
+#pragma unroll
+    for (int k = 0; k < NA; k++) if (a == (uint32_t)k) b[k].add(x);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(FULL, b[a].m, o);
+      const double s2 = __shfl_xor_sync(FULL, b[a].s, o);
+      const uint32_t c2 = __shfl_xor_sync(FULL, b[a].c, o);
+      // symmetric combine: both partners end up with bit-identical (max, sum, count)
+      const float m = fmaxf(b[a].m, m2);
+      const double sa = (b[a].m == -CUDART_INF_F) ? 0.0 : b[a].s * (double)expf(b[a].m - m);
+      const double sb = (m2 == -CUDART_INF_F) ? 0.0 : s2 * (double)expf(m2 - m);
+      b[a].s = sa + sb;
+      b[a].m = m; b[a].c += c2;
+    }
+    if (lane == 0) { sm_m[a][warp] = b[a].m; sm_s[a][warp] = b[a].s; sm_c[a][warp] = b[a].c; }
+  }
+  __syncthreads();
+  if (threadIdx.x < NA) {
+    const int a = threadIdx.x;
+    Lse g; g.init();
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) g.merge(sm_m[a][w], sm_s[a][w], sm_c[a][w]);
+    float* o = part + (((size_t)slot * gridDim.x + blockIdx.x) * NA + a) * 3;
+    o[0] = g.m; o[1] = (float)g.s; o[2] = __uint_as_float(g.c);
+  }
+  const unsigned long long r = block_sum(tr, red);
+  if (threadIdx.x == 0 && r) atomicAdd(transitions, r);
+}
+__global__ void reduce_merge_kernel(const float* __restrict__ part, int chunks, long long nstarts,
+                                    float* __restrict__ acc_max, float* __restrict__ acc_sum, uint32_t* __restrict__ acc_cnt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // slot*4 + a
+  if (i >= nstarts * NA) return;
+  const long long slot = i / NA;
+  const int a = (int)(i % NA);
+  Lse g; g.m = acc_max[i]; g.s = acc_sum[i]; g.c = acc_cnt[i];
+  for (int c = 0; c < chunks; c++) {
+    const float* o = part + (((size_t)slot * chunks + c) * NA + a) * 3;
+    g.merge(o[0], o[1], __float_as_uint(o[2]));
+  }
+  acc_max[i] = g.m; acc_sum[i] = (float)g.s; acc_cnt[i] = g.c;
+}
+
+constexpr long long REDUCE_FEW_SLOTS = 2048;
+static int reduce_chunks(long long npaths, long long nstarts, int num_sms) {
+  const long long per_slot = (npaths + nstarts - 1) / nstarts;
+  long long c = (per_slot + 256 * 8 - 1) / (256 * 8);          // >= 8 records per thread
+  const long long cap = (4LL * num_sms + nstarts - 1) / nstarts; // ~4 CTAs per SM in total
+  if (c > cap) c = cap;
+  if (c < 1) c = 1;
+  return (int)c;
+}
+size_t reduce_scratch_floats(long long npaths, long long nstarts) {
+  if (nstarts > REDUCE_FEW_SLOTS) return 0;
+  return (size_t)nstarts * reduce_chunks(npaths, nstarts, 148) * NA * 3;
+}
+void launch_reduce(const float* logw, const uint32_t* meta, long long path0, long long npaths, long long nstarts,
+                   float* acc_max, float* acc_sum, uint32_t* acc_cnt, float* scratch, size_t scratch_floats,
+                   unsigned long long* transitions, int num_sms, cudaStream_t st) {
+  if (npaths <= 0) return;
+  if (nstarts > REDUCE_FEW_SLOTS) {
+    reduce_by_slot_kernel<<<(unsigned)((nstarts + 255) / 256), 256, 0, st>>>(logw, meta, path0, npaths, nstarts, acc_max,
+                                                                             acc_sum, acc_cnt, transitions);
+    g_launches++;
+  } else {
+    (void)num_sms;
+    const int chunks = reduce_chunks(npaths, nstarts, 148);
+    (void)scratch_floats;
+    dim3 grid(chunks, (unsigned)nstarts);
+    reduce_block_kernel<<<grid, 256, 0, st>>>(logw, meta, path0, npaths, nstarts, scratch, transitions);
+    reduce_merge_kernel<<<(unsigned)((nstarts * NA + 127) / 128), 128, 0, st>>>(scratch, chunks, nstarts, acc_max, acc_sum, acc_cnt);
+    g_launches += 2;
+  }
+}
+
+// ---- accumulator maintenance -----------------------------------------------------------------------
+__global__ void mc_reset_kernel(float* m, float* s, uint32_t* c, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { m[i] = -CUDART_INF_F; s[i] = 0.f; c[i] = 0u; }
+}
+void launch_mc_reset(float* acc_max, float* acc_sum, uint32_t* acc_cnt, long long n, cudaStream_t st) {
+  mc_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc_max, acc_sum, acc_cnt, n);
+  g_launches++;
+}
+// counters[0]: transitions since the last reset, counters[1]: running total over resets
+__global__ void fold_counter_kernel(unsigned long long* counters) {
+  counters[1] += counters[0];
+  counters[0] = 0ull;
+}
+void launch_fold_counter(unsigned long long* counters, cudaStream_t st) {
+  fold_counter_kernel<<<1, 1, 0, st>>>(counters);
+  g_launches++;
+}
+// After an all-reduce(MAX) of lse_max across shards: bring the local sum to the global shift so
+// that an all-reduce(SUM) of lse_sum finishes the log-sum-exp.
+__global__ void mc_rescale_kernel(float* m, float* s, const float* __restrict__ gmax, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float g = gmax[i], l = m[i];
+    s[i] = (l == -CUDART_INF_F) ? 0.f : s[i] * expf(l - g);
+    m[i] = g;
+  }
+}
+void launch_mc_rescale(float* acc_max, float* acc_sum, const float* gmax, long long n, cudaStream_t st) {
+  mc_rescale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc_max, acc_sum, gmax, n);
+  g_launches++;
+}
+__global__ void mc_finalize_kernel(const float* __restrict__ m, const float* __restrict__ s, const uint32_t* __restrict__ c,
+                                   const int* __restrict__ starts, long long nstarts, double* __restrict__ logz_sa,
+                                   unsigned long long* __restrict__ count_sa, double* __restrict__ logz_s) {
+  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= nstarts) return;
+  const size_t cellidx = (size_t)starts[slot];
+  double mm = -CUDART_INF;
+  unsigned long long ctot = 0;
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+    const size_t i = (size_t)slot * NA + a;
+    const uint32_t cnt = c[i];
+    if (logz_sa) logz_sa[cellidx * NA + a] = cnt ? (double)m[i] + log((double)s[i]) - log((double)cnt) : CUDART_NAN;
+    if (count_sa) count_sa[cellidx * NA + a] = cnt;
+    if (cnt && (double)m[i] > mm) mm = (double)m[i];
+    ctot += cnt;
+  }
+  if (logz_s) {
+    double tot = 0.0;
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+      const size_t i = (size_t)slot * NA + a;
+      if (c[i]) tot += (double)s[i] * exp((double)m[i] - mm);
+    }
+    logz_s[cellidx] = ctot ? mm + log(tot) - log((double)ctot) : CUDART_NAN;
+  }
+}
+void launch_mc_finalize(const float* acc_max, const float* acc_sum, const uint32_t* acc_cnt, const int* starts,
+                        long long nstarts, double* logz_sa, unsigned long long* count_sa, double* logz_s,
+                        cudaStream_t st) {
+  mc_finalize_kernel<<<(unsigned)((nstarts + 255) / 256), 256, 0, st>>>(acc_max, acc_sum, acc_cnt, starts, nstarts, logz_sa,
+                                                                        count_sa, logz_s);
+  g_launches++;
+}
+__global__ void fill_f64_kernel(double* dst, double v, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
+}
+void launch_fill_f64(double* dst, double v, long long n, cudaStream_t st) {
+  fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, v, n);
+  g_launches++;
+}
+
+int configure_rollout_kernels() { return 0; }
+
+}  // namespace piql

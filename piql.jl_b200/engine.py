@@ -1,0 +1,267 @@
+"""numpy-level wrapper of one piql_ctx (one GPU).  Thin: argument marshalling and error mapping.
+
+Per-cell arrays are (H, W) Fortran-ordered float64 (the Julia layout the C ABI expects);
+per-(cell, action) arrays are (H*W, 4) C-ordered, i.e. action fastest.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as K
+
+
+def _pd(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _cell(a, H, W, name):
+    if a is None:
+        return None
+    a = np.asfortranarray(a, dtype=np.float64)
+    if a.shape != (H, W):
+        raise ValueError("%s must have shape (%d, %d), got %s" % (name, H, W, a.shape))
+    return a
+
+
+def _sa(a, H, W, name):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1, 4)
+    if a.shape[0] != H * W:
+        raise ValueError("%s must have H*W*4 entries" % name)
+    return a
+
+
+class Engine:
+    def __init__(self, device=0):
+        self._lib = K.load()
+        self._ctx = C.c_void_p()
+        rc = self._lib.piql_create(C.byref(self._ctx), int(device))
+        if rc != K.OK:
+            self._ctx = None
+            raise K.PiqlError(rc, {K.ERR_NO_DEVICE: "no CUDA device visible (there is no CPU fallback)",
+                                   K.ERR_UNSUPPORTED: "device is not sm_100 (B200)",
+                                   K.ERR_ARG: "bad device id"}.get(rc, "piql_create failed"))
+        self.device = int(device)
+        self.H = self.W = 0
+        self.walls = None
+        self.grid_key = None
+
+    # ---- plumbing ----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.piql_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, allow=()):
+        if rc != K.OK and rc not in allow:
+            raise K.PiqlError(rc, self._lib.piql_last_error(self._ctx).decode())
+        return rc
+
+    @property
+    def stream(self):
+        p = C.c_void_p()
+        self._ck(self._lib.piql_stream(self._ctx, C.byref(p)))
+        return p.value or 0
+
+    @property
+    def launches(self):
+        n = C.c_int64()
+        self._ck(self._lib.piql_launch_count(self._ctx, C.byref(n)))
+        return n.value
+
+    # ---- problem -----------------------------------------------------------------------------
+    def load_grid(self, walls, goal, randomness, step_cost, reward, gamma):
+        w = np.asfortranarray(walls, dtype=np.uint8)
+        H, W = w.shape
+        p = K.GridParams(float(randomness), float(step_cost), float(reward), float(gamma))
+        self._ck(self._lib.piql_grid_load(self._ctx, w.ctypes.data_as(C.POINTER(C.c_uint8)), H, W, int(goal[0]),
+                                          int(goal[1]), C.byref(p)))
+        self.H, self.W, self.walls = H, W, w
+        self.goal = (int(goal[0]), int(goal[1]))
+        n = C.c_int64()
+        self._ck(self._lib.piql_grid_free_count(self._ctx, C.byref(n)))
+        self.nfree = n.value
+
+    @staticmethod
+    def _opts(tol, max_sweeps, precision, check_every):
+        prec = {"f64": K.F64, "f32": K.F32, K.F64: K.F64, K.F32: K.F32}[precision]
+        return K.SolveOpts(float(tol), int(max_sweeps), prec, int(check_every))
+
+    def _out(self):
+        return np.empty((self.H, self.W), dtype=np.float64, order="F")
+
+    # ---- soft value iteration ----------------------------------------------------------------
+    def solve_nu(self, reward_scale=1.0, tol=1e-12, max_sweeps=10 ** 7, precision="f64", check_every=0,
+                 allow_unconverged=False):
+        out, st = self._out(), K.SolveStats()
+        o = self._opts(tol, max_sweeps, precision, check_every)
+        self._ck(self._lib.piql_solve_nu(self._ctx, float(reward_scale), C.byref(o), _pd(out), C.byref(st)),
+                 allow=(K.ERR_NOT_CONVERGED,) if allow_unconverged else ())
+        return out, st
+
+    def solve_logz(self, V, beta=1.0, Q=None, tol=1e-12, max_sweeps=10 ** 7, precision="f64", check_every=0,
+                   allow_unconverged=False):
+        V, Q = _cell(V, self.H, self.W, "V"), _sa(Q, self.H, self.W, "Q")
+        out, st = self._out(), K.SolveStats()
+        o = self._opts(tol, max_sweeps, precision, check_every)
+        self._ck(self._lib.piql_solve_logz(self._ctx, _pd(V), _pd(Q), float(beta), C.byref(o), _pd(out), C.byref(st)),
+                 allow=(K.ERR_NOT_CONVERGED,) if allow_unconverged else ())
+        return out, st
+
+    def update_v(self, V, beta=1.0, tol=1e-12, max_sweeps=10 ** 7, precision="f64", check_every=0,
+                 allow_unconverged=False, want_logz=False):
+        V = _cell(V, self.H, self.W, "V")
+        out, st = self._out(), K.SolveStats()
+        logz = self._out() if want_logz else None
+        o = self._opts(tol, max_sweeps, precision, check_every)
+        self._ck(self._lib.piql_update_v(self._ctx, _pd(V), float(beta), C.byref(o), _pd(out), _pd(logz), C.byref(st)),
+                 allow=(K.ERR_NOT_CONVERGED,) if allow_unconverged else ())
+        return (out, logz, st) if want_logz else (out, st)
+
+    def solve_gap(self, V, nu, Q=None, tol=1e-12, max_sweeps=10 ** 7, precision="f64", check_every=0,
+                  allow_unconverged=False):
+        V, nu, Q = _cell(V, self.H, self.W, "V"), _cell(nu, self.H, self.W, "nu"), _sa(Q, self.H, self.W, "Q")
+        out, st = self._out(), K.SolveStats()
+        o = self._opts(tol, max_sweeps, precision, check_every)
+        self._ck(self._lib.piql_solve_gap(self._ctx, _pd(V), _pd(Q), _pd(nu), C.byref(o), _pd(out), C.byref(st)),
+                 allow=(K.ERR_NOT_CONVERGED,) if allow_unconverged else ())
+        return out, st
+
+    def sweep_once(self, kind, x, V=None, Q=None, nu=None, beta=1.0, reward_scale=1.0, precision="f64"):
+        kind = {"nu": K.KIND_NU, "logz": K.KIND_LOGZ, "gap": K.KIND_GAP}[kind]
+        prec = {"f64": K.F64, "f32": K.F32}[precision]
+        x = _cell(np.nan_to_num(np.asarray(x, dtype=np.float64)), self.H, self.W, "x")
+        V, nu, Q = _cell(V, self.H, self.W, "V"), _cell(nu, self.H, self.W, "nu"), _sa(Q, self.H, self.W, "Q")
+        out, res = self._out(), C.c_double()
+        self._ck(self._lib.piql_sweep_once(self._ctx, kind, _pd(V), _pd(Q), _pd(nu), float(beta), float(reward_scale),
+                                           prec, _pd(x), _pd(out), C.byref(res)))
+        return out, res.value
+
+    # device-resident sweeps (bench)
+    def vi_prepare(self, kind, V=None, Q=None, nu=None, beta=1.0, reward_scale=1.0, precision="f32"):
+        kind = {"nu": K.KIND_NU, "logz": K.KIND_LOGZ, "gap": K.KIND_GAP}[kind]
+        prec = {"f64": K.F64, "f32": K.F32}[precision]
+        V, nu, Q = _cell(V, self.H, self.W, "V"), _cell(nu, self.H, self.W, "nu"), _sa(Q, self.H, self.W, "Q")
+        self._ck(self._lib.piql_vi_prepare_dev(self._ctx, kind, _pd(V), _pd(Q), _pd(nu), float(beta),
+                                               float(reward_scale), prec))
+
+    def vi_sweeps(self, sweeps):
+        self._ck(self._lib.piql_vi_sweeps_dev(self._ctx, int(sweeps)))
+
+    def vi_fetch(self, want_x=True):
+        out, res = (self._out() if want_x else None), C.c_double()
+        self._ck(self._lib.piql_vi_fetch(self._ctx, _pd(out), C.byref(res)))
+        return out, res.value
+
+    # ---- Monte-Carlo -------------------------------------------------------------------------
+    def policy_table(self, V, beta=1.0, Q=None, download=True):
+        V, Q = _cell(V, self.H, self.W, "V"), _sa(Q, self.H, self.W, "Q")
+        tab = np.empty((self.H * self.W, 8), dtype=np.float32) if download else None
+        self._ck(self._lib.piql_policy_table(self._ctx, _pd(V), _pd(Q), float(beta),
+                                             None if tab is None else tab.ctypes.data_as(C.POINTER(C.c_float))))
+        return tab
+
+    def policy_table_set(self, table, v_goal):
+        table = np.ascontiguousarray(table, dtype=np.float32)
+        assert table.size == self.H * self.W * 8
+        self._ck(self._lib.piql_policy_table_set(self._ctx, table.ctypes.data_as(C.POINTER(C.c_float)), float(v_goal)))
+
+    def _mc_opts(self, npaths, path0=0, seed=0, estimator="A", horizon=1 << 20, starts=None, injected=None):
+        keep = []
+        o = K.McOpts()
+        o.npaths, o.path0, o.seed = int(npaths), int(path0), int(seed)
+        o.estimator = {"A": K.EST_SAMPLED_STOP, "B": K.EST_DISCOUNTED}[estimator]
+        o.horizon = int(horizon)
+        if starts is None:
+            o.start_mode, o.starts, o.nstarts = K.START_ALL_FREE, None, 0
+        else:
+            s = np.ascontiguousarray(starts, dtype=np.int32)
+            keep.append(s)
+            o.start_mode, o.starts, o.nstarts = K.START_LIST, s.ctypes.data_as(C.POINTER(C.c_int32)), len(s)
+        if injected is not None:
+            u = np.ascontiguousarray(injected, dtype=np.float32)
+            assert u.ndim == 3 and u.shape[0] == npaths and u.shape[2] == 4
+            keep.append(u)
+            o.injected, o.injected_steps = u.ctypes.data_as(C.POINTER(C.c_float)), u.shape[1]
+        else:
+            o.injected, o.injected_steps = None, 0
+        return o, keep
+
+    def mc_logz(self, V, beta=1.0, Q=None, npaths=1 << 20, want=("sa", "count", "s"), **kw):
+        V, Q = _cell(V, self.H, self.W, "V"), _sa(Q, self.H, self.W, "Q")
+        o, _keep = self._mc_opts(npaths, **kw)
+        n = self.H * self.W
+        sa = np.empty((n, 4), dtype=np.float64) if "sa" in want else None
+        cnt = np.empty((n, 4), dtype=np.uint64) if "count" in want else None
+        s = np.empty((self.H, self.W), dtype=np.float64, order="F") if "s" in want else None
+        st = K.McStats()
+        self._ck(self._lib.piql_mc_logz(self._ctx, _pd(V), _pd(Q), float(beta), C.byref(o), _pd(sa),
+                                        None if cnt is None else cnt.ctypes.data_as(C.POINTER(C.c_uint64)), _pd(s),
+                                        C.byref(st)))
+        return sa, cnt, s, st
+
+    def trace_paths(self, npaths, max_steps, **kw):
+        o, _keep = self._mc_opts(npaths, **kw)
+        tr = np.empty((npaths, max_steps, 3), dtype=np.int32)
+        logw = np.empty(npaths, dtype=np.float32)
+        meta = np.empty(npaths, dtype=np.uint32)
+        self._ck(self._lib.piql_trace_paths(self._ctx, C.byref(o), int(max_steps), tr.ctypes.data_as(C.POINTER(C.c_int32)),
+                                            logw.ctypes.data_as(C.POINTER(C.c_float)),
+                                            meta.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return tr, logw, meta
+
+    # device-resident pieces (bench, multi-GPU)
+    def mc_reset(self, starts=None):
+        o, _keep = self._mc_opts(0, starts=starts)
+        self._ck(self._lib.piql_mc_reset_dev(self._ctx, C.byref(o)))
+
+    def mc_rollout(self, npaths, **kw):
+        o, _keep = self._mc_opts(npaths, **kw)
+        self._ck(self._lib.piql_mc_rollout_dev(self._ctx, C.byref(o)))
+
+    def mc_stats_ptrs(self):
+        m, s, c, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._ck(self._lib.piql_mc_stats_dev(self._ctx, C.byref(m), C.byref(s), C.byref(c), C.byref(n)))
+        return m.value, s.value, c.value, n.value
+
+    def mc_rescale(self, global_max_ptr):
+        self._ck(self._lib.piql_mc_rescale_dev(self._ctx, C.c_void_p(global_max_ptr)))
+
+    def mc_finalize(self, want=("sa", "count", "s"), out=None):
+        """out: optional preallocated (sa (n,4) f64, count (n,4) u64, s (H,W) f64 F-order), e.g. pinned."""
+        n = self.H * self.W
+        if out is not None:
+            sa, cnt, s = out
+        else:
+            sa = np.empty((n, 4), dtype=np.float64) if "sa" in want else None
+            cnt = np.empty((n, 4), dtype=np.uint64) if "count" in want else None
+            s = np.empty((self.H, self.W), dtype=np.float64, order="F") if "s" in want else None
+        st = K.McStats()
+        self._ck(self._lib.piql_mc_finalize(self._ctx, _pd(sa),
+                                            None if cnt is None else cnt.ctypes.data_as(C.POINTER(C.c_uint64)), _pd(s),
+                                            C.byref(st)))
+        return sa, cnt, s, st
+
+    def mc_timing(self):
+        ro, re, n = C.c_double(), C.c_double(), C.c_int64()
+        self._ck(self._lib.piql_mc_timing(self._ctx, C.byref(ro), C.byref(re), C.byref(n)))
+        return ro.value, re.value, n.value
+
+    def mc_transitions_total(self):
+        n = C.c_uint64()
+        self._ck(self._lib.piql_mc_transitions_total(self._ctx, C.byref(n)))
+        return n.value
+
+    def mc_records(self, n):
+        logw = np.empty(n, dtype=np.float32)
+        meta = np.empty(n, dtype=np.uint32)
+        self._ck(self._lib.piql_mc_records(self._ctx, logw.ctypes.data_as(C.POINTER(C.c_float)),
+                                           meta.ctypes.data_as(C.POINTER(C.c_uint32)), int(n)))
+        return logw, meta

@@ -1,0 +1,244 @@
+"""Host-side mirror of PIQL's solver entry points; the work happens in the CUDA library.
+
+Same names, arguments and return types as the reference (γ/β/ν spelled out in ASCII):
+    Growable                              src/value_iteration.jl:3-18
+    generate_nu (generate_ν)              src/value_iteration.jl:77-87
+    generate_logz                         src/value_iteration.jl:107-117
+    logz_updateV                          src/value_iteration.jl:119-124
+    generate_optimality_gap               src/value_iteration.jl:144-154
+    kl_cost, choose_action, path_transitions, fitness_reward_estimate
+                                          src/path_functions.jl:12-41 (repaired: the reference
+                                          file does not load as written)
+    average_reward, controlV, Qnormalization, controlQ, action_probability, fitness
+                                          src/PIQL.jl:55-89 (host algebra on closures, for
+                                          callers and tests; the kernels restate it per cell)
+    mc_logz                               new: Monte-Carlo estimate of generate_logz's fixed point
+    learning_traj, run_experiment         scripts/experiments.jl:10-39
+Every solver returns a Growable, as in the reference; `.array` is the dense (H, W) view
+(NaN at walls) the library produced.
+"""
+import math
+
+import numpy as np
+
+from . import gridworld as gwmod
+from .engine import Engine
+
+_engines = {}
+
+
+def engine_for(ctrl, device=0):
+    """The per-device Engine with ctrl's tabulated problem loaded (re-used while it is unchanged)."""
+    tab = gwmod.tabulate(ctrl)
+    eng = _engines.get(device)
+    if eng is None:
+        eng = _engines[device] = Engine(device)
+    if eng.grid_key != tab.key():
+        eng.load_grid(tab.walls, tab.goal, tab.randomness, tab.step_cost, tab.reward, tab.gamma)
+        eng.grid_key = tab.key()
+        eng._tab = tab  # keeps the wall array alive so the key's address stays unique
+    return eng
+
+
+class Growable:
+    """Callable value function backed by a dictionary that grows on demand (value_iteration.jl:3-18).
+
+    Results coming back from the GPU carry the dense array as well, so V(s) is an array lookup
+    and `.dict` is only materialised when somebody asks for it.
+    """
+
+    def __init__(self, s=None, default=lambda x: 0.0, array=None, walls=None):
+        self.default = default
+        self.array = array
+        self._walls = walls
+        self._dict = None if array is not None else ({} if s is None else {tuple(s): 0.0})
+
+    @classmethod
+    def from_dense(cls, array, walls, default=lambda x: 0.0):
+        return cls(default=default, array=np.asfortranarray(array, dtype=np.float64), walls=np.asarray(walls) != 0)
+
+    @property
+    def dict(self):
+        if self._dict is None:
+            idx = np.argwhere(~self._walls)
+            self._dict = {(int(i), int(j)): float(self.array[i, j]) for i, j in idx}
+        return self._dict
+
+    def __call__(self, s):
+        s = tuple(s)
+        if self._dict is None and self.array is not None:
+            if not self._walls[s]:
+                return float(self.array[s])
+            self.dict  # a wall cell was asked for: fall through to the growing dictionary
+        if s not in self._dict:
+            self._dict[s] = self.default(s)
+        return self._dict[s]
+
+    def dense(self, walls):
+        """(H, W) array with NaN at walls, for handing the function back to the library."""
+        if self.array is not None:
+            return self.array
+        out = np.full(walls.shape, np.nan, order="F")
+        for (i, j), v in self._dict.items():
+            out[i, j] = v
+        return out
+
+
+def _dense(V, eng):
+    if isinstance(V, Growable):
+        return np.nan_to_num(V.dense(eng.walls))
+    return np.nan_to_num(np.asarray(V, dtype=np.float64))
+
+
+# ---- KL-control algebra on closures (src/PIQL.jl:55-89) ---------------------------------------------
+def average_reward(ctrl, s, a):
+    return ctrl.propagator_average(s, a, lambda s1: ctrl.reward_function(s, a, s1))
+
+
+def controlV(ctrl, V, s, a):
+    return ctrl.gamma * ctrl.propagator_average(s, a, V) - V(s) + average_reward(ctrl, s, a)
+
+
+def Qnormalization(ctrl, Q, s):
+    x = [math.log(ctrl.action_prior(s, a)) + Q(s, a) for a in ctrl.action_space]
+    m = max(x)
+    return m + math.log(sum(math.exp(v - m) for v in x))
+
+
+def controlQ(ctrl, Q, s, a):
+    return Q(s, a) - Qnormalization(ctrl, Q, s)
+
+
+def action_probability(ctrl, Q, s, a):
+    return ctrl.action_prior(s, a) * math.exp(controlQ(ctrl, Q, s, a))
+
+
+def fitness(ctrl, V, Q, s, a):
+    return controlV(ctrl, V, s, a) - controlQ(ctrl, Q, s, a)
+
+
+def kl_cost(ctrl, s, Q):
+    """sum_a klterm(pi_Q(a|s), pi_0(a|s)), klterm(x, y) = xlogx(x) - xlogy(x, y)   path_functions.jl:17-20"""
+    out = 0.0
+    for a in ctrl.action_space:
+        x, y = action_probability(ctrl, Q, s, a), ctrl.action_prior(s, a)
+        out += (x * math.log(x) if x > 0 else 0.0) - (x * math.log(y) if x > 0 else 0.0)
+    return out
+
+
+def choose_action(ctrl, s, Q, rng):
+    """sample(action_space, Weights(w)): t = rand()*sum(w), walk while cw < t   path_functions.jl:12-15"""
+    w = [action_probability(ctrl, Q, s, a) for a in ctrl.action_space]
+    t = rng.random() * sum(w)
+    i, cw = 0, w[0]
+    while cw < t and i < len(w) - 1:
+        i += 1
+        cw += w[i]
+    return list(ctrl.action_space)[i]
+
+
+def path_transitions(ctrl, s0, Q, rng, nsteps=20):
+    """Generator of (s, a, s') along one path under pi_Q   path_functions.jl:23-32"""
+    s = s0
+    for _ in range(nsteps):
+        a = choose_action(ctrl, s, Q, rng)
+        ss = ctrl.propagator(s, a)
+        yield (s, a, ss)
+        s = ss
+
+
+def fitness_reward_estimate(ctrl, s0, V, Q, rng, nsteps=20):
+    """Running V(s0) + sum_t fitness(s_t, a_t) along one path   path_functions.jl:34-41"""
+    total, out = V(s0), []
+    for (s, a, _ss) in path_transitions(ctrl, s0, Q, rng, nsteps=nsteps):
+        total += fitness(ctrl, V, Q, s, a)
+        out.append(total)
+    return out
+
+
+# ---- solvers on the GPU -----------------------------------------------------------------------------
+def generate_nu(ctrl, tol=1e-12, max_sweeps=10 ** 7, precision="f64", device=0, return_stats=False):
+    eng = engine_for(ctrl, device)
+    out, st = eng.solve_nu(1.0, tol=tol, max_sweeps=max_sweeps, precision=precision)
+    g = Growable.from_dense(out, eng.walls)
+    return (g, st) if return_stats else g
+
+
+generate_ν = generate_nu
+
+
+def generate_logz(ctrl, V, beta=1.0, β=None, Q=None, tol=1e-12, max_sweeps=10 ** 7, precision="f64", device=0,
+                  return_stats=False):
+    beta = beta if β is None else β
+    eng = engine_for(ctrl, device)
+    out, st = eng.solve_logz(_dense(V, eng), beta=beta, Q=Q, tol=tol, max_sweeps=max_sweeps, precision=precision)
+    g = Growable.from_dense(out, eng.walls)
+    return (g, st) if return_stats else g
+
+
+def logz_updateV(ctrl, V, beta=1.0, β=None, tol=1e-12, max_sweeps=10 ** 7, precision="f64", device=0,
+                 return_stats=False):
+    beta = beta if β is None else β
+    eng = engine_for(ctrl, device)
+    out, st = eng.update_v(_dense(V, eng), beta=beta, tol=tol, max_sweeps=max_sweeps, precision=precision)
+    g = Growable.from_dense(out, eng.walls, default=getattr(V, "default", lambda x: 0.0))
+    return (g, st) if return_stats else g
+
+
+def generate_optimality_gap(ctrl, V, nu=None, ν=None, Q=None, tol=1e-12, max_sweeps=10 ** 7, precision="f64", device=0,
+                            return_stats=False):
+    nu = nu if ν is None else ν
+    if nu is None:
+        nu = generate_nu(ctrl, device=device)
+    eng = engine_for(ctrl, device)
+    out, st = eng.solve_gap(_dense(V, eng), _dense(nu, eng), Q=Q, tol=tol, max_sweeps=max_sweeps, precision=precision)
+    g = Growable.from_dense(out, eng.walls)
+    return (g, st) if return_stats else g
+
+
+class McResult:
+    """log Z estimates per (start cell, first action) and per start cell, with path counts."""
+
+    def __init__(self, logz_sa, count_sa, logz_s, stats, walls):
+        H, W = walls.shape
+        self.logz_sa = logz_sa.reshape(W, H, 4).transpose(1, 0, 2)   # [i, j, a]
+        self.count_sa = count_sa.reshape(W, H, 4).transpose(1, 0, 2)
+        self.logz = Growable.from_dense(logz_s, walls)
+        self.transitions = int(stats.transitions)
+        self.paths = int(stats.paths)
+        self.device_seconds = float(stats.device_seconds)
+
+
+def mc_logz(ctrl, V, beta=1.0, β=None, Q=None, npaths=1 << 20, seed=0, estimator="A", horizon=1 << 20, starts=None,
+            device=0):
+    """Monte-Carlo estimate of generate_logz(ctrl, V; β) from rollouts under pi_Q.
+
+    starts: list of (i, j) start states (path p starts at starts[p % len]); None = every free cell.
+    """
+    beta = beta if β is None else β
+    eng = engine_for(ctrl, device)
+    cells = None if starts is None else [int(s[0]) + eng.H * int(s[1]) for s in starts]
+    sa, cnt, s, st = eng.mc_logz(_dense(V, eng), beta=beta, Q=Q, npaths=npaths, seed=seed, estimator=estimator,
+                                 horizon=horizon, starts=cells)
+    return McResult(sa, cnt, s, st, eng.walls)
+
+
+# ---- experiment protocol (scripts/experiments.jl:10-39) -------------------------------------------------
+def learning_traj(ctrl, v0, beta=1.0, n=20, **kw):
+    out, vnew = [v0], v0
+    for _ in range(n):
+        vnew = logz_updateV(ctrl, vnew, beta=beta, **kw)
+        out.append(vnew)
+    return out
+
+
+def run_experiment(gw, randomness=0.01, gamma=0.99, starting_temp=0.1, betarange=None, n=5, **kw):
+    betarange = np.exp(np.linspace(-6, 0, 8)) if betarange is None else betarange
+    ctrl = gwmod.gridworld_ctrl(gw, randomness=randomness, gamma=gamma)
+    weaker = gwmod.modify(ctrl, reward_function=lambda s, a, ss: starting_temp * ctrl.reward_function(s, a, ss))
+    nu = generate_nu(ctrl, **kw)
+    furthest = min(nu.dict, key=nu.dict.get)
+    V_lo = generate_nu(weaker, **kw)
+    traj = {float(b): learning_traj(ctrl, V_lo, beta=float(b), n=n, **kw) for b in betarange}
+    gap = {b: [generate_optimality_gap(ctrl, v, nu=nu, **kw) for v in vec] for b, vec in traj.items()}
+    return dict(nu=nu, traj=traj, gap=gap, randomness=randomness, gamma=gamma, ctrl=ctrl, s0=furthest)
