@@ -207,15 +207,15 @@ def run_ours(args, rank, world, local_rank):
         step_no[0] += 1
 
     with torch.cuda.stream(stream):
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()        # nvidia-smi needs ~0.1 s to come up: it also sees the warm-up steps
         for _ in range(args.warmup):
             step()
         barrier()
         eng.mc_timing()            # drop warm-up launches from the kernel timers
         tr0 = eng.mc_transitions_total()
         l0 = eng.launches
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):

@@ -1,0 +1,151 @@
+# PIQLB200.jl -- Julia side of the drop-in boundary (UNEXECUTED here: this image has no julia).
+#
+# `using PIQL, PIQLB200` keeps PIQL's public API and problem interface and re-routes the hot
+# path (generate_ν, generate_logz, logz_updateV, generate_optimality_gap, plus mc_logz) to
+# libpiql_b200.so through `ccall`.  Every call mirrors one entry point of include/piql_b200.h;
+# the Python binding in piql.jl_b200/_capi.py exercises exactly the same ABI in the tests.
+module PIQLB200
+
+using PIQL
+import PIQL: Growable, ControlProblem
+
+const LIB = get(ENV, "PIQL_B200_LIB", joinpath(@__DIR__, "..", "piql.jl_b200", "lib", "libpiql_b200.so"))
+
+struct GridParams          # piql_grid_params
+    randomness::Cdouble
+    step_cost::Cdouble
+    reward::Cdouble
+    gamma::Cdouble
+end
+struct SolveOpts           # piql_solve_opts
+    tol::Cdouble
+    max_sweeps::Int64
+    precision::Int32       # 0 = Float64, 1 = Float32
+    check_every::Int32
+end
+mutable struct SolveStats  # piql_solve_stats
+    sweeps::Int64
+    residual::Cdouble
+    device_seconds::Cdouble
+    backups::Int64
+    converged::Int32
+    kernel::Int32
+    SolveStats() = new(0, 0.0, 0.0, 0, 0, 0)
+end
+struct McOpts              # piql_mc_opts
+    npaths::Int64
+    path0::Int64
+    seed::UInt64
+    estimator::Int32
+    start_mode::Int32
+    horizon::Int64
+    starts::Ptr{Int32}
+    nstarts::Int64
+    injected::Ptr{Cfloat}
+    injected_steps::Int64
+end
+mutable struct McStats     # piql_mc_stats
+    transitions::UInt64
+    paths::UInt64
+    device_seconds::Cdouble
+    rollout_seconds::Cdouble
+    McStats() = new(0, 0, 0.0, 0.0)
+end
+
+mutable struct Context
+    ptr::Ptr{Cvoid}
+    walls::Array{Bool,2}
+    function Context(device::Integer = 0)
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:piql_create, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32), ref, device)
+        rc == 0 || error("piql_create failed with status $rc (no CPU fallback)")
+        ctx = new(ref[], Array{Bool}(undef, 0, 0))
+        finalizer(c -> ccall((:piql_destroy, LIB), Int32, (Ptr{Cvoid},), c.ptr), ctx)
+    end
+end
+
+function check(ctx::Context, rc::Int32; allow = ())
+    (rc == 0 || rc in allow) && return rc
+    msg = unsafe_string(ccall((:piql_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.ptr))
+    error("piql_b200 error $rc: $msg")
+end
+
+# ---- tabulation: ControlProblem closures -> the flat arguments of piql_grid_load -------------------
+# gridworld_ctrl captures `walls`, `gw.goal`, `randomness`, `step_cost`, `reward` in its closures
+# (src/Problems/GridWorld.jl:96-121); the wall array and the goal are read from the captured
+# Gridworld, the rewards by probing ctrl.reward_function so that modify(ctrl, reward_function = ...)
+# (test/runtests.jl:7-8, scripts/experiments.jl:26) is honoured.
+function tabulate(ctrl::ControlProblem, gw; randomness)
+    goal = gw.goal
+    other = first(ii for ii in CartesianIndices(gw.walls) if !gw.walls[ii] && ii != goal)
+    reward = ctrl.reward_function(other, 0, goal)
+    step_cost = -ctrl.reward_function(other, 0, other)
+    return (walls = gw.walls, goal = goal, params = GridParams(randomness, step_cost, reward, ctrl.γ))
+end
+
+function load!(ctx::Context, ctrl::ControlProblem, gw; randomness)
+    t = tabulate(ctrl, gw; randomness)
+    walls8 = UInt8.(t.walls)                       # column-major, border included
+    H, W = size(walls8)
+    GC.@preserve walls8 check(ctx, ccall((:piql_grid_load, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64, Int64, Int64, Ref{GridParams}),
+        ctx.ptr, walls8, H, W, t.goal[1] - 1, t.goal[2] - 1, t.params))   # goal is 0-based in the ABI
+    ctx.walls = t.walls
+    return ctx
+end
+
+dense(ctx::Context, V) = [ctx.walls[ii] ? NaN : V(ii) for ii in CartesianIndices(ctx.walls)]
+function growable(ctx::Context, A::Matrix{Float64}; default = x -> 0.0)
+    Growable(Dict(ii => A[ii] for ii in CartesianIndices(ctx.walls) if !ctx.walls[ii]), default)
+end
+opts(; tol = 1e-12, max_sweeps = 10^7, precision = 0, check_every = 0) = SolveOpts(tol, max_sweeps, precision, check_every)
+
+# ---- PIQL's solver entry points (src/value_iteration.jl) -----------------------------------------------
+function generate_ν(ctx::Context; reward_scale = 1.0, kw...)
+    out = Matrix{Float64}(undef, size(ctx.walls)); st = SolveStats()
+    GC.@preserve out check(ctx, ccall((:piql_solve_nu, LIB), Int32,
+        (Ptr{Cvoid}, Cdouble, Ref{SolveOpts}, Ptr{Cdouble}, Ref{SolveStats}), ctx.ptr, reward_scale, opts(; kw...), out, st))
+    growable(ctx, out)
+end
+function generate_logz(ctx::Context, V; β = 1.0, kw...)
+    Vd = dense(ctx, V); out = similar(Vd); st = SolveStats()
+    GC.@preserve Vd out check(ctx, ccall((:piql_solve_logz, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ref{SolveOpts}, Ptr{Cdouble}, Ref{SolveStats}),
+        ctx.ptr, Vd, C_NULL, β, opts(; kw...), out, st))
+    growable(ctx, out)
+end
+function logz_updateV(ctx::Context, V; β = 1.0, kw...)
+    Vd = dense(ctx, V); out = similar(Vd); st = SolveStats()
+    GC.@preserve Vd out check(ctx, ccall((:piql_update_v, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Cdouble, Ref{SolveOpts}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{SolveStats}),
+        ctx.ptr, Vd, β, opts(; kw...), out, C_NULL, st))
+    growable(ctx, out; default = V.default)
+end
+function generate_optimality_gap(ctx::Context, V; ν, kw...)
+    Vd = dense(ctx, V); nd = dense(ctx, ν); out = similar(Vd); st = SolveStats()
+    GC.@preserve Vd nd out check(ctx, ccall((:piql_solve_gap, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{SolveOpts}, Ptr{Cdouble}, Ref{SolveStats}),
+        ctx.ptr, Vd, C_NULL, nd, opts(; kw...), out, st))
+    growable(ctx, out)
+end
+
+# ---- Monte-Carlo estimate of generate_logz's fixed point (replaces src/path_functions.jl:12-41) ----
+function mc_logz(ctx::Context, V; β = 1.0, npaths = 2^20, seed = 0, estimator = 0, horizon = 2^20,
+                 starts::Vector{CartesianIndex{2}} = CartesianIndex{2}[])
+    H = size(ctx.walls, 1)
+    cells = Int32[(s[1] - 1) + H * (s[2] - 1) for s in starts]
+    Vd = dense(ctx, V)
+    logz_sa = Array{Float64}(undef, 4, size(ctx.walls)...)      # Q-like layout: action fastest
+    count = Array{UInt64}(undef, 4, size(ctx.walls)...)
+    logz_s = similar(Vd); st = McStats()
+    GC.@preserve cells Vd logz_sa count logz_s begin
+        o = McOpts(npaths, 0, seed, estimator, isempty(cells) ? 0 : 1, horizon,
+                   isempty(cells) ? C_NULL : pointer(cells), length(cells), C_NULL, 0)
+        check(ctx, ccall((:piql_mc_logz, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ref{McOpts}, Ptr{Cdouble}, Ptr{UInt64}, Ptr{Cdouble}, Ref{McStats}),
+            ctx.ptr, Vd, C_NULL, β, o, logz_sa, count, logz_s, st))
+    end
+    (logz = growable(ctx, logz_s), logz_sa = logz_sa, count = count, transitions = st.transitions)
+end
+
+end # module

@@ -294,7 +294,7 @@ RolloutArgs make_rollout_args(piql_ctx* ctx, const piql_mc_opts* o) {
   a.lgam = (float)std::log(ctx->g.gamma); a.l1mg = (float)std::log(1.0 - ctx->g.gamma);
   a.estimator = o->estimator; a.horizon = o->horizon;
   a.starts = ctx->d_starts; a.nstarts = ctx->nstarts;
-  a.seed_lo = (uint32_t)o->seed; a.seed_hi = (uint32_t)(o->seed >> 32);
+  a.keys = philox_expand((uint32_t)o->seed, (uint32_t)(o->seed >> 32));
   return a;
 }
 

@@ -67,21 +67,26 @@ template <typename T> __device__ __forceinline__ T block_sum(T v, T* smem /* >= 
 }
 
 // ---- Philox4x32-10 (Salmon, Moraes, Dror, Shaw; SC'11) -------------------------------------------
-struct Philox {
-  uint32_t k0, k1;
-  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
-    uint32_t a = k0, b = k1;
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-      const uint32_t lo0 = 0xD2511F53u * c0, hi0 = __umulhi(0xD2511F53u, c0);
-      const uint32_t lo1 = 0xCD9E8D57u * c2, hi1 = __umulhi(0xCD9E8D57u, c2);
-      const uint32_t n0 = hi1 ^ c1 ^ a, n2 = hi0 ^ c3 ^ b;
-      c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-      a += 0x9E3779B9u; b += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
-  }
+// The ten round keys (k0 + r*0x9E3779B9, k1 + r*0xBB67AE85) are expanded on the host and travel in
+// the kernel parameters, so a round is 2 IMAD.WIDE + 2 LOP3 with constant-bank operands.
+struct PhiloxKeys {
+  uint32_t k[20];
 };
+inline PhiloxKeys philox_expand(uint32_t k0, uint32_t k1) {
+  PhiloxKeys o;
+  for (int r = 0; r < 10; r++) { o.k[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u; o.k[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u; }
+  return o;
+}
+__device__ __forceinline__ uint4 philox4x32_10(const PhiloxKeys& K, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t lo0 = 0xD2511F53u * c0, hi0 = __umulhi(0xD2511F53u, c0);
+    const uint32_t lo1 = 0xCD9E8D57u * c2, hi1 = __umulhi(0xCD9E8D57u, c2);
+    const uint32_t n0 = hi1 ^ c1 ^ K.k[2 * r], n2 = hi0 ^ c3 ^ K.k[2 * r + 1];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
 // 24-bit uniform in [0,1): exactly representable, identical on host and device.
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
 

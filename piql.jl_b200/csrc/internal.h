@@ -59,7 +59,7 @@ struct RolloutArgs {
   long long path0, npaths;
   const int* starts;
   long long nstarts;
-  uint32_t seed_lo, seed_hi;
+  PhiloxKeys keys;       // round keys of Philox4x32-10 for (seed lo, seed hi)
   const float* injected;
   long long injected_steps;
   float* logw;           // [npaths]

@@ -90,89 +90,111 @@ rollout_kernel(const RolloutArgs p) {
   const unsigned lt_mask = (1u << lane) - 1u;
   const long long nwarps = (long long)gridDim.x * (ROLL_THREADS / 32);
   const long long wid = (long long)blockIdx.x * (ROLL_THREADS / 32) + (threadIdx.x >> 5);
-  // contiguous range of local path indices for this warp
+  // contiguous range of local path indices for this warp: [wbase, wbase + wcount)
   const long long per = (p.npaths + nwarps - 1) / nwarps;
-  long long next = wid * per;
-  const long long wend = min(p.npaths, next + per);
-  const Philox rng{p.seed_lo, p.seed_hi};
+  const long long wbase = wid * per;
+  if (wbase >= p.npaths) return;  // warp-uniform
+  const uint32_t wcount = (uint32_t)min(per, p.npaths - wbase);
+  const unsigned long long gbase = (unsigned long long)(p.path0 + wbase);  // global id of the warp's first path
+  const uint32_t nstarts = (uint32_t)p.nstarts;
+  // start slot of the next path to hand out, kept incrementally (one 64-bit division per warp, not per path)
+  uint32_t slot_next = (uint32_t)(gbase % (unsigned long long)p.nstarts);
+  uint32_t next = 0;  // paths of this warp handed out so far
+  const uint32_t hor = (uint32_t)min(INJ ? min(p.horizon, p.injected_steps) : p.horizon, 0xffffffffLL);
+  const int H = p.H, goal = p.goal;
+  const float gam = p.gamma, rho = p.rho;
 
   bool active = false;
-  long long q = 0;          // local path index
-  uint32_t plo = 0, phi = 0;  // global path id
+  uint32_t q = 0;             // path index within the warp's range
+  uint32_t plo = 0, phi = 0;  // global path id (Philox counter words 2, 3)
   int s = 0;
-  uint32_t t = 0, len = 0, a0 = 0;
+  uint32_t t = 0, a0 = 0;
   float logw = 0.f, acc = -CUDART_INF_F;
 
   for (;;) {
     const unsigned need = __ballot_sync(FULL, !active);
     if (need) {
-      if (!active) {
-        const long long qq = next + __popc(need & lt_mask);
-        if (qq < wend) {
-          q = qq;
-          const unsigned long long gp = (unsigned long long)(p.path0 + qq);
-          plo = (uint32_t)gp; phi = (uint32_t)(gp >> 32);
-          s = p.starts[gp % (unsigned long long)p.nstarts];
-          t = 0; len = 0; a0 = 0; logw = 0.f; acc = -CUDART_INF_F;
-          active = true;
-        }
+      const uint32_t rank = __popc(need & lt_mask);
+      if (!active && next + rank < wcount) {
+        q = next + rank;
+        const unsigned long long gp = gbase + q;
+        plo = (uint32_t)gp; phi = (uint32_t)(gp >> 32);
+        uint32_t slot = slot_next + rank;
+        if (nstarts >= 32u) { if (slot >= nstarts) slot -= nstarts; }
+        else slot %= nstarts;
+        s = __ldg(p.starts + slot);
+        t = 0; a0 = 0; logw = 0.f; acc = -CUDART_INF_F;
+        active = true;
       }
-      next += __popc(need);
+      const uint32_t handed = __popc(need);
+      next += handed;
+      slot_next += handed;
+      if (nstarts >= 32u) { if (slot_next >= nstarts) slot_next -= nstarts; }
+      else slot_next %= nstarts;
       if (!__any_sync(FULL, active)) break;
     }
     if (active) {
-      bool done = false;
-      if (s == p.goal) {
+      bool done;
+      if (s == goal) {
         // Z(goal) = exp(0 - V(goal))   value_iteration.jl:93-94
         if (EST == 0) logw = __fsub_rn(logw, p.vgoal);
         else acc = logaddexpf_dev(acc, __fadd_rn(__fmul_rn((float)t, p.lgam), __fsub_rn(logw, p.vgoal)));
         done = true;
-      } else if ((long long)t >= p.horizon || (INJ && (long long)t >= p.injected_steps)) {
+      } else if (t >= hor) {
         done = true;
       } else {
-        float u0, u1, u2, u3;
+        float u0, u1, u2;
         int aslip;
         if (INJ) {
-          const float4 u = *reinterpret_cast<const float4*>(p.injected + ((size_t)q * p.injected_steps + t) * 4);
-          u0 = u.x; u1 = u.y; u2 = u.z; u3 = u.w;
-          aslip = min((int)(4.0f * u3), 3);
+          const float4 u = *reinterpret_cast<const float4*>(
+              p.injected + (((size_t)wbase + q) * (size_t)p.injected_steps + t) * 4);
+          u0 = u.x; u1 = u.y; u2 = u.z;
+          aslip = min((int)(4.0f * u.w), 3);
         } else {
-          const uint4 r = rng(t, 0u, plo, phi);
+          const uint4 r = philox4x32_10(p.keys, t, 0u, plo, phi);
           u0 = u01(r.x); u1 = u01(r.y); u2 = u01(r.z);
           aslip = (int)(r.w >> 30);
         }
-        const float4 r0 = __ldg(p.table + 2 * (size_t)s);
-        const float4 r1 = __ldg(p.table + 2 * (size_t)s + 1);
+        // the whole 32-byte record in one 256-bit load (LDG.E.256, sm_100): one L1 wavefront per
+        // distinct line instead of two passes over the same sector
+        float4 r0, r1;
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(r0.x), "=f"(r0.y), "=f"(r0.z), "=f"(r0.w), "=f"(r1.x), "=f"(r1.y), "=f"(r1.z), "=f"(r1.w)
+                     : "l"(p.table + 2 * (size_t)s));
         // StatsBase sample(a, Weights): i = 1; cw = w[1]; while cw < t && i < n: i += 1; cw += w[i]
-        const int a = (int)(r0.x < u0) + (int)(r0.y < u0) + (int)(r0.z < u0);
-        const float bf = a == 0 ? r1.x : a == 1 ? r1.y : a == 2 ? r1.z : r1.w;
+        // c0 <= c1 <= c2, so the walk stops at the number of running sums below u0 (branch-free).
+        const bool b0 = r0.x < u0, b1 = r0.y < u0, b2 = r0.z < u0;
+        const int a = (int)b0 + (int)b1 + (int)b2;
+        float bf = r1.x;
+        bf = b0 ? r1.y : bf;
+        bf = b1 ? r1.z : bf;
+        bf = b2 ? r1.w : bf;
         logw = __fadd_rn(logw, bf);
-        if (t == 0) a0 = (uint32_t)a;
-        bool stop = false;
-        if (EST == 0) stop = (u1 >= p.gamma);  // continue w.p. gamma, else the (1 - gamma) * 1 branch
-        else acc = logaddexpf_dev(acc, __fadd_rn(__fadd_rn(__fmul_rn((float)t, p.lgam), p.l1mg), logw));
-        if (stop) {
-          done = true;
-        } else {
+        a0 = (t == 0u) ? (uint32_t)a : a0;
+        if (EST == 1) acc = logaddexpf_dev(acc, __fadd_rn(__fadd_rn(__fmul_rn((float)t, p.lgam), p.l1mg), logw));
+        // estimator A: continue w.p. gamma, else take the (1 - gamma) * 1 branch of z_recursion and stop
+        done = (EST == 0) && (u1 >= gam);
+        if (!done) {
           // propagator: take_step(s, ifelse(rand() < randomness, sample(0:3), a))   GridWorld.jl:113-115
-          const int aa = (u2 < p.rho) ? aslip : a;
-          const unsigned mask = __float_as_uint(r0.w);
-          const int delta = (aa & 2) ? p.H : 1;
-          const int s1 = ((mask >> aa) & 1u) ? s : s + ((aa & 1) ? -delta : delta);
+          const int aa = (u2 < rho) ? aslip : a;
+          const unsigned blocked = (__float_as_uint(r0.w) >> aa) & 1u;
+          int d = (aa & 2) ? H : 1;
+          d = (aa & 1) ? -d : d;
+          d = blocked ? 0 : d;
           if (TRACE) {
             if ((long long)t < p.trace_steps) {
-              int* tr = p.trace + ((size_t)q * p.trace_steps + t) * 3;
-              tr[0] = s; tr[1] = a; tr[2] = s1;
+              int* tr = p.trace + (((size_t)wbase + q) * (size_t)p.trace_steps + t) * 3;
+              tr[0] = s; tr[1] = a; tr[2] = s + d;
             }
           }
-          s = s1;
-          len++;
-          t++;
+          s += d;
+          t++;  // t counts sampled transitions: it is also the path's length
         }
       }
       if (done) {
-        p.logw[q] = (EST == 0) ? logw : acc;
-        p.meta[q] = a0 | (len << 2);
+        const size_t o = (size_t)wbase + q;
+        p.logw[o] = (EST == 0) ? logw : acc;
+        p.meta[o] = a0 | (t << 2);
         active = false;
       }
     }

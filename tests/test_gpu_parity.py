@@ -143,8 +143,8 @@ def test_generic_kernel_solve_matches_oracle(engine):
     ref, _ = org.solve("nu", tol=1e-11, nthreads=8)
     assert nmax(nu, ref) < 1e-9
     V = np.nan_to_num(org.solve("nu", reward_scale=0.1, tol=1e-11, nthreads=8)[0])
-    v1, st = engine.update_v(V, beta=0.5, tol=1e-10)
-    assert nmax(v1, org.logz_updateV(V, beta=0.5, tol=1e-10, nthreads=8)) < 1e-8
+    v1, st1 = engine.update_v(V, beta=0.5, tol=1e-10)
+    assert st1.converged and nmax(v1, org.logz_updateV(V, beta=0.5, tol=1e-10, nthreads=8)) < 1e-8
     # bit-stable: the same solve twice gives identical bits and sweep counts
     nu2, st2 = engine.solve_nu(tol=1e-11, check_every=32)
     assert st2.sweeps == st.sweeps
