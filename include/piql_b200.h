@@ -41,7 +41,9 @@ enum {
   PIQL_ERR_NOT_CONVERGED = 6 /* max_sweeps reached; outputs hold the last iterate */
 };
 
-enum { PIQL_F64 = 0, PIQL_F32 = 1 };
+/* Arithmetic and storage type of the soft-VI sweeps.  PIQL_F32_FAST: fp32 with the hardware
+ * ex2/lg2 approximations (MUFU) in the tiled sweep kernel; same storage as PIQL_F32. */
+enum { PIQL_F64 = 0, PIQL_F32 = 1, PIQL_F32_FAST = 2 };
 
 typedef struct piql_ctx piql_ctx;
 
@@ -58,7 +60,7 @@ typedef struct {
 typedef struct {
   double tol;          /* <= 0: run exactly max_sweeps */
   int64_t max_sweeps;  /* hard cap */
-  int32_t precision;   /* PIQL_F64 | PIQL_F32: arithmetic and storage type of the sweep */
+  int32_t precision;   /* PIQL_F64 | PIQL_F32 | PIQL_F32_FAST */
   int32_t check_every; /* residual is evaluated every this many sweeps; <= 0: library default */
 } piql_solve_opts;
 
@@ -68,7 +70,7 @@ typedef struct {
   double device_seconds; /* CUDA-event time of the sweeps */
   int64_t backups;       /* state backups performed = sweeps * free cells */
   int32_t converged;
-  int32_t kernel;        /* 0 = one launch per sweep, 1 = single-CTA resident solver */
+  int32_t kernel;        /* 1 = single-CTA resident solver, 2 = tiled multi-sweep kernel (4 sweeps per launch) */
 } piql_solve_stats;
 
 enum { PIQL_EST_SAMPLED_STOP = 0 /* estimator A */, PIQL_EST_DISCOUNTED = 1 /* estimator B */ };
@@ -189,6 +191,8 @@ int32_t piql_mc_records(piql_ctx* ctx, float* logw_out, uint32_t* meta_out, int6
  * piql_vi_prepare_dev uploads V/Q/nu (as needed) and resets the iterate. */
 int32_t piql_vi_prepare_dev(piql_ctx* ctx, int32_t kind, const double* V, const double* Q, const double* nu,
                             double beta, double reward_scale, int32_t precision);
+/* Replaces the current iterate (warm start / resume from a caller-kept array; wall cells ignored). */
+int32_t piql_vi_set_iterate(piql_ctx* ctx, const double* x);
 int32_t piql_vi_sweeps_dev(piql_ctx* ctx, int64_t sweeps);
 int32_t piql_vi_fetch(piql_ctx* ctx, double* x_out, double* residual_out);
 

@@ -10,7 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpiql_b200.so")
 
 OK, ERR_ARG, ERR_STATE, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_NOT_CONVERGED = range(7)
-F64, F32 = 0, 1
+F64, F32, F32_FAST = 0, 1, 2
+PRECISIONS = {"f64": F64, "f32": F32, "f32fast": F32_FAST, F64: F64, F32: F32, F32_FAST: F32_FAST}
 EST_SAMPLED_STOP, EST_DISCOUNTED = 0, 1
 START_ALL_FREE, START_LIST = 0, 1
 KIND_NU, KIND_LOGZ, KIND_GAP = 0, 1, 2
@@ -75,6 +76,7 @@ SYMBOLS = {
     "piql_mc_transitions_total": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     "piql_mc_records": (C.c_int32, [_P, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_int64]),
     "piql_vi_prepare_dev": (C.c_int32, [_P, C.c_int32, _D, _D, _D, C.c_double, C.c_double, C.c_int32]),
+    "piql_vi_set_iterate": (C.c_int32, [_P, C.POINTER(C.c_double)]),
     "piql_vi_sweeps_dev": (C.c_int32, [_P, C.c_int64]),
     "piql_vi_fetch": (C.c_int32, [_P, _D, _D]),
     "piql_launch_count": (C.c_int32, [_P, C.POINTER(C.c_int64)]),

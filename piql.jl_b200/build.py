@@ -4,8 +4,8 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("backup.cu", "rollout.cu", "api.cu")]
-HDR = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "internal.h")] + \
+SRC = [os.path.join(HERE, "csrc", f) for f in ("backup.cu", "tile.cu", "rollout.cu", "api.cu")]
+HDR = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "algebra.cuh", "internal.h")] + \
       [os.path.join(HERE, "..", "include", "piql_b200.h")]
 OUT = os.path.join(HERE, "lib", "libpiql_b200.so")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

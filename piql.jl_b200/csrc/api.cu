@@ -37,6 +37,7 @@ struct piql_ctx {
   double* d_scalars = nullptr;  // [0] residual, [1..2] resident solver output
   double* h_scalars = nullptr;  // pinned mirror
   long long vi_sweeps_done = 0;
+  TileBuffers tb;  // padded copy of the iterate for the tiled multi-sweep kernel
 
   // Monte-Carlo
   float4* d_table = nullptr;
@@ -114,6 +115,7 @@ void free_vi(piql_ctx* c) {
   c->d_Q = c->d_nu = nullptr;
   c->vi_cap = 0;
   c->vs_ready = false;
+  tile_free(c->tb);
 }
 
 int ensure_vi(piql_ctx* ctx) {
@@ -145,7 +147,10 @@ int vi_prepare(piql_ctx* ctx, int kind, const double* V, const double* Q, const 
                double reward_scale, int precision) {
   NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded (call piql_grid_load first)");
   NEED(kind >= 0 && kind <= 2, PIQL_ERR_ARG, "kind must be 0 (nu), 1 (logz) or 2 (gap)");
-  NEED(precision == PIQL_F64 || precision == PIQL_F32, PIQL_ERR_ARG, "precision must be PIQL_F64 or PIQL_F32");
+  NEED(precision == PIQL_F64 || precision == PIQL_F32 || precision == PIQL_F32_FAST, PIQL_ERR_ARG,
+       "precision must be PIQL_F64, PIQL_F32 or PIQL_F32_FAST");
+  const bool fast = precision == PIQL_F32_FAST;
+  if (fast) precision = PIQL_F32;
   NEED(kind == KIND_NU || V != nullptr, PIQL_ERR_ARG, "V is required for logz / gap");
   NEED(kind != KIND_GAP || nu != nullptr, PIQL_ERR_ARG, "nu is required for the optimality gap");
   NEED(kind == KIND_NU || (beta == beta), PIQL_ERR_ARG, "beta is NaN");
@@ -155,6 +160,8 @@ int vi_prepare(piql_ctx* ctx, int kind, const double* V, const double* Q, const 
   cudaStream_t st = ctx->stream;
   ViState& vs = ctx->vs;
   vs.precision = precision; vs.kind = kind; vs.beta = beta; vs.reward_scale = reward_scale; vs.cur = 0;
+  vs.fast = fast;
+  ctx->tb.active = false;
   vs.nblocks = (n + SWEEP_THREADS - 1) / SWEEP_THREADS;
   vs.v_goal = 0.0;
   vs.residual = ctx->d_scalars;
@@ -204,11 +211,12 @@ int vi_solve(piql_ctx* ctx, const piql_solve_opts* opts, double* out, piql_solve
     sweeps = (long long)ctx->h_scalars[1];
     residual = ctx->h_scalars[2];
   } else {
+    kernel = 2;
+    CK(tile_begin(ctx->g, ctx->d_cell, vs, ctx->tb, ctx->num_sms, st));
     const long long every = opts->check_every > 0 ? opts->check_every : 64;
     while (sweeps < opts->max_sweeps) {
       long long batch = opts->max_sweeps - sweeps < every ? opts->max_sweeps - sweeps : every;
-      for (long long i = 0; i < batch; i++) launch_sweep(ctx->g, ctx->d_cell, vs, i == batch - 1, st);
-      CK_LAST();
+      CK(tile_sweeps(ctx->g, vs, ctx->tb, batch, true, st));
       sweeps += batch;
       CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
@@ -216,6 +224,8 @@ int vi_solve(piql_ctx* ctx, const piql_solve_opts* opts, double* out, piql_solve
       if (!(residual == residual)) return fail(ctx, PIQL_ERR_CUDA, "soft-VI residual is NaN (diverged)");
       if (tol > 0 && residual < tol) break;
     }
+    tile_unpack(ctx->g, vs, ctx->tb, st);
+    CK_LAST();
   }
   CK(cudaEventRecord(ctx->ev1, st));
   if (out) {
@@ -628,7 +638,25 @@ int32_t piql_vi_prepare_dev(piql_ctx* ctx, int32_t kind, const double* V, const 
   if (!ctx) return PIQL_ERR_ARG;
   LaunchScope ls(ctx);
   CK(cudaSetDevice(ctx->device));
-  return vi_prepare(ctx, kind, V, Q, nu, beta, reward_scale, precision);
+  int rc = vi_prepare(ctx, kind, V, Q, nu, beta, reward_scale, precision);
+  if (rc) return rc;
+  if (ctx->g.n > RESIDENT_MAX_CELLS) CK(tile_begin(ctx->g, ctx->d_cell, ctx->vs, ctx->tb, ctx->num_sms, ctx->stream));
+  return PIQL_OK;
+}
+int32_t piql_vi_set_iterate(piql_ctx* ctx, const double* x) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  NEED(ctx->vs_ready, PIQL_ERR_STATE, "call piql_vi_prepare_dev first");
+  NEED(x != nullptr, PIQL_ERR_ARG, "x is null");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int n = ctx->g.n;
+  CK(cudaMemcpyAsync(ctx->d_out, x, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+  launch_convert_in(ctx->d_out, ctx->vs.x[ctx->vs.cur], n, ctx->vs.precision, st);
+  CK_LAST();
+  if (n > RESIDENT_MAX_CELLS) CK(tile_begin(ctx->g, ctx->d_cell, ctx->vs, ctx->tb, ctx->num_sms, st));
+  CK(cudaStreamSynchronize(st));  // x is the caller's buffer
+  return PIQL_OK;
 }
 int32_t piql_vi_sweeps_dev(piql_ctx* ctx, int64_t sweeps) {
   if (!ctx) return PIQL_ERR_ARG;
@@ -636,8 +664,12 @@ int32_t piql_vi_sweeps_dev(piql_ctx* ctx, int64_t sweeps) {
   NEED(ctx->vs_ready, PIQL_ERR_STATE, "call piql_vi_prepare_dev first");
   NEED(sweeps > 0, PIQL_ERR_ARG, "sweeps must be positive");
   CK(cudaSetDevice(ctx->device));
-  for (int64_t i = 0; i < sweeps; i++) launch_sweep(ctx->g, ctx->d_cell, ctx->vs, i == sweeps - 1, ctx->stream);
-  CK_LAST();
+  if (ctx->tb.active) {
+    CK(tile_sweeps(ctx->g, ctx->vs, ctx->tb, sweeps, true, ctx->stream));
+  } else {
+    for (int64_t i = 0; i < sweeps; i++) launch_sweep(ctx->g, ctx->d_cell, ctx->vs, i == sweeps - 1, ctx->stream);
+    CK_LAST();
+  }
   ctx->vi_sweeps_done += sweeps;
   return PIQL_OK;
 }
@@ -649,6 +681,7 @@ int32_t piql_vi_fetch(piql_ctx* ctx, double* x_out, double* residual_out) {
   cudaStream_t st = ctx->stream;
   const int n = ctx->g.n;
   if (x_out) {
+    if (ctx->tb.active) tile_unpack(ctx->g, ctx->vs, ctx->tb, st);
     launch_convert_out(ctx->vs.x[ctx->vs.cur], ctx->d_cell, ctx->d_out, n, ctx->vs.precision, st);
     CK_LAST();
     CK(cudaMemcpyAsync(x_out, ctx->d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));

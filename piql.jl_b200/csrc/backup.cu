@@ -12,100 +12,11 @@
 // (ping-pong): every cell's new value depends only on the previous iterate, so the result is
 // independent of grid/block shape and of how many GPUs a caller splits the grid over.
 #include "internal.h"
+#include "algebra.cuh"
 
 namespace piql {
 
 thread_local long long g_launches = 0;
-
-// Constants of one sweep in the sweep's precision.
-template <typename T> struct K {
-  int H, n, goal;
-  T w_on, w_off;        // (a==aa)*(1-randomness) + randomness/len      GridWorld.jl:101
-  T lw_on, lw_off;      // their logs (log_pa, GridWorld.jl:106)
-  T gamma, lgamma, l1mgamma;
-  T rwd_goal, rwd_step; // reward_function values times the modify() scale   GridWorld.jl:116
-  T log_prior;          // log(1/len)                                       GridWorld.jl:112
-  T beta;
-};
-template <typename T> static K<T> make_k(const GridDev& g, double reward_scale, double beta) {
-  K<T> k;
-  k.H = g.H; k.n = g.n; k.goal = g.goal;
-  const double w_on = 1.0 * (1.0 - g.randomness) + g.randomness / NA;
-  const double w_off = 0.0 * (1.0 - g.randomness) + g.randomness / NA;
-  k.w_on = (T)w_on; k.w_off = (T)w_off;
-  k.lw_on = (T)log(w_on); k.lw_off = (T)log(w_off);
-  k.gamma = (T)g.gamma; k.lgamma = (T)log(g.gamma); k.l1mgamma = (T)log(1.0 - g.gamma);
-  k.rwd_goal = (T)(reward_scale * g.reward); k.rwd_step = (T)(reward_scale * -g.step_cost);
-  k.log_prior = (T)log(1.0 / NA);
-  k.beta = (T)beta;
-  return k;
-}
-
-// ---- per-cell algebra on a gathered 5-point stencil ----------------------------------------------
-template <typename T>
-__device__ __forceinline__ void gather(const T* __restrict__ X, int s, int H, unsigned ci, T& c, T (&nb)[NA]) {
-  // f(take_step(s,aa)): the neighbour, or the cell itself when a wall blocks the move  GridWorld.jl:29-32
-  c = X[s];
-  nb[0] = (ci & 1u) ? c : X[s + 1];
-  nb[1] = (ci & 2u) ? c : X[s - 1];
-  nb[2] = (ci & 4u) ? c : X[s + H];
-  nb[3] = (ci & 8u) ? c : X[s - H];
-}
-template <typename T> __device__ __forceinline__ T pa(const K<T>& k, int a, const T (&f)[NA]) {
-  T out = 0;  // propagator_average, same accumulation order as GridWorld.jl:98-104
-#pragma unroll
-  for (int aa = 0; aa < NA; aa++) out += (a == aa ? k.w_on : k.w_off) * f[aa];
-  return out;
-}
-template <typename T>
-__device__ __forceinline__ void avg_rewards(const K<T>& k, int s, unsigned ci, T (&rbar)[NA]) {
-  // average_reward(ctrl,s,a) = pa(s,a, s1 -> reward_function(s,a,s1))   PIQL.jl:55-57
-  T r[NA];
-  r[0] = (!(ci & 1u) && s + 1 == k.goal) ? k.rwd_goal : k.rwd_step;
-  r[1] = (!(ci & 2u) && s - 1 == k.goal) ? k.rwd_goal : k.rwd_step;
-  r[2] = (!(ci & 4u) && s + k.H == k.goal) ? k.rwd_goal : k.rwd_step;
-  r[3] = (!(ci & 8u) && s - k.H == k.goal) ? k.rwd_goal : k.rwd_step;
-#pragma unroll
-  for (int a = 0; a < NA; a++) rbar[a] = pa(k, a, r);
-}
-template <typename T>
-__device__ __forceinline__ void control_v(const K<T>& k, T c, const T (&nb)[NA], const T (&rbar)[NA], T (&cv)[NA]) {
-#pragma unroll
-  for (int a = 0; a < NA; a++) cv[a] = k.gamma * pa(k, a, nb) - c + rbar[a];  // PIQL.jl:63-66
-}
-
-template <typename T>
-__device__ __forceinline__ T backup_nu(const K<T>& k, int s, unsigned ci, const T (&nb)[NA]) {
-  T rbar[NA], x[NA];
-  avg_rewards(k, s, ci, rbar);
-#pragma unroll
-  for (int a = 0; a < NA; a++) x[a] = k.log_prior + k.gamma * pa(k, a, nb) + rbar[a];
-  return lse4(x);
-}
-// A[a] = log prior + beta*controlV + (1-beta)*controlQ (fixed during the solve, from prep_kernel)
-template <typename T>
-__device__ __forceinline__ T backup_logz(const K<T>& k, const T (&A)[NA], const T (&nb)[NA]) {
-  // log_pa(s,a,logz) = logsumexp_aa(log P(aa|a) + logz(step(s,aa))), with the four exponentials
-  // shared between the actions: P(aa|a) takes two values only.
-  const T m = fmax(fmax(nb[0], nb[1]), fmax(nb[2], nb[3]));
-  T e[NA], esum = 0;
-#pragma unroll
-  for (int aa = 0; aa < NA; aa++) { e[aa] = xexp(nb[aa] - m); esum += e[aa]; }
-  T x[NA];
-#pragma unroll
-  for (int a = 0; a < NA; a++) {
-    const T inner = m + xlog(k.w_on * e[a] + k.w_off * (esum - e[a]));
-    x[a] = A[a] + logaddexp(k.lgamma + inner, k.l1mgamma);
-  }
-  return lse4(x);
-}
-template <typename T>
-__device__ __forceinline__ T backup_gap(const K<T>& k, const T (&P)[NA], T D, const T (&nb)[NA]) {
-  T out = D;  // D = sum_a pi_a (controlQ - controlV(nu)); gap term has no gamma (value_iteration.jl:165)
-#pragma unroll
-  for (int a = 0; a < NA; a++) out += P[a] * pa(k, a, nb);
-  return out;
-}
 
 template <typename T> struct Vec4;
 template <> struct Vec4<float> { using type = float4; };
@@ -380,6 +291,11 @@ static void sweep_t(const GridDev& g, const uint8_t* cell, ViState& vs, bool wit
     g_launches++;
   }
   vs.cur ^= 1;
+}
+
+void launch_residual_final(const double* partial, int nblocks, double* out, cudaStream_t st) {
+  residual_final_kernel<<<1, 1024, 0, st>>>(partial, nblocks, out);
+  g_launches++;
 }
 
 void launch_sweep(const GridDev& g, const uint8_t* cell, ViState& vs, bool with_residual, cudaStream_t st) {

@@ -24,7 +24,36 @@ struct ViState {
   double* partial;    // per-block residual partials
   double* residual;   // device scalar
   int nblocks;
+  bool fast;          // fp32 only: MUFU ex2/lg2 approximations in the tiled sweeps (PIQL_F32_FAST)
 };
+
+// tile.cu: temporally blocked sweeps on a padded copy of the iterate ---------------------------
+constexpr int TILE_KH = 4;  // halo width = Jacobi sweeps per launch
+struct TilePlan {
+  int TJ, EJ;            // interior / staged columns per tile (EJ = TJ + 2*TILE_KH); rows are 120 / 128
+  int tiles_i, tiles_j;
+  int nw;                // warps per CTA
+  int ld, Wp;            // padded leading dimension and column count
+  long long np;          // ld * Wp
+  size_t smem;           // dynamic shared memory per CTA
+  int ctas_per_sm;
+};
+struct TileBuffers {
+  void* x[2] = {nullptr, nullptr};  // padded ping-pong iterate
+  void* aux = nullptr;              // five padded planes (logz: exp(A_a - max A), max A; gap: pi_a, D)
+  uint8_t* mask = nullptr;          // padded cell bytes (ghost frame = wall)
+  double* partial = nullptr;        // per-tile residual partials
+  size_t cap_x = 0, cap_aux = 0, cap_mask = 0;
+  long long cap_partial = 0;
+  TilePlan plan{};
+  int cur = 0;
+  bool active = false;
+};
+TilePlan make_tile_plan(int H, int W, int precision, int kind, int num_sms);
+cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs, TileBuffers& tb, int num_sms, cudaStream_t st);
+cudaError_t tile_sweeps(const GridDev& g, const ViState& vs, TileBuffers& tb, long long nsweeps, bool want_res, cudaStream_t st);
+void tile_unpack(const GridDev& g, const ViState& vs, const TileBuffers& tb, cudaStream_t st);
+void tile_free(TileBuffers& tb);
 
 constexpr int SWEEP_THREADS = 256;
 constexpr int RESIDENT_MAX_CELLS = 8192;  // single-CTA resident solver limit
@@ -47,6 +76,7 @@ void launch_update_v(const double* V, const void* logz, const uint8_t* cell, dou
                      int precision, cudaStream_t st);
 size_t resident_smem_bytes(int n, int precision);
 int configure_backup_kernels();
+void launch_residual_final(const double* partial, int nblocks, double* out, cudaStream_t st);
 
 // rollout.cu --------------------------------------------------------------------------------
 struct RolloutArgs {

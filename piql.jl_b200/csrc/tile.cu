@@ -1,0 +1,477 @@
+// tile.cu -- temporally blocked soft value-iteration sweeps for grids that do not fit one CTA (sm_100a).
+//
+// The same three recursions as backup.cu (truevalue_recursion src/PIQL.jl:95-101 driven by update_ν!
+// src/value_iteration.jl:62-75; logz_recursion src/PIQL.jl:125-130 driven by update_logz! :89-105;
+// optimality_gap_recursion :160-169 driven by update_optimality_gap! :129-142), restructured for the
+// machine: a value array of 10^6..10^7 cells is 4..67 MB, L2-resident, and one Jacobi sweep at the HBM
+// roofline lasts 1.3..20 us -- below a kernel launch.  So one launch performs TILE_KH sweeps:
+//
+//   * the grid lives in a padded layout (ghost frame of TILE_KH cells, leading dimension a multiple of
+//     32 floats) so that every tile load is an aligned, unpredicated 128-bit access;
+//   * a CTA stages a tile of 128 x EJ cells (interior 120 x TJ + halo TILE_KH) and its 1-byte wall
+//     masks in shared memory, runs TILE_KH Jacobi sweeps there (ping-pong), the valid region shrinking
+//     by one ring per sweep, and writes the interior back: global traffic per sweep drops by TILE_KH;
+//   * a warp owns a column: lane l holds the 4-cell strip of rows 4l..4l+3 in registers (one LDS.128
+//     for itself, one each for the left and right columns), the vertical neighbours across strips come
+//     from two warp shuffles, and the wall test is a bit of the mask word -> a select;
+//   * per-cell algebra is refactored so that the four exponentials are shared between the actions
+//     (P(a'|a) takes two values) and, in the fast fp32 mode, map 1:1 onto MUFU.EX2 / MUFU.LG2.
+//
+// Jacobi makes every cell's update a pure function of the previous iterate, so the values are
+// independent of the tiling (halo cells recomputed by two CTAs get identical bits).
+#include <algorithm>
+#include <cstdlib>
+
+#include "algebra.cuh"
+#include "internal.h"
+
+namespace piql {
+
+constexpr int TKH = TILE_KH;
+constexpr int TEI = 128;            // rows of the shared-memory tile: 32 lanes x 4-cell strips
+constexpr int TTI = TEI - 2 * TKH;  // interior rows per tile
+
+// Constants of the tiled sweeps.
+template <typename T> struct TileK {
+  int ld, np;          // leading dimension and size of the padded arrays
+  int TJ, EJ, tiles_i;
+  int goal_pi, goal_pj, goal_p;  // goal in padded coordinates
+  T kc, a1, b1, a2;    // nu: x_a = kc + a1*n_a + b1*S;  a2 = a1*log2(e)
+  T kc_lo, a1_lo;      // fp32: what rounding kc and a1 to float lost (a constant per-sweep bias is amplified by 1/(1-gamma))
+  T w_off, dw;         // P(a'|a) = w_off + dw*[a'==a]
+  T gamma, omg;        // gamma, 1 - gamma
+  T term;              // value of the terminal cell
+  K<T> k;              // constants of the general formula (H := ld, goal := goal_p), for the cells next to the goal
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <typename T> __device__ __forceinline__ void lds4(const T* p, T (&o)[4]);
+template <> __device__ __forceinline__ void lds4<float>(const float* p, float (&o)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <> __device__ __forceinline__ void lds4<double>(const double* p, double (&o)[4]) {
+  const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+template <typename T> __device__ __forceinline__ void sts4(T* p, const T (&v)[4]);
+template <> __device__ __forceinline__ void sts4<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void sts4<double>(double* p, const double (&v)[4]) {
+  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
+template <typename T> __device__ __forceinline__ void ldg4(const T* p, T (&o)[4]);
+template <> __device__ __forceinline__ void ldg4<float>(const float* p, float (&o)[4]) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <> __device__ __forceinline__ void ldg4<double>(const double* p, double (&o)[4]) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p + 2));
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+
+// ---- per-cell backups on the four (already wall-resolved) neighbour values ----------------------------
+// nu: logsumexp_a[log 1/4 + gamma*pa(s,a,nu) + rbar] with pa = w_off*S + dw*n_a and rbar = -step_cost away
+// from the goal, i.e. kc + b1*S + a1*max + log sum_a exp(a1*(n_a - max)).
+template <typename T, bool FAST>
+__device__ __forceinline__ T nu_cell(const TileK<T>& k, T n0, T n1, T n2, T n3) {
+  const T S = (n0 + n1) + (n2 + n3);
+  const T m = fmax(fmax(n0, n1), fmax(n2, n3));
+  if constexpr (FAST) {
+    const float t = -m * k.a2;
+    const float sum = (ex2_approx(fmaf(n0, k.a2, t)) + ex2_approx(fmaf(n1, k.a2, t))) +
+                      (ex2_approx(fmaf(n2, k.a2, t)) + ex2_approx(fmaf(n3, k.a2, t)));
+    // ln 2 = 0.693147182464599609375 (float) - 1.904654e-09
+    const float lg = lg2_approx(sum);
+    const float hi = fmaf(0.693147180559945f, lg, fmaf(k.b1, S, fmaf(k.a1, m, k.kc)));
+    return hi + fmaf(-1.904654e-09f, lg, fmaf(k.a1_lo, m, k.kc_lo));
+  } else {
+    const T sum = (xexp(k.a1 * (n0 - m)) + xexp(k.a1 * (n1 - m))) + (xexp(k.a1 * (n2 - m)) + xexp(k.a1 * (n3 - m)));
+    if (sizeof(T) == 4) return (k.kc + k.b1 * S + k.a1 * m + xlog(sum)) + (k.kc_lo + k.a1_lo * m);
+    return k.kc + k.b1 * S + k.a1 * m + xlog(sum);
+  }
+}
+// eta = 1/2 damping of update_logz!: logaddexp(log(1/2) + new, log(1/2) + old)   value_iteration.jl:101-102
+template <typename T, bool FAST> __device__ __forceinline__ T damp_half(T nw, T c) {
+  const T d = fabs(nw - c), mx = fmax(nw, c);
+  if constexpr (FAST) return fmaf(0.693147180559945f, lg2_approx(fmaf(0.5f, ex2_approx(-1.44269504088896f * d), 0.5f)), mx);
+  else return mx + xlog((T)0.5 + (T)0.5 * xexp(-d));
+}
+// logz: with Z = exp(logz), Z_new = sum_a exp(A_a) * (gamma * sum_a' P(a'|a) Z(n_a') + 1 - gamma), evaluated
+// with the neighbour maximum m and M = max(m, 0) factored out (both exponents stay <= 0); ea_a = exp(A_a - amax).
+template <typename T, bool FAST>
+__device__ __forceinline__ T logz_cell(const TileK<T>& k, T c, T n0, T n1, T n2, T n3, T ea0, T ea1, T ea2, T ea3, T amax) {
+  const T m = fmax(fmax(n0, n1), fmax(n2, n3));
+  T e0, e1, e2, e3, em;
+  if constexpr (FAST) {
+    const float l2e = 1.44269504088896f, t = -m * l2e;
+    e0 = ex2_approx(fmaf(n0, l2e, t)); e1 = ex2_approx(fmaf(n1, l2e, t));
+    e2 = ex2_approx(fmaf(n2, l2e, t)); e3 = ex2_approx(fmaf(n3, l2e, t));
+    em = ex2_approx(-fabsf(m) * l2e);
+  } else {
+    e0 = xexp(n0 - m); e1 = xexp(n1 - m); e2 = xexp(n2 - m); e3 = xexp(n3 - m);
+    em = xexp(-fabs(m));
+  }
+  const T wE = k.w_off * ((e0 + e1) + (e2 + e3));
+  const bool pos = m >= (T)0;
+  const T g1 = k.gamma * (pos ? (T)1 : em), g0 = k.omg * (pos ? em : (T)1);
+  const T base = g1 * wE + g0, gd = g1 * k.dw;
+  const T sum = (ea0 * (gd * e0 + base) + ea1 * (gd * e1 + base)) + (ea2 * (gd * e2 + base) + ea3 * (gd * e3 + base));
+  T nw;
+  if constexpr (FAST) nw = fmaf(0.693147180559945f, lg2_approx(sum), fmaxf(m, 0.f) + amax);
+  else nw = fmax(m, (T)0) + amax + xlog(sum);
+  return damp_half<T, FAST>(nw, c);
+}
+// gap: D + sum_a pi_a * pa(s,a,gap), no discount on the gap term   value_iteration.jl:165
+template <typename T>
+__device__ __forceinline__ T gap_cell(const TileK<T>& k, T n0, T n1, T n2, T n3, T p0, T p1, T p2, T p3, T D) {
+  const T wS = k.w_off * ((n0 + n1) + (n2 + n3));
+  return D + ((p0 * (wS + k.dw * n0) + p1 * (wS + k.dw * n1)) + (p2 * (wS + k.dw * n2) + p3 * (wS + k.dw * n3)));
+}
+
+// |new - old| of the reference's stop rule from the two last iterates.  logz stores the damped value:
+// stored = log(1/2 e^new + 1/2 e^old)  =>  new - old = log(2 e^(stored-old) - 1).
+template <int KIND> __device__ __forceinline__ double sweep_diff(double stored, double old) {
+  const double d = stored - old;
+  if (KIND != KIND_LOGZ) return fabs(d);
+  const double x = 2.0 * expm1(d);
+  return x > -1.0 ? fabs(log1p(x)) : CUDART_INF;
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------
+// grid = tiles_i * tiles_j CTAs of NW warps; dynamic shared memory = EJ * (2 * 128 * sizeof(T) + 128) bytes.
+template <typename T, int KIND, bool FAST>
+__global__ void __launch_bounds__(512)
+tile_sweep_kernel(const TileK<T> k, const uint8_t* __restrict__ maskp, const T* __restrict__ X, T* __restrict__ Y,
+                  const T* __restrict__ aux, int nsub, int want_res, double* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  __shared__ double red[32];
+  const int EJ = k.EJ, ld = k.ld;
+  T* bufA = reinterpret_cast<T*>(tile_smem);
+  T* bufB = bufA + EJ * TEI;
+  uint32_t* msk = reinterpret_cast<uint32_t*>(bufB + EJ * TEI);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+  const int ti = blockIdx.x % k.tiles_i, tj = blockIdx.x / k.tiles_i;
+  const int org = ti * TTI + ld * (tj * k.TJ);  // padded index of the tile's (row 0, column 0)
+
+  // stage the tile (every access in bounds thanks to the ghost frame)
+  for (int jj = warp; jj < EJ; jj += NW) {
+    const int g = org + jj * ld + 4 * lane;
+    T v[4];
+    ldg4(X + g, v);
+    sts4(bufA + jj * TEI + 4 * lane, v);
+    if (jj == 0 || jj == EJ - 1) sts4(bufB + jj * TEI + 4 * lane, v);  // never recomputed: keep both copies defined
+    msk[jj * 32 + lane] = __ldg(reinterpret_cast<const uint32_t*>(maskp + g));
+  }
+  __syncthreads();
+
+  // is the goal (or one of its neighbours) inside this tile?  block-uniform
+  const int gi = k.goal_pi - ti * TTI, gj = k.goal_pj - tj * k.TJ;
+  const bool near_goal = gi >= -1 && gi <= TEI && gj >= -1 && gj <= EJ;
+
+  T* src = bufA;
+  T* dst = bufB;
+  for (int sub = 0; sub < nsub; sub++) {
+    for (int jj = 1 + warp; jj < EJ - 1; jj += NW) {
+      T v[4], L[4], R[4], out[4];
+      lds4(src + jj * TEI + 4 * lane, v);
+      lds4(src + (jj - 1) * TEI + 4 * lane, L);
+      lds4(src + (jj + 1) * TEI + 4 * lane, R);
+      const uint32_t mk = msk[jj * 32 + lane];
+      // rows 0 and 127 have no vertical neighbour in the tile: they are halo, any value will do
+      const T up = __shfl_up_sync(FULL, v[3], 1), dn = __shfl_down_sync(FULL, v[0], 1);
+      const int sidx = org + jj * ld + 4 * lane;
+      T ax[5][4];
+      if (KIND != KIND_NU) {
+#pragma unroll
+        for (int pl = 0; pl < 5; pl++) ldg4(aux + (size_t)pl * k.np + sidx, ax[pl]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const uint32_t b = mk >> (8 * r);
+        const T c = v[r];
+        // f(take_step(s,a)): the neighbour, or the cell itself when a wall blocks the move  GridWorld.jl:29-32
+        const T n0 = (b & 1u) ? c : (r < 3 ? v[r < 3 ? r + 1 : 3] : dn);
+        const T n1 = (b & 2u) ? c : (r > 0 ? v[r > 0 ? r - 1 : 0] : up);
+        const T n2 = (b & 4u) ? c : R[r];
+        const T n3 = (b & 8u) ? c : L[r];
+        T o;
+        if (KIND == KIND_NU) o = nu_cell<T, FAST>(k, n0, n1, n2, n3);
+        else if (KIND == KIND_LOGZ) o = logz_cell<T, FAST>(k, c, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
+        else o = gap_cell<T>(k, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
+        if (near_goal) {
+          const int cidx = sidx + r;
+          if (cidx == k.goal_p) {
+            // terminal_condition: nu, gap -> 0; logz -> 0 - V(goal), damped like every other state
+            o = (KIND == KIND_LOGZ) ? damp_half<T, FAST>(k.term, c) : k.term;
+          } else if (KIND == KIND_NU && (cidx == k.goal_p + 1 || cidx == k.goal_p - 1 || cidx == k.goal_p + ld ||
+                                         cidx == k.goal_p - ld)) {
+            const T nb[NA] = {n0, n1, n2, n3};  // a step into the goal earns the reward: general formula
+            o = backup_nu(k.k, cidx, b & 0xffu, nb);
+          }
+        }
+        out[r] = o;
+      }
+      sts4(dst + jj * TEI + 4 * lane, out);
+    }
+    __syncthreads();
+    T* t = src; src = dst; dst = t;
+  }
+
+  // write the interior back (src: last iterate, dst: the one before); residual of the last sweep
+  double res = 0.0;
+  if (lane >= TKH / 4 && lane < 32 - TKH / 4) {
+    for (int jj = TKH + warp; jj < TKH + k.TJ; jj += NW) {
+      T f[4];
+      lds4(src + jj * TEI + 4 * lane, f);
+      const int g = org + jj * ld + 4 * lane;
+      if (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(Y + g) = make_float4((float)f[0], (float)f[1], (float)f[2], (float)f[3]);
+      } else {
+        *reinterpret_cast<double2*>(Y + g) = make_double2((double)f[0], (double)f[1]);
+        *reinterpret_cast<double2*>(Y + g + 2) = make_double2((double)f[2], (double)f[3]);
+      }
+      if (want_res) {
+        T p[4];
+        lds4(dst + jj * TEI + 4 * lane, p);
+        const uint32_t mk = msk[jj * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+          if (!((mk >> (8 * r)) & CELL_WALL)) res += sweep_diff<KIND>((double)f[r], (double)p[r]);
+      }
+    }
+  }
+  if (want_res) {  // uniform
+    const double s = block_sum(res, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  }
+}
+
+// ---- packing between the dense H x W arrays of the ABI side and the padded tile layout -------------------
+struct PadGeom {
+  int H, W, ld, Wp;
+};
+template <typename T>
+__global__ void tile_pack_kernel(PadGeom g, const T* __restrict__ dense, T* __restrict__ padded) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.ld * g.Wp) return;
+  const int i = p % g.ld - TKH, j = p / g.ld - TKH;
+  padded[p] = (i >= 0 && i < g.H && j >= 0 && j < g.W) ? dense[i + g.H * j] : (T)0;
+}
+__global__ void tile_pack_mask_kernel(PadGeom g, const uint8_t* __restrict__ cell, uint8_t* __restrict__ maskp) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.ld * g.Wp) return;
+  const int i = p % g.ld - TKH, j = p / g.ld - TKH;
+  maskp[p] = (i >= 0 && i < g.H && j >= 0 && j < g.W) ? cell[i + g.H * j] : (uint8_t)(CELL_WALL | CELL_BLOCK_MASK);
+}
+// aux4 [cell][4] (+ aux1 [cell]) -> five planes.  logz: exp(A_a - max A), max A; gap: pi_a, D.
+template <typename T, int KIND>
+__global__ void tile_pack_aux_kernel(PadGeom g, const T* __restrict__ aux4, const T* __restrict__ aux1, T* __restrict__ auxp) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int np = g.ld * g.Wp;
+  if (p >= np) return;
+  const int i = p % g.ld - TKH, j = p / g.ld - TKH;
+  T o[5] = {0, 0, 0, 0, 0};
+  if (i >= 0 && i < g.H && j >= 0 && j < g.W) {
+    const int s = i + g.H * j;
+    T a[4];
+    ldg4(aux4 + 4 * (size_t)s, a);
+    if (KIND == KIND_LOGZ) {
+      const T am = fmax(fmax(a[0], a[1]), fmax(a[2], a[3]));
+#pragma unroll
+      for (int q = 0; q < 4; q++) o[q] = xexp(a[q] - am);
+      o[4] = am;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; q++) o[q] = a[q];
+      o[4] = aux1[s];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 5; q++) auxp[(size_t)q * np + p] = o[q];
+}
+template <typename T>
+__global__ void tile_unpack_kernel(PadGeom g, const T* __restrict__ padded, T* __restrict__ dense) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= g.H * g.W) return;
+  const int i = s % g.H, j = s / g.H;
+  dense[s] = padded[(i + TKH) + g.ld * (j + TKH)];
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+static size_t tile_smem_bytes(int EJ, int precision) {
+  return (size_t)EJ * (2 * TEI * (precision == 0 ? 8 : 4) + TEI);
+}
+
+TilePlan make_tile_plan(int H, int W, int precision, int kind, int num_sms) {
+  TilePlan best{};
+  double best_cost = 1e300;
+  const int tiles_i = (H + TTI - 1) / TTI;
+  const char* env_tj = getenv("PIQL_TILE_TJ");
+  const char* env_nw = getenv("PIQL_TILE_NW");
+  for (int nw : {8, 16}) {
+    if (env_nw && atoi(env_nw) != nw) continue;
+    for (int cols = nw; cols <= 96; cols += 8) {  // computed columns EJ - 2: a multiple of 8 warps' worth
+      const int EJ = cols + 2, TJ = EJ - 2 * TKH;
+      if (TJ < 8) continue;
+      if (env_tj && atoi(env_tj) != TJ) continue;
+      const size_t smem = tile_smem_bytes(EJ, precision);
+      if (smem > 200 * 1024) continue;
+      int ctas = (int)((227 * 1024) / (smem + 1024));
+      const int by_threads = 2048 / (32 * nw), by_regs = kind == KIND_NU ? 65536 / (48 * 32 * nw) : 65536 / (64 * 32 * nw);
+      ctas = std::min(ctas, std::min(by_threads, by_regs));
+      if (ctas < 1) continue;
+      const int tiles_j = (W + TJ - 1) / TJ;
+      const long long tiles = (long long)tiles_i * tiles_j;
+      const long long per_sm = (tiles + num_sms - 1) / num_sms;
+      // work on the busiest SM in column units (+4: staging and write-back), derated when few warps share an SM
+      const int rounds = (cols + nw - 1) / nw;
+      double cost = (double)per_sm * (rounds * nw + 4.0 * nw / 8.0);
+      const long long resident = std::min<long long>(per_sm, ctas);
+      if (resident * nw < 16) cost *= 1.5;
+      else if (resident * nw < 24) cost *= 1.2;
+      if (cost < best_cost || (cost == best_cost && TJ > best.TJ)) {
+        best_cost = cost;
+        best.TJ = TJ; best.EJ = EJ; best.tiles_i = tiles_i; best.tiles_j = tiles_j; best.nw = nw;
+        best.smem = smem; best.ctas_per_sm = ctas;
+      }
+    }
+  }
+  best.ld = ((best.tiles_i * TTI + 2 * TKH + 31) / 32) * 32;
+  best.Wp = best.tiles_j * best.TJ + 2 * TKH;
+  best.np = (long long)best.ld * best.Wp;
+  return best;
+}
+
+template <typename T> static TileK<T> make_tile_k(const GridDev& g, const ViState& vs, const TilePlan& pl) {
+  TileK<T> k;
+  k.ld = pl.ld; k.np = (int)pl.np; k.TJ = pl.TJ; k.EJ = pl.EJ; k.tiles_i = pl.tiles_i;
+  k.goal_pi = g.goal % g.H + TKH; k.goal_pj = g.goal / g.H + TKH; k.goal_p = k.goal_pi + pl.ld * k.goal_pj;
+  const double w_on = 1.0 * (1.0 - g.randomness) + g.randomness / NA, w_off = 0.0 * (1.0 - g.randomness) + g.randomness / NA;
+  const double a1 = g.gamma * (w_on - w_off);
+  const double kc = log(1.0 / NA) + vs.reward_scale * -g.step_cost;
+  k.kc = (T)kc; k.kc_lo = (T)(kc - (double)k.kc);
+  k.a1 = (T)a1; k.a1_lo = (T)(a1 - (double)k.a1); k.b1 = (T)(g.gamma * w_off); k.a2 = (T)(a1 * 1.4426950408889634);
+  k.w_off = (T)w_off; k.dw = (T)(w_on - w_off);
+  k.gamma = (T)g.gamma; k.omg = (T)(1.0 - g.gamma);
+  k.term = vs.kind == KIND_LOGZ ? (T)(0.0 - vs.v_goal) : (T)0;
+  k.k = make_k<T>(g, vs.reward_scale, vs.beta);
+  k.k.H = pl.ld; k.k.n = (int)pl.np; k.k.goal = k.goal_p;
+  return k;
+}
+
+static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+void tile_free(TileBuffers& tb) {
+  for (void* p : {tb.x[0], tb.x[1], tb.aux, (void*)tb.mask, (void*)tb.partial}) if (p) cudaFree(p);
+  tb = TileBuffers{};
+}
+
+template <typename T>
+static void pack_t(const GridDev& g, const uint8_t* cell, const ViState& vs, TileBuffers& tb, cudaStream_t st) {
+  const PadGeom pg{g.H, g.W, tb.plan.ld, tb.plan.Wp};
+  const unsigned nb = nblk(tb.plan.np, 256);
+  tile_pack_kernel<T><<<nb, 256, 0, st>>>(pg, (const T*)vs.x[vs.cur], (T*)tb.x[0]);
+  tile_pack_kernel<T><<<nb, 256, 0, st>>>(pg, (const T*)vs.x[vs.cur], (T*)tb.x[1]);
+  tile_pack_mask_kernel<<<nb, 256, 0, st>>>(pg, cell, tb.mask);
+  g_launches += 3;
+  if (vs.kind == KIND_LOGZ) {
+    tile_pack_aux_kernel<T, KIND_LOGZ><<<nb, 256, 0, st>>>(pg, (const T*)vs.aux4, nullptr, (T*)tb.aux);
+    g_launches++;
+  } else if (vs.kind == KIND_GAP) {
+    tile_pack_aux_kernel<T, KIND_GAP><<<nb, 256, 0, st>>>(pg, (const T*)vs.aux4, (const T*)vs.aux1, (T*)tb.aux);
+    g_launches++;
+  }
+}
+
+cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs, TileBuffers& tb, int num_sms, cudaStream_t st) {
+  const TilePlan pl = make_tile_plan(g.H, g.W, vs.precision, vs.kind, num_sms);
+  const size_t e = vs.precision == 0 ? 8 : 4;
+  const size_t need_x = e * (size_t)pl.np, need_aux = vs.kind == KIND_NU ? 0 : 5 * need_x;
+  const long long ntiles = (long long)pl.tiles_i * pl.tiles_j;
+  if (need_x > tb.cap_x || need_aux > tb.cap_aux || (size_t)pl.np > tb.cap_mask || ntiles > tb.cap_partial) {
+    cudaError_t err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) return err;
+    tile_free(tb);
+    // sized for double and all five planes so that later solves of any kind / precision reuse them
+    const size_t bx = 8 * (size_t)pl.np;
+    if ((err = cudaMalloc(&tb.x[0], bx)) != cudaSuccess) return err;
+    if ((err = cudaMalloc(&tb.x[1], bx)) != cudaSuccess) return err;
+    if ((err = cudaMalloc(&tb.aux, 5 * bx)) != cudaSuccess) return err;
+    if ((err = cudaMalloc((void**)&tb.mask, (size_t)pl.np)) != cudaSuccess) return err;
+    if ((err = cudaMalloc((void**)&tb.partial, sizeof(double) * (size_t)ntiles)) != cudaSuccess) return err;
+    tb.cap_x = bx; tb.cap_aux = 5 * bx; tb.cap_mask = (size_t)pl.np; tb.cap_partial = ntiles;
+  }
+  tb.plan = pl;
+  tb.cur = 0;
+  if (vs.precision == 0) pack_t<double>(g, cell, vs, tb, st);
+  else pack_t<float>(g, cell, vs, tb, st);
+  tb.active = true;
+  return cudaGetLastError();
+}
+
+template <typename T, int KIND, bool FAST>
+static cudaError_t launch_tile_t(const GridDev& g, const ViState& vs, TileBuffers& tb, int nsub, bool want_res, cudaStream_t st) {
+  static bool configured[64] = {};  // shared-memory opt-in, once per instantiation and device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(tile_sweep_kernel<T, KIND, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  const TileK<T> k = make_tile_k<T>(g, vs, tb.plan);
+  const unsigned grid = (unsigned)(tb.plan.tiles_i * tb.plan.tiles_j);
+  tile_sweep_kernel<T, KIND, FAST><<<grid, 32 * tb.plan.nw, tb.plan.smem, st>>>(
+      k, tb.mask, (const T*)tb.x[tb.cur], (T*)tb.x[tb.cur ^ 1], (const T*)tb.aux, nsub, want_res ? 1 : 0, tb.partial);
+  g_launches++;
+  tb.cur ^= 1;
+  return cudaSuccess;
+}
+
+template <typename T, bool FAST>
+static cudaError_t launch_tile_k(const GridDev& g, const ViState& vs, TileBuffers& tb, int nsub, bool want_res, cudaStream_t st) {
+  switch (vs.kind) {
+    case KIND_NU: return launch_tile_t<T, KIND_NU, FAST>(g, vs, tb, nsub, want_res, st);
+    case KIND_LOGZ: return launch_tile_t<T, KIND_LOGZ, FAST>(g, vs, tb, nsub, want_res, st);
+    default: return launch_tile_t<T, KIND_GAP, FAST>(g, vs, tb, nsub, want_res, st);
+  }
+}
+
+// nsweeps Jacobi sweeps in ceil(nsweeps / TILE_KH) launches; the residual of the last sweep lands in vs.residual.
+cudaError_t tile_sweeps(const GridDev& g, const ViState& vs, TileBuffers& tb, long long nsweeps, bool want_res, cudaStream_t st) {
+  while (nsweeps > 0) {
+    const int nsub = (int)std::min<long long>(nsweeps, TKH);
+    nsweeps -= nsub;
+    const bool res = want_res && nsweeps == 0;
+    cudaError_t e;
+    if (vs.precision == 0) e = launch_tile_k<double, false>(g, vs, tb, nsub, res, st);
+    else if (vs.fast) e = launch_tile_k<float, true>(g, vs, tb, nsub, res, st);
+    else e = launch_tile_k<float, false>(g, vs, tb, nsub, res, st);
+    if (e != cudaSuccess) return e;
+    if (res) launch_residual_final(tb.partial, tb.plan.tiles_i * tb.plan.tiles_j, vs.residual, st);
+  }
+  return cudaGetLastError();
+}
+
+// Copies the current iterate back into the dense array vs.x[vs.cur].
+void tile_unpack(const GridDev& g, const ViState& vs, const TileBuffers& tb, cudaStream_t st) {
+  const PadGeom pg{g.H, g.W, tb.plan.ld, tb.plan.Wp};
+  if (vs.precision == 0) tile_unpack_kernel<double><<<nblk(g.n, 256), 256, 0, st>>>(pg, (const double*)tb.x[tb.cur], (double*)vs.x[vs.cur]);
+  else tile_unpack_kernel<float><<<nblk(g.n, 256), 256, 0, st>>>(pg, (const float*)tb.x[tb.cur], (float*)vs.x[vs.cur]);
+  g_launches++;
+}
+
+}  // namespace piql

@@ -91,7 +91,7 @@ class Engine:
 
     @staticmethod
     def _opts(tol, max_sweeps, precision, check_every):
-        prec = {"f64": K.F64, "f32": K.F32, K.F64: K.F64, K.F32: K.F32}[precision]
+        prec = K.PRECISIONS[precision]
         return K.SolveOpts(float(tol), int(max_sweeps), prec, int(check_every))
 
     def _out(self):
@@ -136,7 +136,7 @@ class Engine:
 
     def sweep_once(self, kind, x, V=None, Q=None, nu=None, beta=1.0, reward_scale=1.0, precision="f64"):
         kind = {"nu": K.KIND_NU, "logz": K.KIND_LOGZ, "gap": K.KIND_GAP}[kind]
-        prec = {"f64": K.F64, "f32": K.F32}[precision]
+        prec = K.PRECISIONS[precision]
         x = _cell(np.nan_to_num(np.asarray(x, dtype=np.float64)), self.H, self.W, "x")
         V, nu, Q = _cell(V, self.H, self.W, "V"), _cell(nu, self.H, self.W, "nu"), _sa(Q, self.H, self.W, "Q")
         out, res = self._out(), C.c_double()
@@ -147,10 +147,14 @@ class Engine:
     # device-resident sweeps (bench)
     def vi_prepare(self, kind, V=None, Q=None, nu=None, beta=1.0, reward_scale=1.0, precision="f32"):
         kind = {"nu": K.KIND_NU, "logz": K.KIND_LOGZ, "gap": K.KIND_GAP}[kind]
-        prec = {"f64": K.F64, "f32": K.F32}[precision]
+        prec = K.PRECISIONS[precision]
         V, nu, Q = _cell(V, self.H, self.W, "V"), _cell(nu, self.H, self.W, "nu"), _sa(Q, self.H, self.W, "Q")
         self._ck(self._lib.piql_vi_prepare_dev(self._ctx, kind, _pd(V), _pd(Q), _pd(nu), float(beta),
                                                float(reward_scale), prec))
+
+    def vi_set_iterate(self, x):
+        x = _cell(np.nan_to_num(np.asarray(x, dtype=np.float64)), self.H, self.W, "x")
+        self._ck(self._lib.piql_vi_set_iterate(self._ctx, _pd(x)))
 
     def vi_sweeps(self, sweeps):
         self._ck(self._lib.piql_vi_sweeps_dev(self._ctx, int(sweeps)))

@@ -134,12 +134,12 @@ def test_reference_runtests_properties(engine, piql):
 
 
 def test_generic_kernel_solve_matches_oracle(engine):
-    # > RESIDENT_MAX_CELLS cells: one launch per sweep with the deterministic residual
+    # > RESIDENT_MAX_CELLS cells: tiled multi-sweep kernel with the deterministic residual
     walls, goal = random_gridworld((100, 100), 0.2, seed=5)
     engine.load_grid(walls, goal, 0.02, 0.02, 0.2, 0.95)
     org = oracle.Grid(walls, goal, randomness=0.02, step_cost=0.02, reward=0.2, gamma=0.95)
     nu, st = engine.solve_nu(tol=1e-11, check_every=32)
-    assert st.kernel == 0 and st.converged
+    assert st.kernel == 2 and st.converged
     ref, _ = org.solve("nu", tol=1e-11, nthreads=8)
     assert nmax(nu, ref) < 1e-9
     V = np.nan_to_num(org.solve("nu", reward_scale=0.1, tol=1e-11, nthreads=8)[0])
