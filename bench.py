@@ -305,6 +305,7 @@ def run_ours(args, rank, world, local_rank):
                                      "bytes_per_state": nbytes, "traffic": None}}
         vi["kernel"] = ("tile_sweep_kernel<T,KIND_NU,FAST>: 4 Jacobi sweeps per launch on 128 x (TJ+8) shared-memory tiles "
                         "(includes the residual reduction on the last launch); f32fast = MUFU ex2/lg2")
+        vi["tile_plan"] = eng.vi_tile_plan("nu", "f32")
         vi["setup_vlo"] = {"sweeps": int(vst.sweeps), "device_seconds": float(vst.device_seconds)}
 
     # ---- CPU baseline beside it (rank 0, N = 1) ------------------------------------------------

@@ -643,6 +643,14 @@ int32_t piql_vi_prepare_dev(piql_ctx* ctx, int32_t kind, const double* V, const 
   if (ctx->g.n > RESIDENT_MAX_CELLS) CK(tile_begin(ctx->g, ctx->d_cell, ctx->vs, ctx->tb, ctx->num_sms, ctx->stream));
   return PIQL_OK;
 }
+int32_t piql_vi_tile_plan(piql_ctx* ctx, int32_t kind, int32_t precision, int32_t* plan_out) {
+  if (!ctx || !plan_out) return PIQL_ERR_ARG;
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded");
+  const TilePlan pl = make_tile_plan(ctx->g.H, ctx->g.W, precision == PIQL_F64 ? 0 : 1, kind, ctx->num_sms);
+  plan_out[0] = pl.TJ; plan_out[1] = pl.nw; plan_out[2] = pl.tiles_i; plan_out[3] = pl.tiles_j;
+  plan_out[4] = pl.ctas_per_sm; plan_out[5] = (int32_t)pl.smem; plan_out[6] = TILE_KH; plan_out[7] = pl.ld;
+  return PIQL_OK;
+}
 int32_t piql_vi_set_iterate(piql_ctx* ctx, const double* x) {
   if (!ctx) return PIQL_ERR_ARG;
   LaunchScope ls(ctx);

@@ -88,17 +88,17 @@ template <> __device__ __forceinline__ void ldg4<double>(const double* p, double
 template <typename T, bool FAST>
 __device__ __forceinline__ T nu_cell(const TileK<T>& k, T n0, T n1, T n2, T n3) {
   const T S = (n0 + n1) + (n2 + n3);
-  const T m = fmax(fmax(n0, n1), fmax(n2, n3));
+  // The largest exponent is exactly 0: sort out the maximum with a 5-comparator network and exponentiate only the
+  // other three (one MUFU less; MUFU is the narrowest pipe of this kernel).
+  const T h1 = fmax(n0, n1), l1 = fmin(n0, n1), h2 = fmax(n2, n3), l2 = fmin(n2, n3);
+  const T m = fmax(h1, h2), mid = fmin(h1, h2);
   if constexpr (FAST) {
     const float t = -m * k.a2;
-    const float sum = (ex2_approx(fmaf(n0, k.a2, t)) + ex2_approx(fmaf(n1, k.a2, t))) +
-                      (ex2_approx(fmaf(n2, k.a2, t)) + ex2_approx(fmaf(n3, k.a2, t)));
-    // ln 2 = 0.693147182464599609375 (float) - 1.904654e-09
-    const float lg = lg2_approx(sum);
-    const float hi = fmaf(0.693147180559945f, lg, fmaf(k.b1, S, fmaf(k.a1, m, k.kc)));
-    return hi + fmaf(-1.904654e-09f, lg, fmaf(k.a1_lo, m, k.kc_lo));
+    const float sum = (1.0f + ex2_approx(fmaf(mid, k.a2, t))) + (ex2_approx(fmaf(l1, k.a2, t)) + ex2_approx(fmaf(l2, k.a2, t)));
+    const float hi = fmaf(0.693147180559945f, lg2_approx(sum), fmaf(k.b1, S, fmaf(k.a1, m, k.kc)));
+    return hi + fmaf(k.a1_lo, m, k.kc_lo);
   } else {
-    const T sum = (xexp(k.a1 * (n0 - m)) + xexp(k.a1 * (n1 - m))) + (xexp(k.a1 * (n2 - m)) + xexp(k.a1 * (n3 - m)));
+    const T sum = ((T)1 + xexp(k.a1 * (mid - m))) + (xexp(k.a1 * (l1 - m)) + xexp(k.a1 * (l2 - m)));
     if (sizeof(T) == 4) return (k.kc + k.b1 * S + k.a1 * m + xlog(sum)) + (k.kc_lo + k.a1_lo * m);
     return k.kc + k.b1 * S + k.a1 * m + xlog(sum);
   }
@@ -150,10 +150,81 @@ template <int KIND> __device__ __forceinline__ double sweep_diff(double stored, 
   return x > -1.0 ? fabs(log1p(x)) : CUDART_INF;
 }
 
+// One Jacobi sweep of the staged tile, src -> dst (columns 1 .. EJ-2; all 128 rows), every cell by the generic
+// formula; the goal and its neighbours are redone by tile_goal_fixup.
+template <typename T, int KIND, bool FAST>
+__device__ __forceinline__ void tile_subsweep(const TileK<T>& k, const T* __restrict__ src, T* __restrict__ dst,
+                                              const uint32_t* __restrict__ msk, const T* __restrict__ aux, int org, int lane,
+                                              int warp, int NW) {
+  const int EJ = k.EJ, ld = k.ld;
+  (void)ld;
+#pragma unroll 2
+  for (int jj = 1 + warp; jj < EJ - 1; jj += NW) {
+    T v[4], L[4], R[4], out[4];
+    lds4(src + jj * TEI + 4 * lane, v);
+    lds4(src + (jj - 1) * TEI + 4 * lane, L);
+    lds4(src + (jj + 1) * TEI + 4 * lane, R);
+    const uint32_t mk = msk[jj * 32 + lane];
+    // rows 0 and 127 have no vertical neighbour in the tile: they are halo, any value will do
+    const T up = __shfl_up_sync(FULL, v[3], 1), dn = __shfl_down_sync(FULL, v[0], 1);
+    T ax[5][4];
+    if (KIND != KIND_NU) {
+      const int sidx = org + jj * ld + 4 * lane;
+#pragma unroll
+      for (int pl = 0; pl < 5; pl++) ldg4(aux + (size_t)pl * k.np + sidx, ax[pl]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const uint32_t b = mk >> (8 * r);
+      const T c = v[r];
+      // f(take_step(s,a)): the neighbour, or the cell itself when a wall blocks the move  GridWorld.jl:29-32
+      const T n0 = (b & 1u) ? c : (r < 3 ? v[r < 3 ? r + 1 : 3] : dn);
+      const T n1 = (b & 2u) ? c : (r > 0 ? v[r > 0 ? r - 1 : 0] : up);
+      const T n2 = (b & 4u) ? c : R[r];
+      const T n3 = (b & 8u) ? c : L[r];
+      T o;
+      if (KIND == KIND_NU) o = nu_cell<T, FAST>(k, n0, n1, n2, n3);
+      else if (KIND == KIND_LOGZ) o = logz_cell<T, FAST>(k, c, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
+      else o = gap_cell<T>(k, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
+      out[r] = o;
+    }
+    sts4(dst + jj * TEI + 4 * lane, out);
+  }
+}
+
+// The goal (terminal value) and, for nu, its four neighbours (a step into the goal earns the reward, so the
+// average reward is not the constant the generic formula assumes) are recomputed from src by five threads.
+template <typename T, int KIND, bool FAST>
+__device__ __noinline__ void tile_goal_fixup(const TileK<T>& k, const T* __restrict__ src, T* __restrict__ dst,
+                                             const uint32_t* __restrict__ msk, int gi, int gj) {
+  const int t = threadIdx.x;  // 0: goal, 1..4: (+1,0) (-1,0) (0,+1) (0,-1)
+  if (t >= (KIND == KIND_NU ? 5 : 1)) return;
+  const int i = gi + (t == 1) - (t == 2), j = gj + (t == 3) - (t == 4);
+  if (i < 0 || i >= TEI || j < 1 || j >= k.EJ - 1) return;  // not a cell this tile computes
+  const uint32_t b = (msk[j * 32 + (i >> 2)] >> (8 * (i & 3))) & 0xffu;
+  const T c = src[j * TEI + i];
+  T o;
+  if (t == 0) {
+    // terminal_condition: nu, gap -> 0; logz -> 0 - V(goal), damped like every other state
+    o = (KIND == KIND_LOGZ) ? damp_half<T, FAST>(k.term, c) : k.term;
+  } else {
+    if (b & CELL_WALL) return;
+    // rows 0 / 127 have no vertical neighbour in the tile; they are halo (never kept), any value will do
+    T nb[NA];
+    nb[0] = (b & 1u) || i + 1 >= TEI ? c : src[j * TEI + i + 1];
+    nb[1] = (b & 2u) || i - 1 < 0 ? c : src[j * TEI + i - 1];
+    nb[2] = (b & 4u) ? c : src[(j + 1) * TEI + i];
+    nb[3] = (b & 8u) ? c : src[(j - 1) * TEI + i];
+    const int cidx = k.goal_p + (t == 1) - (t == 2) + k.ld * ((t == 3) - (t == 4));
+    o = backup_nu(k.k, cidx, b, nb);
+  }
+  dst[j * TEI + i] = o;
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------------
 // grid = tiles_i * tiles_j CTAs of NW warps; dynamic shared memory = EJ * (2 * 128 * sizeof(T) + 128) bytes.
 template <typename T, int KIND, bool FAST>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, sizeof(T) == 4 ? 2 : 1)
 tile_sweep_kernel(const TileK<T> k, const uint8_t* __restrict__ maskp, const T* __restrict__ X, T* __restrict__ Y,
                   const T* __restrict__ aux, int nsub, int want_res, double* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char tile_smem[];
@@ -165,6 +236,11 @@ tile_sweep_kernel(const TileK<T> k, const uint8_t* __restrict__ maskp, const T* 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
   const int ti = blockIdx.x % k.tiles_i, tj = blockIdx.x / k.tiles_i;
   const int org = ti * TTI + ld * (tj * k.TJ);  // padded index of the tile's (row 0, column 0)
+
+  // Programmatic dependent launch: this grid may be scheduled while the previous launch (which wrote X) drains;
+  // let the next one do the same, then wait for the previous grid's memory before the first global read.
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // stage the tile (every access in bounds thanks to the ghost frame)
   for (int jj = warp; jj < EJ; jj += NW) {
@@ -184,49 +260,12 @@ tile_sweep_kernel(const TileK<T> k, const uint8_t* __restrict__ maskp, const T* 
   T* src = bufA;
   T* dst = bufB;
   for (int sub = 0; sub < nsub; sub++) {
-    for (int jj = 1 + warp; jj < EJ - 1; jj += NW) {
-      T v[4], L[4], R[4], out[4];
-      lds4(src + jj * TEI + 4 * lane, v);
-      lds4(src + (jj - 1) * TEI + 4 * lane, L);
-      lds4(src + (jj + 1) * TEI + 4 * lane, R);
-      const uint32_t mk = msk[jj * 32 + lane];
-      // rows 0 and 127 have no vertical neighbour in the tile: they are halo, any value will do
-      const T up = __shfl_up_sync(FULL, v[3], 1), dn = __shfl_down_sync(FULL, v[0], 1);
-      const int sidx = org + jj * ld + 4 * lane;
-      T ax[5][4];
-      if (KIND != KIND_NU) {
-#pragma unroll
-        for (int pl = 0; pl < 5; pl++) ldg4(aux + (size_t)pl * k.np + sidx, ax[pl]);
-      }
-#pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const uint32_t b = mk >> (8 * r);
-        const T c = v[r];
-        // f(take_step(s,a)): the neighbour, or the cell itself when a wall blocks the move  GridWorld.jl:29-32
-        const T n0 = (b & 1u) ? c : (r < 3 ? v[r < 3 ? r + 1 : 3] : dn);
-        const T n1 = (b & 2u) ? c : (r > 0 ? v[r > 0 ? r - 1 : 0] : up);
-        const T n2 = (b & 4u) ? c : R[r];
-        const T n3 = (b & 8u) ? c : L[r];
-        T o;
-        if (KIND == KIND_NU) o = nu_cell<T, FAST>(k, n0, n1, n2, n3);
-        else if (KIND == KIND_LOGZ) o = logz_cell<T, FAST>(k, c, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
-        else o = gap_cell<T>(k, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
-        if (near_goal) {
-          const int cidx = sidx + r;
-          if (cidx == k.goal_p) {
-            // terminal_condition: nu, gap -> 0; logz -> 0 - V(goal), damped like every other state
-            o = (KIND == KIND_LOGZ) ? damp_half<T, FAST>(k.term, c) : k.term;
-          } else if (KIND == KIND_NU && (cidx == k.goal_p + 1 || cidx == k.goal_p - 1 || cidx == k.goal_p + ld ||
-                                         cidx == k.goal_p - ld)) {
-            const T nb[NA] = {n0, n1, n2, n3};  // a step into the goal earns the reward: general formula
-            o = backup_nu(k.k, cidx, b & 0xffu, nb);
-          }
-        }
-        out[r] = o;
-      }
-      sts4(dst + jj * TEI + 4 * lane, out);
-    }
+    tile_subsweep<T, KIND, FAST>(k, src, dst, msk, aux, org, lane, warp, NW);
     __syncthreads();
+    if (near_goal) {  // block-uniform
+      tile_goal_fixup<T, KIND, FAST>(k, src, dst, msk, gi, gj);
+      __syncthreads();
+    }
     T* t = src; src = dst; dst = t;
   }
 
@@ -315,34 +354,43 @@ static size_t tile_smem_bytes(int EJ, int precision) {
   return (size_t)EJ * (2 * TEI * (precision == 0 ? 8 : 4) + TEI);
 }
 
+// Tile shape (TJ interior columns, nw warps per CTA) by a small cost model, in SM cycles per launch:
+// a wave of c CTAs per SM runs its TILE_KH sub-sweeps at the slower of the SM's issue rate (c * cols warp-strips
+// of ~140 instructions) and one warp's dependent-issue latency per strip times its strips per sub-sweep; staging and write-back add a fixed latency per wave.  Small grids want exactly one
+// full wave, large ones wide tiles (less halo).  PIQL_TILE_TJ / PIQL_TILE_NW override (tuning, tests).
 TilePlan make_tile_plan(int H, int W, int precision, int kind, int num_sms) {
   TilePlan best{};
   double best_cost = 1e300;
   const int tiles_i = (H + TTI - 1) / TTI;
   const char* env_tj = getenv("PIQL_TILE_TJ");
   const char* env_nw = getenv("PIQL_TILE_NW");
-  for (int nw : {8, 16}) {
+  const int regs = precision == 0 ? 128 : 64;  // per thread: the __launch_bounds__ of the instantiations
+  // measured on B200 (fp32 nu): an SM retires one 128-cell warp-strip per ~61 cycles when >= 30 warps are resident;
+  // a lone warp needs ~1800 cycles per strip
+  const double strip_issue = 61.0, strip_latency = 1700.0, wave_fixed = 8000.0;
+  for (int nw = 4; nw <= 16; nw++) {
     if (env_nw && atoi(env_nw) != nw) continue;
-    for (int cols = nw; cols <= 96; cols += 8) {  // computed columns EJ - 2: a multiple of 8 warps' worth
-      const int EJ = cols + 2, TJ = EJ - 2 * TKH;
-      if (TJ < 8) continue;
+    for (int TJ = 8; TJ <= 120; TJ++) {
       if (env_tj && atoi(env_tj) != TJ) continue;
+      const int EJ = TJ + 2 * TKH, cols = EJ - 2;
       const size_t smem = tile_smem_bytes(EJ, precision);
       if (smem > 200 * 1024) continue;
       int ctas = (int)((227 * 1024) / (smem + 1024));
-      const int by_threads = 2048 / (32 * nw), by_regs = kind == KIND_NU ? 65536 / (48 * 32 * nw) : 65536 / (64 * 32 * nw);
-      ctas = std::min(ctas, std::min(by_threads, by_regs));
+      ctas = std::min(ctas, std::min(2048 / (32 * nw), 65536 / (regs * 32 * nw)));
+      ctas = std::min(ctas, 16);
       if (ctas < 1) continue;
       const int tiles_j = (W + TJ - 1) / TJ;
-      const long long tiles = (long long)tiles_i * tiles_j;
-      const long long per_sm = (tiles + num_sms - 1) / num_sms;
-      // work on the busiest SM in column units (+4: staging and write-back), derated when few warps share an SM
+      long long left = (long long)tiles_i * tiles_j;
       const int rounds = (cols + nw - 1) / nw;
-      double cost = (double)per_sm * (rounds * nw + 4.0 * nw / 8.0);
-      const long long resident = std::min<long long>(per_sm, ctas);
-      if (resident * nw < 16) cost *= 1.5;
-      else if (resident * nw < 24) cost *= 1.2;
-      if (cost < best_cost || (cost == best_cost && TJ > best.TJ)) {
+      double cost = 0.0;
+      const long long slots = (long long)num_sms * ctas;
+      while (left > 0) {
+        const long long now = std::min(left, slots);
+        const int c = (int)((now + num_sms - 1) / num_sms);
+        cost += wave_fixed + TKH * std::max(c * cols * strip_issue, rounds * strip_latency);
+        left -= now;
+      }
+      if (cost < best_cost) {
         best_cost = cost;
         best.TJ = TJ; best.EJ = EJ; best.tiles_i = tiles_i; best.tiles_j = tiles_j; best.nw = nw;
         best.smem = smem; best.ctas_per_sm = ctas;
@@ -434,8 +482,15 @@ static cudaError_t launch_tile_t(const GridDev& g, const ViState& vs, TileBuffer
   }
   const TileK<T> k = make_tile_k<T>(g, vs, tb.plan);
   const unsigned grid = (unsigned)(tb.plan.tiles_i * tb.plan.tiles_j);
-  tile_sweep_kernel<T, KIND, FAST><<<grid, 32 * tb.plan.nw, tb.plan.smem, st>>>(
-      k, tb.mask, (const T*)tb.x[tb.cur], (T*)tb.x[tb.cur ^ 1], (const T*)tb.aux, nsub, want_res ? 1 : 0, tb.partial);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * tb.plan.nw); cfg.dynamicSmemBytes = tb.plan.smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, tile_sweep_kernel<T, KIND, FAST>, k, (const uint8_t*)tb.mask, (const T*)tb.x[tb.cur],
+                                      (T*)tb.x[tb.cur ^ 1], (const T*)tb.aux, nsub, want_res ? 1 : 0, tb.partial);
+  if (le != cudaSuccess) return le;
   g_launches++;
   tb.cur ^= 1;
   return cudaSuccess;

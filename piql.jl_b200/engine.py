@@ -152,6 +152,12 @@ class Engine:
         self._ck(self._lib.piql_vi_prepare_dev(self._ctx, kind, _pd(V), _pd(Q), _pd(nu), float(beta),
                                                float(reward_scale), prec))
 
+    def vi_tile_plan(self, kind="nu", precision="f32"):
+        out = (C.c_int32 * 8)()
+        self._ck(self._lib.piql_vi_tile_plan(self._ctx, {"nu": K.KIND_NU, "logz": K.KIND_LOGZ, "gap": K.KIND_GAP}[kind],
+                                             K.PRECISIONS[precision], out))
+        return dict(zip(("TJ", "warps", "tiles_i", "tiles_j", "ctas_per_sm", "smem", "sweeps_per_launch", "ld"), list(out)))
+
     def vi_set_iterate(self, x):
         x = _cell(np.nan_to_num(np.asarray(x, dtype=np.float64)), self.H, self.W, "x")
         self._ck(self._lib.piql_vi_set_iterate(self._ctx, _pd(x)))
