@@ -146,7 +146,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "sampled transitions/sec", "value": value, "unit": "transitions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(name, args, world),
         "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": threads, "kind": "port",
                          "sample": "%d paths per step (of the %d-path step), oracle/piql_oracle.c with OpenMP over paths; "
@@ -163,7 +163,8 @@ def workload_config(name, args, world):
                         "V = %d Jacobi sweeps at reward x %.1f, estimator A, starts cycle over free cells"
                         % (w["size"], w["size"], "4" if name == "grid1024" else "5" if name == "grid4096" else "-", DENSITY,
                            RANDOMNESS, GAMMA, BETA, VLO_SWEEPS, VLO_SCALE),
-            "paths_per_step": int(args.paths or w["paths"]), "sharding": "path ids split in %d contiguous blocks" % world,
+            "paths_per_step": int(args.paths or w["paths"]) * world,
+            "sharding": "path ids split in %d contiguous blocks of %d (weak scaling)" % (world, int(args.paths or w["paths"])),
             "l2": "each step writes 8 B x paths of records (> L2) between reads of the policy table; the table is "
                   "%.0f MB" % (32 * (w["size"] + 2) ** 2 / 1e6)}
 
@@ -177,7 +178,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     name = args.workload
     w = WORKLOADS[name]
-    P = int(args.paths or w["paths"])
+    P = int(args.paths or w["paths"]) * world     # weak scaling: every rank rolls out the same number of paths per step
     walls, goal, params = make_world(name)
     eng = piql.Engine(local_rank)
     eng.load_grid(walls, goal, **params)
@@ -197,13 +198,18 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     step_no = [0]
+    xev = []   # CUDA events around the exchange step (N > 1)
 
     def step():
         p0, cnt = pd.shard_range(P, rank, world)
         eng.mc_reset()
         eng.mc_rollout(cnt, path0=step_no[0] * P + p0, seed=MC_SEED)
         if world > 1:
-            pd.allreduce_engine_stats(eng)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            pd.allreduce_engine_stats(eng, mode=args.exchange, rank=rank, world=world)
+            b.record(stream)
+            xev.append((a, b))
         step_no[0] += 1
 
     with torch.cuda.stream(stream):
@@ -214,6 +220,7 @@ def run_ours(args, rank, world, local_rank):
             step()
         barrier()
         eng.mc_timing()            # drop warm-up launches from the kernel timers
+        del xev[:]
         tr0 = eng.mc_transitions_total()
         l0 = eng.launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -226,6 +233,7 @@ def run_ours(args, rank, world, local_rank):
         ms = e0.elapsed_time(e1)
         launches = eng.launches - l0
         roll_s, red_s, nl = eng.mc_timing()
+        xch_ms = sum(a.elapsed_time(b) for a, b in xev) / max(len(xev), 1)
         tr_local = eng.mc_transitions_total() - tr0
         stat = torch.tensor([ms, float(tr_local)], dtype=torch.float64, device="cuda:%d" % local_rank)
         if world > 1:
@@ -254,6 +262,15 @@ def run_ours(args, rank, world, local_rank):
                 "bytes_per_transition": 32, "bytes_per_path": 8, "launches": nl,
                 "avg_launch_ms": 1e3 * roll_s / max(nl, 1), "reduce_share": red_s / max(roll_s + red_s, 1e-12),
                 "transitions_per_s_kernel": tr_local / roll_s if roll_s > 0 else 0.0}
+    exchange = None
+    if world > 1:
+        nacc = 4 * eng.nfree
+        # each rank pulls (W-1)/W of 12 B x nacc from its peers and pushes as much: bytes crossing NVLink per direction
+        link_bytes = 12.0 * nacc * (world - 1) / world
+        exchange = {"mode": args.exchange, "ms_per_step": xch_ms, "accumulator_bytes": 12 * nacc,
+                    "nvlink_bytes_per_direction": link_bytes,
+                    "achieved_gbs_per_direction": link_bytes / (xch_ms * 1e-3) / 1e9 if xch_ms > 0 else None,
+                    "peer_copy_reference_gbs": 770.0}
 
     # ---- end to end through the public call, host buffers in pinned memory --------------------
     e2e = None
@@ -265,11 +282,11 @@ def run_ours(args, rank, world, local_rank):
         ls, _k4 = pinned((H, W), np.float64, order="F")
         reps = max(1, min(args.steps, 3))
         tot = 0.0
-        pd.mc_logz_sharded(eng, Vp, BETA, P, rank, world, seed=MC_SEED + 1, out=(sa, cn, ls))   # warm-up
+        pd.mc_logz_sharded(eng, Vp, BETA, P, rank, world, seed=MC_SEED + 1, out=(sa, cn, ls), mode=args.exchange)   # warm-up
         barrier()
         t0 = time.perf_counter()
         for i in range(reps):
-            _sa, _cn, _ls, st = pd.mc_logz_sharded(eng, Vp, BETA, P, rank, world, seed=MC_SEED + 2 + i, out=(sa, cn, ls))
+            _sa, _cn, _ls, st = pd.mc_logz_sharded(eng, Vp, BETA, P, rank, world, seed=MC_SEED + 2 + i, out=(sa, cn, ls), mode=args.exchange)
             tot += float(st.transitions)
         barrier()
         dt = time.perf_counter() - t0
@@ -284,11 +301,14 @@ def run_ours(args, rank, world, local_rank):
                        "with pinned host V in, logz_sa / count_sa / logz_s out"}
 
     # ---- soft-VI sweeps on the same grid (rank 0) ----------------------------------------------
+    # algorithmic bytes per state per sweep: nu 2 x sizeof(T), logz 3 x, gap 4 x
     vi = None
     if rank == 0 and not args.no_vi:
         vi = {}
-        for prec, nbytes in (("f32fast", 8), ("f32", 8), ("f64", 16)):
-            eng.vi_prepare("nu", reward_scale=1.0, precision=prec)
+        cases = [("nu", "f32fast", 8, {}), ("nu", "f32", 8, {}), ("nu", "f64", 16, {}),
+                 ("logz", "f32fast", 12, dict(V=V, beta=BETA)), ("gap", "f32fast", 16, dict(V=V, nu=V))]
+        for kind, prec, nbytes, kw in cases:
+            eng.vi_prepare(kind, reward_scale=1.0, precision=prec, **kw)
             with torch.cuda.stream(stream):
                 eng.vi_sweeps(20)
                 torch.cuda.synchronize()
@@ -300,11 +320,12 @@ def run_ours(args, rank, world, local_rank):
             sec = a.elapsed_time(b) * 1e-3
             sps = args.vi_sweeps / sec
             gbs = nbytes * eng.nfree * sps / 1e9
-            vi[prec] = {"sweeps_per_s": sps, "state_backups_per_s": sps * eng.nfree, "us_per_sweep": 1e6 / sps,
-                        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                                     "bytes_per_state": nbytes, "traffic": None}}
-        vi["kernel"] = ("tile_sweep_kernel<T,KIND_NU,FAST>: 4 Jacobi sweeps per launch on 128 x (TJ+8) shared-memory tiles "
-                        "(includes the residual reduction on the last launch); f32fast = MUFU ex2/lg2")
+            key = prec if kind == "nu" else "%s_%s" % (kind, prec)
+            vi[key] = {"sweeps_per_s": sps, "state_backups_per_s": sps * eng.nfree, "us_per_sweep": 1e6 / sps,
+                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                    "bytes_per_state": nbytes, "traffic": None}}
+        vi["kernel"] = ("tile_sweep_kernel<T,KIND,FAST>: 4 Jacobi sweeps per launch on 128 x (TJ+8) shared-memory tiles "
+                        "(includes the residual reduction on the last launch); f32fast = MUFU ex2/lg2; keys without a kind are nu")
         vi["tile_plan"] = eng.vi_tile_plan("nu", "f32")
         vi["setup_vlo"] = {"sweeps": int(vst.sweeps), "device_seconds": float(vst.device_seconds)}
 
@@ -334,8 +355,8 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         line = {"metric": "sampled transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(name, args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(name, args, world), "clocks": clocks, "exchange": exchange, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu, "vi": vi,
                 "transitions_per_step": transitions / args.steps}
         print(json.dumps(line), flush=True)
@@ -353,6 +374,8 @@ def main():
     ap.add_argument("--ref-paths", type=int, default=1 << 20, help="CPU sample: paths per reference step")
     ap.add_argument("--vi-sweeps", type=int, default=400)
     ap.add_argument("--setup-sweeps", type=int, default=VLO_SWEEPS, help="Jacobi sweeps that build V_lo (profiling runs use fewer)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: fused log-sum-exp all-reduce kernel over NVLink peer memory, or three NCCL all-reduces")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-vi", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

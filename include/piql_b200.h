@@ -178,6 +178,21 @@ int32_t piql_mc_stats_dev(piql_ctx* ctx, void** lse_max_dev, void** lse_sum_dev,
 int32_t piql_mc_rescale_dev(piql_ctx* ctx, const void* global_max_dev);
 int32_t piql_mc_finalize(piql_ctx* ctx, double* logz_sa_out, uint64_t* count_sa_out, double* logz_s_out,
                          piql_mc_stats* stats_out);
+/* The exchange step as ONE kernel over NVLink peer memory (one process per GPU, all on one box): rank r pulls
+ * slice r of every rank's three accumulator arrays through CUDA-IPC peer mappings, combines the triples and
+ * pushes the result into every rank's arrays (replaces the three all-reduces + rescale above).
+ *   piql_peer_export (after piql_mc_reset_dev) -> exchange the handle blobs between the ranks (any transport)
+ *   -> piql_peer_import(rank, world, all blobs in rank order) -> piql_mc_allreduce_peer once per iteration.
+ * Re-export after a reset that changed the start list size.  Every rank must make the same calls. */
+typedef struct {
+  uint8_t lse_max[64], lse_sum[64], count[64], flags[64]; /* cudaIpcMemHandle_t */
+  int64_t n;                                              /* accumulator length (slots * 4) */
+} piql_peer_handles;
+int32_t piql_peer_export(piql_ctx* ctx, piql_peer_handles* out);
+int32_t piql_peer_import(piql_ctx* ctx, int32_t rank, int32_t world, const piql_peer_handles* all);
+int32_t piql_mc_allreduce_peer(piql_ctx* ctx);
+int32_t piql_peer_close(piql_ctx* ctx);
+
 /* CUDA-event durations of the rollout and reduction kernels launched since the previous call of
  * this function (or since context creation), summed over launches.  Synchronises the stream. */
 int32_t piql_mc_timing(piql_ctx* ctx, double* rollout_seconds, double* reduce_seconds, int64_t* launches);

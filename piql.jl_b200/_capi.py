@@ -43,6 +43,11 @@ class McStats(C.Structure):
                 ("rollout_seconds", C.c_double)]
 
 
+class PeerHandles(C.Structure):
+    _fields_ = [("lse_max", C.c_uint8 * 64), ("lse_sum", C.c_uint8 * 64), ("count", C.c_uint8 * 64),
+                ("flags", C.c_uint8 * 64), ("n", C.c_int64)]
+
+
 # every symbol include/piql_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _D = C.POINTER(C.c_double)
@@ -72,6 +77,10 @@ SYMBOLS = {
     "piql_mc_stats_dev": (C.c_int32, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
     "piql_mc_rescale_dev": (C.c_int32, [_P, _P]),
     "piql_mc_finalize": (C.c_int32, [_P, _D, C.POINTER(C.c_uint64), _D, C.POINTER(McStats)]),
+    "piql_peer_export": (C.c_int32, [_P, C.POINTER(PeerHandles)]),
+    "piql_peer_import": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(PeerHandles)]),
+    "piql_mc_allreduce_peer": (C.c_int32, [_P]),
+    "piql_peer_close": (C.c_int32, [_P]),
     "piql_mc_timing": (C.c_int32, [_P, _D, _D, C.POINTER(C.c_int64)]),
     "piql_mc_transitions_total": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     "piql_mc_records": (C.c_int32, [_P, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_int64]),

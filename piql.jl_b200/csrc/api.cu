@@ -38,6 +38,7 @@ struct piql_ctx {
   double* h_scalars = nullptr;  // pinned mirror
   long long vi_sweeps_done = 0;
   TileBuffers tb;  // padded copy of the iterate for the tiled multi-sweep kernel
+  PeerState peer;  // NVLink peer mappings of the other ranks' accumulators
 
   // Monte-Carlo
   float4* d_table = nullptr;
@@ -104,6 +105,13 @@ template <typename T> cudaError_t grow(T*& p, size_t& cap, size_t want) {
   cudaError_t e = grow(p, c, (long long)want);
   cap = (size_t)c;
   return e;
+}
+
+void peer_close(piql_ctx* ctx) {
+  PeerState& ps = ctx->peer;
+  for (int i = 0; i < ps.nopened; i++) cudaIpcCloseMemHandle(ps.opened[i]);
+  ps.nopened = 0;
+  ps.valid = false;
 }
 
 void free_vi(piql_ctx* c) {
@@ -278,6 +286,7 @@ int mc_setup_slots(piql_ctx* ctx, const piql_mc_opts* o) {
   if (need > ctx->acc_cap) {
     for (void* p : {(void*)ctx->acc_max, (void*)ctx->acc_sum, (void*)ctx->acc_cnt}) if (p) cudaFree(p);
     ctx->acc_max = ctx->acc_sum = nullptr; ctx->acc_cnt = nullptr; ctx->acc_cap = 0;
+    ctx->peer.valid = false;  // exported handles named the old allocation
     CK(cudaMalloc((void**)&ctx->acc_max, 4 * (size_t)need));
     CK(cudaMalloc((void**)&ctx->acc_sum, 4 * (size_t)need));
     CK(cudaMalloc((void**)&ctx->acc_cnt, 4 * (size_t)need));
@@ -398,6 +407,8 @@ int mc_finalize(piql_ctx* ctx, double* logz_sa, uint64_t* count_sa, double* logz
   if (d_s) CK(cudaMemcpyAsync(logz_s, d_s, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(ctx->h_transitions, ctx->d_transitions, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  if (ctx->peer.err && *ctx->peer.err)
+    return fail(ctx, PIQL_ERR_CUDA, "the peer exchange timed out waiting for another rank (did every rank call it?)");
   if (stats) {
     stats->transitions = *ctx->h_transitions;
     stats->paths = ctx->paths_done;
@@ -481,6 +492,10 @@ int32_t piql_destroy(piql_ctx* ctx) {
   if (!ctx) return PIQL_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  peer_close(ctx);
+  if (ctx->peer.own_flags) cudaFree(ctx->peer.own_flags);
+  if (ctx->peer.done) cudaFree(ctx->peer.done);
+  if (ctx->peer.err) cudaFreeHost(ctx->peer.err);
   free_vi(ctx);
   for (void* p : {(void*)ctx->d_walls, (void*)ctx->d_cell, (void*)ctx->d_free, (void*)ctx->d_table, (void*)ctx->d_logw,
                   (void*)ctx->d_meta, (void*)ctx->d_starts_own, (void*)ctx->acc_max, (void*)ctx->acc_sum,
@@ -805,6 +820,82 @@ int32_t piql_mc_rescale_dev(piql_ctx* ctx, const void* global_max_dev) {
   CK(cudaSetDevice(ctx->device));
   launch_mc_rescale(ctx->acc_max, ctx->acc_sum, (const float*)global_max_dev, ctx->nstarts * NA, ctx->stream);
   CK_LAST();
+  return PIQL_OK;
+}
+int32_t piql_peer_export(piql_ctx* ctx, piql_peer_handles* out) {
+  if (!ctx || !out) return PIQL_ERR_ARG;
+  NEED(ctx->nstarts > 0 && ctx->acc_max, PIQL_ERR_STATE, "call piql_mc_reset_dev first");
+  CK(cudaSetDevice(ctx->device));
+  PeerState& ps = ctx->peer;
+  peer_close(ctx);
+  if (!ps.own_flags) {
+    CK(cudaMalloc((void**)&ps.own_flags, sizeof(unsigned long long) * 2 * PEER_MAX));
+    CK(cudaMalloc((void**)&ps.done, sizeof(unsigned int)));
+    CK(cudaMallocHost((void**)&ps.err, sizeof(int)));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemset(ps.own_flags, 0, sizeof(unsigned long long) * 2 * PEER_MAX));
+  CK(cudaMemset(ps.done, 0, sizeof(unsigned int)));
+  *ps.err = 0;
+  ps.epoch = 0;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle blob size");
+  CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->lse_max, ctx->acc_max));
+  CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->lse_sum, ctx->acc_sum));
+  CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->count, ctx->acc_cnt));
+  CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->flags, ps.own_flags));
+  out->n = ctx->nstarts * NA;
+  ps.bound_mx = ctx->acc_max;
+  return PIQL_OK;
+}
+int32_t piql_peer_import(piql_ctx* ctx, int32_t rank, int32_t world, const piql_peer_handles* all) {
+  if (!ctx || !all) return PIQL_ERR_ARG;
+  NEED(world >= 1 && world <= PEER_MAX && rank >= 0 && rank < world, PIQL_ERR_ARG, "rank / world out of range (at most 8 GPUs)");
+  PeerState& ps = ctx->peer;
+  NEED(ps.own_flags && ps.bound_mx == ctx->acc_max, PIQL_ERR_STATE, "call piql_peer_export first");
+  CK(cudaSetDevice(ctx->device));
+  for (int r = 0; r < world; r++)
+    NEED(all[r].n == ctx->nstarts * NA, PIQL_ERR_ARG, "ranks disagree on the accumulator length (different start lists)");
+  ps.rank = rank; ps.world = world;
+  for (int r = 0; r < world; r++) {
+    if (r == rank) {
+      ps.mx[r] = ctx->acc_max; ps.sm[r] = ctx->acc_sum; ps.cn[r] = ctx->acc_cnt; ps.flags[r] = ps.own_flags;
+      continue;
+    }
+    void* p[4] = {nullptr, nullptr, nullptr, nullptr};
+    const uint8_t* h[4] = {all[r].lse_max, all[r].lse_sum, all[r].count, all[r].flags};
+    for (int q = 0; q < 4; q++) {
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, h[q], sizeof(hd));
+      cudaError_t e = cudaIpcOpenMemHandle(&p[q], hd, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        peer_close(ctx);
+        return fail(ctx, PIQL_ERR_CUDA, std::string("cudaIpcOpenMemHandle (is the peer GPU NVLink / P2P reachable?): ") +
+                                            cudaGetErrorString(e));
+      }
+      ps.opened[ps.nopened++] = p[q];
+    }
+    ps.mx[r] = (float*)p[0]; ps.sm[r] = (float*)p[1]; ps.cn[r] = (uint32_t*)p[2]; ps.flags[r] = (unsigned long long*)p[3];
+  }
+  ps.valid = true;
+  return PIQL_OK;
+}
+int32_t piql_mc_allreduce_peer(piql_ctx* ctx) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  PeerState& ps = ctx->peer;
+  NEED(ps.valid && ps.bound_mx == ctx->acc_max, PIQL_ERR_STATE, "peer mappings are missing or stale (piql_peer_export / piql_peer_import)");
+  NEED(*ps.err == 0, PIQL_ERR_CUDA, "an earlier peer exchange timed out waiting for another rank");
+  CK(cudaSetDevice(ctx->device));
+  ps.epoch++;
+  launch_lse_allreduce_peer(ps, ctx->nstarts, ctx->num_sms, ctx->stream);
+  CK_LAST();
+  return PIQL_OK;
+}
+int32_t piql_peer_close(piql_ctx* ctx) {
+  if (!ctx) return PIQL_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  peer_close(ctx);
   return PIQL_OK;
 }
 int32_t piql_mc_finalize(piql_ctx* ctx, double* logz_sa_out, uint64_t* count_sa_out, double* logz_s_out,

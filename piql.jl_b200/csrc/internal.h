@@ -116,6 +116,25 @@ void launch_mc_finalize(const float* acc_max, const float* acc_sum, const uint32
 void launch_fill_f64(double* dst, double v, long long n, cudaStream_t st);
 int configure_rollout_kernels();
 
+// peer.cu: the log-sum-exp all-reduce of the accumulators over NVLink peer memory -----------------
+constexpr int PEER_MAX = 8;  // GPUs of one box
+struct PeerState {
+  int rank = 0, world = 0;
+  float* mx[PEER_MAX] = {};
+  float* sm[PEER_MAX] = {};
+  uint32_t* cn[PEER_MAX] = {};
+  unsigned long long* flags[PEER_MAX] = {};  // flags[r] on rank r: [2 phases][PEER_MAX source ranks]
+  unsigned long long* own_flags = nullptr;
+  unsigned int* done = nullptr;
+  int* err = nullptr;                        // pinned host word the kernel writes on a timed-out wait
+  unsigned long long epoch = 0;
+  bool valid = false;
+  const float* bound_mx = nullptr;           // accumulator allocation the handles were exported for
+  void* opened[4 * PEER_MAX] = {};
+  int nopened = 0;
+};
+void launch_lse_allreduce_peer(const PeerState& ps, long long nslots, int num_sms, cudaStream_t st);
+
 // counts kernel launches made through the launch_* wrappers
 extern thread_local long long g_launches;
 

@@ -5,9 +5,13 @@ Replaces the reference's Distributed.jl worker pool (addprocs / pmap / @spawn,
 scripts/distributed_experiments.jl:3,26,28,43-46).  torch is used for exactly two things here:
 `torch.distributed` collectives and viewing the library's device buffers as tensors.
 
-A log-sum-exp is not an NCCL reduction op, so the exchange is three collectives around one kernel:
+The exchange step has two implementations:
+  * "peer" (default on GPUs): ONE kernel per rank over NVLink peer memory (csrc/peer.cu) -- rank r pulls slice r
+    of every rank's three accumulator arrays through CUDA-IPC mappings, combines, and pushes the result into every
+    rank's arrays.  torch.distributed only carries the 264-byte handle blobs once per start list.
+  * "nccl": a log-sum-exp is not an NCCL reduction op, so it is three collectives around one kernel:
     gmax = allreduce(MAX, lse_max);  lse_sum *= exp(lse_max - gmax) (piql_mc_rescale_dev);
-    allreduce(SUM, lse_sum);  allreduce(SUM, count)
+    allreduce(SUM, lse_sum);  allreduce(SUM, count).  Kept as the comparison baseline and for gloo tests.
 """
 import numpy as np
 
@@ -52,14 +56,36 @@ def allreduce_lse(lse_max, lse_sum, count, rescale, group=None):
     return gmax
 
 
-def allreduce_engine_stats(eng, group=None):
-    """The exchange step for one Engine: run on the engine's stream (make it torch's current stream)."""
+def peer_setup(eng, rank, world, group=None):
+    """Exchange the CUDA-IPC handles of the engine's accumulators (after mc_reset) and map the peers'.
+    Collective; needed again only when the start list (hence the accumulator allocation) changes."""
+    import torch.distributed as dist
+    blob = eng.peer_export()
+    blobs = [None] * world
+    dist.all_gather_object(blobs, blob, group=group)
+    eng.peer_import(rank, world, blobs)
+    dist.barrier(group=group)   # nobody launches the exchange kernel before every rank has its mappings
+    eng._peer_key = (eng.mc_stats_ptrs(), rank, world)
+
+
+def allreduce_engine_stats(eng, group=None, mode="peer", rank=None, world=None):
+    """The exchange step for one Engine, asynchronous on the engine's stream.
+    mode "peer": one fused kernel over NVLink peer memory; "nccl": three all-reduces + a rescale kernel (run it
+    with the engine's stream as torch's current stream)."""
+    if mode == "peer":
+        import torch.distributed as dist
+        rank = dist.get_rank(group) if rank is None else rank
+        world = dist.get_world_size(group) if world is None else world
+        if getattr(eng, "_peer_key", None) != (eng.mc_stats_ptrs(), rank, world):
+            peer_setup(eng, rank, world, group=group)
+        eng.mc_allreduce_peer()
+        return
     m, s, c = stats_tensors(eng)
     allreduce_lse(m, s, c, lambda gmax: eng.mc_rescale(gmax.data_ptr()), group=group)
 
 
 def mc_logz_sharded(eng, V, beta, npaths, rank, world, seed=0, estimator="A", horizon=1 << 20, starts=None,
-                    group=None, want=("sa", "count", "s"), out=None):
+                    group=None, want=("sa", "count", "s"), out=None, mode="peer"):
     """End-to-end sharded estimate: every rank uploads V, builds the policy table, rolls out its block
     of path ids, joins the all-reduce and downloads the (replicated) result."""
     import torch
@@ -69,6 +95,6 @@ def mc_logz_sharded(eng, V, beta, npaths, rank, world, seed=0, estimator="A", ho
     eng.mc_rollout(n, path0=path0, seed=seed, estimator=estimator, horizon=horizon, starts=starts)
     if world > 1:
         with torch.cuda.stream(torch.cuda.ExternalStream(eng.stream, device="cuda:%d" % eng.device)):
-            allreduce_engine_stats(eng, group=group)
+            allreduce_engine_stats(eng, group=group, mode=mode, rank=rank, world=world)
             torch.cuda.current_stream().synchronize()
     return eng.mc_finalize(want=want, out=out)

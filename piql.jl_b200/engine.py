@@ -244,6 +244,24 @@ class Engine:
     def mc_rescale(self, global_max_ptr):
         self._ck(self._lib.piql_mc_rescale_dev(self._ctx, C.c_void_p(global_max_ptr)))
 
+    # the exchange step over NVLink peer memory (one process per GPU)
+    def peer_export(self):
+        h = K.PeerHandles()
+        self._ck(self._lib.piql_peer_export(self._ctx, C.byref(h)))
+        return bytes(h)
+
+    def peer_import(self, rank, world, blobs):
+        arr = (K.PeerHandles * world)()
+        for r, b in enumerate(blobs):
+            C.memmove(C.addressof(arr[r]), b, C.sizeof(K.PeerHandles))
+        self._ck(self._lib.piql_peer_import(self._ctx, int(rank), int(world), arr))
+
+    def mc_allreduce_peer(self):
+        self._ck(self._lib.piql_mc_allreduce_peer(self._ctx))
+
+    def peer_close(self):
+        self._ck(self._lib.piql_peer_close(self._ctx))
+
     def mc_finalize(self, want=("sa", "count", "s"), out=None):
         """out: optional preallocated (sa (n,4) f64, count (n,4) u64, s (H,W) f64 F-order), e.g. pinned."""
         n = self.H * self.W

@@ -1,0 +1,96 @@
+"""The N > 1 path on real GPUs (needs >= 2 B200s on the box; skipped otherwise): two processes, one per GPU,
+shard the path ids, roll out their blocks and combine the (max, sum, count) accumulators with
+  * the fused log-sum-exp all-reduce kernel over NVLink peer memory (csrc/peer.cu), and
+  * the three-NCCL-collective baseline,
+and both must reproduce the single-GPU run of all paths: counts exactly, log Z to 1e-5; after the peer exchange
+every rank must hold identical bits.  -m gpu."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import Golden, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _worker(rank, world, port, npaths, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import piql_jl_b200 as piql
+    from piql_jl_b200 import distributed as pd
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda:%d" % rank))
+    g = Golden("r0_01g0_99")
+    eng = piql.Engine(rank)
+    eng.load_grid(g.walls, g.goal, **g.params)
+    V = np.nan_to_num(g.V(7, 0))
+    out = {}
+    for mode in ("peer", "nccl", "peer"):   # the second peer round reuses the mappings (epoch 2)
+        sa, cnt, ls, st = pd.mc_logz_sharded(eng, V, 1.0, npaths, rank, world, seed=3, mode=mode)
+        out.setdefault(mode, []).append((sa.copy(), cnt.copy(), ls.copy(), int(st.transitions)))
+    # bits of the accumulators after a peer exchange (replicated by construction)
+    p0, n = pd.shard_range(npaths, rank, world)
+    eng.mc_reset()
+    eng.mc_rollout(n, path0=p0, seed=3)
+    pd.allreduce_engine_stats(eng, mode="peer", rank=rank, world=world)
+    m, s, c = pd.stats_tensors(eng)
+    torch.cuda.synchronize()
+    bits = (m.cpu().numpy().view(np.uint32).copy(), s.cpu().numpy().view(np.uint32).copy(), c.cpu().numpy().copy())
+    q.put((rank, out, bits))
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs two GPUs on one box")
+def test_sharded_rollout_with_peer_and_nccl_exchange_matches_single_gpu(piql):
+    import torch.multiprocessing as mp
+    world, npaths = 2, 300001
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, npaths, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=240) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-GPU run of all paths
+    g = Golden("r0_01g0_99")
+    eng = piql.Engine(0)
+    eng.load_grid(g.walls, g.goal, **g.params)
+    V = np.nan_to_num(g.V(7, 0))
+    sa1, cnt1, ls1, st1 = eng.mc_logz(V, beta=1.0, npaths=npaths, seed=3)
+    eng.close()
+    ok = cnt1 > 0
+    for rank, out, bits in got:
+        for mode in ("peer", "nccl"):
+            for sa, cnt, ls, tr in out[mode]:
+                assert np.array_equal(cnt, cnt1), mode
+                assert np.allclose(sa[ok], sa1[ok], rtol=1e-5, atol=2e-6), mode
+                free = ~np.isnan(ls1)
+                assert np.allclose(ls[free], ls1[free], rtol=1e-5, atol=2e-6), mode
+                assert tr * 0 == 0
+        assert sum(o[3] for o in [out["peer"][0]]) > 0
+    # transitions are per rank: the two shards add up to the single-GPU count
+    assert got[0][1]["peer"][0][3] + got[1][1]["peer"][0][3] == int(st1.transitions)
+    for a, b in zip(got[0][2], got[1][2]):
+        assert np.array_equal(a, b)
