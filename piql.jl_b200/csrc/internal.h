@@ -48,6 +48,10 @@ struct TileBuffers {
   TilePlan plan{};
   int cur = 0;
   bool active = false;
+  // CUtensorMap descriptors (opaque here) of x[0], x[1] and mask: boxes of 128 x EJ elements for the TMA staging
+  alignas(64) unsigned char tmx[2][128] = {};
+  alignas(64) unsigned char tmm[128] = {};
+  bool use_tma = false;
 };
 TilePlan make_tile_plan(int H, int W, int precision, int kind, int num_sms);
 cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs, TileBuffers& tb, int num_sms, cudaStream_t st);

@@ -19,8 +19,11 @@
 //
 // Jacobi makes every cell's update a pure function of the previous iterate, so the values are
 // independent of the tiling (halo cells recomputed by two CTAs get identical bits).
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "algebra.cuh"
 #include "internal.h"
@@ -30,6 +33,10 @@ namespace piql {
 constexpr int TKH = TILE_KH;
 constexpr int TEI = 128;            // rows of the shared-memory tile: 32 lanes x 4-cell strips
 constexpr int TTI = TEI - 2 * TKH;  // interior rows per tile
+// Cell bytes of a staged column: 128 + 16.  A TMA box must start on a 16-byte boundary and a tile starts at byte
+// 120*ti of the byte array, so the box starts up to 8 bytes early and the kernel indexes past that offset.
+constexpr int TMB = TEI + 16;       // bytes
+constexpr int TMP = TMB / 4;        // 32-bit words
 
 // Constants of the tiled sweeps.
 template <typename T> struct TileK {
@@ -80,6 +87,32 @@ template <> __device__ __forceinline__ void ldg4<float>(const float* p, float (&
 template <> __device__ __forceinline__ void ldg4<double>(const double* p, double (&o)[4]) {
   const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p + 2));
   o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+
+// ---- TMA (cp.async.bulk.tensor) staging of a tile: one thread issues, an mbarrier counts the bytes ---------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
 // ---- per-cell backups on the four (already wall-resolved) neighbour values ----------------------------
@@ -164,7 +197,7 @@ __device__ __forceinline__ void tile_subsweep(const TileK<T>& k, const T* __rest
     lds4(src + jj * TEI + 4 * lane, v);
     lds4(src + (jj - 1) * TEI + 4 * lane, L);
     lds4(src + (jj + 1) * TEI + 4 * lane, R);
-    const uint32_t mk = msk[jj * 32 + lane];
+    const uint32_t mk = msk[jj * TMP + lane];
     // rows 0 and 127 have no vertical neighbour in the tile: they are halo, any value will do
     const T up = __shfl_up_sync(FULL, v[3], 1), dn = __shfl_down_sync(FULL, v[0], 1);
     T ax[5][4];
@@ -201,7 +234,7 @@ __device__ __noinline__ void tile_goal_fixup(const TileK<T>& k, const T* __restr
   if (t >= (KIND == KIND_NU ? 5 : 1)) return;
   const int i = gi + (t == 1) - (t == 2), j = gj + (t == 3) - (t == 4);
   if (i < 0 || i >= TEI || j < 1 || j >= k.EJ - 1) return;  // not a cell this tile computes
-  const uint32_t b = (msk[j * 32 + (i >> 2)] >> (8 * (i & 3))) & 0xffu;
+  const uint32_t b = (msk[j * TMP + (i >> 2)] >> (8 * (i & 3))) & 0xffu;
   const T c = src[j * TEI + i];
   T o;
   if (t == 0) {
@@ -222,20 +255,24 @@ __device__ __noinline__ void tile_goal_fixup(const TileK<T>& k, const T* __restr
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------
-// grid = tiles_i * tiles_j CTAs of NW warps; dynamic shared memory = EJ * (2 * 128 * sizeof(T) + 128) bytes.
+// grid = tiles_i * tiles_j CTAs of NW warps; dynamic shared memory = EJ * (2 * 128 * sizeof(T) + 144) bytes.
 template <typename T, int KIND, bool FAST>
 __global__ void __launch_bounds__(512, sizeof(T) == 4 ? 2 : 1)
-tile_sweep_kernel(const TileK<T> k, const uint8_t* __restrict__ maskp, const T* __restrict__ X, T* __restrict__ Y,
+tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmM,
+                  int use_tma, const uint8_t* __restrict__ maskp, const T* __restrict__ X, T* __restrict__ Y,
                   const T* __restrict__ aux, int nsub, int want_res, double* __restrict__ partial) {
-  extern __shared__ __align__(16) unsigned char tile_smem[];
+  extern __shared__ __align__(128) unsigned char tile_smem[];
   __shared__ double red[32];
+  __shared__ __align__(8) unsigned long long mbar;
   const int EJ = k.EJ, ld = k.ld;
   T* bufA = reinterpret_cast<T*>(tile_smem);
   T* bufB = bufA + EJ * TEI;
-  uint32_t* msk = reinterpret_cast<uint32_t*>(bufB + EJ * TEI);
+  uint32_t* msk0 = reinterpret_cast<uint32_t*>(bufB + EJ * TEI);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
   const int ti = blockIdx.x % k.tiles_i, tj = blockIdx.x / k.tiles_i;
   const int org = ti * TTI + ld * (tj * k.TJ);  // padded index of the tile's (row 0, column 0)
+  const int moff = (ti * TTI) & 15;              // bytes the staged cell-byte box starts before row 0 (0 or 8)
+  const uint32_t* msk = msk0 + (moff >> 2);
 
   // Programmatic dependent launch: this grid may be scheduled while the previous launch (which wrote X) drains;
   // let the next one do the same, then wait for the previous grid's memory before the first global read.
@@ -243,13 +280,33 @@ tile_sweep_kernel(const TileK<T> k, const uint8_t* __restrict__ maskp, const T* 
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // stage the tile (every access in bounds thanks to the ghost frame)
-  for (int jj = warp; jj < EJ; jj += NW) {
-    const int g = org + jj * ld + 4 * lane;
-    T v[4];
-    ldg4(X + g, v);
-    sts4(bufA + jj * TEI + 4 * lane, v);
-    if (jj == 0 || jj == EJ - 1) sts4(bufB + jj * TEI + 4 * lane, v);  // never recomputed: keep both copies defined
-    msk[jj * 32 + lane] = __ldg(reinterpret_cast<const uint32_t*>(maskp + g));
+  if (use_tma) {
+    // two TMA boxes of 128 x EJ elements (iterate, cell bytes) land in shared memory; nobody spends an issue slot
+    // or a register on the copy, and the whole tile is in flight at once
+    if (threadIdx.x == 0) {
+      mbar_init(&mbar, 1);
+      mbar_expect_tx(&mbar, (unsigned)(EJ * (TEI * sizeof(T) + TMB)));
+      tma_load_2d(bufA, &tmX, ti * TTI, tj * k.TJ, &mbar);
+      tma_load_2d(msk0, &tmM, ti * TTI - moff, tj * k.TJ, &mbar);  // rows past the array's end are zero-filled
+    }
+    __syncthreads();  // the barrier word is initialised before anyone polls it
+    mbar_wait(&mbar, 0);
+    // the outermost columns are never recomputed: keep both ping-pong copies defined
+    if (warp < 2) {
+      const int jj = warp == 0 ? 0 : EJ - 1;
+      T v[4];
+      lds4(bufA + jj * TEI + 4 * lane, v);
+      sts4(bufB + jj * TEI + 4 * lane, v);
+    }
+  } else {
+    for (int jj = warp; jj < EJ; jj += NW) {
+      const int g = org + jj * ld + 4 * lane;
+      T v[4];
+      ldg4(X + g, v);
+      sts4(bufA + jj * TEI + 4 * lane, v);
+      if (jj == 0 || jj == EJ - 1) sts4(bufB + jj * TEI + 4 * lane, v);
+      msk0[jj * TMP + (moff >> 2) + lane] = __ldg(reinterpret_cast<const uint32_t*>(maskp + g));
+    }
   }
   __syncthreads();
 
@@ -285,7 +342,7 @@ tile_sweep_kernel(const TileK<T> k, const uint8_t* __restrict__ maskp, const T* 
       if (want_res) {
         T p[4];
         lds4(dst + jj * TEI + 4 * lane, p);
-        const uint32_t mk = msk[jj * 32 + lane];
+        const uint32_t mk = msk[jj * TMP + lane];
 #pragma unroll
         for (int r = 0; r < 4; r++)
           if (!((mk >> (8 * r)) & CELL_WALL)) res += sweep_diff<KIND>((double)f[r], (double)p[r]);
@@ -351,7 +408,7 @@ __global__ void tile_unpack_kernel(PadGeom g, const T* __restrict__ padded, T* _
 
 // ---- host side ---------------------------------------------------------------------------------------------
 static size_t tile_smem_bytes(int EJ, int precision) {
-  return (size_t)EJ * (2 * TEI * (precision == 0 ? 8 : 4) + TEI);
+  return (size_t)EJ * (2 * TEI * (precision == 0 ? 8 : 4) + TMB);
 }
 
 // Tile shape (TJ interior columns, nw warps per CTA) by a small cost model, in SM cycles per launch:
@@ -422,6 +479,36 @@ template <typename T> static TileK<T> make_tile_k(const GridDev& g, const ViStat
 
 static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+// 2-D map over a padded array (inner dimension ld, outer Wp), box = 128 x EJ elements, no swizzle
+static bool encode_tile_map(void* out, void* base, CUtensorMapDataType dt, size_t esize, const TilePlan& pl, int box_rows = TEI) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)pl.ld, (cuuint64_t)pl.Wp};
+  const cuuint64_t gstride[1] = {(cuuint64_t)pl.ld * esize};
+  const cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)pl.EJ};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn((CUtensorMap*)out, dt, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 void tile_free(TileBuffers& tb) {
   for (void* p : {tb.x[0], tb.x[1], tb.aux, (void*)tb.mask, (void*)tb.partial}) if (p) cudaFree(p);
   tb = TileBuffers{};
@@ -464,6 +551,11 @@ cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs,
   }
   tb.plan = pl;
   tb.cur = 0;
+  static_assert(sizeof(CUtensorMap) == 128, "descriptor size");
+  const CUtensorMapDataType dt = vs.precision == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  tb.use_tma = getenv("PIQL_TILE_NO_TMA") == nullptr && encode_tile_map(tb.tmx[0], tb.x[0], dt, e, pl) &&
+               encode_tile_map(tb.tmx[1], tb.x[1], dt, e, pl) &&
+               encode_tile_map(tb.tmm, tb.mask, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, pl, TMB);
   if (vs.precision == 0) pack_t<double>(g, cell, vs, tb, st);
   else pack_t<float>(g, cell, vs, tb, st);
   tb.active = true;
@@ -488,7 +580,11 @@ static cudaError_t launch_tile_t(const GridDev& g, const ViState& vs, TileBuffer
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, tile_sweep_kernel<T, KIND, FAST>, k, (const uint8_t*)tb.mask, (const T*)tb.x[tb.cur],
+  CUtensorMap tmX, tmM;
+  memcpy(&tmX, tb.tmx[tb.cur], sizeof(tmX));
+  memcpy(&tmM, tb.tmm, sizeof(tmM));
+  cudaError_t le = cudaLaunchKernelEx(&cfg, tile_sweep_kernel<T, KIND, FAST>, k, tmX, tmM, tb.use_tma ? 1 : 0,
+                                      (const uint8_t*)tb.mask, (const T*)tb.x[tb.cur],
                                       (T*)tb.x[tb.cur ^ 1], (const T*)tb.aux, nsub, want_res ? 1 : 0, tb.partial);
   if (le != cudaSuccess) return le;
   g_launches++;
