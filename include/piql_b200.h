@@ -70,7 +70,7 @@ typedef struct {
   double device_seconds; /* CUDA-event time of the sweeps */
   int64_t backups;       /* state backups performed = sweeps * free cells */
   int32_t converged;
-  int32_t kernel;        /* 1 = single-CTA resident solver, 2 = tiled multi-sweep kernel (4 sweeps per launch) */
+  int32_t kernel;        /* 1 = single-CTA resident solver, 2 = tiled multi-sweep kernel (4 sweeps per launch), 3 = batched resident */
 } piql_solve_stats;
 
 enum { PIQL_EST_SAMPLED_STOP = 0 /* estimator A */, PIQL_EST_DISCOUNTED = 1 /* estimator B */ };
@@ -131,6 +131,17 @@ int32_t piql_update_v(piql_ctx* ctx, const double* V, double beta, const piql_so
 /* generate_optimality_gap(ctrl, V; ν)   src/value_iteration.jl:129-169 */
 int32_t piql_solve_gap(piql_ctx* ctx, const double* V, const double* Q, const double* nu,
                        const piql_solve_opts* opts, double* gap_out, piql_solve_stats* stats_out);
+/* The experiment protocol in two calls (run_experiment, scripts/experiments.jl:20-39; its distributed twin
+ * scripts/distributed_experiments.jl:15-33 fans the same work out with pmap over beta and over iterates):
+ *   piql_learning_traj: for every beta, learning_traj(ctrl, V0; beta, n = nupdates) (scripts/experiments.jl:10-18):
+ *     traj_out[b][0] = V0, traj_out[b][k] = logz_updateV(ctrl, traj_out[b][k-1]; beta_b);  nbeta*(nupdates+1)*H*W doubles,
+ *     stats_out (optional) nbeta*nupdates entries.  The chains are independent: one CTA each, in one launch.
+ *   piql_solve_gap_batch: generate_optimality_gap(ctrl, Vs[i]; nu) for m value functions at once (m*H*W doubles in and out).
+ * Problems too large for one CTA's shared memory run the same solves one after the other with the tiled kernel. */
+int32_t piql_learning_traj(piql_ctx* ctx, const double* V0, const double* betas, int32_t nbeta, int32_t nupdates,
+                           const piql_solve_opts* opts, double* traj_out, piql_solve_stats* stats_out);
+int32_t piql_solve_gap_batch(piql_ctx* ctx, const double* Vs, int32_t m, const double* nu, const piql_solve_opts* opts,
+                             double* gaps_out, piql_solve_stats* stats_out);
 /* One Jacobi sweep from x_in (kind: 0 nu, 1 logz, 2 gap), for parity tests of the backup itself. */
 int32_t piql_sweep_once(piql_ctx* ctx, int32_t kind, const double* V, const double* Q, const double* nu,
                         double beta, double reward_scale, int32_t precision, const double* x_in,

@@ -85,6 +85,8 @@ SYMBOLS = {
     "piql_mc_transitions_total": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     "piql_mc_records": (C.c_int32, [_P, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_int64]),
     "piql_vi_prepare_dev": (C.c_int32, [_P, C.c_int32, _D, _D, _D, C.c_double, C.c_double, C.c_int32]),
+    "piql_learning_traj": (C.c_int32, [_P, _D, _D, C.c_int32, C.c_int32, C.POINTER(SolveOpts), _D, C.POINTER(SolveStats)]),
+    "piql_solve_gap_batch": (C.c_int32, [_P, _D, C.c_int32, _D, C.POINTER(SolveOpts), _D, C.POINTER(SolveStats)]),
     "piql_vi_set_iterate": (C.c_int32, [_P, C.POINTER(C.c_double)]),
     "piql_vi_tile_plan": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "piql_vi_sweeps_dev": (C.c_int32, [_P, C.c_int64]),

@@ -25,6 +25,8 @@ struct piql_ctx {
   long long nfree = 0;
   uint8_t* d_walls = nullptr;
   uint8_t* d_cell = nullptr;
+  std::vector<uint8_t> h_walls;  // host copy of the wall bytes (NaN pattern of host-composed outputs)
+  bool h_walls_nan(long long s) const { return h_walls[(size_t)s] != 0; }
   int* d_free = nullptr;  // free cells in index order
 
   // soft VI
@@ -569,6 +571,7 @@ int32_t piql_grid_load(piql_ctx* ctx, const uint8_t* walls, int64_t H, int64_t W
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   free(h_free);
   if (e != cudaSuccess) return fail(ctx, PIQL_ERR_CUDA, std::string("piql_grid_load: ") + cudaGetErrorString(e));
+  ctx->h_walls.assign(walls, walls + n);
   ctx->nfree = nfree;
   ctx->has_grid = true;
   return PIQL_OK;
@@ -624,6 +627,106 @@ int32_t piql_update_v(piql_ctx* ctx, const double* V, double beta, const piql_so
   CK(cudaMemcpyAsync(vnew_out, ctx->d_out, 8 * (size_t)ctx->g.n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return rc;
+}
+
+// ---- batched entry points: the experiment protocol in two launches ------------------------------------------
+static int batch_run(piql_ctx* ctx, int kind, const double* Vin, long long vin_count, const double* nu, const double* betas,
+                     int nproblems, int nupdates, const piql_solve_opts* opts, double* out, piql_solve_stats* stats_out) {
+  const int n = ctx->g.n;
+  cudaStream_t st = ctx->stream;
+  const int prec = opts->precision == PIQL_F64 ? 0 : 1;
+  const int nsolves = kind == KIND_LOGZ ? nupdates : 1;
+  const size_t out_per = (kind == KIND_LOGZ ? (size_t)(nupdates + 1) : 1) * (size_t)n;
+  double *d_v = nullptr, *d_nu = nullptr, *d_b = nullptr, *d_o = nullptr, *d_s = nullptr;
+  std::vector<double> h_s((size_t)nproblems * nsolves * 2);
+  cudaError_t e = cudaMalloc((void**)&d_v, 8 * (size_t)n * (size_t)vin_count);
+  if (e == cudaSuccess && nu) e = cudaMalloc((void**)&d_nu, 8 * (size_t)n);
+  if (e == cudaSuccess && betas) e = cudaMalloc((void**)&d_b, 8 * (size_t)nproblems);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_o, 8 * out_per * nproblems);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_s, 8 * h_s.size());
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_v, Vin, 8 * (size_t)n * (size_t)vin_count, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && nu) e = cudaMemcpyAsync(d_nu, nu, 8 * (size_t)n, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && betas) e = cudaMemcpyAsync(d_b, betas, 8 * (size_t)nproblems, cudaMemcpyHostToDevice, st);
+  float ms = 0.f;
+  if (e == cudaSuccess) {
+    cudaEventRecord(ctx->ev0, st);
+    launch_resident_batch(ctx->g, ctx->d_cell, kind, prec, 1.0, nproblems, d_v, vin_count > 1 ? n : 0, d_nu, d_b, nupdates,
+                          opts->tol > 0 ? opts->tol : -1.0, opts->max_sweeps, d_o, d_s, st);
+    e = cudaGetLastError();
+    cudaEventRecord(ctx->ev1, st);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, 8 * out_per * nproblems, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_s.data(), d_s, 8 * h_s.size(), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  for (void* p : {(void*)d_v, (void*)d_nu, (void*)d_b, (void*)d_o, (void*)d_s}) if (p) cudaFree(p);
+  if (e != cudaSuccess) return fail(ctx, PIQL_ERR_CUDA, std::string("batched solve: ") + cudaGetErrorString(e));
+  bool all = true;
+  for (size_t i = 0; i < h_s.size() / 2; i++) {
+    const bool conv = opts->tol > 0 ? h_s[2 * i + 1] < opts->tol : true;
+    all = all && conv;
+    if (stats_out) {
+      piql_solve_stats& o = stats_out[i];
+      o.sweeps = (int64_t)h_s[2 * i]; o.residual = h_s[2 * i + 1]; o.device_seconds = ms * 1e-3;  // of the whole batch
+      o.backups = o.sweeps * ctx->nfree; o.converged = conv ? 1 : 0; o.kernel = 3;
+    }
+  }
+  if (!all) return fail(ctx, PIQL_ERR_NOT_CONVERGED, "max_sweeps reached before the residual fell below tol in at least one solve");
+  return PIQL_OK;
+}
+
+int32_t piql_learning_traj(piql_ctx* ctx, const double* V0, const double* betas, int32_t nbeta, int32_t nupdates,
+                           const piql_solve_opts* opts, double* traj_out, piql_solve_stats* stats_out) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded (call piql_grid_load first)");
+  NEED(V0 && betas && opts && traj_out, PIQL_ERR_ARG, "V0 / betas / opts / traj_out is null");
+  NEED(nbeta > 0 && nupdates > 0, PIQL_ERR_ARG, "nbeta and nupdates must be positive");
+  NEED(opts->max_sweeps > 0, PIQL_ERR_ARG, "max_sweeps must be positive");
+  NEED(opts->precision >= PIQL_F64 && opts->precision <= PIQL_F32_FAST, PIQL_ERR_ARG, "bad precision");
+  for (int b = 0; b < nbeta; b++) NEED(betas[b] == betas[b] && betas[b] != 0.0, PIQL_ERR_ARG, "beta must be non-zero and not NaN");
+  NEED(V0[ctx->g.goal] == V0[ctx->g.goal], PIQL_ERR_ARG, "V(goal) is NaN");
+  CK(cudaSetDevice(ctx->device));
+  const int n = ctx->g.n;
+  if (resident_batch_smem_bytes(n, opts->precision == PIQL_F64 ? 0 : 1) <= 200 * 1024)
+    return batch_run(ctx, KIND_LOGZ, V0, 1, nullptr, betas, nbeta, nupdates, opts, traj_out, stats_out);
+  // large grids: the chains run one after the other on the whole GPU (tiled kernel)
+  int worst = PIQL_OK;
+  for (int b = 0; b < nbeta; b++) {
+    double* tb = traj_out + (size_t)b * (nupdates + 1) * n;
+    for (int s = 0; s < n; s++) tb[s] = ctx->h_walls_nan(s) ? NAN : V0[s];
+    for (int u = 0; u < nupdates; u++) {
+      std::vector<double> vin(tb + (size_t)u * n, tb + (size_t)(u + 1) * n);
+      for (double& v : vin) if (!(v == v)) v = 0.0;
+      int rc = piql_update_v(ctx, vin.data(), betas[b], opts, tb + (size_t)(u + 1) * n, nullptr,
+                             stats_out ? stats_out + (size_t)b * nupdates + u : nullptr);
+      if (rc && rc != PIQL_ERR_NOT_CONVERGED) return rc;
+      if (rc) worst = rc;
+    }
+  }
+  return worst;
+}
+
+int32_t piql_solve_gap_batch(piql_ctx* ctx, const double* Vs, int32_t m, const double* nu, const piql_solve_opts* opts,
+                             double* gaps_out, piql_solve_stats* stats_out) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded (call piql_grid_load first)");
+  NEED(Vs && nu && opts && gaps_out, PIQL_ERR_ARG, "Vs / nu / opts / gaps_out is null");
+  NEED(m > 0, PIQL_ERR_ARG, "m must be positive");
+  NEED(opts->max_sweeps > 0, PIQL_ERR_ARG, "max_sweeps must be positive");
+  NEED(opts->precision >= PIQL_F64 && opts->precision <= PIQL_F32_FAST, PIQL_ERR_ARG, "bad precision");
+  CK(cudaSetDevice(ctx->device));
+  const int n = ctx->g.n;
+  if (resident_batch_smem_bytes(n, opts->precision == PIQL_F64 ? 0 : 1) <= 200 * 1024)
+    return batch_run(ctx, KIND_GAP, Vs, m, nu, nullptr, m, 1, opts, gaps_out, stats_out);
+  int worst = PIQL_OK;
+  for (int b = 0; b < m; b++) {
+    int rc = piql_solve_gap(ctx, Vs + (size_t)b * n, nullptr, nu, opts, gaps_out + (size_t)b * n, stats_out ? stats_out + b : nullptr);
+    if (rc && rc != PIQL_ERR_NOT_CONVERGED) return rc;
+    if (rc) worst = rc;
+  }
+  return worst;
 }
 
 int32_t piql_sweep_once(piql_ctx* ctx, int32_t kind, const double* V, const double* Q, const double* nu, double beta,

@@ -153,6 +153,144 @@ resident_solve_kernel(K<T> k, const uint8_t* __restrict__ cell, const T* __restr
   if (threadIdx.x == 0) { out2[0] = (double)sweeps; out2[1] = res; }
 }
 
+
+// ---- batched resident solves: one CTA per problem, everything in shared memory -----------------------------
+// The experiment protocol of the reference (run_experiment, scripts/experiments.jl:20-39; learning_traj :10-18)
+// is 8 independent beta chains of 5 dependent logz_updateV solves and then 48 independent optimality-gap solves
+// on one 251-state problem: 10^3..10^4 sweeps each, far too small for more than one CTA but perfectly parallel
+// across problems.  Each CTA keeps V, the iterate (ping-pong) and the per-cell constants in shared memory, builds
+// the constants itself (what prep_kernel does for a single solve), iterates to the reference's stop rule, and --
+// for a chain -- applies V <- V + logz/beta (logz_updateV, value_iteration.jl:119-124) and goes on.
+// kind KIND_LOGZ: chain of nupdates solves, out[b][0..nupdates][n];  KIND_GAP / KIND_NU: one solve, out[b][n].
+template <typename T>
+__global__ void __launch_bounds__(1024)
+resident_batch_kernel(K<T> k, int kind, const uint8_t* __restrict__ cell, const double* __restrict__ Vin, long long vin_stride,
+                      const double* __restrict__ nu, const double* __restrict__ betas, int nupdates, double tol,
+                      long long max_sweeps, double* __restrict__ out, double* __restrict__ stats /*[b][nupdates][2]*/) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[32];
+  __shared__ double s_res;
+  const int n = k.n, b = blockIdx.x;
+  T* V = reinterpret_cast<T*>(smem_raw);
+  T* A = V + n;
+  T* B = A + n;
+  T* aux = B + n;  // five planes: logz A_a (4); gap pi_a (4), D
+  uint8_t* cs = reinterpret_cast<uint8_t*>(aux + 5 * (size_t)n);
+  if (betas) k.beta = (T)betas[b];
+  const double beta_d = betas ? betas[b] : 1.0;
+  for (int s = threadIdx.x; s < n; s += blockDim.x) {
+    const double v = Vin ? Vin[(size_t)b * vin_stride + s] : 0.0;
+    V[s] = (v == v) ? (T)v : (T)0;
+    cs[s] = cell[s];
+  }
+  __syncthreads();
+  const int nsolves = kind == KIND_LOGZ ? nupdates : 1;
+  double* outb = out + (size_t)b * (kind == KIND_LOGZ ? (size_t)(nupdates + 1) * n : (size_t)n);
+  if (kind == KIND_LOGZ)
+    for (int s = threadIdx.x; s < n; s += blockDim.x) outb[s] = (cs[s] & CELL_WALL) ? CUDART_NAN : (double)V[s];
+  for (int u = 0; u < nsolves; u++) {
+    // per-cell constants from the current V (PIQL.jl:63-85)
+    for (int s = threadIdx.x; s < n; s += blockDim.x) {
+      const unsigned ci = cs[s];
+      T o4[NA] = {0, 0, 0, 0}, o1 = 0;
+      if (kind != KIND_NU && !(ci & (CELL_WALL | CELL_GOAL))) {
+        T c, nb[NA], rbar[NA], cv[NA], x[NA];
+        gather(V, s, k.H, ci, c, nb);
+        avg_rewards(k, s, ci, rbar);
+        control_v(k, c, nb, rbar, cv);
+#pragma unroll
+        for (int a = 0; a < NA; a++) x[a] = k.log_prior + cv[a];
+        const T norm = lse4(x);  // Qnormalization of the V-determined Q
+        if (kind == KIND_LOGZ) {
+#pragma unroll
+          for (int a = 0; a < NA; a++) o4[a] = k.log_prior + k.beta * cv[a] + ((T)1 - k.beta) * (cv[a] - norm);
+        } else {
+          T nc, nnb[NA], cvn[NA];
+          nc = (T)nu[s];
+          nnb[0] = (ci & 1u) ? nc : (T)nu[s + 1];
+          nnb[1] = (ci & 2u) ? nc : (T)nu[s - 1];
+          nnb[2] = (ci & 4u) ? nc : (T)nu[s + k.H];
+          nnb[3] = (ci & 8u) ? nc : (T)nu[s - k.H];
+          control_v(k, nc, nnb, rbar, cvn);
+#pragma unroll
+          for (int a = 0; a < NA; a++) {
+            const T cq = cv[a] - norm;
+            o4[a] = (T)0.25 * xexp(cq);
+            o1 += o4[a] * (cq - cvn[a]);
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NA; a++) aux[(size_t)a * n + s] = o4[a];
+      aux[(size_t)4 * n + s] = o1;
+      A[s] = (T)0;  // Growable default x -> 0.0
+      B[s] = (T)0;
+    }
+    __syncthreads();
+    const T term = kind == KIND_LOGZ ? (T)0 - V[k.goal] : (T)0;
+    T* X = A;
+    T* Y = B;
+    long long sweeps = 0;
+    double res = CUDART_INF;
+    while (sweeps < max_sweeps) {
+      double d = 0.0;
+      for (int s = threadIdx.x; s < n; s += blockDim.x) {
+        const unsigned ci = cs[s];
+        if (ci & CELL_WALL) continue;
+        T c, nb[NA], nw;
+        gather(X, s, k.H, ci, c, nb);
+        if (ci & CELL_GOAL) nw = term;
+        else if (kind == KIND_NU) nw = backup_nu(k, s, ci, nb);
+        else {
+          const T a4[NA] = {aux[s], aux[(size_t)n + s], aux[(size_t)2 * n + s], aux[(size_t)3 * n + s]};
+          nw = kind == KIND_LOGZ ? backup_logz(k, a4, nb) : backup_gap(k, a4, aux[(size_t)4 * n + s], nb);
+        }
+        d += fabs((double)nw - (double)c);
+        Y[s] = kind == KIND_LOGZ ? logaddexp((T)(-0.6931471805599453) + nw, (T)(-0.6931471805599453) + c) : nw;
+      }
+      const double r = block_sum(d, red);
+      if (threadIdx.x == 0) s_res = r;
+      __syncthreads();
+      res = s_res;
+      T* t = X; X = Y; Y = t;
+      sweeps++;
+      if (res < tol) break;
+    }
+    if (threadIdx.x == 0) { stats[((size_t)b * nsolves + u) * 2] = (double)sweeps; stats[((size_t)b * nsolves + u) * 2 + 1] = res; }
+    if (kind == KIND_LOGZ) {
+      double* o = outb + (size_t)(u + 1) * n;
+      for (int s = threadIdx.x; s < n; s += blockDim.x) {
+        const bool wall = cs[s] & CELL_WALL;
+        // V(k) + logz(k)/beta in double from the stored iterate, like piql_update_v
+        const double vn = (double)V[s] + (double)X[s] / beta_d;
+        if (!wall) V[s] = (T)vn;
+        o[s] = wall ? CUDART_NAN : (sizeof(T) == 8 ? vn : (double)V[s]);
+      }
+    } else {
+      for (int s = threadIdx.x; s < n; s += blockDim.x) outb[s] = (cs[s] & CELL_WALL) ? CUDART_NAN : (double)X[s];
+    }
+    __syncthreads();
+  }
+}
+
+size_t resident_batch_smem_bytes(int n, int precision) {
+  const size_t e = precision == 0 ? 8 : 4;
+  return 8 * e * (size_t)n + (((size_t)n + 15) / 16) * 16;
+}
+void launch_resident_batch(const GridDev& g, const uint8_t* cell, int kind, int precision, double reward_scale, int nproblems,
+                           const double* Vin, long long vin_stride, const double* nu, const double* betas, int nupdates,
+                           double tol, long long max_sweeps, double* out, double* stats, cudaStream_t st) {
+  const size_t smem = resident_batch_smem_bytes(g.n, precision);
+  const int threads = g.n >= 1024 ? 1024 : ((g.n + 31) / 32) * 32;
+  if (precision == 0)
+    resident_batch_kernel<double><<<nproblems, threads, smem, st>>>(make_k<double>(g, reward_scale, 1.0), kind, cell, Vin, vin_stride,
+                                                                    nu, betas, nupdates, tol, max_sweeps, out, stats);
+  else
+    resident_batch_kernel<float><<<nproblems, threads, smem, st>>>(make_k<float>(g, reward_scale, 1.0), kind, cell, Vin, vin_stride,
+                                                                   nu, betas, nupdates, tol, max_sweeps, out, stats);
+  g_launches++;
+}
+
 // Per-cell constants of the logz / gap sweeps.
 template <typename T, int KIND>
 __global__ void __launch_bounds__(SWEEP_THREADS)
@@ -343,6 +481,8 @@ int configure_backup_kernels() {
   PIQL_SET(double, KIND_NU) PIQL_SET(double, KIND_LOGZ) PIQL_SET(double, KIND_GAP)
   PIQL_SET(float, KIND_NU) PIQL_SET(float, KIND_LOGZ) PIQL_SET(float, KIND_GAP)
 #undef PIQL_SET
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(resident_batch_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(resident_batch_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   return (int)e;
 }
 

@@ -79,6 +79,11 @@ void launch_resident_solve(const GridDev& g, const uint8_t* cell, ViState& vs, d
 void launch_update_v(const double* V, const void* logz, const uint8_t* cell, double beta, double* out, int n,
                      int precision, cudaStream_t st);
 size_t resident_smem_bytes(int n, int precision);
+// One CTA per problem (beta chain of logz_updateV solves, or single nu / gap solves), everything in shared memory.
+size_t resident_batch_smem_bytes(int n, int precision);
+void launch_resident_batch(const GridDev& g, const uint8_t* cell, int kind, int precision, double reward_scale, int nproblems,
+                           const double* Vin, long long vin_stride, const double* nu, const double* betas, int nupdates,
+                           double tol, long long max_sweeps, double* out, double* stats, cudaStream_t st);
 int configure_backup_kernels();
 void launch_residual_final(const double* partial, int nblocks, double* out, cudaStream_t st);
 

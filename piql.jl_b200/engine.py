@@ -134,6 +134,30 @@ class Engine:
                  allow=(K.ERR_NOT_CONVERGED,) if allow_unconverged else ())
         return out, st
 
+    def learning_traj(self, V0, betas, n=5, tol=1e-12, max_sweeps=10 ** 7, precision="f64", allow_unconverged=False):
+        """All beta chains of learning_traj in one call: returns traj[nbeta, n+1, H, W] (F-order cells) and stats."""
+        V0 = _cell(np.nan_to_num(np.asarray(V0, dtype=np.float64)), self.H, self.W, "V0")
+        betas = np.ascontiguousarray(betas, dtype=np.float64)
+        out = np.empty((len(betas), n + 1, self.W, self.H), dtype=np.float64)   # cell index i + H*j: (W, H) C-order
+        st = (K.SolveStats * (len(betas) * n))()
+        o = self._opts(tol, max_sweeps, precision, 0)
+        self._ck(self._lib.piql_learning_traj(self._ctx, _pd(V0), _pd(betas), len(betas), int(n), C.byref(o), _pd(out), st),
+                 allow=(K.ERR_NOT_CONVERGED,) if allow_unconverged else ())
+        return out.transpose(0, 1, 3, 2), list(st)
+
+    def solve_gap_batch(self, Vs, nu, tol=1e-12, max_sweeps=10 ** 7, precision="f64", allow_unconverged=False):
+        """generate_optimality_gap for a stack of value functions Vs[m, H, W]; returns gaps[m, H, W] and stats."""
+        Vs = np.nan_to_num(np.asarray(Vs, dtype=np.float64))
+        m = Vs.shape[0]
+        vin = np.ascontiguousarray(Vs.transpose(0, 2, 1))                       # (m, W, H) C-order = column-major cells
+        nu = _cell(np.nan_to_num(np.asarray(nu, dtype=np.float64)), self.H, self.W, "nu")
+        out = np.empty((m, self.W, self.H), dtype=np.float64)
+        st = (K.SolveStats * m)()
+        o = self._opts(tol, max_sweeps, precision, 0)
+        self._ck(self._lib.piql_solve_gap_batch(self._ctx, _pd(vin), m, _pd(nu), C.byref(o), _pd(out), st),
+                 allow=(K.ERR_NOT_CONVERGED,) if allow_unconverged else ())
+        return out.transpose(0, 2, 1), list(st)
+
     def sweep_once(self, kind, x, V=None, Q=None, nu=None, beta=1.0, reward_scale=1.0, precision="f64"):
         kind = {"nu": K.KIND_NU, "logz": K.KIND_LOGZ, "gap": K.KIND_GAP}[kind]
         prec = K.PRECISIONS[precision]

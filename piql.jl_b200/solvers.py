@@ -13,7 +13,8 @@ Same names, arguments and return types as the reference (γ/β/ν spelled out in
                                           src/PIQL.jl:55-89 (host algebra on closures, for
                                           callers and tests; the kernels restate it per cell)
     mc_logz                               new: Monte-Carlo estimate of generate_logz's fixed point
-    learning_traj, run_experiment         scripts/experiments.jl:10-39
+    learning_traj, run_experiment         scripts/experiments.jl:10-39 (+ batched forms: all beta chains / all gap
+                                          solves in one library call, scripts/distributed_experiments.jl:26,28)
 Every solver returns a Growable, as in the reference; `.array` is the dense (H, W) view
 (NaN at walls) the library produced.
 """
@@ -232,13 +233,45 @@ def learning_traj(ctrl, v0, beta=1.0, n=20, **kw):
     return out
 
 
-def run_experiment(gw, randomness=0.01, gamma=0.99, starting_temp=0.1, betarange=None, n=5, **kw):
+def learning_traj_batch(ctrl, v0, betas, n=5, tol=1e-12, max_sweeps=10 ** 7, precision="f64", device=0):
+    """learning_traj for every beta in one library call (one CTA per chain): {beta: [V_0 .. V_n]}.
+    Replaces the pmap over beta of scripts/distributed_experiments.jl:26."""
+    eng = engine_for(ctrl, device)
+    traj, _st = eng.learning_traj(_dense(v0, eng), [float(b) for b in betas], n=n, tol=tol, max_sweeps=max_sweeps,
+                                  precision=precision)
+    default = getattr(v0, "default", lambda x: 0.0)
+    return {float(b): [Growable.from_dense(traj[i, k], eng.walls, default=default) for k in range(n + 1)]
+            for i, b in enumerate(betas)}
+
+
+def generate_optimality_gap_batch(ctrl, Vs, nu, tol=1e-12, max_sweeps=10 ** 7, precision="f64", device=0):
+    """generate_optimality_gap for a list of value functions in one library call (one CTA per value function).
+    Replaces the pmap over iterates of scripts/distributed_experiments.jl:28."""
+    eng = engine_for(ctrl, device)
+    gaps, _st = eng.solve_gap_batch(np.stack([_dense(v, eng) for v in Vs]), _dense(nu, eng), tol=tol,
+                                    max_sweeps=max_sweeps, precision=precision)
+    return [Growable.from_dense(gaps[i], eng.walls) for i in range(len(Vs))]
+
+
+def run_experiment(gw, randomness=0.01, gamma=0.99, starting_temp=0.1, betarange=None, n=5, batched=True, **kw):
+    """run_experiment (scripts/experiments.jl:20-39) == run_experiment_distributed (scripts/distributed_experiments.jl
+    :15-33): nu, V_lo, 8 beta x n logz_updateV iterates and the optimality gap of every iterate.  batched=True sends
+    the beta chains and the gap solves to the GPU as two batched calls instead of one call per solve."""
     betarange = np.exp(np.linspace(-6, 0, 8)) if betarange is None else betarange
     ctrl = gwmod.gridworld_ctrl(gw, randomness=randomness, gamma=gamma)
     weaker = gwmod.modify(ctrl, reward_function=lambda s, a, ss: starting_temp * ctrl.reward_function(s, a, ss))
     nu = generate_nu(ctrl, **kw)
     furthest = min(nu.dict, key=nu.dict.get)
     V_lo = generate_nu(weaker, **kw)
-    traj = {float(b): learning_traj(ctrl, V_lo, beta=float(b), n=n, **kw) for b in betarange}
-    gap = {b: [generate_optimality_gap(ctrl, v, nu=nu, **kw) for v in vec] for b, vec in traj.items()}
+    if batched:
+        traj = learning_traj_batch(ctrl, V_lo, betarange, n=n, **kw)
+        flat = [v for b in traj for v in traj[b]]
+        gaps = generate_optimality_gap_batch(ctrl, flat, nu, **kw)
+        gap = {b: gaps[i * (n + 1):(i + 1) * (n + 1)] for i, b in enumerate(traj)}
+    else:
+        traj = {float(b): learning_traj(ctrl, V_lo, beta=float(b), n=n, **kw) for b in betarange}
+        gap = {b: [generate_optimality_gap(ctrl, v, nu=nu, **kw) for v in vec] for b, vec in traj.items()}
     return dict(nu=nu, traj=traj, gap=gap, randomness=randomness, gamma=gamma, ctrl=ctrl, s0=furthest)
+
+
+run_experiment_distributed = run_experiment
