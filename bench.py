@@ -157,6 +157,53 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_golden_experiment(device, with_cpu=True, name="r0_01g0_99"):
+    """run_experiment of the reference (scripts/experiments.jl:20-39) on its own 20x20 gridworld, Float64, host buffers in
+    and out: nu, V_lo, 8 beta x 5 logz_updateV, 48 optimality gaps; checked against the stored data/*.jld2 values."""
+    import piql_jl_b200 as piql
+    d = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    walls = np.asfortranarray(d["walls"])
+    goal = tuple(int(v) - 1 for v in d["goal"])
+    params = dict(randomness=float(d["randomness"]), step_cost=float(d["step_cost"]), reward=float(d["reward"]), gamma=float(d["gamma"]))
+    betas = [float(b) for b in d["betas"]]
+    states = d["states"] - 1
+    eng = piql.Engine(device)
+    eng.load_grid(walls, goal, **params)
+
+    def once():
+        nu, s1 = eng.solve_nu()
+        vlo, s2 = eng.solve_nu(reward_scale=0.1)
+        traj, st = eng.learning_traj(np.nan_to_num(vlo), betas, n=5)
+        gaps, gst = eng.solve_gap_batch(np.nan_to_num(traj.reshape(48, *walls.shape)), np.nan_to_num(nu))
+        return nu, traj, gaps, s1.sweeps + s2.sweeps + sum(x.sweeps for x in st) + sum(x.sweeps for x in gst)
+    once()
+    t0 = time.perf_counter()
+    nu, traj, gaps, sweeps = once()
+    sec = time.perf_counter() - t0
+    i, j = states[:, 0], states[:, 1]
+    err = max(float(np.abs(nu[i, j] - d["nu"]).max()),
+              float(np.abs(traj[7, 5][i, j] - d["traj"][7, 5]).max()), float(np.abs(gaps.reshape(8, 6, *walls.shape)[7, 1][i, j] - d["gap"][7, 1]).max()))
+    out = {"config": "golden gridworld %s (BASELINE configs 1-2), f64, tol 1e-12" % name, "solves": "2 nu + 40 logz_updateV + 48 optimality gap",
+           "seconds": sec, "sweeps": int(sweeps), "state_backups_per_s": sweeps * eng.nfree / sec,
+           "max_abs_err_vs_reference_data": err, "call": "piql_solve_nu x2 + piql_learning_traj + piql_solve_gap_batch"}
+    eng.close()
+    if with_cpu:
+        import oracle
+        org = oracle.Grid(walls, goal, **params)
+        V = np.nan_to_num(traj[7, 0])
+        t0 = time.perf_counter()
+        _x, a = org.solve("logz", V=V, beta=1.0, mode="faithful")
+        t1 = time.perf_counter()
+        _y, b = org.solve("gap", V=np.nan_to_num(traj[7, 1]), nu=np.nan_to_num(nu), mode="faithful")
+        t2 = time.perf_counter()
+        out["cpu_baseline"] = {"kind": "port", "cores": 1, "unit": "s",
+                               "sample": "1 of the 40 logz solves (beta=1, k=0) and 1 of the 48 gap solves (beta=1, k=1), oracle 'faithful' mode "
+                                         "(hash-map Growable, shuffled Gauss-Seidel, nested closure recomputation), one thread = one Julia worker",
+                               "logz_solve_seconds": t1 - t0, "logz_sweeps": int(a.sweeps), "gap_solve_seconds": t2 - t1, "gap_sweeps": int(b.sweeps),
+                               "state_backups_per_s": (a.sweeps + b.sweeps) * len(states) / (t2 - t0)}
+    return out
+
+
 def workload_config(name, args, world):
     w = WORKLOADS[name]
     return {"workload": "synthetic %dx%d gridworld (BASELINE config %s), density %.1f, randomness %.2f, gamma %.2f, beta %.0f, "
@@ -352,12 +399,17 @@ def run_ours(args, rank, world, local_rank):
             vi["cpu_baseline"] = {"sweeps_per_s": 3 / (time.perf_counter() - t0), "cores": threads, "kind": "port",
                                   "sample": "3 dense OpenMP Jacobi sweeps (f64)"}
 
+    # ---- the reference's own experiment (BASELINE configs 1-3: golden 20x20 grid) through the batched calls ------
+    experiment = None
+    if rank == 0 and world == 1 and not args.no_exp:
+        experiment = run_golden_experiment(local_rank, with_cpu=not args.no_cpu)
+
     if rank == 0:
         line = {"metric": "sampled transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(name, args, world), "clocks": clocks, "exchange": exchange, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "vi": vi,
+                "roofline": roofline, "cpu_baseline": cpu, "vi": vi, "experiment": experiment,
                 "transitions_per_step": transitions / args.steps}
         print(json.dumps(line), flush=True)
     eng.close()
@@ -379,6 +431,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-vi", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-exp", action="store_true", help="skip the golden-grid experiment (2 nu + 40 logz_updateV + 48 gap solves)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

@@ -148,4 +148,37 @@ function mc_logz(ctx::Context, V; β = 1.0, npaths = 2^20, seed = 0, estimator =
     (logz = growable(ctx, logz_s), logz_sa = logz_sa, count = count, transitions = st.transitions)
 end
 
+# ---- the experiment protocol in two ccalls (scripts/experiments.jl:20-39; replaces the pmap over beta and over
+# ---- iterates of scripts/distributed_experiments.jl:26,28) ---------------------------------------------------
+function learning_traj_batch(ctx::Context, V0, βrange; n = 5, kw...)
+    Vd = dense(ctx, V0); βs = collect(Float64, βrange); H, W = size(ctx.walls)
+    traj = Array{Float64}(undef, H, W, n + 1, length(βs))          # column-major: [cell, k, beta] as the ABI lays it out
+    st = Vector{SolveStats}(undef, n * length(βs))
+    GC.@preserve Vd βs traj st check(ctx, ccall((:piql_learning_traj, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Int32, Int32, Ref{SolveOpts}, Ptr{Cdouble}, Ptr{SolveStats}),
+        ctx.ptr, Vd, βs, length(βs), n, opts(; kw...), traj, st))
+    Dict(β => [growable(ctx, traj[:, :, k, b]; default = V0.default) for k in 1:n+1] for (b, β) in enumerate(βs))
+end
+function optimality_gap_batch(ctx::Context, Vs::Vector, ν; kw...)
+    H, W = size(ctx.walls); m = length(Vs)
+    Vd = Array{Float64}(undef, H, W, m)
+    for (i, V) in enumerate(Vs); Vd[:, :, i] = dense(ctx, V); end
+    nd = dense(ctx, ν); out = similar(Vd); st = Vector{SolveStats}(undef, m)
+    GC.@preserve Vd nd out st check(ctx, ccall((:piql_solve_gap_batch, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Int32, Ptr{Cdouble}, Ref{SolveOpts}, Ptr{Cdouble}, Ptr{SolveStats}),
+        ctx.ptr, Vd, m, nd, opts(; kw...), out, st))
+    [growable(ctx, out[:, :, i]) for i in 1:m]
+end
+
+# ---- multi-GPU exchange over NVLink peer memory: one worker process per GPU (replaces addprocs/pmap/@spawn,
+# ---- scripts/distributed_experiments.jl:3,26,28,43-46).  The handle blobs travel over Distributed.jl itself.
+struct PeerHandles; lse_max::NTuple{64,UInt8}; lse_sum::NTuple{64,UInt8}; count::NTuple{64,UInt8}; flags::NTuple{64,UInt8}; n::Int64; end
+function peer_export(ctx::Context)
+    h = Ref{PeerHandles}()
+    check(ctx, ccall((:piql_peer_export, LIB), Int32, (Ptr{Cvoid}, Ref{PeerHandles}), ctx.ptr, h)); h[]
+end
+peer_import(ctx::Context, rank, world, blobs::Vector{PeerHandles}) =
+    check(ctx, ccall((:piql_peer_import, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{PeerHandles}), ctx.ptr, rank, world, blobs))
+mc_allreduce_peer(ctx::Context) = check(ctx, ccall((:piql_mc_allreduce_peer, LIB), Int32, (Ptr{Cvoid},), ctx.ptr))
+
 end # module
