@@ -183,46 +183,49 @@ template <int KIND> __device__ __forceinline__ double sweep_diff(double stored, 
   return x > -1.0 ? fabs(log1p(x)) : CUDART_INF;
 }
 
-// One Jacobi sweep of the staged tile, src -> dst (columns 1 .. EJ-2; all 128 rows), every cell by the generic
-// formula; the goal and its neighbours are redone by tile_goal_fixup.
+// One column of one Jacobi sweep of the staged tile: lane l recomputes rows 4l .. 4l+3 of column jj from src into dst,
+// every cell by the generic formula (the goal and its neighbours are redone by tile_goal_fixup).
+template <typename T, int KIND, bool FAST>
+__device__ __forceinline__ void tile_strip(const TileK<T>& k, const T* __restrict__ src, T* __restrict__ dst,
+                                           const uint32_t* __restrict__ msk, const T* __restrict__ aux, int org, int lane, int jj) {
+  T v[4], L[4], R[4], out[4];
+  lds4(src + jj * TEI + 4 * lane, v);
+  lds4(src + (jj - 1) * TEI + 4 * lane, L);
+  lds4(src + (jj + 1) * TEI + 4 * lane, R);
+  const uint32_t mk = msk[jj * TMP + lane];
+  // rows 0 and 127 have no vertical neighbour in the tile: they are halo, any value will do
+  const T up = __shfl_up_sync(FULL, v[3], 1), dn = __shfl_down_sync(FULL, v[0], 1);
+  T ax[5][4];
+  if (KIND != KIND_NU) {
+    const int sidx = org + jj * k.ld + 4 * lane;
+#pragma unroll
+    for (int pl = 0; pl < 5; pl++) ldg4(aux + (size_t)pl * k.np + sidx, ax[pl]);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const uint32_t b = mk >> (8 * r);
+    const T c = v[r];
+    // f(take_step(s,a)): the neighbour, or the cell itself when a wall blocks the move  GridWorld.jl:29-32
+    const T n0 = (b & 1u) ? c : (r < 3 ? v[r < 3 ? r + 1 : 3] : dn);
+    const T n1 = (b & 2u) ? c : (r > 0 ? v[r > 0 ? r - 1 : 0] : up);
+    const T n2 = (b & 4u) ? c : R[r];
+    const T n3 = (b & 8u) ? c : L[r];
+    T o;
+    if (KIND == KIND_NU) o = nu_cell<T, FAST>(k, n0, n1, n2, n3);
+    else if (KIND == KIND_LOGZ) o = logz_cell<T, FAST>(k, c, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
+    else o = gap_cell<T>(k, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
+    out[r] = o;
+  }
+  sts4(dst + jj * TEI + 4 * lane, out);
+}
+
+// One Jacobi sweep of the staged tile, src -> dst (columns 1 .. EJ-2; all 128 rows); the caller puts a CTA barrier after it.
 template <typename T, int KIND, bool FAST>
 __device__ __forceinline__ void tile_subsweep(const TileK<T>& k, const T* __restrict__ src, T* __restrict__ dst,
                                               const uint32_t* __restrict__ msk, const T* __restrict__ aux, int org, int lane,
                                               int warp, int NW) {
-  const int EJ = k.EJ, ld = k.ld;
-  (void)ld;
 #pragma unroll 2
-  for (int jj = 1 + warp; jj < EJ - 1; jj += NW) {
-    T v[4], L[4], R[4], out[4];
-    lds4(src + jj * TEI + 4 * lane, v);
-    lds4(src + (jj - 1) * TEI + 4 * lane, L);
-    lds4(src + (jj + 1) * TEI + 4 * lane, R);
-    const uint32_t mk = msk[jj * TMP + lane];
-    // rows 0 and 127 have no vertical neighbour in the tile: they are halo, any value will do
-    const T up = __shfl_up_sync(FULL, v[3], 1), dn = __shfl_down_sync(FULL, v[0], 1);
-    T ax[5][4];
-    if (KIND != KIND_NU) {
-      const int sidx = org + jj * ld + 4 * lane;
-#pragma unroll
-      for (int pl = 0; pl < 5; pl++) ldg4(aux + (size_t)pl * k.np + sidx, ax[pl]);
-    }
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const uint32_t b = mk >> (8 * r);
-      const T c = v[r];
-      // f(take_step(s,a)): the neighbour, or the cell itself when a wall blocks the move  GridWorld.jl:29-32
-      const T n0 = (b & 1u) ? c : (r < 3 ? v[r < 3 ? r + 1 : 3] : dn);
-      const T n1 = (b & 2u) ? c : (r > 0 ? v[r > 0 ? r - 1 : 0] : up);
-      const T n2 = (b & 4u) ? c : R[r];
-      const T n3 = (b & 8u) ? c : L[r];
-      T o;
-      if (KIND == KIND_NU) o = nu_cell<T, FAST>(k, n0, n1, n2, n3);
-      else if (KIND == KIND_LOGZ) o = logz_cell<T, FAST>(k, c, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
-      else o = gap_cell<T>(k, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
-      out[r] = o;
-    }
-    sts4(dst + jj * TEI + 4 * lane, out);
-  }
+  for (int jj = 1 + warp; jj < k.EJ - 1; jj += NW) tile_strip<T, KIND, FAST>(k, src, dst, msk, aux, org, lane, jj);
 }
 
 // The goal (terminal value) and, for nu, its four neighbours (a step into the goal earns the reward, so the
@@ -319,7 +322,7 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
   for (int sub = 0; sub < nsub; sub++) {
     tile_subsweep<T, KIND, FAST>(k, src, dst, msk, aux, org, lane, warp, NW);
     __syncthreads();
-    if (near_goal) {  // block-uniform
+    if (near_goal) {  // block-uniform: the tile(s) around the goal redo those cells after every sweep
       tile_goal_fixup<T, KIND, FAST>(k, src, dst, msk, gi, gj);
       __syncthreads();
     }
