@@ -310,6 +310,7 @@ int mc_reset(piql_ctx* ctx, const piql_mc_opts* o) {
 RolloutArgs make_rollout_args(piql_ctx* ctx, const piql_mc_opts* o) {
   RolloutArgs a{};
   a.table = ctx->d_table;
+  a.table_bytes = 32LL * ctx->g.n;
   a.goal = ctx->g.goal; a.H = ctx->g.H;
   a.gamma = (float)ctx->g.gamma; a.rho = (float)ctx->g.randomness; a.vgoal = (float)ctx->v_goal;
   a.lgam = (float)std::log(ctx->g.gamma); a.l1mg = (float)std::log(1.0 - ctx->g.gamma);

@@ -90,6 +90,7 @@ void launch_residual_final(const double* partial, int nblocks, double* out, cuda
 // rollout.cu --------------------------------------------------------------------------------
 struct RolloutArgs {
   const float4* table;   // 2 x float4 per cell
+  long long table_bytes; // 32 * cells
   int goal;
   int H;
   float gamma, rho, vgoal, lgam, l1mg;

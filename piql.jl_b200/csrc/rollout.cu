@@ -11,6 +11,8 @@
 // sector per sampled transition; one 8-byte record per finished path {logw, a0|len<<2}.
 // One trajectory per thread; a warp owns a contiguous range of path ids and refills finished
 // lanes warp-synchronously (ballot + popc), so path -> lane assignment is deterministic.
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace piql {
@@ -83,9 +85,25 @@ __device__ __forceinline__ float logaddexpf_dev(float x, float y) {
 
 constexpr int ROLL_THREADS = 256;
 
-template <int EST, bool INJ, bool TRACE>
+// STAGED: the whole policy table (<= ROLL_STAGE_MAX_BYTES: the reference-scale problems) is copied into shared memory
+// by one bulk asynchronous copy per CTA and every step reads its record with two LDS.128 instead of a global load.
+constexpr size_t ROLL_STAGE_MAX_BYTES = 24 * 1024;  // x 8 resident CTAs per SM
+
+template <int EST, bool INJ, bool TRACE, bool STAGED>
 __global__ void __launch_bounds__(ROLL_THREADS)
 rollout_kernel(const RolloutArgs p) {
+  extern __shared__ __align__(128) unsigned char roll_smem[];
+  __shared__ __align__(8) unsigned long long stage_bar;
+  if (STAGED) {
+    if (threadIdx.x == 0) {
+      mbar_init(&stage_bar, 1);
+      mbar_expect_tx(&stage_bar, (unsigned)p.table_bytes);
+      bulk_load_1d(roll_smem, p.table, (unsigned)p.table_bytes, &stage_bar);
+    }
+    __syncthreads();
+    mbar_wait(&stage_bar, 0);
+  }
+  const float4* const stab = reinterpret_cast<const float4*>(roll_smem);
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
   const long long nwarps = (long long)gridDim.x * (ROLL_THREADS / 32);
@@ -158,9 +176,14 @@ rollout_kernel(const RolloutArgs p) {
         // the whole 32-byte record in one 256-bit load (LDG.E.256, sm_100): one L1 wavefront per
         // distinct line instead of two passes over the same sector
         float4 r0, r1;
-        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=f"(r0.x), "=f"(r0.y), "=f"(r0.z), "=f"(r0.w), "=f"(r1.x), "=f"(r1.y), "=f"(r1.z), "=f"(r1.w)
-                     : "l"(p.table + 2 * (size_t)s));
+        if (STAGED) {
+          r0 = stab[2 * s];
+          r1 = stab[2 * s + 1];
+        } else {
+          asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+              : "=f"(r0.x), "=f"(r0.y), "=f"(r0.z), "=f"(r0.w), "=f"(r1.x), "=f"(r1.y), "=f"(r1.z), "=f"(r1.w)
+              : "l"(p.table + 2 * (size_t)s));
+        }
         // StatsBase sample(a, Weights): i = 1; cw = w[1]; while cw < t && i < n: i += 1; cw += w[i]
         // c0 <= c1 <= c2, so the walk stops at the number of running sums below u0 (branch-free).
         const bool b0 = r0.x < u0, b1 = r0.y < u0, b2 = r0.z < u0;
@@ -208,8 +231,13 @@ void launch_rollout(const RolloutArgs& a, int num_sms, cudaStream_t st) {
   long long cap = (long long)num_sms * 8;
   const int grid = (int)(want < cap ? want : cap);
   const bool inj = a.injected != nullptr, tr = a.trace != nullptr;
-#define PIQL_ROLL(E, I, T) rollout_kernel<E, I, T><<<grid, ROLL_THREADS, 0, st>>>(a)
-  if (a.estimator == 0) {
+#define PIQL_ROLL(E, I, T) rollout_kernel<E, I, T, false><<<grid, ROLL_THREADS, 0, st>>>(a)
+  static const bool no_stage = getenv("PIQL_ROLL_NO_STAGE") != nullptr;  // A/B timing only
+  if (!no_stage && !inj && !tr && a.table_bytes > 0 && a.table_bytes <= (long long)ROLL_STAGE_MAX_BYTES) {
+    // reference-scale tables: staged in shared memory
+    if (a.estimator == 0) rollout_kernel<0, false, false, true><<<grid, ROLL_THREADS, (size_t)a.table_bytes, st>>>(a);
+    else rollout_kernel<1, false, false, true><<<grid, ROLL_THREADS, (size_t)a.table_bytes, st>>>(a);
+  } else if (a.estimator == 0) {
     if (inj) { if (tr) PIQL_ROLL(0, true, true); else PIQL_ROLL(0, true, false); }
     else { if (tr) PIQL_ROLL(0, false, true); else PIQL_ROLL(0, false, false); }
   } else {
