@@ -314,6 +314,10 @@ RolloutArgs make_rollout_args(piql_ctx* ctx, const piql_mc_opts* o) {
   a.goal = ctx->g.goal; a.H = ctx->g.H;
   a.gamma = (float)ctx->g.gamma; a.rho = (float)ctx->g.randomness; a.vgoal = (float)ctx->v_goal;
   a.lgam = (float)std::log(ctx->g.gamma); a.l1mg = (float)std::log(1.0 - ctx->g.gamma);
+  // integer forms of `u >= gamma` / `u < randomness` for u = k * 2^-24: a.gamma and a.rho are floats in [0,1], so their
+  // products with 2^24 are exact and k >= gamma*2^24 <=> k >= ceil(gamma*2^24), k < rho*2^24 <=> k < ceil(rho*2^24)
+  a.gamma_k = (uint32_t)std::ceil((double)a.gamma * 16777216.0);
+  a.rho_k = (uint32_t)std::ceil((double)a.rho * 16777216.0);
   a.estimator = o->estimator; a.horizon = o->horizon;
   a.starts = ctx->d_starts; a.nstarts = ctx->nstarts;
   a.keys = philox_expand((uint32_t)o->seed, (uint32_t)(o->seed >> 32));

@@ -94,6 +94,7 @@ struct RolloutArgs {
   int goal;
   int H;
   float gamma, rho, vgoal, lgam, l1mg;
+  uint32_t gamma_k, rho_k;  // ceil(gamma * 2^24), ceil(randomness * 2^24): thresholds on the 24-bit integers behind the uniforms
   int estimator;
   long long horizon;
   long long path0, npaths;

@@ -161,16 +161,23 @@ rollout_kernel(const RolloutArgs p) {
       } else if (t >= hor) {
         done = true;
       } else {
-        float u0, u1, u2;
+        float u0;
+        bool stop, slip;
         int aslip;
         if (INJ) {
           const float4 u = *reinterpret_cast<const float4*>(
               p.injected + (((size_t)wbase + q) * (size_t)p.injected_steps + t) * 4);
-          u0 = u.x; u1 = u.y; u2 = u.z;
+          u0 = u.x;
+          stop = u.y >= gam;
+          slip = u.z < rho;
           aslip = min((int)(4.0f * u.w), 3);
         } else {
+          // u = k * 2^-24 with the 24-bit integer k = word >> 8, so the float tests u >= gamma and u < randomness are
+          // exactly k >= ceil(gamma * 2^24) and k < ceil(randomness * 2^24)
           const uint4 r = philox4x32_10(p.keys, t, 0u, plo, phi);
-          u0 = u01(r.x); u1 = u01(r.y); u2 = u01(r.z);
+          u0 = u01(r.x);
+          stop = (r.y >> 8) >= p.gamma_k;
+          slip = (r.z >> 8) < p.rho_k;
           aslip = (int)(r.w >> 30);
         }
         // the whole 32-byte record in one 256-bit load (LDG.E.256, sm_100): one L1 wavefront per
@@ -196,10 +203,10 @@ rollout_kernel(const RolloutArgs p) {
         a0 = (t == 0u) ? (uint32_t)a : a0;
         if (EST == 1) acc = logaddexpf_dev(acc, __fadd_rn(__fadd_rn(__fmul_rn((float)t, p.lgam), p.l1mg), logw));
         // estimator A: continue w.p. gamma, else take the (1 - gamma) * 1 branch of z_recursion and stop
-        done = (EST == 0) && (u1 >= gam);
+        done = (EST == 0) && stop;
         if (!done) {
           // propagator: take_step(s, ifelse(rand() < randomness, sample(0:3), a))   GridWorld.jl:113-115
-          const int aa = (u2 < rho) ? aslip : a;
+          const int aa = slip ? aslip : a;
           const unsigned blocked = (__float_as_uint(r0.w) >> aa) & 1u;
           int d = (aa & 2) ? H : 1;
           d = (aa & 1) ? -d : d;
