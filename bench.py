@@ -311,12 +311,29 @@ def run_ours(args, rank, world, local_rank):
                 "transitions_per_s_kernel": tr_local / roll_s if roll_s > 0 else 0.0}
     exchange = None
     if world > 1:
+        # the exchange alone: ranks aligned by a barrier first, so no rank waits for a slower rollout
+        iso = []
+        with torch.cuda.stream(stream):
+            for _ in range(5):
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                pd.allreduce_engine_stats(eng, mode=args.exchange, rank=rank, world=world)
+                b.record(stream)
+                torch.cuda.synchronize()
+                iso.append(a.elapsed_time(b))
+        iso_t = torch.tensor([min(iso[1:])], dtype=torch.float64, device="cuda:%d" % local_rank)
+        dist.all_reduce(iso_t, op=dist.ReduceOp.MAX)
+        iso_ms = float(iso_t[0])
         nacc = 4 * eng.nfree
-        # each rank pulls (W-1)/W of 12 B x nacc from its peers and pushes as much: bytes crossing NVLink per direction
-        link_bytes = 12.0 * nacc * (world - 1) / world
+        # each rank pulls (W-1)/W of 12 B x nacc from its peers and pushes as much; one direction of its links carries the
+        # read responses of its pulls AND the peers' pushes (the other direction: its pushes and the peers' read responses)
+        link_bytes = 2 * 12.0 * nacc * (world - 1) / world
         exchange = {"mode": args.exchange, "ms_per_step": xch_ms, "accumulator_bytes": 12 * nacc,
                     "nvlink_bytes_per_direction": link_bytes,
-                    "achieved_gbs_per_direction": link_bytes / (xch_ms * 1e-3) / 1e9 if xch_ms > 0 else None,
+                    "isolated_ms": iso_ms, "achieved_gbs_per_direction": link_bytes / (iso_ms * 1e-3) / 1e9 if iso_ms > 0 else None,
+                    "note": "ms_per_step is measured inside the step and includes waiting for the slowest rank's rollout; "
+                            "isolated_ms is the exchange alone after a barrier (max over ranks of the best of 4)",
                     "peer_copy_reference_gbs": 770.0}
 
     # ---- end to end through the public call, host buffers in pinned memory --------------------
@@ -329,11 +346,11 @@ def run_ours(args, rank, world, local_rank):
         ls, _k4 = pinned((H, W), np.float64, order="F")
         reps = max(1, min(args.steps, 3))
         tot = 0.0
-        pd.mc_logz_sharded(eng, Vp, BETA, P, rank, world, seed=MC_SEED + 1, out=(sa, cn, ls), mode=args.exchange)   # warm-up
+        pd.mc_logz_sharded(eng, Vp, BETA, P, rank, world, seed=MC_SEED + 1, out=(sa, cn, ls), mode=args.exchange, root_only=True)   # warm-up
         barrier()
         t0 = time.perf_counter()
         for i in range(reps):
-            _sa, _cn, _ls, st = pd.mc_logz_sharded(eng, Vp, BETA, P, rank, world, seed=MC_SEED + 2 + i, out=(sa, cn, ls), mode=args.exchange)
+            _sa, _cn, _ls, st = pd.mc_logz_sharded(eng, Vp, BETA, P, rank, world, seed=MC_SEED + 2 + i, out=(sa, cn, ls), mode=args.exchange, root_only=True)
             tot += float(st.transitions)
         barrier()
         dt = time.perf_counter() - t0
@@ -345,7 +362,7 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": tot / dt, "unit": "transitions/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 72 * n,
                "steps": reps, "ms_per_step": 1e3 * dt / reps,
                "call": "piql_policy_table + piql_mc_reset_dev + piql_mc_rollout_dev (+ all-reduce) + piql_mc_finalize "
-                       "with pinned host V in, logz_sa / count_sa / logz_s out"}
+                       "with pinned host V in on every rank, logz_sa / count_sa / logz_s out on rank 0 (results are replicated)"}
 
     # ---- soft-VI sweeps on the same grid (rank 0) ----------------------------------------------
     # algorithmic bytes per state per sweep: nu 2 x sizeof(T), logz 3 x, gap 4 x

@@ -8,6 +8,9 @@
 // that slice of all three arrays from every peer with 128-bit loads over NVLink, combines the W triples exactly
 // (global max first, then one rescaled sum in rank order), and pushes the result into every rank's arrays --
 // reduce-scatter + all-gather in one pass, no temporary, no second kernel, identical bits on every rank.
+// Link traffic per rank and direction: (W-1)/W of the 12 B x n accumulators twice (read responses for the pulled
+// slices + the peers' pushes); measured on 2 x B200: 642 MB in 1.05 ms = 612 GB/s per direction (peer-copy
+// reference 770 GB/s); pull alone 0.60 ms, push alone 0.56 ms -- they share each direction, so they add up.
 //
 // Cross-GPU ordering uses two flag words per (rank, peer) in peer-visible memory, written with system-scope
 // fences: an entry barrier (everyone's local reduction has finished -- stream order on each device) and an exit
@@ -127,7 +130,7 @@ void launch_lse_allreduce_peer(const PeerState& ps, long long nslots, int num_sm
   a.done = ps.done; a.err = ps.err;
   const long long slice = nslots / ps.world + 1;
   long long want = (slice + 255) / 256;
-  const long long cap = 4LL * num_sms;
+  const long long cap = 4LL * num_sms;  // measured: 2x..16x SMs all give the same time; the links are the limit
   const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
   switch (ps.world) {
     case 1: lse_allreduce_peer_kernel<1><<<grid, 256, 0, st>>>(a); break;

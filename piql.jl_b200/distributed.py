@@ -85,9 +85,10 @@ def allreduce_engine_stats(eng, group=None, mode="peer", rank=None, world=None):
 
 
 def mc_logz_sharded(eng, V, beta, npaths, rank, world, seed=0, estimator="A", horizon=1 << 20, starts=None,
-                    group=None, want=("sa", "count", "s"), out=None, mode="peer"):
+                    group=None, want=("sa", "count", "s"), out=None, mode="peer", root_only=False):
     """End-to-end sharded estimate: every rank uploads V, builds the policy table, rolls out its block
-    of path ids, joins the all-reduce and downloads the (replicated) result."""
+    of path ids, joins the exchange and downloads the (replicated) result -- with root_only, rank 0 alone
+    downloads it (the reference's master collects the results of its workers; the others return stats only)."""
     import torch
     path0, n = shard_range(npaths, rank, world)
     eng.policy_table(V, beta=beta, download=False)
@@ -97,4 +98,6 @@ def mc_logz_sharded(eng, V, beta, npaths, rank, world, seed=0, estimator="A", ho
         with torch.cuda.stream(torch.cuda.ExternalStream(eng.stream, device="cuda:%d" % eng.device)):
             allreduce_engine_stats(eng, group=group, mode=mode, rank=rank, world=world)
             torch.cuda.current_stream().synchronize()
+    if root_only and rank != 0:
+        return eng.mc_finalize(want=())
     return eng.mc_finalize(want=want, out=out)
