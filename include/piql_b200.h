@@ -219,7 +219,7 @@ int32_t piql_vi_prepare_dev(piql_ctx* ctx, int32_t kind, const double* V, const 
                             double beta, double reward_scale, int32_t precision);
 /* Shape of the tiled soft-VI kernel for the loaded grid (grids above 8192 cells): plan_out[8] =
  * {interior columns per tile, warps per CTA, tile rows, tile columns, CTAs per SM, shared bytes per CTA,
- *  sweeps per launch, padded leading dimension}. */
+ *  sweeps per round, 1 if all tiles are resident at once (persistent kernel: one cooperative launch per batch)}. */
 int32_t piql_vi_tile_plan(piql_ctx* ctx, int32_t kind, int32_t precision, int32_t* plan_out);
 /* Replaces the current iterate (warm start / resume from a caller-kept array; wall cells ignored). */
 int32_t piql_vi_set_iterate(piql_ctx* ctx, const double* x);

@@ -236,6 +236,8 @@ int vi_solve(piql_ctx* ctx, const piql_solve_opts* opts, double* out, piql_solve
     }
     tile_unpack(ctx->g, vs, ctx->tb, st);
     CK_LAST();
+    CK(cudaStreamSynchronize(st));
+    NEED(!(ctx->tb.err && *ctx->tb.err), PIQL_ERR_CUDA, "the persistent sweep kernel timed out waiting for a neighbouring tile");
   }
   CK(cudaEventRecord(ctx->ev1, st));
   if (out) {
@@ -769,9 +771,14 @@ int32_t piql_vi_prepare_dev(piql_ctx* ctx, int32_t kind, const double* V, const 
 int32_t piql_vi_tile_plan(piql_ctx* ctx, int32_t kind, int32_t precision, int32_t* plan_out) {
   if (!ctx || !plan_out) return PIQL_ERR_ARG;
   NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded");
-  const TilePlan pl = make_tile_plan(ctx->g.H, ctx->g.W, precision == PIQL_F64 ? 0 : 1, kind, ctx->num_sms);
+  bool persistent = false;
+  TilePlan pl = choose_tile_plan(ctx->g.H, ctx->g.W, precision == PIQL_F64 ? 0 : 1, kind, ctx->num_sms, &persistent);
+  if (ctx->tb.active && ctx->vs.kind == kind && ctx->vs.precision == (precision == PIQL_F64 ? 0 : 1)) {
+    pl = ctx->tb.plan;  // the shape in use (timed on the device), not just the model's choice
+    persistent = ctx->tb.persistent;
+  }
   plan_out[0] = pl.TJ; plan_out[1] = pl.nw; plan_out[2] = pl.tiles_i; plan_out[3] = pl.tiles_j;
-  plan_out[4] = pl.ctas_per_sm; plan_out[5] = (int32_t)pl.smem; plan_out[6] = TILE_KH; plan_out[7] = pl.ld;
+  plan_out[4] = pl.ctas_per_sm; plan_out[5] = (int32_t)pl.smem; plan_out[6] = TILE_KH; plan_out[7] = persistent ? 1 : 0;
   return PIQL_OK;
 }
 int32_t piql_vi_set_iterate(piql_ctx* ctx, const double* x) {

@@ -52,8 +52,19 @@ struct TileBuffers {
   alignas(64) unsigned char tmx[2][128] = {};
   alignas(64) unsigned char tmm[128] = {};
   bool use_tma = false;
+  // persistent variant (all tiles resident at once): one cooperative launch per batch of sweeps
+  bool persistent = false;
+  unsigned* flags = nullptr;   // rounds completed per tile
+  long long cap_flags = 0;
+  int* err = nullptr;          // pinned host word: set when a neighbour wait timed out (copied from d_err after a launch)
+  int* d_err = nullptr;        // device word the kernel polls and sets
+  // shape found fastest on the device for the problem `tuned_key` (grid, precision, kind)
+  long long tuned_key = -1;
+  TilePlan tuned_plan{};
+  bool tuned_persistent = false;
 };
 TilePlan make_tile_plan(int H, int W, int precision, int kind, int num_sms);
+TilePlan choose_tile_plan(int H, int W, int precision, int kind, int num_sms, bool* persistent);
 cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs, TileBuffers& tb, int num_sms, cudaStream_t st);
 cudaError_t tile_sweeps(const GridDev& g, const ViState& vs, TileBuffers& tb, long long nsweeps, bool want_res, cudaStream_t st);
 void tile_unpack(const GridDev& g, const ViState& vs, const TileBuffers& tb, cudaStream_t st);

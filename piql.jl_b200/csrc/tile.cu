@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "algebra.cuh"
 #include "internal.h"
@@ -90,6 +91,11 @@ template <> __device__ __forceinline__ void ldg4<double>(const double* p, double
 }
 
 // ---- TMA (cp.async.bulk.tensor) staging of a tile: one thread issues, an mbarrier (common.cuh) counts the bytes ----
+__device__ __forceinline__ unsigned long long globaltimer_ns_tile() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
@@ -338,6 +344,131 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
   }
 }
 
+// ---- the persistent variant: all rounds of a batch of sweeps in ONE cooperative launch ---------------------------
+// For grids whose tiles are all resident at once (<= CTAs per SM x SMs: the 10^6-cell problems), a launch per
+// TILE_KH sweeps pays a grid-wide barrier, a tail and a pipeline refill every few microseconds.  Here every CTA keeps
+// its tile for the whole batch and synchronises with its (up to 8) neighbouring tiles only: round r waits until they
+// have published round r-1 (a counter per tile, release/acquire at gpu scope), re-stages the tile from the ping-pong
+// global arrays with TMA, sweeps, writes its interior back and publishes r.  Waiting for "neighbours finished r-1"
+// before round r also makes the write-back of round r safe: it overwrites the copy they staged in round r-1.
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <typename T, int KIND, bool FAST>
+__global__ void __launch_bounds__(512, sizeof(T) == 4 ? 2 : 1)
+tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmM, T* __restrict__ XA, T* __restrict__ XB, const T* __restrict__ aux,
+                    int nrounds, int nsub_last, int want_res, double* __restrict__ partial, unsigned* __restrict__ flags,
+                    int tiles_j, int* __restrict__ err) {
+  extern __shared__ __align__(128) unsigned char tile_smem[];
+  __shared__ double red[32];
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ int s_abort;
+  const int EJ = k.EJ, ld = k.ld;
+  T* bufA = reinterpret_cast<T*>(tile_smem);
+  T* bufB = bufA + EJ * TEI;
+  uint32_t* msk0 = reinterpret_cast<uint32_t*>(bufB + EJ * TEI);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+  const int ti = blockIdx.x % k.tiles_i, tj = blockIdx.x / k.tiles_i;
+  const int org = ti * TTI + ld * (tj * k.TJ);
+  const int moff = (ti * TTI) & 15;
+  const uint32_t* msk = msk0 + (moff >> 2);
+  const int gi = k.goal_pi - ti * TTI, gj = k.goal_pj - tj * k.TJ;
+  const bool near_goal = gi >= -1 && gi <= TEI && gj >= -1 && gj <= EJ;
+
+  if (threadIdx.x == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+  T* src = bufA;
+  T* dst = bufB;
+  for (int r = 0; r < nrounds; r++) {
+    const int nsub = r == nrounds - 1 ? nsub_last : TKH;
+    const T* Xin = (r & 1) ? XB : XA;
+    T* Xout = (r & 1) ? XA : XB;
+    // neighbours (8-connected: a 4-deep halo reaches into the diagonal tiles) have finished round r-1
+    if (r > 0 && threadIdx.x < 8) {
+      const int q = threadIdx.x < 4 ? threadIdx.x : threadIdx.x + 1;  // skip the centre of the 3 x 3 stencil
+      const int ni = ti + q % 3 - 1, nj = tj + q / 3 - 1;
+      if (ni >= 0 && ni < k.tiles_i && nj >= 0 && nj < tiles_j) {
+        const unsigned* f = flags + ni + k.tiles_i * nj;
+        const unsigned long long t0 = globaltimer_ns_tile();
+        while (ld_acquire_gpu(f) < (unsigned)r) {
+          if (globaltimer_ns_tile() - t0 > 5000000000ull || *(volatile int*)err) { *err = 1; break; }
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_abort = *(volatile int*)err;
+    __syncthreads();
+    if (s_abort) break;  // block-uniform: somebody timed out; the host reports it
+    if (threadIdx.x == 0) {
+      // order this CTA's earlier generic-proxy accesses of the buffers, and the neighbours' global writes just
+      // acquired, before the TMA engine (async proxy) overwrites / reads them
+      asm volatile("fence.proxy.async;" ::: "memory");
+      mbar_expect_tx(&mbar, (unsigned)(EJ * TEI * sizeof(T) + (r == 0 ? EJ * TMB : 0)));
+      tma_load_2d(bufA, (r & 1) ? &tmB : &tmA, ti * TTI, tj * k.TJ, &mbar);
+      if (r == 0) tma_load_2d(msk0, &tmM, ti * TTI - moff, tj * k.TJ, &mbar);  // the cell bytes stay for all rounds
+    }
+    mbar_wait(&mbar, r & 1);
+    if (warp < 2) {  // the outermost columns are never recomputed: keep both ping-pong copies defined
+      const int jj = warp == 0 ? 0 : EJ - 1;
+      T v[4];
+      lds4(bufA + jj * TEI + 4 * lane, v);
+      sts4(bufB + jj * TEI + 4 * lane, v);
+    }
+    __syncthreads();
+    src = bufA; dst = bufB;
+    for (int sub = 0; sub < nsub; sub++) {
+      tile_subsweep<T, KIND, FAST>(k, src, dst, msk, aux, org, lane, warp, NW);
+      __syncthreads();
+      if (near_goal) {
+        tile_goal_fixup<T, KIND, FAST>(k, src, dst, msk, gi, gj);
+        __syncthreads();
+      }
+      T* t = src; src = dst; dst = t;
+    }
+    (void)Xin;
+    if (lane >= TKH / 4 && lane < 32 - TKH / 4) {
+      for (int jj = TKH + warp; jj < TKH + k.TJ; jj += NW) {
+        T f[4];
+        lds4(src + jj * TEI + 4 * lane, f);
+        const int g = org + jj * ld + 4 * lane;
+        if (sizeof(T) == 4) {
+          *reinterpret_cast<float4*>(Xout + g) = make_float4((float)f[0], (float)f[1], (float)f[2], (float)f[3]);
+        } else {
+          *reinterpret_cast<double2*>(Xout + g) = make_double2((double)f[0], (double)f[1]);
+          *reinterpret_cast<double2*>(Xout + g + 2) = make_double2((double)f[2], (double)f[3]);
+        }
+      }
+    }
+    __threadfence();
+    __syncthreads();  // every thread's stores are fenced; also: all reads of src/dst done before the next TMA overwrite
+    if (threadIdx.x == 0) st_release_gpu(flags + blockIdx.x, (unsigned)(r + 1));
+  }
+  // residual of the last sweep (src: last iterate, dst: the one before)
+  if (want_res) {
+    double res = 0.0;
+    if (lane >= TKH / 4 && lane < 32 - TKH / 4) {
+      for (int jj = TKH + warp; jj < TKH + k.TJ; jj += NW) {
+        T f[4], p[4];
+        lds4(src + jj * TEI + 4 * lane, f);
+        lds4(dst + jj * TEI + 4 * lane, p);
+        const uint32_t mk = msk[jj * TMP + lane];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (!((mk >> (8 * q)) & CELL_WALL)) res += sweep_diff<KIND>((double)f[q], (double)p[q]);
+      }
+    }
+    const double s = block_sum(res, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  }
+}
+
 // ---- packing between the dense H x W arrays of the ABI side and the padded tile layout -------------------
 struct PadGeom {
   int H, W, ld, Wp;
@@ -394,19 +525,26 @@ static size_t tile_smem_bytes(int EJ, int precision) {
   return (size_t)EJ * (2 * TEI * (precision == 0 ? 8 : 4) + TMB);
 }
 
-// Tile shape (TJ interior columns, nw warps per CTA) by a small cost model, in SM cycles per launch:
-// a wave of c CTAs per SM runs its TILE_KH sub-sweeps at the slower of the SM's issue rate (c * cols warp-strips
-// of ~140 instructions) and one warp's dependent-issue latency per strip times its strips per sub-sweep; staging and write-back add a fixed latency per wave.  Small grids want exactly one
-// full wave, large ones wide tiles (less halo).  PIQL_TILE_TJ / PIQL_TILE_NW override (tuning, tests).
-TilePlan make_tile_plan(int H, int W, int precision, int kind, int num_sms) {
-  TilePlan best{};
-  double best_cost = 1e300;
+// Candidate tile shapes (TJ interior columns, nw warps per CTA), cheapest first by a small cost model in SM cycles per
+// round of TILE_KH sweeps.  Measured on B200 (fp32 nu): an SM retires one 128-cell warp-strip (~140 instructions) per
+// ~61 cycles when ~32 warps are resident, and a warp needs ~1700 cycles per strip however few warps share the SM.
+//   multi-launch: waves of c CTAs per SM, each the slower of c*cols*61 and rounds*1700, plus a fixed cost per wave
+//                 (launch, staging, tail);
+//   persistent:   every tile resident at once (tiles <= SMs x CTAs per SM); everybody advances at the pace of the
+//                 busiest SM, c*rounds*nw*61 with at least 24 resident warps.
+// The model only ranks; tile_begin times the leading candidates on the device and keeps the fastest.
+// PIQL_TILE_TJ / PIQL_TILE_NW pin the shape (tests, tuning sweeps).
+struct PlanCand {
+  double cost;
+  TilePlan plan;
+};
+static std::vector<PlanCand> enumerate_plans(int H, int W, int precision, int kind, int num_sms, bool persistent) {
+  (void)kind;
+  std::vector<PlanCand> out;
   const int tiles_i = (H + TTI - 1) / TTI;
   const char* env_tj = getenv("PIQL_TILE_TJ");
   const char* env_nw = getenv("PIQL_TILE_NW");
   const int regs = precision == 0 ? 128 : 64;  // per thread: the __launch_bounds__ of the instantiations
-  // measured on B200 (fp32 nu): an SM retires one 128-cell warp-strip per ~61 cycles when >= 30 warps are resident;
-  // a lone warp needs ~1800 cycles per strip
   const double strip_issue = 61.0, strip_latency = 1700.0, wave_fixed = 8000.0;
   for (int nw = 4; nw <= 16; nw++) {
     if (env_nw && atoi(env_nw) != nw) continue;
@@ -420,27 +558,47 @@ TilePlan make_tile_plan(int H, int W, int precision, int kind, int num_sms) {
       ctas = std::min(ctas, 16);
       if (ctas < 1) continue;
       const int tiles_j = (W + TJ - 1) / TJ;
-      long long left = (long long)tiles_i * tiles_j;
+      const long long tiles = (long long)tiles_i * tiles_j;
       const int rounds = (cols + nw - 1) / nw;
-      double cost = 0.0;
       const long long slots = (long long)num_sms * ctas;
-      while (left > 0) {
-        const long long now = std::min(left, slots);
-        const int c = (int)((now + num_sms - 1) / num_sms);
-        cost += wave_fixed + TKH * std::max(c * cols * strip_issue, rounds * strip_latency);
-        left -= now;
+      double cost = 0.0;
+      if (persistent) {
+        if (tiles > slots) continue;
+        const int c = (int)((tiles + num_sms - 1) / num_sms);
+        if (c * nw < 24 && !(env_tj || env_nw)) continue;
+        cost = TKH * (double)c * rounds * nw * strip_issue + 3000.0;
+      } else {
+        long long left = tiles;
+        while (left > 0) {
+          const long long now = std::min(left, slots);
+          const int c = (int)((now + num_sms - 1) / num_sms);
+          cost += wave_fixed + TKH * std::max(c * cols * strip_issue, rounds * strip_latency);
+          left -= now;
+        }
       }
-      if (cost < best_cost) {
-        best_cost = cost;
-        best.TJ = TJ; best.EJ = EJ; best.tiles_i = tiles_i; best.tiles_j = tiles_j; best.nw = nw;
-        best.smem = smem; best.ctas_per_sm = ctas;
-      }
+      TilePlan p{};
+      p.TJ = TJ; p.EJ = EJ; p.tiles_i = tiles_i; p.tiles_j = tiles_j; p.nw = nw; p.smem = smem; p.ctas_per_sm = ctas;
+      p.ld = ((tiles_i * TTI + 2 * TKH + 31) / 32) * 32;
+      p.Wp = tiles_j * TJ + 2 * TKH;
+      p.np = (long long)p.ld * p.Wp;
+      out.push_back({cost, p});
     }
   }
-  best.ld = ((best.tiles_i * TTI + 2 * TKH + 31) / 32) * 32;
-  best.Wp = best.tiles_j * best.TJ + 2 * TKH;
-  best.np = (long long)best.ld * best.Wp;
-  return best;
+  std::stable_sort(out.begin(), out.end(), [](const PlanCand& a, const PlanCand& b) {
+    return a.cost < b.cost || (a.cost == b.cost && a.plan.TJ > b.plan.TJ);
+  });
+  return out;
+}
+TilePlan make_tile_plan(int H, int W, int precision, int kind, int num_sms) {
+  const std::vector<PlanCand> c = enumerate_plans(H, W, precision, kind, num_sms, false);
+  return c.empty() ? TilePlan{} : c[0].plan;
+}
+// The model's choice: the persistent shape when every tile can be resident at once, else the multi-launch one.
+TilePlan choose_tile_plan(int H, int W, int precision, int kind, int num_sms, bool* persistent) {
+  const bool allow = getenv("PIQL_TILE_NO_PERSIST") == nullptr && getenv("PIQL_TILE_NO_TMA") == nullptr;
+  const std::vector<PlanCand> pp = allow ? enumerate_plans(H, W, precision, kind, num_sms, true) : std::vector<PlanCand>();
+  if (persistent) *persistent = !pp.empty();
+  return pp.empty() ? make_tile_plan(H, W, precision, kind, num_sms) : pp[0].plan;
 }
 
 template <typename T> static TileK<T> make_tile_k(const GridDev& g, const ViState& vs, const TilePlan& pl) {
@@ -493,8 +651,13 @@ static bool encode_tile_map(void* out, void* base, CUtensorMapDataType dt, size_
 }
 
 void tile_free(TileBuffers& tb) {
-  for (void* p : {tb.x[0], tb.x[1], tb.aux, (void*)tb.mask, (void*)tb.partial}) if (p) cudaFree(p);
+  for (void* p : {tb.x[0], tb.x[1], tb.aux, (void*)tb.mask, (void*)tb.partial, (void*)tb.flags, (void*)tb.d_err}) if (p) cudaFree(p);
+  if (tb.err) cudaFreeHost(tb.err);
+  const long long key = tb.tuned_key;
+  const TilePlan plan = tb.tuned_plan;
+  const bool pers = tb.tuned_persistent;
   tb = TileBuffers{};
+  tb.tuned_key = key; tb.tuned_plan = plan; tb.tuned_persistent = pers;
 }
 
 template <typename T>
@@ -514,23 +677,31 @@ static void pack_t(const GridDev& g, const uint8_t* cell, const ViState& vs, Til
   }
 }
 
-cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs, TileBuffers& tb, int num_sms, cudaStream_t st) {
-  const TilePlan pl = make_tile_plan(g.H, g.W, vs.precision, vs.kind, num_sms);
+// (Re)allocates for the plan, encodes the TMA descriptors and packs vs.x[vs.cur] (+ constants, masks) into the padded layout.
+static cudaError_t tile_setup(const GridDev& g, const uint8_t* cell, const ViState& vs, TileBuffers& tb, const TilePlan& pl,
+                              bool persist, cudaStream_t st) {
   const size_t e = vs.precision == 0 ? 8 : 4;
   const size_t need_x = e * (size_t)pl.np, need_aux = vs.kind == KIND_NU ? 0 : 5 * need_x;
   const long long ntiles = (long long)pl.tiles_i * pl.tiles_j;
-  if (need_x > tb.cap_x || need_aux > tb.cap_aux || (size_t)pl.np > tb.cap_mask || ntiles > tb.cap_partial) {
+  if (need_x > tb.cap_x || need_aux > tb.cap_aux || (size_t)pl.np > tb.cap_mask || ntiles > tb.cap_partial ||
+      ntiles > tb.cap_flags) {
     cudaError_t err = cudaStreamSynchronize(st);
     if (err != cudaSuccess) return err;
     tile_free(tb);
-    // sized for double and all five planes so that later solves of any kind / precision reuse them
-    const size_t bx = 8 * (size_t)pl.np;
+    // sized for double and all five planes so that later solves of any kind / precision reuse them (+ slack for re-tiling)
+    const size_t bx = 8 * (size_t)pl.np + 8 * (size_t)pl.np / 8;
+    const long long nt = ntiles * 2 + 64;
     if ((err = cudaMalloc(&tb.x[0], bx)) != cudaSuccess) return err;
     if ((err = cudaMalloc(&tb.x[1], bx)) != cudaSuccess) return err;
     if ((err = cudaMalloc(&tb.aux, 5 * bx)) != cudaSuccess) return err;
-    if ((err = cudaMalloc((void**)&tb.mask, (size_t)pl.np)) != cudaSuccess) return err;
-    if ((err = cudaMalloc((void**)&tb.partial, sizeof(double) * (size_t)ntiles)) != cudaSuccess) return err;
-    tb.cap_x = bx; tb.cap_aux = 5 * bx; tb.cap_mask = (size_t)pl.np; tb.cap_partial = ntiles;
+    if ((err = cudaMalloc((void**)&tb.mask, bx / 8)) != cudaSuccess) return err;
+    if ((err = cudaMalloc((void**)&tb.partial, sizeof(double) * (size_t)nt)) != cudaSuccess) return err;
+    if ((err = cudaMalloc((void**)&tb.flags, sizeof(unsigned) * (size_t)nt)) != cudaSuccess) return err;
+    if ((err = cudaMallocHost((void**)&tb.err, sizeof(int))) != cudaSuccess) return err;
+    if ((err = cudaMalloc((void**)&tb.d_err, sizeof(int))) != cudaSuccess) return err;
+    if ((err = cudaMemset(tb.d_err, 0, sizeof(int))) != cudaSuccess) return err;
+    *tb.err = 0;
+    tb.cap_x = bx; tb.cap_aux = 5 * bx; tb.cap_mask = bx / 8; tb.cap_partial = nt; tb.cap_flags = nt;
   }
   tb.plan = pl;
   tb.cur = 0;
@@ -539,10 +710,54 @@ cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs,
   tb.use_tma = getenv("PIQL_TILE_NO_TMA") == nullptr && encode_tile_map(tb.tmx[0], tb.x[0], dt, e, pl) &&
                encode_tile_map(tb.tmx[1], tb.x[1], dt, e, pl) &&
                encode_tile_map(tb.tmm, tb.mask, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, pl, TMB);
+  tb.persistent = persist && tb.use_tma;
   if (vs.precision == 0) pack_t<double>(g, cell, vs, tb, st);
   else pack_t<float>(g, cell, vs, tb, st);
   tb.active = true;
   return cudaGetLastError();
+}
+
+cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs, TileBuffers& tb, int num_sms, cudaStream_t st) {
+  const long long key = (((long long)g.H * 65537 + g.W) * 4 + vs.precision * 2 + (vs.fast ? 1 : 0)) * 4 + vs.kind;
+  const bool pinned = getenv("PIQL_TILE_TJ") || getenv("PIQL_TILE_NW") || getenv("PIQL_TILE_NO_TUNE");
+  if (!pinned && tb.tuned_key == key) return tile_setup(g, cell, vs, tb, tb.tuned_plan, tb.tuned_persistent, st);
+  bool persist = false;
+  const TilePlan model = choose_tile_plan(g.H, g.W, vs.precision, vs.kind, num_sms, &persist);
+  if (pinned) return tile_setup(g, cell, vs, tb, model, persist, st);
+  // time the leading candidates of both kinds on the device (a few launches each) and keep the fastest for this problem
+  struct Try { TilePlan plan; bool persist; };
+  std::vector<Try> tries;
+  const bool allow_p = getenv("PIQL_TILE_NO_PERSIST") == nullptr && getenv("PIQL_TILE_NO_TMA") == nullptr;
+  if (allow_p) {
+    const std::vector<PlanCand> pp = enumerate_plans(g.H, g.W, vs.precision, vs.kind, num_sms, true);
+    for (size_t i = 0; i < pp.size() && i < 5; i++) tries.push_back({pp[i].plan, true});
+  }
+  const std::vector<PlanCand> mm = enumerate_plans(g.H, g.W, vs.precision, vs.kind, num_sms, false);
+  for (size_t i = 0; i < mm.size() && i < 5; i++) tries.push_back({mm[i].plan, false});
+  cudaEvent_t e0, e1;
+  cudaError_t err = cudaEventCreate(&e0);
+  if (err != cudaSuccess) return err;
+  if ((err = cudaEventCreate(&e1)) != cudaSuccess) { cudaEventDestroy(e0); return err; }
+  double best = 1e300;
+  Try chosen{model, persist};
+  const long long probe = 8 * TKH;
+  for (const Try& t : tries) {
+    if ((err = tile_setup(g, cell, vs, tb, t.plan, t.persist, st)) != cudaSuccess) break;
+    if ((err = tile_sweeps(g, vs, tb, 2 * TKH, false, st)) != cudaSuccess) break;
+    cudaEventRecord(e0, st);
+    if ((err = tile_sweeps(g, vs, tb, probe, false, st)) != cudaSuccess) break;
+    cudaEventRecord(e1, st);
+    if ((err = cudaStreamSynchronize(st)) != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (tb.err && *tb.err) { err = cudaErrorLaunchTimeout; break; }
+    if (ms < best) { best = ms; chosen = t; chosen.persist = tb.persistent; }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (err != cudaSuccess) return err;
+  tb.tuned_key = key; tb.tuned_plan = chosen.plan; tb.tuned_persistent = chosen.persist;
+  return tile_setup(g, cell, vs, tb, chosen.plan, chosen.persist, st);  // re-pack: the probes advanced the iterate
 }
 
 template <typename T, int KIND, bool FAST>
@@ -575,6 +790,53 @@ static cudaError_t launch_tile_t(const GridDev& g, const ViState& vs, TileBuffer
   return cudaSuccess;
 }
 
+// All rounds of nsweeps sweeps in one cooperative launch (tb.persistent).  cudaErrorCooperativeLaunchTooLarge means the
+// occupancy estimate of the plan was optimistic for this instantiation: the caller falls back to one launch per round.
+template <typename T, int KIND, bool FAST>
+static cudaError_t launch_persist_t(const GridDev& g, const ViState& vs, TileBuffers& tb, long long nsweeps, bool want_res,
+                                    cudaStream_t st) {
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(tile_persist_kernel<T, KIND, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  const TileK<T> k = make_tile_k<T>(g, vs, tb.plan);
+  const unsigned grid = (unsigned)(tb.plan.tiles_i * tb.plan.tiles_j);
+  const int nrounds = (int)((nsweeps + TKH - 1) / TKH), nsub_last = (int)(nsweeps - (long long)(nrounds - 1) * TKH);
+  cudaError_t e = cudaMemsetAsync(tb.flags, 0, sizeof(unsigned) * grid, st);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * tb.plan.nw); cfg.dynamicSmemBytes = tb.plan.smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CUtensorMap tmA, tmB, tmM;
+  memcpy(&tmA, tb.tmx[tb.cur], sizeof(tmA));
+  memcpy(&tmB, tb.tmx[tb.cur ^ 1], sizeof(tmB));
+  memcpy(&tmM, tb.tmm, sizeof(tmM));
+  e = cudaLaunchKernelEx(&cfg, tile_persist_kernel<T, KIND, FAST>, k, tmA, tmB, tmM, (T*)tb.x[tb.cur], (T*)tb.x[tb.cur ^ 1],
+                         (const T*)tb.aux, nrounds, nsub_last, want_res ? 1 : 0, tb.partial, tb.flags, tb.plan.tiles_j, tb.d_err);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(tb.err, tb.d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return e;
+  g_launches++;
+  tb.cur = (tb.cur + nrounds) & 1;
+  return cudaSuccess;
+}
+template <typename T, bool FAST>
+static cudaError_t launch_persist_k(const GridDev& g, const ViState& vs, TileBuffers& tb, long long nsweeps, bool want_res,
+                                    cudaStream_t st) {
+  switch (vs.kind) {
+    case KIND_NU: return launch_persist_t<T, KIND_NU, FAST>(g, vs, tb, nsweeps, want_res, st);
+    case KIND_LOGZ: return launch_persist_t<T, KIND_LOGZ, FAST>(g, vs, tb, nsweeps, want_res, st);
+    default: return launch_persist_t<T, KIND_GAP, FAST>(g, vs, tb, nsweeps, want_res, st);
+  }
+}
+
 template <typename T, bool FAST>
 static cudaError_t launch_tile_k(const GridDev& g, const ViState& vs, TileBuffers& tb, int nsub, bool want_res, cudaStream_t st) {
   switch (vs.kind) {
@@ -586,6 +848,20 @@ static cudaError_t launch_tile_k(const GridDev& g, const ViState& vs, TileBuffer
 
 // nsweeps Jacobi sweeps in ceil(nsweeps / TILE_KH) launches; the residual of the last sweep lands in vs.residual.
 cudaError_t tile_sweeps(const GridDev& g, const ViState& vs, TileBuffers& tb, long long nsweeps, bool want_res, cudaStream_t st) {
+  if (tb.persistent && nsweeps > TKH) {
+    if (tb.err && *tb.err) return cudaErrorLaunchTimeout;  // an earlier persistent launch gave up waiting for a neighbour
+    cudaError_t e;
+    if (vs.precision == 0) e = launch_persist_k<double, false>(g, vs, tb, nsweeps, want_res, st);
+    else if (vs.fast) e = launch_persist_k<float, true>(g, vs, tb, nsweeps, want_res, st);
+    else e = launch_persist_k<float, false>(g, vs, tb, nsweeps, want_res, st);
+    if (e == cudaSuccess) {
+      if (want_res) launch_residual_final(tb.partial, tb.plan.tiles_i * tb.plan.tiles_j, vs.residual, st);
+      return cudaGetLastError();
+    }
+    if (e != cudaErrorCooperativeLaunchTooLarge) return e;
+    cudaGetLastError();
+    tb.persistent = false;  // not all tiles fit at once after all: one launch per round from here on
+  }
   while (nsweeps > 0) {
     const int nsub = (int)std::min<long long>(nsweeps, TKH);
     nsweeps -= nsub;

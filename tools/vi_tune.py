@@ -47,11 +47,11 @@ def main():
             except Exception as e:  # shape not feasible
                 continue
             p = eng.vi_tile_plan(kind, prec)
-            res.append((us, nw, tj, p["tiles_i"] * p["tiles_j"], p["ctas_per_sm"]))
+            res.append((us, nw, tj, p["tiles_i"] * p["tiles_j"], p["ctas_per_sm"], p["persistent"]))
     os.environ.pop("PIQL_TILE_TJ"); os.environ.pop("PIQL_TILE_NW")
     res.sort()
-    for us, nw, tj, tiles, c in res[:25]:
-        print("%s %s %s nw=%d TJ=%d tiles=%d ctas/SM=%d  %.2f us/sweep" % (name, prec, kind, nw, tj, tiles, c, us))
+    for us, nw, tj, tiles, c, pers in res[:25]:
+        print("%s %s %s nw=%d TJ=%d tiles=%d ctas/SM=%d persistent=%d  %.2f us/sweep" % (name, prec, kind, nw, tj, tiles, c, pers, us))
     print("worst %.2f" % res[-1][0])
     print("default plan", eng.vi_tile_plan(kind, prec), "%.2f us/sweep" % run())
 
