@@ -169,6 +169,12 @@ int32_t piql_mc_logz(piql_ctx* ctx, const double* V, const double* Q, double bet
                      double* logz_sa_out, uint64_t* count_sa_out, double* logz_s_out,
                      piql_mc_stats* stats_out);
 
+/* The Monte-Carlo form of logz_updateV (src/value_iteration.jl:119-124), niter times, device-resident: each iteration
+ * rebuilds the policy table from the current V, rolls out opts->npaths paths (seed opts->seed + iteration), reduces them and
+ * applies V(s) += log Z^(s) / beta at every start cell that received paths.  vnew_out: H*W doubles, NaN at walls. */
+int32_t piql_mc_update_v(piql_ctx* ctx, const double* V, double beta, const piql_mc_opts* opts, int32_t niter,
+                         double* vnew_out, piql_mc_stats* stats_out);
+
 /* Debug export for bit-exact trajectory parity: the (s, a, s') triples of each path (int32 cell
  * indices, -1 padded, [npaths][max_steps][3]) and the per-path record: logw (float) and
  * meta = a0 | (len << 2).  Uses the current policy table. */

@@ -19,5 +19,5 @@ from .gridworld import (ControlProblem, Gridworld, gridworld_ctrl, make_gridworl
                         state_iterator, tabulate, take_step)
 from .solvers import (Growable, McResult, Qnormalization, action_probability, average_reward, choose_action,
                       controlQ, controlV, engine_for, fitness, fitness_reward_estimate, generate_logz, generate_nu,
-                      generate_optimality_gap, generate_optimality_gap_batch, generate_ν, kl_cost, learning_traj, learning_traj_batch, logz_updateV, mc_logz,
+                      generate_optimality_gap, generate_optimality_gap_batch, generate_ν, kl_cost, learning_traj, learning_traj_batch, logz_updateV, mc_logz, mc_logz_updateV,
                       path_transitions, run_experiment, run_experiment_distributed)

@@ -77,6 +77,7 @@ SYMBOLS = {
     "piql_mc_stats_dev": (C.c_int32, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
     "piql_mc_rescale_dev": (C.c_int32, [_P, _P]),
     "piql_mc_finalize": (C.c_int32, [_P, _D, C.POINTER(C.c_uint64), _D, C.POINTER(McStats)]),
+    "piql_mc_update_v": (C.c_int32, [_P, _D, C.c_double, C.POINTER(McOpts), C.c_int32, _D, C.POINTER(McStats)]),
     "piql_peer_export": (C.c_int32, [_P, C.POINTER(PeerHandles)]),
     "piql_peer_import": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(PeerHandles)]),
     "piql_mc_allreduce_peer": (C.c_int32, [_P]),

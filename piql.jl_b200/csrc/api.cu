@@ -871,6 +871,61 @@ int32_t piql_mc_logz(piql_ctx* ctx, const double* V, const double* Q, double bet
   return mc_finalize(ctx, logz_sa_out, count_sa_out, logz_s_out, stats);
 }
 
+int32_t piql_mc_update_v(piql_ctx* ctx, const double* V, double beta, const piql_mc_opts* opts, int32_t niter,
+                         double* vnew_out, piql_mc_stats* stats) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded (call piql_grid_load first)");
+  NEED(V != nullptr && vnew_out != nullptr, PIQL_ERR_ARG, "V / vnew_out is null");
+  NEED(beta == beta && beta != 0.0, PIQL_ERR_ARG, "beta must be non-zero and not NaN");
+  NEED(niter > 0, PIQL_ERR_ARG, "niter must be positive");
+  int rc = mc_check_opts(ctx, opts);
+  if (rc) return rc;
+  NEED(opts->injected == nullptr, PIQL_ERR_ARG, "injected uniforms are for single rollouts, not for the update loop");
+  rc = ensure_vi(ctx);
+  if (rc) return rc;
+  const int n = ctx->g.n;
+  cudaStream_t st = ctx->stream;
+  NEED(V[ctx->g.goal] == V[ctx->g.goal], PIQL_ERR_ARG, "V(goal) is NaN");
+  CK(cudaMemcpyAsync(ctx->d_in0, V, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+  launch_convert_in(ctx->d_in0, ctx->d_in1, n, PIQL_F64, st);  // NaN at walls -> 0; V lives in d_in1 from here on
+  CK_LAST();
+  ctx->tev_used = 0;
+  unsigned long long transitions = 0, paths = 0;
+  piql_mc_opts o = *opts;
+  for (int it = 0; it < niter; it++) {
+    // the value at the goal enters the kernel as a scalar: fetch it (8 bytes; also the loop's only host sync)
+    CK(cudaMemcpyAsync(ctx->h_scalars + 4, ctx->d_in1 + ctx->g.goal, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->v_goal = ctx->h_scalars[4];
+    launch_policy_table(ctx->g, ctx->d_cell, ctx->d_in1, nullptr, beta, 1.0, ctx->d_table, st);
+    ctx->has_table = true;
+    rc = mc_reset(ctx, &o);
+    if (rc) return rc;
+    rc = mc_rollout(ctx, &o, nullptr, 0);
+    if (rc) return rc;
+    launch_mc_apply_update(ctx->acc_max, ctx->acc_sum, ctx->acc_cnt, ctx->d_starts, ctx->nstarts, beta, ctx->d_in1, st);
+    CK_LAST();
+    CK(cudaMemcpyAsync(ctx->h_transitions, ctx->d_transitions, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    transitions += *ctx->h_transitions;
+    paths += (unsigned long long)o.npaths;
+    o.seed += 1;                    // fresh, reproducible stream per iteration
+  }
+  launch_convert_out(ctx->d_in1, ctx->d_cell, ctx->d_out, n, PIQL_F64, st);
+  CK_LAST();
+  CK(cudaMemcpyAsync(vnew_out, ctx->d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (stats) {
+    double ro = 0.0, re = 0.0;
+    rc = mc_timing(ctx, &ro, &re, nullptr, false);
+    if (rc) return rc;
+    stats->transitions = transitions; stats->paths = paths; stats->rollout_seconds = ro; stats->device_seconds = ro + re;
+  }
+  return PIQL_OK;
+}
+
 int32_t piql_trace_paths(piql_ctx* ctx, const piql_mc_opts* opts, int64_t max_steps, int32_t* triples_out,
                          float* logw_out, uint32_t* meta_out) {
   if (!ctx) return PIQL_ERR_ARG;

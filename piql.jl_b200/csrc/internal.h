@@ -136,6 +136,8 @@ void launch_mc_finalize(const float* acc_max, const float* acc_sum, const uint32
                         long long nstarts, double* logz_sa, unsigned long long* count_sa, double* logz_s,
                         cudaStream_t st);
 void launch_fill_f64(double* dst, double v, long long n, cudaStream_t st);
+void launch_mc_apply_update(const float* acc_max, const float* acc_sum, const uint32_t* acc_cnt, const int* starts,
+                            long long nstarts, double beta, double* V, cudaStream_t st);
 int configure_rollout_kernels();
 
 // peer.cu: the log-sum-exp all-reduce of the accumulators over NVLink peer memory -----------------

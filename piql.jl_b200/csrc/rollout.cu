@@ -481,6 +481,34 @@ void launch_mc_finalize(const float* acc_max, const float* acc_sum, const uint32
                                                                         count_sa, logz_s);
   g_launches++;
 }
+// The Monte-Carlo form of logz_updateV (value_iteration.jl:119-124): V(s) += log Z^(s) / beta for every start slot that
+// received paths, log Z^(s) pooling the slot's four first-action buckets.
+__global__ void mc_apply_update_kernel(const float* __restrict__ m, const float* __restrict__ s, const uint32_t* __restrict__ c,
+                                       const int* __restrict__ starts, long long nstarts, double beta, double* __restrict__ V) {
+  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= nstarts) return;
+  double mm = -CUDART_INF;
+  unsigned long long ctot = 0;
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+    const size_t i = (size_t)slot * NA + a;
+    if (c[i] && (double)m[i] > mm) mm = (double)m[i];
+    ctot += c[i];
+  }
+  if (!ctot) return;
+  double tot = 0.0;
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+    const size_t i = (size_t)slot * NA + a;
+    if (c[i]) tot += (double)s[i] * exp((double)m[i] - mm);
+  }
+  V[starts[slot]] += (mm + log(tot) - log((double)ctot)) / beta;
+}
+void launch_mc_apply_update(const float* acc_max, const float* acc_sum, const uint32_t* acc_cnt, const int* starts,
+                            long long nstarts, double beta, double* V, cudaStream_t st) {
+  mc_apply_update_kernel<<<(unsigned)((nstarts + 255) / 256), 256, 0, st>>>(acc_max, acc_sum, acc_cnt, starts, nstarts, beta, V);
+  g_launches++;
+}
 __global__ void fill_f64_kernel(double* dst, double v, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = v;

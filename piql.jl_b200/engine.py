@@ -241,6 +241,14 @@ class Engine:
                                         C.byref(st)))
         return sa, cnt, s, st
 
+    def mc_update_v(self, V, beta=1.0, npaths=1 << 20, niter=1, **kw):
+        """niter Monte-Carlo logz_updateV iterations on the device; returns (V_new (H, W) with NaN at walls, stats)."""
+        V = _cell(np.nan_to_num(np.asarray(V, dtype=np.float64)), self.H, self.W, "V")
+        o, _keep = self._mc_opts(npaths, **kw)
+        out, st = self._out(), K.McStats()
+        self._ck(self._lib.piql_mc_update_v(self._ctx, _pd(V), float(beta), C.byref(o), int(niter), _pd(out), C.byref(st)))
+        return out, st
+
     def trace_paths(self, npaths, max_steps, **kw):
         o, _keep = self._mc_opts(npaths, **kw)
         tr = np.empty((npaths, max_steps, 3), dtype=np.int32)

@@ -224,6 +224,18 @@ def mc_logz(ctrl, V, beta=1.0, β=None, Q=None, npaths=1 << 20, seed=0, estimato
     return McResult(sa, cnt, s, st, eng.walls)
 
 
+def mc_logz_updateV(ctrl, V, beta=1.0, β=None, npaths=1 << 22, niter=1, seed=0, estimator="A", horizon=1 << 20, device=0,
+                    return_stats=False):
+    """logz_updateV with the Monte-Carlo estimate of log Z in place of generate_logz's fixed point, niter times on the
+    device: V <- V + log Z^/beta from rollouts under the soft policy of the current V (paths start at every free cell)."""
+    beta = beta if β is None else β
+    eng = engine_for(ctrl, device)
+    out, st = eng.mc_update_v(_dense(V, eng), beta=beta, npaths=npaths, niter=niter, seed=seed, estimator=estimator,
+                              horizon=horizon)
+    g = Growable.from_dense(out, eng.walls, default=getattr(V, "default", lambda x: 0.0))
+    return (g, st) if return_stats else g
+
+
 # ---- experiment protocol (scripts/experiments.jl:10-39) -------------------------------------------------
 def learning_traj(ctrl, v0, beta=1.0, n=20, **kw):
     out, vnew = [v0], v0

@@ -80,3 +80,40 @@ def test_run_experiment_through_the_reference_interface(piql):
             assert nmax(a["traj"][beta][k].array, b["traj"][beta][k].array) < 1e-12
             assert nmax(a["gap"][beta][k].array, b["gap"][beta][k].array) < 1e-12
     assert a["s0"] == b["s0"]
+
+
+def test_monte_carlo_update_tracks_the_exact_update(engine, golden01):
+    """piql_mc_update_v: V + log Z^/beta from rollouts approximates logz_updateV (exact log Z) within Monte-Carlo error,
+    one iteration and a chain of three; same seed -> same bits."""
+    g = golden01
+    engine.load_grid(g.walls, g.goal, **g.params)
+    V0 = np.nan_to_num(g.V(7, 0))
+    free = g.walls == 0
+    exact = V0
+    for _ in range(3):
+        exact, _ = engine.update_v(np.nan_to_num(exact), beta=1.0)
+    one_exact, _ = engine.update_v(V0, beta=1.0)
+    n = 1 << 24
+    one, st = engine.mc_update_v(V0, beta=1.0, npaths=n, niter=1, seed=5)
+    assert np.array_equal(np.isnan(one), g.walls != 0) and st.paths == n and st.transitions > n
+    err = np.abs(one[free] - one_exact[free])
+    assert err.max() < 0.03 and err.mean() < 4e-3, (err.max(), err.mean())
+    again, _ = engine.mc_update_v(V0, beta=1.0, npaths=n, niter=1, seed=5)
+    assert np.array_equal(one[free], again[free])
+    three, st3 = engine.mc_update_v(V0, beta=1.0, npaths=n, niter=3, seed=5)
+    assert st3.paths == 3 * n
+    err3 = np.abs(three[free] - exact[free])
+    assert err3.max() < 0.05 and err3.mean() < 8e-3, (err3.max(), err3.mean())
+    # the goal: log Z(goal) = -V(goal) exactly, also by Monte-Carlo (every path from the goal stops at once)
+    assert abs(one[g.goal] - one_exact[g.goal]) < 1e-6
+
+
+def test_mc_update_through_the_reference_interface(piql):
+    gw = piql.make_gridworld((10, 10), density=0.1, rng=np.random.default_rng(8))
+    ctrl = piql.gridworld_ctrl(gw, randomness=0.05, gamma=0.95)
+    weaker = piql.modify(ctrl, reward_function=lambda s, a, ss: 0.1 * ctrl.reward_function(s, a, ss))
+    V_lo = piql.generate_nu(weaker)
+    exact = piql.logz_updateV(ctrl, V_lo, beta=1.0)
+    mc = piql.mc_logz_updateV(ctrl, V_lo, beta=1.0, npaths=1 << 22, seed=2)
+    err = np.array([mc(s) - exact(s) for s in exact.dict])
+    assert np.abs(err).max() < 0.05 and abs(err.mean()) < 3e-3
