@@ -70,7 +70,7 @@ typedef struct {
   double device_seconds; /* CUDA-event time of the sweeps */
   int64_t backups;       /* state backups performed = sweeps * free cells */
   int32_t converged;
-  int32_t kernel;        /* 1 = single-CTA resident solver, 2 = tiled multi-sweep kernel (4 sweeps per launch), 3 = batched resident */
+  int32_t kernel;        /* 1 = single-CTA resident solver, 2 = tiled multi-sweep kernel (4 sweeps per launch), 3 = batched resident, 4 = table */
 } piql_solve_stats;
 
 enum { PIQL_EST_SAMPLED_STOP = 0 /* estimator A */, PIQL_EST_DISCOUNTED = 1 /* estimator B */ };
@@ -142,6 +142,32 @@ int32_t piql_learning_traj(piql_ctx* ctx, const double* V0, const double* betas,
                            const piql_solve_opts* opts, double* traj_out, piql_solve_stats* stats_out);
 int32_t piql_solve_gap_batch(piql_ctx* ctx, const double* Vs, int32_t m, const double* nu, const piql_solve_opts* opts,
                              double* gaps_out, piql_solve_stats* stats_out);
+/* ---- tabulated ControlProblems ---------------------------------------------------------------
+ * Any finite problem behind the closure interface of src/PIQL.jl:12-23 (e.g. src/Problems/BinaryBandit.jl), tabulated by
+ * the host: states 0..nstates-1, actions 0..nactions-1 (<= 16), and for every (state, action) row s*nactions + a the
+ * entries row_ptr[row] .. row_ptr[row+1]-1 of (successor, probability, reward_function(s, a, s')):
+ *   propagator_average(s,a,f) = sum_e prob[e] f(succ[e])      logpropagatorexp(s,a,f) = log sum_e prob[e] exp f(succ[e])
+ * log_prior[row] = log action_prior(s, a); terminal[s] = terminal_condition(s); gamma in (0, 1] (1: finite-horizon problems).
+ * Solvers as for the grid (V-determined Q, Float64, Jacobi, stop rule of the reference); arrays are nstates long. */
+typedef struct {
+  int64_t nstates;
+  int32_t nactions;
+  const int64_t* row_ptr;
+  const int32_t* succ;
+  const double* prob;
+  const double* reward;
+  const double* log_prior;
+  const uint8_t* terminal;
+  double gamma;
+} piql_table_problem;
+int32_t piql_table_load(piql_ctx* ctx, const piql_table_problem* problem);
+/* kind 0: generate_ν (reward_function scaled by reward_scale); 1: generate_logz(ctrl, V; β); 2: generate_optimality_gap(ctrl, V; ν) */
+int32_t piql_table_solve(piql_ctx* ctx, int32_t kind, const double* V, const double* nu, double beta, double reward_scale,
+                         const piql_solve_opts* opts, double* x_out, piql_solve_stats* stats_out);
+/* logz_updateV(ctrl, V; β) on the tabulated problem; logz_out optional */
+int32_t piql_table_update_v(piql_ctx* ctx, const double* V, double beta, const piql_solve_opts* opts, double* vnew_out,
+                            double* logz_out, piql_solve_stats* stats_out);
+
 /* One Jacobi sweep from x_in (kind: 0 nu, 1 logz, 2 gap), for parity tests of the backup itself. */
 int32_t piql_sweep_once(piql_ctx* ctx, int32_t kind, const double* V, const double* Q, const double* nu,
                         double beta, double reward_scale, int32_t precision, const double* x_in,

@@ -170,6 +170,46 @@ function optimality_gap_batch(ctx::Context, Vs::Vector, ν; kw...)
     [growable(ctx, out[:, :, i]) for i in 1:m]
 end
 
+# ---- any other ControlProblem (e.g. binary_bandit_problem, src/Problems/BinaryBandit.jl): tabulate through the closures ----
+struct TableProblem
+    nstates::Int64; nactions::Int32; row_ptr::Ptr{Int64}; succ::Ptr{Int32}; prob::Ptr{Cdouble}; reward::Ptr{Cdouble}
+    log_prior::Ptr{Cdouble}; terminal::Ptr{UInt8}; gamma::Cdouble
+end
+# successors of (s, a) from propagator_average alone: one recording probe, then one indicator probe per successor
+function successors(ctrl, s, a)
+    seen = Any[]; ctrl.propagator_average(s, a, s1 -> (s1 in seen || push!(seen, s1); 0.0))
+    [(s1, ctrl.propagator_average(s, a, x -> x == s1 ? 1.0 : 0.0)) for s1 in seen]
+end
+function load_table!(ctx::Context, ctrl::ControlProblem; roots = [ctrl.initial_state()])
+    states = collect(roots); index = Dict(s => i - 1 for (i, s) in enumerate(states)); acts = collect(ctrl.action_space)
+    ptr = Int64[0]; succ = Int32[]; prob = Float64[]; rew = Float64[]; lp = Float64[]; term = UInt8[]
+    i = 1
+    while i <= length(states)
+        s = states[i]; t = ctrl.terminal_condition(s); push!(term, t)
+        for a in acts
+            if !t
+                for (s1, p) in successors(ctrl, s, a)
+                    haskey(index, s1) || (push!(states, s1); index[s1] = length(states) - 1)
+                    push!(succ, index[s1]); push!(prob, p); push!(rew, ctrl.reward_function(s, a, s1))
+                end
+            end
+            push!(ptr, length(succ)); push!(lp, log(ctrl.action_prior(s, a)))
+        end
+        i += 1
+    end
+    GC.@preserve ptr succ prob rew lp term check(ctx, ccall((:piql_table_load, LIB), Int32, (Ptr{Cvoid}, Ref{TableProblem}), ctx.ptr,
+        TableProblem(length(states), length(acts), pointer(ptr), pointer(succ), pointer(prob), pointer(rew), pointer(lp), pointer(term), ctrl.γ)))
+    states
+end
+function table_solve(ctx::Context, states, kind; V = nothing, ν = nothing, β = 1.0, reward_scale = 1.0, kw...)
+    Vd = V === nothing ? C_NULL : Float64[V(s) for s in states]; nd = ν === nothing ? C_NULL : Float64[ν(s) for s in states]
+    out = Vector{Float64}(undef, length(states)); st = SolveStats()
+    GC.@preserve Vd nd out check(ctx, ccall((:piql_table_solve, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cdouble, Ref{SolveOpts}, Ptr{Cdouble}, Ref{SolveStats}),
+        ctx.ptr, kind, Vd, nd, β, reward_scale, opts(; kw...), out, st))
+    Growable(Dict(s => out[i] for (i, s) in enumerate(states)), x -> 0.0)
+end
+
 # ---- multi-GPU exchange over NVLink peer memory: one worker process per GPU (replaces addprocs/pmap/@spawn,
 # ---- scripts/distributed_experiments.jl:3,26,28,43-46).  The handle blobs travel over Distributed.jl itself.
 struct PeerHandles; lse_max::NTuple{64,UInt8}; lse_sum::NTuple{64,UInt8}; count::NTuple{64,UInt8}; flags::NTuple{64,UInt8}; n::Int64; end

@@ -210,3 +210,24 @@ def wall_unreachable(walls, goal_idx):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def table_solve(tab, kind, V=None, nu=None, beta=1.0, reward_scale=1.0, tol=1e-12, max_sweeps=10 ** 7, x0=None):
+    """Soft VI on a tabulated ControlProblem (piql_jl_b200.tables.ProblemTable): the restatement in piql_oracle.c
+    (orc_table_solve) of PIQL.jl:55-130 / value_iteration.jl:62-169 over CSR rows.  Returns (x, sweeps, residual)."""
+    ns = len(tab.terminal)
+    out = np.empty(ns, dtype=np.float64)
+    sweeps, res = C.c_int64(), C.c_double()
+    V = None if V is None else np.ascontiguousarray(V, dtype=np.float64)
+    nu = None if nu is None else np.ascontiguousarray(nu, dtype=np.float64)
+    x0 = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+    a = [np.ascontiguousarray(tab.row_ptr, dtype=np.int64), np.ascontiguousarray(tab.succ, dtype=np.int32),
+         np.ascontiguousarray(tab.prob, dtype=np.float64), np.ascontiguousarray(tab.reward, dtype=np.float64),
+         np.ascontiguousarray(tab.log_prior, dtype=np.float64), np.ascontiguousarray(tab.terminal, dtype=np.uint8)]
+    rc = lib().orc_table_solve(C.c_int(KIND[kind]), C.c_int64(ns), C.c_int(len(tab.actions)), _p(a[0], C.c_int64),
+                               _p(a[1], C.c_int32), _p(a[2], C.c_double), _p(a[3], C.c_double), _p(a[4], C.c_double),
+                               _p(a[5], C.c_uint8), C.c_double(tab.gamma), C.c_double(reward_scale), _p(V, C.c_double),
+                               _p(nu, C.c_double), C.c_double(beta), _p(x0, C.c_double), C.c_double(tol),
+                               C.c_int64(max_sweeps), _p(out, C.c_double), C.byref(sweeps), C.byref(res))
+    assert rc == 0
+    return out, sweeps.value, res.value

@@ -670,3 +670,98 @@ int orc_num_threads(void) {
   return 1;
 #endif
 }
+
+/* ======================================================================================================
+ * Tabulated ControlProblems (any finite problem behind the closure interface of src/PIQL.jl:12-23):
+ * states 0..ns-1, actions 0..na-1, CSR over (state, action) of (successor, probability, reward).
+ *   propagator_average(s,a,f) = sum_e p_e f(s'_e);  logpropagatorexp(s,a,f) = log sum_e p_e exp f(s'_e)
+ * The same recursions as above (PIQL.jl:55-130, value_iteration.jl:62-169), V-determined Q, Jacobi sweeps.
+ * Used to check the CUDA table path and, through a tabulated gridworld, against the grid restatement.
+ * ====================================================================================================== */
+typedef struct {
+  int64_t ns; int na;
+  const int64_t *ptr; const int32_t *succ; const double *prob, *rew, *lprior; const uint8_t *term;
+  double gamma, scale;
+} orc_table;
+
+static double lse_n(const double *x, int n) {
+  double m = -INFINITY;
+  for (int i = 0; i < n; i++) if (x[i] > m) m = x[i];
+  if (m == -INFINITY) return m;
+  double s = 0.0;
+  for (int i = 0; i < n; i++) s += exp(x[i] - m);
+  return m + log(s);
+}
+static double t_pa(const orc_table *t, int64_t s, int a, const double *f) { /* propagator_average */
+  double out = 0.0;
+  for (int64_t e = t->ptr[s * t->na + a]; e < t->ptr[s * t->na + a + 1]; e++) out += t->prob[e] * f[t->succ[e]];
+  return out;
+}
+static double t_rbar(const orc_table *t, int64_t s, int a) { /* average_reward  PIQL.jl:55-57 */
+  double out = 0.0;
+  for (int64_t e = t->ptr[s * t->na + a]; e < t->ptr[s * t->na + a + 1]; e++) out += t->prob[e] * (t->scale * t->rew[e]);
+  return out;
+}
+static double t_cV(const orc_table *t, const double *V, int64_t s, int a) { /* controlV  PIQL.jl:63-66 */
+  return t->gamma * t_pa(t, s, a, V) - V[s] + t_rbar(t, s, a);
+}
+static double t_log_pa(const orc_table *t, int64_t s, int a, const double *f) { /* logpropagatorexp */
+  double m = -INFINITY;
+  const int64_t e0 = t->ptr[s * t->na + a], e1 = t->ptr[s * t->na + a + 1];
+  for (int64_t e = e0; e < e1; e++) { const double x = log(t->prob[e]) + f[t->succ[e]]; if (x > m) m = x; }
+  if (m == -INFINITY) return m;
+  double acc = 0.0;
+  for (int64_t e = e0; e < e1; e++) acc += exp(log(t->prob[e]) + f[t->succ[e]] - m);
+  return m + log(acc);
+}
+static double t_backup(int kind, const orc_table *t, const double *V, const double *nu, double beta, const double *X, int64_t s) {
+  double x[64] = {0}, cv[64] = {0};
+  const int na = t->na;
+  if (t->term[s]) return kind == 1 ? 0.0 - V[s] : 0.0; /* value_iteration.jl:66-67,93-94,133-134 */
+  if (kind == 0) { /* truevalue_recursion  PIQL.jl:95-101 */
+    for (int a = 0; a < na; a++) x[a] = t->lprior[s * na + a] + t->gamma * t_pa(t, s, a, X) + t_rbar(t, s, a);
+    return lse_n(x, na);
+  }
+  for (int a = 0; a < na; a++) { cv[a] = t_cV(t, V, s, a); x[a] = t->lprior[s * na + a] + cv[a]; }
+  const double norm = lse_n(x, na); /* Qnormalization of (s,a) -> controlV(ctrl,V,s,a)  PIQL.jl:72-75 */
+  if (kind == 1) { /* logz_recursion  PIQL.jl:125-130 */
+    for (int a = 0; a < na; a++)
+      x[a] = t->lprior[s * na + a] + beta * cv[a] + (1.0 - beta) * (cv[a] - norm) +
+             logaddexp_(log(t->gamma) + t_log_pa(t, s, a, X), log(1.0 - t->gamma));
+    return lse_n(x, na);
+  }
+  double out = 0.0; /* optimality_gap_recursion  value_iteration.jl:160-169 */
+  for (int a = 0; a < na; a++) {
+    const double cq = cv[a] - norm;
+    out += exp(t->lprior[s * na + a] + cq) * (cq - t_cV(t, nu, s, a) + t_pa(t, s, a, X));
+  }
+  return out;
+}
+int orc_table_solve(int kind, int64_t ns, int na, const int64_t *ptr, const int32_t *succ, const double *prob,
+                    const double *rew, const double *lprior, const uint8_t *term, double gamma, double scale,
+                    const double *V, const double *nu, double beta, const double *x0, double tol, int64_t max_sweeps,
+                    double *out, int64_t *sweeps_out, double *residual_out) {
+  if (na > 64) return 1;
+  const orc_table t = {ns, na, ptr, succ, prob, rew, lprior, term, gamma, scale};
+  double *X = (double *)malloc(sizeof(double) * (size_t)ns), *Y = (double *)malloc(sizeof(double) * (size_t)ns);
+  for (int64_t s = 0; s < ns; s++) X[s] = x0 ? x0[s] : 0.0;
+  int64_t sweeps = 0;
+  double res = INFINITY;
+  while (sweeps < max_sweeps) {
+    double d = 0.0;
+    for (int64_t s = 0; s < ns; s++) {
+      const double nw = t_backup(kind, &t, V, nu, beta, X, s);
+      d += fabs(nw - X[s]);
+      Y[s] = kind == 1 ? logaddexp_(log(0.5) + nw, log(0.5) + X[s]) : nw; /* eta = 0.5  value_iteration.jl:101-102 */
+    }
+    double *tmp = X; X = Y; Y = tmp;
+    sweeps++;
+    res = d;
+    if (res < tol) break;
+  }
+  memcpy(out, X, sizeof(double) * (size_t)ns);
+  free(X); free(Y);
+  if (sweeps_out) *sweeps_out = sweeps;
+  if (residual_out) *residual_out = res;
+  return 0;
+}

@@ -17,6 +17,8 @@ from ._capi import PiqlError
 from .engine import Engine
 from .gridworld import (ControlProblem, Gridworld, gridworld_ctrl, make_gridworld, make_walls, modify,
                         state_iterator, tabulate, take_step)
+from .tables import (BanditState, ProblemTable, bandit_state_iterator, binary_bandit_problem, reachable, tabulate_problem,
+                     update)
 from .solvers import (Growable, McResult, Qnormalization, action_probability, average_reward, choose_action,
                       controlQ, controlV, engine_for, fitness, fitness_reward_estimate, generate_logz, generate_nu,
                       generate_optimality_gap, generate_optimality_gap_batch, generate_ν, kl_cost, learning_traj, learning_traj_batch, logz_updateV, mc_logz, mc_logz_updateV,

@@ -43,6 +43,12 @@ class McStats(C.Structure):
                 ("rollout_seconds", C.c_double)]
 
 
+class TableProblem(C.Structure):
+    _fields_ = [("nstates", C.c_int64), ("nactions", C.c_int32), ("row_ptr", C.POINTER(C.c_int64)),
+                ("succ", C.POINTER(C.c_int32)), ("prob", C.POINTER(C.c_double)), ("reward", C.POINTER(C.c_double)),
+                ("log_prior", C.POINTER(C.c_double)), ("terminal", C.POINTER(C.c_uint8)), ("gamma", C.c_double)]
+
+
 class PeerHandles(C.Structure):
     _fields_ = [("lse_max", C.c_uint8 * 64), ("lse_sum", C.c_uint8 * 64), ("count", C.c_uint8 * 64),
                 ("flags", C.c_uint8 * 64), ("n", C.c_int64)]
@@ -88,6 +94,9 @@ SYMBOLS = {
     "piql_vi_prepare_dev": (C.c_int32, [_P, C.c_int32, _D, _D, _D, C.c_double, C.c_double, C.c_int32]),
     "piql_learning_traj": (C.c_int32, [_P, _D, _D, C.c_int32, C.c_int32, C.POINTER(SolveOpts), _D, C.POINTER(SolveStats)]),
     "piql_solve_gap_batch": (C.c_int32, [_P, _D, C.c_int32, _D, C.POINTER(SolveOpts), _D, C.POINTER(SolveStats)]),
+    "piql_table_load": (C.c_int32, [_P, C.POINTER(TableProblem)]),
+    "piql_table_solve": (C.c_int32, [_P, C.c_int32, _D, _D, C.c_double, C.c_double, C.POINTER(SolveOpts), _D, C.POINTER(SolveStats)]),
+    "piql_table_update_v": (C.c_int32, [_P, _D, C.c_double, C.POINTER(SolveOpts), _D, _D, C.POINTER(SolveStats)]),
     "piql_vi_set_iterate": (C.c_int32, [_P, C.POINTER(C.c_double)]),
     "piql_vi_tile_plan": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "piql_vi_sweeps_dev": (C.c_int32, [_P, C.c_int64]),

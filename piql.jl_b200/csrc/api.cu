@@ -1,4 +1,5 @@
 // api.cu -- the C ABI (include/piql_b200.h): context, device buffers, call sequencing.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -41,6 +42,14 @@ struct piql_ctx {
   long long vi_sweeps_done = 0;
   TileBuffers tb;  // padded copy of the iterate for the tiled multi-sweep kernel
   PeerState peer;  // NVLink peer mappings of the other ranks' accumulators
+
+  // tabulated (non-grid) problem
+  bool has_table_problem = false;
+  TableDev tab{};
+  long long tab_nnz = 0;
+  std::vector<void*> tab_bufs;  // every device allocation of the table path
+  double *tb_V = nullptr, *tb_nu = nullptr, *tb_x[2] = {nullptr, nullptr}, *tb_aux = nullptr, *tb_aux1 = nullptr,
+         *tb_partial = nullptr, *tb_out = nullptr;
 
   // Monte-Carlo
   float4* d_table = nullptr;
@@ -114,6 +123,12 @@ void peer_close(piql_ctx* ctx) {
   for (int i = 0; i < ps.nopened; i++) cudaIpcCloseMemHandle(ps.opened[i]);
   ps.nopened = 0;
   ps.valid = false;
+}
+
+void free_table(piql_ctx* c) {
+  for (void* p : c->tab_bufs) cudaFree(p);
+  c->tab_bufs.clear();
+  c->has_table_problem = false;
 }
 
 void free_vi(piql_ctx* c) {
@@ -502,6 +517,7 @@ int32_t piql_destroy(piql_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   peer_close(ctx);
+  free_table(ctx);
   if (ctx->peer.own_flags) cudaFree(ctx->peer.own_flags);
   if (ctx->peer.done) cudaFree(ctx->peer.done);
   if (ctx->peer.err) cudaFreeHost(ctx->peer.err);
@@ -734,6 +750,143 @@ int32_t piql_solve_gap_batch(piql_ctx* ctx, const double* Vs, int32_t m, const d
     if (rc) worst = rc;
   }
   return worst;
+}
+
+// ---- tabulated ControlProblems ---------------------------------------------------------------------------------
+int32_t piql_table_load(piql_ctx* ctx, const piql_table_problem* p) {
+  if (!ctx) return PIQL_ERR_ARG;
+  NEED(p != nullptr, PIQL_ERR_ARG, "problem is null");
+  NEED(p->nstates > 0 && p->nstates < (1LL << 31), PIQL_ERR_ARG, "nstates must lie in [1, 2^31)");
+  NEED(p->nactions >= 1 && p->nactions <= 16, PIQL_ERR_ARG, "nactions must lie in [1, 16]");
+  NEED(p->row_ptr && p->succ && p->prob && p->reward && p->log_prior && p->terminal, PIQL_ERR_ARG, "a table array is null");
+  NEED(p->gamma > 0.0 && p->gamma <= 1.0, PIQL_ERR_ARG, "gamma must lie in (0, 1]");
+  const long long rows = p->nstates * p->nactions;
+  NEED(p->row_ptr[0] == 0, PIQL_ERR_ARG, "row_ptr[0] must be 0");
+  for (long long r = 0; r < rows; r++) NEED(p->row_ptr[r + 1] >= p->row_ptr[r], PIQL_ERR_ARG, "row_ptr must be non-decreasing");
+  const long long nnz = p->row_ptr[rows];
+  for (long long s = 0; s < p->nstates; s++) {
+    for (int a = 0; a < p->nactions; a++) {
+      double tot = 0.0;
+      for (long long e = p->row_ptr[s * p->nactions + a]; e < p->row_ptr[s * p->nactions + a + 1]; e++) {
+        NEED(p->succ[e] >= 0 && p->succ[e] < p->nstates, PIQL_ERR_ARG, "successor index out of range");
+        NEED(p->prob[e] >= 0.0, PIQL_ERR_ARG, "negative transition probability");
+        tot += p->prob[e];
+      }
+      NEED(p->terminal[s] || std::fabs(tot - 1.0) < 1e-9, PIQL_ERR_ARG, "transition probabilities of a non-terminal (s, a) must sum to 1");
+    }
+  }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CK(cudaStreamSynchronize(st));
+  free_table(ctx);
+  auto up = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, bytes ? bytes : 8);
+    if (e != cudaSuccess) return e;
+    ctx->tab_bufs.push_back(*dst);
+    return src ? cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+  };
+  void *d_ptr, *d_succ, *d_prob, *d_rew, *d_lp, *d_term;
+  const size_t ns = (size_t)p->nstates;
+  CK(up(p->row_ptr, 8 * (size_t)(rows + 1), &d_ptr));
+  CK(up(p->succ, 4 * (size_t)nnz, &d_succ));
+  CK(up(p->prob, 8 * (size_t)nnz, &d_prob));
+  CK(up(p->reward, 8 * (size_t)nnz, &d_rew));
+  CK(up(p->log_prior, 8 * (size_t)rows, &d_lp));
+  CK(up(p->terminal, ns, &d_term));
+  CK(up(nullptr, 8 * ns, (void**)&ctx->tb_V));
+  CK(up(nullptr, 8 * ns, (void**)&ctx->tb_nu));
+  CK(up(nullptr, 8 * ns, (void**)&ctx->tb_x[0]));
+  CK(up(nullptr, 8 * ns, (void**)&ctx->tb_x[1]));
+  CK(up(nullptr, 8 * (size_t)rows, (void**)&ctx->tb_aux));
+  CK(up(nullptr, 8 * ns, (void**)&ctx->tb_aux1));
+  CK(up(nullptr, 8 * (size_t)table_blocks(p->nstates), (void**)&ctx->tb_partial));
+  CK(up(nullptr, 8 * ns, (void**)&ctx->tb_out));
+  CK(cudaStreamSynchronize(st));
+  TableDev& t = ctx->tab;
+  t.ns = p->nstates; t.na = p->nactions;
+  t.ptr = (const long long*)d_ptr; t.succ = (const int*)d_succ; t.prob = (const double*)d_prob; t.rew = (const double*)d_rew;
+  t.lprior = (const double*)d_lp; t.term = (const uint8_t*)d_term;
+  t.gamma = p->gamma; t.lgamma = std::log(p->gamma); t.l1mgamma = std::log(1.0 - p->gamma);  // -inf at gamma = 1
+  ctx->tab_nnz = nnz;
+  ctx->has_table_problem = true;
+  return PIQL_OK;
+}
+
+static int table_solve(piql_ctx* ctx, int kind, const double* V, const double* nu, double beta, double reward_scale,
+                       const piql_solve_opts* opts, double* x_out, piql_solve_stats* stats, int* cur_out) {
+  NEED(ctx->has_table_problem, PIQL_ERR_STATE, "no tabulated problem loaded (call piql_table_load first)");
+  NEED(kind >= 0 && kind <= 2, PIQL_ERR_ARG, "kind must be 0 (nu), 1 (logz) or 2 (gap)");
+  NEED(opts != nullptr && opts->max_sweeps > 0, PIQL_ERR_ARG, "opts is null or max_sweeps is not positive");
+  NEED(kind == KIND_NU || V != nullptr, PIQL_ERR_ARG, "V is required for logz / gap");
+  NEED(kind != KIND_GAP || nu != nullptr, PIQL_ERR_ARG, "nu is required for the optimality gap");
+  const TableDev& t = ctx->tab;
+  cudaStream_t st = ctx->stream;
+  const size_t nb = 8 * (size_t)t.ns;
+  if (V) CK(cudaMemcpyAsync(ctx->tb_V, V, nb, cudaMemcpyHostToDevice, st));
+  if (nu) CK(cudaMemcpyAsync(ctx->tb_nu, nu, nb, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ctx->tb_x[0], 0, nb, st));  // Growable default x -> 0.0
+  if (kind != KIND_NU) launch_table_prep(t, kind, reward_scale, beta, ctx->tb_V, ctx->tb_nu, ctx->tb_aux, ctx->tb_aux1, st);
+  CK_LAST();
+  const long long every = opts->check_every > 0 ? opts->check_every : 16;
+  long long sweeps = 0;
+  double residual = INFINITY;
+  int cur = 0;
+  CK(cudaEventRecord(ctx->ev0, st));
+  while (sweeps < opts->max_sweeps) {
+    const long long batch = std::min<long long>(opts->max_sweeps - sweeps, every);
+    for (long long i = 0; i < batch; i++) {
+      const bool last = i == batch - 1;
+      launch_table_sweep(t, kind, reward_scale, ctx->tb_x[cur], ctx->tb_x[cur ^ 1], ctx->tb_V, ctx->tb_aux, ctx->tb_aux1,
+                         last ? ctx->tb_partial : nullptr, ctx->d_scalars, st);
+      cur ^= 1;
+    }
+    CK_LAST();
+    sweeps += batch;
+    CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    residual = ctx->h_scalars[0];
+    if (!(residual == residual)) return fail(ctx, PIQL_ERR_CUDA, "soft-VI residual is NaN (diverged)");
+    if (opts->tol > 0 && residual < opts->tol) break;
+  }
+  CK(cudaEventRecord(ctx->ev1, st));
+  if (x_out) CK(cudaMemcpyAsync(x_out, ctx->tb_x[cur], nb, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  const bool conv = opts->tol > 0 ? residual < opts->tol : true;
+  if (stats) {
+    stats->sweeps = sweeps; stats->residual = residual; stats->device_seconds = ms * 1e-3;
+    stats->backups = sweeps * t.ns; stats->converged = conv ? 1 : 0; stats->kernel = 4;
+  }
+  if (cur_out) *cur_out = cur;
+  if (!conv) return fail(ctx, PIQL_ERR_NOT_CONVERGED, "max_sweeps reached before the residual fell below tol");
+  return PIQL_OK;
+}
+
+int32_t piql_table_solve(piql_ctx* ctx, int32_t kind, const double* V, const double* nu, double beta, double reward_scale,
+                         const piql_solve_opts* opts, double* x_out, piql_solve_stats* stats) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  NEED(x_out != nullptr, PIQL_ERR_ARG, "output pointer is null");
+  CK(cudaSetDevice(ctx->device));
+  return table_solve(ctx, kind, V, nu, beta, reward_scale, opts, x_out, stats, nullptr);
+}
+
+int32_t piql_table_update_v(piql_ctx* ctx, const double* V, double beta, const piql_solve_opts* opts, double* vnew_out,
+                            double* logz_out, piql_solve_stats* stats) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  NEED(vnew_out != nullptr, PIQL_ERR_ARG, "output pointer is null");
+  NEED(beta == beta && beta != 0.0, PIQL_ERR_ARG, "beta must be non-zero and not NaN");
+  CK(cudaSetDevice(ctx->device));
+  int cur = 0;
+  int rc = table_solve(ctx, KIND_LOGZ, V, nullptr, beta, 1.0, opts, logz_out, stats, &cur);
+  if (rc && rc != PIQL_ERR_NOT_CONVERGED) return rc;
+  launch_table_update_v(ctx->tab.ns, ctx->tb_V, ctx->tb_x[cur], beta, ctx->tb_out, ctx->stream);
+  CK_LAST();
+  CK(cudaMemcpyAsync(vnew_out, ctx->tb_out, 8 * (size_t)ctx->tab.ns, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return rc;
 }
 
 int32_t piql_sweep_once(piql_ctx* ctx, int32_t kind, const double* V, const double* Q, const double* nu, double beta,

@@ -140,6 +140,26 @@ void launch_mc_apply_update(const float* acc_max, const float* acc_sum, const ui
                             long long nstarts, double beta, double* V, cudaStream_t st);
 int configure_rollout_kernels();
 
+// table.cu: soft VI on a tabulated ControlProblem (CSR over (state, action)) -------------------------
+struct TableDev {
+  long long ns;
+  int na;
+  const long long* ptr;   // [ns*na + 1]
+  const int* succ;        // [nnz]
+  const double* prob;     // [nnz]
+  const double* rew;      // [nnz] reward_function(s, a, s')
+  const double* lprior;   // [ns*na] log action_prior(s, a)
+  const uint8_t* term;    // [ns]
+  double gamma, lgamma, l1mgamma;
+};
+void launch_table_prep(const TableDev& t, int kind, double scale, double beta, const double* V, const double* nu, double* aux,
+                       double* aux1, cudaStream_t st);
+// One Jacobi sweep X -> Y; partial != nullptr: also the residual sum |new - old| into *residual.
+void launch_table_sweep(const TableDev& t, int kind, double scale, const double* X, double* Y, const double* V, const double* aux,
+                        const double* aux1, double* partial, double* residual, cudaStream_t st);
+void launch_table_update_v(long long ns, const double* V, const double* logz, double beta, double* out, cudaStream_t st);
+int table_blocks(long long ns);
+
 // peer.cu: the log-sum-exp all-reduce of the accumulators over NVLink peer memory -----------------
 constexpr int PEER_MAX = 8;  // GPUs of one box
 struct PeerState {

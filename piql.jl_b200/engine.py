@@ -158,6 +158,40 @@ class Engine:
                  allow=(K.ERR_NOT_CONVERGED,) if allow_unconverged else ())
         return out.transpose(0, 2, 1), list(st)
 
+    # ---- tabulated (non-grid) problems ---------------------------------------------------------------
+    def load_table(self, tab):
+        """tab: tables.ProblemTable (CSR over (state, action))."""
+        a = dict(row_ptr=np.ascontiguousarray(tab.row_ptr, dtype=np.int64), succ=np.ascontiguousarray(tab.succ, dtype=np.int32),
+                 prob=np.ascontiguousarray(tab.prob, dtype=np.float64), reward=np.ascontiguousarray(tab.reward, dtype=np.float64),
+                 log_prior=np.ascontiguousarray(tab.log_prior, dtype=np.float64),
+                 terminal=np.ascontiguousarray(tab.terminal, dtype=np.uint8))
+        p = K.TableProblem(len(tab.terminal), len(tab.actions), a["row_ptr"].ctypes.data_as(C.POINTER(C.c_int64)),
+                           a["succ"].ctypes.data_as(C.POINTER(C.c_int32)), _pd(a["prob"]), _pd(a["reward"]), _pd(a["log_prior"]),
+                           a["terminal"].ctypes.data_as(C.POINTER(C.c_uint8)), float(tab.gamma))
+        self._ck(self._lib.piql_table_load(self._ctx, C.byref(p)))
+        self.table_n = len(tab.terminal)
+        self.table_key = tab.key()
+
+    def table_solve(self, kind, V=None, nu=None, beta=1.0, reward_scale=1.0, tol=1e-12, max_sweeps=10 ** 7, check_every=0,
+                    allow_unconverged=False):
+        kind = {"nu": K.KIND_NU, "logz": K.KIND_LOGZ, "gap": K.KIND_GAP}[kind]
+        V = None if V is None else np.ascontiguousarray(V, dtype=np.float64)
+        nu = None if nu is None else np.ascontiguousarray(nu, dtype=np.float64)
+        out, st = np.empty(self.table_n, dtype=np.float64), K.SolveStats()
+        o = self._opts(tol, max_sweeps, "f64", check_every)
+        self._ck(self._lib.piql_table_solve(self._ctx, kind, _pd(V), _pd(nu), float(beta), float(reward_scale), C.byref(o),
+                                            _pd(out), C.byref(st)),
+                 allow=(K.ERR_NOT_CONVERGED,) if allow_unconverged else ())
+        return out, st
+
+    def table_update_v(self, V, beta=1.0, tol=1e-12, max_sweeps=10 ** 7, check_every=0, allow_unconverged=False):
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        out, logz, st = np.empty(self.table_n, dtype=np.float64), np.empty(self.table_n, dtype=np.float64), K.SolveStats()
+        o = self._opts(tol, max_sweeps, "f64", check_every)
+        self._ck(self._lib.piql_table_update_v(self._ctx, _pd(V), float(beta), C.byref(o), _pd(out), _pd(logz), C.byref(st)),
+                 allow=(K.ERR_NOT_CONVERGED,) if allow_unconverged else ())
+        return out, logz, st
+
     def sweep_once(self, kind, x, V=None, Q=None, nu=None, beta=1.0, reward_scale=1.0, precision="f64"):
         kind = {"nu": K.KIND_NU, "logz": K.KIND_LOGZ, "gap": K.KIND_GAP}[kind]
         prec = K.PRECISIONS[precision]

@@ -48,15 +48,23 @@ class Growable:
     and `.dict` is only materialised when somebody asks for it.
     """
 
-    def __init__(self, s=None, default=lambda x: 0.0, array=None, walls=None):
+    def __init__(self, s=None, default=lambda x: 0.0, array=None, walls=None, key=tuple):
         self.default = default
         self.array = array
         self._walls = walls
-        self._dict = None if array is not None else ({} if s is None else {tuple(s): 0.0})
+        self._key = key   # grid states are index pairs (any sequence); other problems use their state objects as they are
+        self._dict = None if array is not None else ({} if s is None else {key(s): 0.0})
 
     @classmethod
     def from_dense(cls, array, walls, default=lambda x: 0.0):
         return cls(default=default, array=np.asfortranarray(array, dtype=np.float64), walls=np.asarray(walls) != 0)
+
+    @classmethod
+    def from_table(cls, tab, values, default=lambda x: 0.0):
+        """Value function over the states of a tabulated (non-grid) problem."""
+        g = cls(default=default, key=lambda s: s)
+        g._dict = {st: float(v) for st, v in zip(tab.states, values)}
+        return g
 
     @property
     def dict(self):
@@ -66,7 +74,7 @@ class Growable:
         return self._dict
 
     def __call__(self, s):
-        s = tuple(s)
+        s = self._key(s)
         if self._dict is None and self.array is not None:
             if not self._walls[s]:
                 return float(self.array[s])
@@ -157,8 +165,36 @@ def fitness_reward_estimate(ctrl, s0, V, Q, rng, nsteps=20):
     return out
 
 
+# ---- problems that are not the implicit gridworld: tabulate through the closures, solve on the table ABI ---------
+_tables = {}
+
+
+def table_for(ctrl, device=0):
+    """(engine, ProblemTable) with ctrl's tabulated problem loaded; the table is built once per ControlProblem object."""
+    from . import tables
+    ent = _tables.get(id(ctrl))
+    if ent is None or ent[0] is not ctrl:
+        ent = _tables[id(ctrl)] = (ctrl, tables.tabulate_problem(ctrl))
+    tab = ent[1]
+    eng = _engines.get(device)
+    if eng is None:
+        eng = _engines[device] = Engine(device)
+    if getattr(eng, "table_key", None) != tab.key():
+        eng.load_table(tab)
+    return eng, tab
+
+
+def _table_values(tab, V):
+    return tab.values(V) if callable(V) else np.asarray(V, dtype=np.float64)
+
+
 # ---- solvers on the GPU -----------------------------------------------------------------------------
 def generate_nu(ctrl, tol=1e-12, max_sweeps=10 ** 7, precision="f64", device=0, return_stats=False):
+    if ctrl.grid is None:
+        eng, tab = table_for(ctrl, device)
+        out, st = eng.table_solve("nu", tol=tol, max_sweeps=max_sweeps)
+        g = Growable.from_table(tab, out)
+        return (g, st) if return_stats else g
     eng = engine_for(ctrl, device)
     out, st = eng.solve_nu(1.0, tol=tol, max_sweeps=max_sweeps, precision=precision)
     g = Growable.from_dense(out, eng.walls)
@@ -171,6 +207,11 @@ generate_ν = generate_nu
 def generate_logz(ctrl, V, beta=1.0, β=None, Q=None, tol=1e-12, max_sweeps=10 ** 7, precision="f64", device=0,
                   return_stats=False):
     beta = beta if β is None else β
+    if ctrl.grid is None:
+        eng, tab = table_for(ctrl, device)
+        out, st = eng.table_solve("logz", V=_table_values(tab, V), beta=beta, tol=tol, max_sweeps=max_sweeps)
+        g = Growable.from_table(tab, out)
+        return (g, st) if return_stats else g
     eng = engine_for(ctrl, device)
     out, st = eng.solve_logz(_dense(V, eng), beta=beta, Q=Q, tol=tol, max_sweeps=max_sweeps, precision=precision)
     g = Growable.from_dense(out, eng.walls)
@@ -180,6 +221,11 @@ def generate_logz(ctrl, V, beta=1.0, β=None, Q=None, tol=1e-12, max_sweeps=10 *
 def logz_updateV(ctrl, V, beta=1.0, β=None, tol=1e-12, max_sweeps=10 ** 7, precision="f64", device=0,
                  return_stats=False):
     beta = beta if β is None else β
+    if ctrl.grid is None:
+        eng, tab = table_for(ctrl, device)
+        out, _logz, st = eng.table_update_v(_table_values(tab, V), beta=beta, tol=tol, max_sweeps=max_sweeps)
+        g = Growable.from_table(tab, out, default=getattr(V, "default", lambda x: 0.0))
+        return (g, st) if return_stats else g
     eng = engine_for(ctrl, device)
     out, st = eng.update_v(_dense(V, eng), beta=beta, tol=tol, max_sweeps=max_sweeps, precision=precision)
     g = Growable.from_dense(out, eng.walls, default=getattr(V, "default", lambda x: 0.0))
@@ -191,6 +237,11 @@ def generate_optimality_gap(ctrl, V, nu=None, ν=None, Q=None, tol=1e-12, max_sw
     nu = nu if ν is None else ν
     if nu is None:
         nu = generate_nu(ctrl, device=device)
+    if ctrl.grid is None:
+        eng, tab = table_for(ctrl, device)
+        out, st = eng.table_solve("gap", V=_table_values(tab, V), nu=_table_values(tab, nu), tol=tol, max_sweeps=max_sweeps)
+        g = Growable.from_table(tab, out)
+        return (g, st) if return_stats else g
     eng = engine_for(ctrl, device)
     out, st = eng.solve_gap(_dense(V, eng), _dense(nu, eng), Q=Q, tol=tol, max_sweeps=max_sweeps, precision=precision)
     g = Growable.from_dense(out, eng.walls)

@@ -1,0 +1,81 @@
+"""The sparse-table path on the GPU (csrc/table.cu, piql_table_*): any ControlProblem the host can tabulate.  Checked
+against the oracle's table restatement on the BinaryBandit and on a tabulated gridworld, against the grid kernels on the same
+gridworld (two independent CUDA paths for one problem), and through the reference-style interface.  -m gpu."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import Golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bandit_solves_match_the_table_oracle(engine, piql):
+    bb = piql.binary_bandit_problem(rounds=8, ncoins=3, payoff=0.6, gamma=0.97)
+    tab = piql.tabulate_problem(bb)
+    engine.load_table(tab)
+    nu, st = engine.table_solve("nu")
+    ref, sw, _ = oracle.table_solve(tab, "nu")
+    assert st.converged and st.kernel == 4 and np.abs(nu - ref).max() < 1e-12
+    vlo, _ = engine.table_solve("nu", reward_scale=0.3)
+    assert np.abs(vlo - oracle.table_solve(tab, "nu", reward_scale=0.3)[0]).max() < 1e-12
+    for beta in (1.0, 0.2):
+        v1, logz, st1 = engine.table_update_v(vlo, beta=beta)
+        lref, _, _ = oracle.table_solve(tab, "logz", V=vlo, beta=beta)
+        assert st1.converged and np.abs(logz - lref).max() < 1e-10 and np.abs(v1 - (vlo + lref / beta)).max() < 1e-9
+    gap, st2 = engine.table_solve("gap", V=vlo, nu=nu)
+    gref, _, _ = oracle.table_solve(tab, "gap", V=vlo, nu=ref)
+    assert st2.converged and np.abs(gap - gref).max() < 1e-10
+    # known answers of the algebra: log Z = 0 and gap = 0 at V = nu
+    lz0, _ = engine.table_solve("logz", V=nu, beta=0.5)
+    g0, _ = engine.table_solve("gap", V=nu, nu=nu)
+    assert np.abs(lz0).max() < 1e-10 and np.abs(g0).max() < 1e-10
+
+
+def test_finite_horizon_bandit_at_gamma_one(engine, piql):
+    bb = piql.binary_bandit_problem(rounds=10, ncoins=2)      # the reference's defaults: gamma = 1
+    tab = piql.tabulate_problem(bb)
+    engine.load_table(tab)
+    nu, st = engine.table_solve("nu", check_every=4)
+    ref, _, _ = oracle.table_solve(tab, "nu")
+    assert st.converged and st.sweeps <= 16 and np.abs(nu - ref).max() < 1e-12
+    v1, logz, _ = engine.table_update_v(0.5 * nu, beta=1.0, check_every=4)
+    lref, _, _ = oracle.table_solve(tab, "logz", V=0.5 * nu, beta=1.0)
+    assert np.abs(logz - lref).max() < 1e-10
+
+
+def test_table_path_equals_grid_path_on_the_reference_gridworld(engine, piql):
+    g = Golden("r0_01g0_99")
+    gw = piql.Gridworld(g.walls != 0, g.goal)
+    ctrl = piql.modify(piql.gridworld_ctrl(gw, **{k: g.params[k] for k in ("randomness", "step_cost", "reward", "gamma")}), grid=None)
+    tab = piql.tabulate_problem(ctrl, roots=[g.goal] + piql.state_iterator(gw))
+    engine.load_table(tab)
+    engine.load_grid(g.walls, g.goal, **g.params)
+    pick = lambda A: np.array([A[s] for s in tab.states])
+    nu_t, _ = engine.table_solve("nu")
+    nu_g, _ = engine.solve_nu()
+    assert np.abs(nu_t - pick(nu_g)).max() < 1e-11 and np.abs(nu_t - pick(g.nu)).max() < 1e-9
+    V = np.nan_to_num(g.V(3, 1))
+    beta = float(g.betas[3])
+    v_t, _, _ = engine.table_update_v(pick(V), beta=beta)
+    v_g, _ = engine.update_v(V, beta=beta)
+    assert np.abs(v_t - pick(v_g)).max() < 1e-9 / beta and np.abs(v_t - pick(g.V(3, 2))).max() < 1e-9 + 5e-12 / beta
+    gp_t, _ = engine.table_solve("gap", V=pick(V), nu=pick(np.nan_to_num(g.nu)))
+    assert np.abs(gp_t - pick(g.G(3, 1))).max() < 2e-9
+
+
+def test_bandit_through_the_reference_interface(piql):
+    bb = piql.binary_bandit_problem(rounds=6, ncoins=2, gamma=0.95)
+    nu = piql.generate_nu(bb)
+    weaker = piql.modify(bb, reward_function=lambda s, a, ss: 0.5 * bb.reward_function(s, a, ss))
+    v_lo = piql.generate_nu(weaker)
+    s0 = bb.initial_state()
+    assert nu(s0) > v_lo(s0) > 0
+    v1 = piql.logz_updateV(bb, v_lo, beta=1.0)
+    v0 = piql.logz_updateV(bb, v_lo, beta=1e-3)
+    # the bounds of test/runtests.jl:33-36, on the bandit
+    assert all(v1(s) >= nu(s) - 1e-2 for s in nu.dict) and all(v0(s) <= nu(s) + 1e-2 for s in nu.dict)
+    gap = piql.generate_optimality_gap(bb, v_lo, nu=nu)
+    assert gap(s0) > 0 and abs(piql.generate_optimality_gap(bb, nu, nu=nu)(s0)) < 1e-10
+    lz = piql.generate_logz(bb, nu, beta=0.7)
+    assert max(abs(v) for v in lz.dict.values()) < 1e-10
