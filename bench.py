@@ -390,6 +390,14 @@ def run_ours(args, rank, world, local_rank):
             vi[key] = {"sweeps_per_s": sps, "state_backups_per_s": sps * eng.nfree, "us_per_sweep": 1e6 / sps,
                        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                                     "bytes_per_state": nbytes, "traffic": None}}
+        # the ground-truth solve itself (config 4: "soft VI ground truth on 1 B200"), host buffers in and out
+        solves = {}
+        for prec, tol in (("f64", 1e-9), ("f32fast", 0.05)):
+            t0 = time.perf_counter()
+            _nu, sst = eng.solve_nu(tol=tol, max_sweeps=20000, precision=prec, allow_unconverged=True)
+            solves[prec] = {"tol_sum_abs_delta": tol, "sweeps": int(sst.sweeps), "converged": bool(sst.converged),
+                            "seconds": time.perf_counter() - t0, "device_seconds": float(sst.device_seconds)}
+        vi["solve_nu"] = solves
         vi["kernel"] = ("tile_sweep_kernel<T,KIND,FAST>: 4 Jacobi sweeps per launch on 128 x (TJ+8) shared-memory tiles "
                         "(includes the residual reduction on the last launch); f32fast = MUFU ex2/lg2; keys without a kind are nu")
         vi["setup_vlo"] = {"sweeps": int(vst.sweeps), "device_seconds": float(vst.device_seconds)}

@@ -168,6 +168,18 @@ int32_t piql_table_solve(piql_ctx* ctx, int32_t kind, const double* V, const dou
 int32_t piql_table_update_v(piql_ctx* ctx, const double* V, double beta, const piql_solve_opts* opts, double* vnew_out,
                             double* logz_out, piql_solve_stats* stats_out);
 
+/* Monte-Carlo estimate of log Z on the tabulated problem (sampled-stop estimator; opts->starts are state indices, or
+ * PIQL_START_ALL_FREE = path p starts at state p mod nstates).  Per step of path p one Philox4x32-10 call, counter
+ * (step, 0, p_lo, p_hi): word 0 -> action (StatsBase walk over the running action probabilities), word 1 -> stop test
+ * u >= gamma, word 2 -> successor (the same walk over the running transition probabilities of the row).
+ * logz_sa_out / count_sa_out: nstates*nactions, logz_s_out: nstates (NaN / 0 where no path started); any may be NULL.
+ * cdf_out, bf_out (nstates*nactions floats) and cum_out (nnz floats) optionally export the sampler's tables (running action
+ * probabilities, beta*fitness, running transition probabilities) for trajectory-parity checks; the per-path records are
+ * read with piql_mc_records (meta = first action | length << 4). */
+int32_t piql_table_mc_logz(piql_ctx* ctx, const double* V, double beta, const piql_mc_opts* opts, double* logz_sa_out,
+                           uint64_t* count_sa_out, double* logz_s_out, piql_mc_stats* stats_out, float* cdf_out,
+                           float* bf_out, float* cum_out);
+
 /* One Jacobi sweep from x_in (kind: 0 nu, 1 logz, 2 gap), for parity tests of the backup itself. */
 int32_t piql_sweep_once(piql_ctx* ctx, int32_t kind, const double* V, const double* Q, const double* nu,
                         double beta, double reward_scale, int32_t precision, const double* x_in,

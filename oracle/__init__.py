@@ -231,3 +231,20 @@ def table_solve(tab, kind, V=None, nu=None, beta=1.0, reward_scale=1.0, tol=1e-1
                                C.c_int64(max_sweeps), _p(out, C.c_double), C.byref(sweeps), C.byref(res))
     assert rc == 0
     return out, sweeps.value, res.value
+
+
+def table_rollout(tab, cdf, bf, cum, vterm, npaths, starts=None, path0=0, seed=0, horizon=1 << 20):
+    """Paths on a tabulated problem with the sampler's float tables (orc_table_rollout): (logw float32, meta uint32)."""
+    ns = len(tab.terminal)
+    logw, meta = np.empty(npaths, dtype=np.float32), np.empty(npaths, dtype=np.uint32)
+    st = None if starts is None else np.ascontiguousarray(starts, dtype=np.int32)
+    a = [np.ascontiguousarray(tab.row_ptr, dtype=np.int64), np.ascontiguousarray(tab.succ, dtype=np.int32),
+         np.ascontiguousarray(tab.terminal, dtype=np.uint8), np.ascontiguousarray(cdf, dtype=np.float32),
+         np.ascontiguousarray(bf, dtype=np.float32), np.ascontiguousarray(cum, dtype=np.float32),
+         np.ascontiguousarray(vterm, dtype=np.float32)]
+    lib().orc_table_rollout(C.c_int64(ns), C.c_int(len(tab.actions)), _p(a[0], C.c_int64), _p(a[1], C.c_int32), _p(a[2], C.c_uint8),
+                            _p(a[3], C.c_float), _p(a[4], C.c_float), _p(a[5], C.c_float), _p(a[6], C.c_float),
+                            C.c_double(tab.gamma), _p(st, C.c_int32), C.c_int64(ns if st is None else len(st)),
+                            C.c_int64(path0), C.c_int64(npaths), C.c_uint64(seed), C.c_int64(horizon),
+                            _p(logw, C.c_float), _p(meta, C.c_uint32))
+    return logw, meta

@@ -765,3 +765,41 @@ int orc_table_solve(int kind, int64_t ns, int na, const int64_t *ptr, const int3
   if (residual_out) *residual_out = res;
   return 0;
 }
+
+/* Path sampling on a tabulated problem with the sampler's float tables (running action probabilities cdf, beta*fitness bf,
+ * running transition probabilities cum, terminal values vterm): the contract of piql_table_mc_logz, one Philox4x32-10 call
+ * per step, words 0 / 1 / 2 -> action walk / stop test u >= gamma / successor walk.  Records: logw, meta = a0 | len << 4. */
+int orc_table_rollout(int64_t ns, int na, const int64_t *ptr, const int32_t *succ, const uint8_t *term, const float *cdf,
+                      const float *bf, const float *cum, const float *vterm, double gamma, const int32_t *starts,
+                      int64_t nstarts, int64_t path0, int64_t npaths, uint64_t seed, int64_t horizon, float *logw_out,
+                      uint32_t *meta_out) {
+  (void)ns;
+  const float gam = (float)gamma;
+  for (int64_t q = 0; q < npaths; q++) {
+    const uint64_t gp = (uint64_t)(path0 + q);
+    int64_t s = starts ? starts[gp % (uint64_t)nstarts] : (int64_t)(gp % (uint64_t)nstarts);
+    uint32_t t = 0, a0 = 0;
+    float logw = 0.f;
+    for (;;) {
+      if (term[s]) { logw = logw - vterm[s]; break; }
+      if ((int64_t)t >= horizon) break;
+      const uint32_t ctr[4] = {t, 0u, (uint32_t)gp, (uint32_t)(gp >> 32)}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+      uint32_t r[4];
+      orc_philox4x32_10(ctr, key, r);
+      const float u0 = u01(r[0]), u1 = u01(r[1]), u2 = u01(r[2]);
+      int a = 0;
+      while (a < na - 1 && cdf[s * na + a] < u0) a++;
+      logw = logw + bf[s * na + a];
+      if (t == 0) a0 = (uint32_t)a;
+      if (u1 >= gam) break;
+      int64_t e = ptr[s * na + a];
+      const int64_t last = ptr[s * na + a + 1] - 1;
+      while (e < last && cum[e] < u2) e++;
+      s = succ[e];
+      t++;
+    }
+    logw_out[q] = logw;
+    meta_out[q] = a0 | (t << 4);
+  }
+  return 0;
+}

@@ -97,6 +97,8 @@ SYMBOLS = {
     "piql_table_load": (C.c_int32, [_P, C.POINTER(TableProblem)]),
     "piql_table_solve": (C.c_int32, [_P, C.c_int32, _D, _D, C.c_double, C.c_double, C.POINTER(SolveOpts), _D, C.POINTER(SolveStats)]),
     "piql_table_update_v": (C.c_int32, [_P, _D, C.c_double, C.POINTER(SolveOpts), _D, _D, C.POINTER(SolveStats)]),
+    "piql_table_mc_logz": (C.c_int32, [_P, _D, C.c_double, C.POINTER(McOpts), _D, C.POINTER(C.c_uint64), _D, C.POINTER(McStats),
+                                        C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "piql_vi_set_iterate": (C.c_int32, [_P, C.POINTER(C.c_double)]),
     "piql_vi_tile_plan": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "piql_vi_sweeps_dev": (C.c_int32, [_P, C.c_int64]),

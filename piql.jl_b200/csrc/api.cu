@@ -889,6 +889,95 @@ int32_t piql_table_update_v(piql_ctx* ctx, const double* V, double beta, const p
   return rc;
 }
 
+int32_t piql_table_mc_logz(piql_ctx* ctx, const double* V, double beta, const piql_mc_opts* o, double* logz_sa_out,
+                           uint64_t* count_sa_out, double* logz_s_out, piql_mc_stats* stats, float* cdf_out, float* bf_out,
+                           float* cum_out) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  NEED(ctx->has_table_problem, PIQL_ERR_STATE, "no tabulated problem loaded (call piql_table_load first)");
+  NEED(V != nullptr && o != nullptr, PIQL_ERR_ARG, "V / opts is null");
+  NEED(beta == beta, PIQL_ERR_ARG, "beta is NaN");
+  NEED(o->npaths >= 0 && o->path0 >= 0 && o->horizon > 0, PIQL_ERR_ARG, "npaths / path0 / horizon out of range");
+  NEED(o->estimator == PIQL_EST_SAMPLED_STOP, PIQL_ERR_UNSUPPORTED, "tabulated problems support the sampled-stop estimator only");
+  NEED(o->injected == nullptr, PIQL_ERR_UNSUPPORTED, "injected uniforms are not supported on tabulated problems");
+  NEED(o->npaths <= MAX_RECORDS_PER_LAUNCH, PIQL_ERR_ARG, "too many paths for one call (at most 2^28)");
+  const TableDev& t = ctx->tab;
+  if (o->start_mode == PIQL_START_LIST) {
+    NEED(o->starts != nullptr && o->nstarts > 0, PIQL_ERR_ARG, "start list is empty");
+    for (long long i = 0; i < o->nstarts; i++) NEED(o->starts[i] >= 0 && o->starts[i] < t.ns, PIQL_ERR_ARG, "start state out of range");
+  }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const long long rows = t.ns * t.na, nstarts = o->start_mode == PIQL_START_LIST ? o->nstarts : t.ns, nb = nstarts * t.na;
+  if (o->npaths > ctx->rec_cap) {
+    if (ctx->d_logw) cudaFree(ctx->d_logw);
+    if (ctx->d_meta) cudaFree(ctx->d_meta);
+    ctx->d_logw = nullptr; ctx->d_meta = nullptr; ctx->rec_cap = 0;
+    CK(cudaMalloc((void**)&ctx->d_logw, 4 * (size_t)(o->npaths ? o->npaths : 1)));
+    CK(cudaMalloc((void**)&ctx->d_meta, 4 * (size_t)(o->npaths ? o->npaths : 1)));
+    ctx->rec_cap = o->npaths ? o->npaths : 1;
+  }
+  std::vector<void*> tmp;
+  auto dev = [&](size_t bytes, void** p) -> cudaError_t {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 8);
+    if (e == cudaSuccess) tmp.push_back(*p);
+    return e;
+  };
+  float *d_cdf, *d_bf, *d_cum, *d_vt;
+  int *d_omax, *d_starts = nullptr;
+  double *d_sum, *d_lsa, *d_ls;
+  unsigned long long *d_cnt, *d_csa;
+  cudaError_t e = dev(4 * (size_t)rows, (void**)&d_cdf);
+  if (e == cudaSuccess) e = dev(4 * (size_t)rows, (void**)&d_bf);
+  if (e == cudaSuccess) e = dev(4 * (size_t)ctx->tab_nnz, (void**)&d_cum);
+  if (e == cudaSuccess) e = dev(4 * (size_t)t.ns, (void**)&d_vt);
+  if (e == cudaSuccess) e = dev(4 * (size_t)nb, (void**)&d_omax);
+  if (e == cudaSuccess) e = dev(8 * (size_t)nb, (void**)&d_sum);
+  if (e == cudaSuccess) e = dev(8 * (size_t)nb, (void**)&d_cnt);
+  if (e == cudaSuccess) e = dev(8 * (size_t)rows, (void**)&d_lsa);
+  if (e == cudaSuccess) e = dev(8 * (size_t)rows, (void**)&d_csa);
+  if (e == cudaSuccess) e = dev(8 * (size_t)t.ns, (void**)&d_ls);
+  if (e == cudaSuccess && o->start_mode == PIQL_START_LIST) {
+    e = dev(4 * (size_t)nstarts, (void**)&d_starts);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_starts, o->starts, 4 * (size_t)nstarts, cudaMemcpyHostToDevice, st);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->tb_V, V, 8 * (size_t)t.ns, cudaMemcpyHostToDevice, st);
+  float ms_roll = 0.f, ms_all = 0.f;
+  if (e == cudaSuccess) {
+    launch_fold_counter(ctx->d_transitions, st);
+    launch_table_policy(t, 1.0, beta, ctx->tb_V, d_cdf, d_bf, d_cum, d_vt, st);
+    launch_fill_f64(d_lsa, NAN, rows, st);
+    launch_fill_f64(d_ls, NAN, t.ns, st);
+    e = cudaMemsetAsync(d_csa, 0, 8 * (size_t)rows, st);
+    cudaEventRecord(ctx->ev0, st);
+    launch_table_rollout(t, d_cdf, d_bf, d_cum, d_vt, t.gamma, o->horizon, o->path0, o->npaths, d_starts, nstarts, o->seed,
+                         ctx->d_logw, ctx->d_meta, ctx->num_sms, st);
+    cudaEventRecord(ctx->ev1, st);
+    launch_table_reduce(ctx->d_logw, ctx->d_meta, o->path0, o->npaths, d_starts, nstarts, t.na, d_omax, d_sum, d_cnt,
+                        ctx->d_transitions, d_lsa, d_csa, d_ls, ctx->num_sms, st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && logz_sa_out) e = cudaMemcpyAsync(logz_sa_out, d_lsa, 8 * (size_t)rows, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && count_sa_out) e = cudaMemcpyAsync(count_sa_out, d_csa, 8 * (size_t)rows, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && logz_s_out) e = cudaMemcpyAsync(logz_s_out, d_ls, 8 * (size_t)t.ns, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && cdf_out) e = cudaMemcpyAsync(cdf_out, d_cdf, 4 * (size_t)rows, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && bf_out) e = cudaMemcpyAsync(bf_out, d_bf, 4 * (size_t)rows, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && cum_out) e = cudaMemcpyAsync(cum_out, d_cum, 4 * (size_t)ctx->tab_nnz, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_transitions, ctx->d_transitions, 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) {
+    cudaEventElapsedTime(&ms_roll, ctx->ev0, ctx->ev1);
+    ms_all = ms_roll;
+  }
+  for (void* p : tmp) cudaFree(p);
+  if (e != cudaSuccess) return fail(ctx, PIQL_ERR_CUDA, std::string("piql_table_mc_logz: ") + cudaGetErrorString(e));
+  if (stats) {
+    stats->transitions = *ctx->h_transitions; stats->paths = (uint64_t)o->npaths;
+    stats->rollout_seconds = ms_roll * 1e-3; stats->device_seconds = ms_all * 1e-3;
+  }
+  return PIQL_OK;
+}
+
 int32_t piql_sweep_once(piql_ctx* ctx, int32_t kind, const double* V, const double* Q, const double* nu, double beta,
                         double reward_scale, int32_t precision, const double* x_in, double* x_out, double* residual_out) {
   if (!ctx) return PIQL_ERR_ARG;

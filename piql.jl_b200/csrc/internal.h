@@ -159,6 +159,16 @@ void launch_table_sweep(const TableDev& t, int kind, double scale, const double*
                         const double* aux1, double* partial, double* residual, cudaStream_t st);
 void launch_table_update_v(long long ns, const double* V, const double* logz, double beta, double* out, cudaStream_t st);
 int table_blocks(long long ns);
+// Monte-Carlo sampling on the table: sampler tables from V, rollout (estimator A), reduction + finalisation
+void launch_table_policy(const TableDev& t, double scale, double beta, const double* V, float* cdf, float* bf, float* cum,
+                         float* vterm, cudaStream_t st);
+void launch_table_rollout(const TableDev& t, const float* cdf, const float* bf, const float* cum, const float* vterm, double gamma,
+                          long long horizon, long long path0, long long npaths, const int* starts, long long nstarts,
+                          uint64_t seed, float* logw, uint32_t* meta, int num_sms, cudaStream_t st);
+void launch_table_reduce(const float* logw, const uint32_t* meta, long long path0, long long npaths, const int* starts,
+                         long long nstarts, int na, int* omax, double* sum, unsigned long long* cnt,
+                         unsigned long long* transitions, double* logz_sa, unsigned long long* count_sa, double* logz_s,
+                         int num_sms, cudaStream_t st);
 
 // peer.cu: the log-sum-exp all-reduce of the accumulators over NVLink peer memory -----------------
 constexpr int PEER_MAX = 8;  // GPUs of one box

@@ -170,6 +170,7 @@ class Engine:
                            a["terminal"].ctypes.data_as(C.POINTER(C.c_uint8)), float(tab.gamma))
         self._ck(self._lib.piql_table_load(self._ctx, C.byref(p)))
         self.table_n = len(tab.terminal)
+        self.table_na = len(tab.actions)
         self.table_key = tab.key()
 
     def table_solve(self, kind, V=None, nu=None, beta=1.0, reward_scale=1.0, tol=1e-12, max_sweeps=10 ** 7, check_every=0,
@@ -191,6 +192,22 @@ class Engine:
         self._ck(self._lib.piql_table_update_v(self._ctx, _pd(V), float(beta), C.byref(o), _pd(out), _pd(logz), C.byref(st)),
                  allow=(K.ERR_NOT_CONVERGED,) if allow_unconverged else ())
         return out, logz, st
+
+    def table_mc_logz(self, V, beta=1.0, npaths=1 << 20, nnz=None, want_tables=False, **kw):
+        """Monte-Carlo log Z on the loaded tabulated problem: (logz_sa (ns, na), count (ns, na), logz_s (ns,), stats[, tables])."""
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        o, _keep = self._mc_opts(npaths, **kw)
+        ns = self.table_n
+        na = self.table_na
+        sa, cnt, s = np.empty((ns, na)), np.empty((ns, na), dtype=np.uint64), np.empty(ns)
+        st = K.McStats()
+        fp = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+        cdf = bf = cum = None
+        if want_tables:
+            cdf, bf, cum = np.empty((ns, na), np.float32), np.empty((ns, na), np.float32), np.empty(int(nnz), np.float32)
+        self._ck(self._lib.piql_table_mc_logz(self._ctx, _pd(V), float(beta), C.byref(o), _pd(sa),
+                                              cnt.ctypes.data_as(C.POINTER(C.c_uint64)), _pd(s), C.byref(st), fp(cdf), fp(bf), fp(cum)))
+        return (sa, cnt, s, st, (cdf, bf, cum)) if want_tables else (sa, cnt, s, st)
 
     def sweep_once(self, kind, x, V=None, Q=None, nu=None, beta=1.0, reward_scale=1.0, precision="f64"):
         kind = {"nu": K.KIND_NU, "logz": K.KIND_LOGZ, "gap": K.KIND_GAP}[kind]

@@ -261,6 +261,18 @@ class McResult:
         self.device_seconds = float(stats.device_seconds)
 
 
+class TableMcResult:
+    """mc_logz on a tabulated problem: estimates keyed by the problem's state objects."""
+
+    def __init__(self, tab, sa, cnt, ls, stats):
+        self.table, self.logz_sa, self.count_sa, self.stats = tab, sa, cnt, stats
+        self.transitions = int(stats.transitions)
+        self.logz = Growable.from_table(tab, ls)
+
+    def logz_q(self, s, a):
+        return float(self.logz_sa[self.table.index[s], list(self.table.actions).index(a)])
+
+
 def mc_logz(ctrl, V, beta=1.0, β=None, Q=None, npaths=1 << 20, seed=0, estimator="A", horizon=1 << 20, starts=None,
             device=0):
     """Monte-Carlo estimate of generate_logz(ctrl, V; β) from rollouts under pi_Q.
@@ -268,6 +280,13 @@ def mc_logz(ctrl, V, beta=1.0, β=None, Q=None, npaths=1 << 20, seed=0, estimato
     starts: list of (i, j) start states (path p starts at starts[p % len]); None = every free cell.
     """
     beta = beta if β is None else β
+    if ctrl.grid is None:
+        if Q is not None or estimator != "A":
+            raise NotImplementedError("tabulated problems: V-determined Q and the sampled-stop estimator only")
+        eng, tab = table_for(ctrl, device)
+        idx = None if starts is None else [tab.index[s] for s in starts]
+        sa, cnt, ls, st = eng.table_mc_logz(_table_values(tab, V), beta=beta, npaths=npaths, seed=seed, horizon=horizon, starts=idx)
+        return TableMcResult(tab, sa, cnt, ls, st)
     eng = engine_for(ctrl, device)
     cells = None if starts is None else [int(s[0]) + eng.H * int(s[1]) for s in starts]
     sa, cnt, s, st = eng.mc_logz(_dense(V, eng), beta=beta, Q=Q, npaths=npaths, seed=seed, estimator=estimator,

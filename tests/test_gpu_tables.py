@@ -79,3 +79,50 @@ def test_bandit_through_the_reference_interface(piql):
     assert gap(s0) > 0 and abs(piql.generate_optimality_gap(bb, nu, nu=nu)(s0)) < 1e-10
     lz = piql.generate_logz(bb, nu, beta=0.7)
     assert max(abs(v) for v in lz.dict.values()) < 1e-10
+
+
+def test_table_rollouts_bit_exact_and_estimate_hits_exact_logz(engine, piql):
+    """Monte-Carlo path sampling on tabulated problems: per-path records equal the oracle's bit for bit (same float tables,
+    same Philox stream), every path lands in one bucket, and the estimate sits within its error of the exact log Z."""
+    for ctrl, roots in ((piql.binary_bandit_problem(rounds=7, ncoins=2, payoff=0.8, gamma=0.96), None),
+                        (None, "grid")):
+        if ctrl is None:
+            g = Golden("r0_01g0_99")
+            gw = piql.Gridworld(g.walls != 0, g.goal)
+            ctrl = piql.modify(piql.gridworld_ctrl(gw, **{k: g.params[k] for k in ("randomness", "step_cost", "reward", "gamma")}), grid=None)
+            tab = piql.tabulate_problem(ctrl, roots=[g.goal] + piql.state_iterator(gw))
+        else:
+            tab = piql.tabulate_problem(ctrl)
+        engine.load_table(tab)
+        nu, _ = engine.table_solve("nu")
+        V = 0.4 * nu
+        exact, _ = engine.table_solve("logz", V=V, beta=1.0)
+        s0 = 1 if roots == "grid" else 0
+        n = 1 << 20
+        sa, cnt, ls, st, (cdf, bf, cum) = engine.table_mc_logz(V, beta=1.0, npaths=n, seed=9, starts=[s0], nnz=len(tab.succ),
+                                                               want_tables=True)
+        logw, meta = engine.mc_records(n)
+        lw_ref, meta_ref = oracle.table_rollout(tab, cdf, bf, cum, V.astype(np.float32), n, starts=[s0], seed=9)
+        assert np.array_equal(meta, meta_ref) and np.array_equal(logw.view(np.uint32), lw_ref.view(np.uint32))
+        assert int(cnt.sum()) == n and int(cnt[s0].sum()) == n and st.transitions == int((meta >> 4).sum())
+        w = np.exp(logw.astype(np.float64) - logw.max())
+        sigma = w.std() / np.sqrt(n) / w.mean()
+        assert abs(ls[s0] - exact[s0]) < 4 * sigma + 2e-6, (ls[s0], exact[s0], sigma)
+        ref_lse = np.log(np.mean(np.exp(lw_ref.astype(np.float64))))
+        assert abs(ls[s0] - ref_lse) < 1e-6
+        # paths from every state: counts tile the states; first-action buckets hold the right paths
+        sa2, cnt2, ls2, _ = engine.table_mc_logz(V, beta=1.0, npaths=len(tab.states) * 64, seed=3)
+        assert np.all(cnt2.sum(axis=1) == 64)
+        term = tab.terminal != 0
+        assert np.allclose(ls2[term], -V[term], atol=1e-6)          # Z(terminal) = exp(-V)
+
+
+def test_bandit_mc_through_the_reference_interface(piql):
+    bb = piql.binary_bandit_problem(rounds=6, ncoins=2, gamma=0.95)
+    nu = piql.generate_nu(bb)
+    v = piql.Growable.from_table(piql.solvers.table_for(bb)[1], 0.5 * np.array(list(nu.dict.values())))
+    exact = piql.generate_logz(bb, v, beta=1.0)
+    s0 = bb.initial_state()
+    res = piql.mc_logz(bb, v, beta=1.0, npaths=1 << 20, seed=4, starts=[s0])
+    assert abs(res.logz(s0) - exact(s0)) < 0.01 and res.transitions > 1 << 20
+    assert res.count_sa.sum() == 1 << 20
