@@ -148,10 +148,15 @@ __device__ __forceinline__ T logz_cell(const TileK<T>& k, T c, T n0, T n1, T n2,
   const T g1 = k.gamma * (pos ? (T)1 : em), g0 = k.omg * (pos ? em : (T)1);
   const T base = g1 * wE + g0, gd = g1 * k.dw;
   const T sum = (ea0 * (gd * e0 + base) + ea1 * (gd * e1 + base)) + (ea2 * (gd * e2 + base) + ea3 * (gd * e3 + base));
-  T nw;
-  if constexpr (FAST) nw = fmaf(0.693147180559945f, lg2_approx(sum), fmaxf(m, 0.f) + amax);
-  else nw = fmax(m, (T)0) + amax + xlog(sum);
-  return damp_half<T, FAST>(nw, c);
+  if constexpr (FAST) {
+    // new = M + amax + log(sum) and the eta = 1/2 damping log(1/2 e^new + 1/2 e^c) fused: c + log(1/2 + 1/2 sum e^(M+amax-c)),
+    // one ex2 and one lg2 instead of lg2 + ex2 + lg2 (exponent clamped: 2^100 is far beyond any transient of the solve)
+    const float r = sum * ex2_approx(fminf((fmaxf(m, 0.f) + amax - c) * 1.44269504088896f, 100.f));
+    return fmaf(0.693147180559945f, lg2_approx(fmaf(0.5f, r, 0.5f)), c);
+  } else {
+    const T nw = fmax(m, (T)0) + amax + xlog(sum);
+    return damp_half<T, FAST>(nw, c);
+  }
 }
 // gap: D + sum_a pi_a * pa(s,a,gap), no discount on the gap term   value_iteration.jl:165
 template <typename T>
