@@ -161,6 +161,18 @@ rollout_kernel(const RolloutArgs p) {
       } else if (t >= hor) {
         done = true;
       } else {
+        // the whole 32-byte record in one 256-bit load (LDG.E.256, sm_100): one L1 wavefront per distinct line instead of
+        // two passes over the same sector; issued first (volatile keeps it there) so that the ~45 instructions of Philox
+        // run under the load's latency -- at 4096^2 half of these loads miss L2
+        float4 r0, r1;
+        if (STAGED) {
+          r0 = stab[2 * s];
+          r1 = stab[2 * s + 1];
+        } else {
+          asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=f"(r0.x), "=f"(r0.y), "=f"(r0.z), "=f"(r0.w), "=f"(r1.x), "=f"(r1.y), "=f"(r1.z), "=f"(r1.w)
+                       : "l"(p.table + 2 * (size_t)s));
+        }
         float u0;
         bool stop, slip;
         int aslip;
@@ -179,17 +191,6 @@ rollout_kernel(const RolloutArgs p) {
           stop = (r.y >> 8) >= p.gamma_k;
           slip = (r.z >> 8) < p.rho_k;
           aslip = (int)(r.w >> 30);
-        }
-        // the whole 32-byte record in one 256-bit load (LDG.E.256, sm_100): one L1 wavefront per
-        // distinct line instead of two passes over the same sector
-        float4 r0, r1;
-        if (STAGED) {
-          r0 = stab[2 * s];
-          r1 = stab[2 * s + 1];
-        } else {
-          asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-              : "=f"(r0.x), "=f"(r0.y), "=f"(r0.z), "=f"(r0.w), "=f"(r1.x), "=f"(r1.y), "=f"(r1.z), "=f"(r1.w)
-              : "l"(p.table + 2 * (size_t)s));
         }
         // StatsBase sample(a, Weights): i = 1; cw = w[1]; while cw < t && i < n: i += 1; cw += w[i]
         // c0 <= c1 <= c2, so the walk stops at the number of running sums below u0 (branch-free).
