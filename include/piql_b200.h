@@ -270,6 +270,22 @@ int32_t piql_vi_set_iterate(piql_ctx* ctx, const double* x);
 int32_t piql_vi_sweeps_dev(piql_ctx* ctx, int64_t sweeps);
 int32_t piql_vi_fetch(piql_ctx* ctx, double* x_out, double* residual_out);
 
+/* Multi-GPU soft VI: the grid is cut into slabs of tile columns, one per rank (one process per GPU on one box); after every
+ * round of sweeps a rank pushes its edge columns into its neighbours' arrays over NVLink peer memory.  Jacobi sweeps and
+ * tiling-independent values make the result bit-identical to the single-GPU solve for any number of ranks.
+ *   piql_vi_prepare_dev [-> piql_vi_set_iterate] -> piql_vi_shard_begin(rank, world, &mine) -> exchange the handle blobs
+ *   -> piql_vi_shard_connect(all blobs in rank order) -> barrier -> piql_vi_sweeps_dev (xN; the residual it leaves is this
+ *   rank's share: sum over ranks) -> piql_vi_fetch (only the columns [col0, col1) of the blob are this rank's) -> piql_vi_shard_end */
+typedef struct {
+  uint8_t x0[64], x1[64], flags[64]; /* cudaIpcMemHandle_t of the padded ping-pong arrays and the halo counters */
+  int64_t np;                        /* padded array length */
+  int32_t tj, tiles_j;               /* tile shape */
+  int64_t col0, col1;                /* columns of the H x W array this rank owns */
+} piql_vi_shard_handles;
+int32_t piql_vi_shard_begin(piql_ctx* ctx, int32_t rank, int32_t world, piql_vi_shard_handles* out);
+int32_t piql_vi_shard_connect(piql_ctx* ctx, const piql_vi_shard_handles* all);
+int32_t piql_vi_shard_end(piql_ctx* ctx);
+
 /* Kernels launched by this context since creation (for the bench's gpu_launches count). */
 int32_t piql_launch_count(piql_ctx* ctx, int64_t* n_out);
 

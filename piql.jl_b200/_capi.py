@@ -49,6 +49,11 @@ class TableProblem(C.Structure):
                 ("log_prior", C.POINTER(C.c_double)), ("terminal", C.POINTER(C.c_uint8)), ("gamma", C.c_double)]
 
 
+class ViShardHandles(C.Structure):
+    _fields_ = [("x0", C.c_uint8 * 64), ("x1", C.c_uint8 * 64), ("flags", C.c_uint8 * 64), ("np", C.c_int64),
+                ("tj", C.c_int32), ("tiles_j", C.c_int32), ("col0", C.c_int64), ("col1", C.c_int64)]
+
+
 class PeerHandles(C.Structure):
     _fields_ = [("lse_max", C.c_uint8 * 64), ("lse_sum", C.c_uint8 * 64), ("count", C.c_uint8 * 64),
                 ("flags", C.c_uint8 * 64), ("n", C.c_int64)]
@@ -99,6 +104,9 @@ SYMBOLS = {
     "piql_table_update_v": (C.c_int32, [_P, _D, C.c_double, C.POINTER(SolveOpts), _D, _D, C.POINTER(SolveStats)]),
     "piql_table_mc_logz": (C.c_int32, [_P, _D, C.c_double, C.POINTER(McOpts), _D, C.POINTER(C.c_uint64), _D, C.POINTER(McStats),
                                         C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "piql_vi_shard_begin": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(ViShardHandles)]),
+    "piql_vi_shard_connect": (C.c_int32, [_P, C.POINTER(ViShardHandles)]),
+    "piql_vi_shard_end": (C.c_int32, [_P]),
     "piql_vi_set_iterate": (C.c_int32, [_P, C.POINTER(C.c_double)]),
     "piql_vi_tile_plan": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "piql_vi_sweeps_dev": (C.c_int32, [_P, C.c_int64]),

@@ -42,6 +42,7 @@ struct piql_ctx {
   long long vi_sweeps_done = 0;
   TileBuffers tb;  // padded copy of the iterate for the tiled multi-sweep kernel
   PeerState peer;  // NVLink peer mappings of the other ranks' accumulators
+  ViPeer vpeer;    // ... and of their padded soft-VI arrays (column-slab sharding)
 
   // tabulated (non-grid) problem
   bool has_table_problem = false;
@@ -125,6 +126,14 @@ void peer_close(piql_ctx* ctx) {
   ps.valid = false;
 }
 
+void vpeer_close(piql_ctx* c) {
+  ViPeer& vp = c->vpeer;
+  for (int i = 0; i < vp.nopened; i++) cudaIpcCloseMemHandle(vp.opened[i]);
+  vp.nopened = 0;
+  vp.valid = false;
+  c->tb.sharded = false;
+}
+
 void free_table(piql_ctx* c) {
   for (void* p : c->tab_bufs) cudaFree(p);
   c->tab_bufs.clear();
@@ -187,6 +196,7 @@ int vi_prepare(piql_ctx* ctx, int kind, const double* V, const double* Q, const 
   vs.precision = precision; vs.kind = kind; vs.beta = beta; vs.reward_scale = reward_scale; vs.cur = 0;
   vs.fast = fast;
   ctx->tb.active = false;
+  if (ctx->tb.sharded) vpeer_close(ctx);  // a new solve starts unsharded; piql_vi_shard_begin shards it again
   vs.nblocks = (n + SWEEP_THREADS - 1) / SWEEP_THREADS;
   vs.v_goal = 0.0;
   vs.residual = ctx->d_scalars;
@@ -517,6 +527,8 @@ int32_t piql_destroy(piql_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   peer_close(ctx);
+  vpeer_close(ctx);
+  if (ctx->vpeer.own_flags) cudaFree(ctx->vpeer.own_flags);
   free_table(ctx);
   if (ctx->peer.own_flags) cudaFree(ctx->peer.own_flags);
   if (ctx->peer.done) cudaFree(ctx->peer.done);
@@ -1028,6 +1040,7 @@ int32_t piql_vi_set_iterate(piql_ctx* ctx, const double* x) {
   LaunchScope ls(ctx);
   NEED(ctx->vs_ready, PIQL_ERR_STATE, "call piql_vi_prepare_dev first");
   NEED(x != nullptr, PIQL_ERR_ARG, "x is null");
+  NEED(!ctx->tb.sharded, PIQL_ERR_STATE, "set the iterate before piql_vi_shard_begin");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const int n = ctx->g.n;
@@ -1044,7 +1057,10 @@ int32_t piql_vi_sweeps_dev(piql_ctx* ctx, int64_t sweeps) {
   NEED(ctx->vs_ready, PIQL_ERR_STATE, "call piql_vi_prepare_dev first");
   NEED(sweeps > 0, PIQL_ERR_ARG, "sweeps must be positive");
   CK(cudaSetDevice(ctx->device));
-  if (ctx->tb.active) {
+  if (ctx->tb.active && ctx->tb.sharded) {
+    NEED(ctx->vpeer.valid, PIQL_ERR_STATE, "call piql_vi_shard_connect first");
+    CK(tile_sweeps_sharded(ctx->g, ctx->vs, ctx->tb, ctx->vpeer, sweeps, true, ctx->stream));
+  } else if (ctx->tb.active) {
     CK(tile_sweeps(ctx->g, ctx->vs, ctx->tb, sweeps, true, ctx->stream));
   } else {
     for (int64_t i = 0; i < sweeps; i++) launch_sweep(ctx->g, ctx->d_cell, ctx->vs, i == sweeps - 1, ctx->stream);
@@ -1068,7 +1084,73 @@ int32_t piql_vi_fetch(piql_ctx* ctx, double* x_out, double* residual_out) {
   }
   CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  NEED(!(ctx->tb.err && *ctx->tb.err), PIQL_ERR_CUDA, "a soft-VI kernel timed out waiting for a neighbouring tile or rank");
   if (residual_out) *residual_out = ctx->h_scalars[0];
+  return PIQL_OK;
+}
+
+int32_t piql_vi_shard_begin(piql_ctx* ctx, int32_t rank, int32_t world, piql_vi_shard_handles* out) {
+  if (!ctx || !out) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  NEED(ctx->vs_ready, PIQL_ERR_STATE, "call piql_vi_prepare_dev first");
+  NEED(world >= 1 && world <= PEER_MAX && rank >= 0 && rank < world, PIQL_ERR_ARG, "rank / world out of range (at most 8 GPUs)");
+  NEED(ctx->g.n > RESIDENT_MAX_CELLS, PIQL_ERR_UNSUPPORTED, "grids of at most 8192 cells are solved by one CTA; nothing to shard");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  vpeer_close(ctx);
+  ViPeer& vp = ctx->vpeer;
+  ctx->tb.sharded = true;
+  // the shape every rank uses, then this rank's slab of tile columns
+  const TilePlan pl = make_tile_plan(ctx->g.H, ctx->g.W, ctx->vs.precision, ctx->vs.kind, ctx->num_sms);
+  NEED(pl.tiles_j >= world, PIQL_ERR_UNSUPPORTED, "fewer tile columns than ranks");
+  ctx->tb.tj0 = (int)((long long)pl.tiles_j * rank / world);
+  ctx->tb.tj1 = (int)((long long)pl.tiles_j * (rank + 1) / world);
+  CK(tile_begin(ctx->g, ctx->d_cell, ctx->vs, ctx->tb, ctx->num_sms, st));  // packs the iterate in the shared shape
+  if (!vp.own_flags) CK(cudaMalloc((void**)&vp.own_flags, 2 * sizeof(unsigned)));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaMemset(vp.own_flags, 0, 2 * sizeof(unsigned)));
+  vp.round = 0; vp.rank = rank; vp.world = world;
+  CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->x0, ctx->tb.x[0]));
+  CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->x1, ctx->tb.x[1]));
+  CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->flags, vp.own_flags));
+  out->np = ctx->tb.plan.np; out->tj = ctx->tb.plan.TJ; out->tiles_j = ctx->tb.plan.tiles_j;
+  // real columns this rank owns: [col0, col1)
+  out->col0 = (int64_t)ctx->tb.tj0 * pl.TJ;
+  out->col1 = std::min<int64_t>((int64_t)ctx->tb.tj1 * pl.TJ, ctx->g.W);
+  return PIQL_OK;
+}
+int32_t piql_vi_shard_connect(piql_ctx* ctx, const piql_vi_shard_handles* all) {
+  if (!ctx || !all) return PIQL_ERR_ARG;
+  ViPeer& vp = ctx->vpeer;
+  NEED(ctx->tb.sharded && vp.own_flags, PIQL_ERR_STATE, "call piql_vi_shard_begin first");
+  CK(cudaSetDevice(ctx->device));
+  for (int r = 0; r < vp.world; r++)
+    NEED(all[r].np == ctx->tb.plan.np && all[r].tj == ctx->tb.plan.TJ, PIQL_ERR_ARG, "ranks disagree on the tile shape (different grids?)");
+  for (int r = 0; r < vp.world; r++) {
+    if (r == vp.rank) { vp.x[0][r] = ctx->tb.x[0]; vp.x[1][r] = ctx->tb.x[1]; vp.flags[r] = vp.own_flags; continue; }
+    if (r != vp.rank - 1 && r != vp.rank + 1) continue;  // only the neighbours are ever touched
+    void* p[3] = {nullptr, nullptr, nullptr};
+    const uint8_t* h[3] = {all[r].x0, all[r].x1, all[r].flags};
+    for (int q = 0; q < 3; q++) {
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, h[q], sizeof(hd));
+      cudaError_t e = cudaIpcOpenMemHandle(&p[q], hd, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        vpeer_close(ctx);
+        return fail(ctx, PIQL_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+      }
+      vp.opened[vp.nopened++] = p[q];
+    }
+    vp.x[0][r] = p[0]; vp.x[1][r] = p[1]; vp.flags[r] = (unsigned*)p[2];
+  }
+  vp.valid = true;
+  return PIQL_OK;
+}
+int32_t piql_vi_shard_end(piql_ctx* ctx) {
+  if (!ctx) return PIQL_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  vpeer_close(ctx);
   return PIQL_OK;
 }
 

@@ -58,6 +58,9 @@ struct TileBuffers {
   long long cap_flags = 0;
   int* err = nullptr;          // pinned host word: set when a neighbour wait timed out (copied from d_err after a launch)
   int* d_err = nullptr;        // device word the kernel polls and sets
+  // multi-GPU column slabs: this rank sweeps tile columns [tj0, tj1) (piql_vi_shard_*)
+  bool sharded = false;
+  int tj0 = 0, tj1 = 0;
   // shape found fastest on the device for the problem `tuned_key` (grid, precision, kind)
   long long tuned_key = -1;
   TilePlan tuned_plan{};
@@ -188,6 +191,20 @@ struct PeerState {
   int nopened = 0;
 };
 void launch_lse_allreduce_peer(const PeerState& ps, long long nslots, int num_sms, cudaStream_t st);
+
+// multi-GPU soft VI (tile.cu): peer mappings of the other ranks' padded ping-pong arrays and halo counters
+struct ViPeer {
+  int rank = 0, world = 0;
+  void* x[2][PEER_MAX] = {};           // x[buffer][rank]
+  unsigned* flags[PEER_MAX] = {};      // flags[r] on rank r: [0] rounds delivered by its left neighbour, [1] by its right one
+  unsigned* own_flags = nullptr;
+  long long round = 0;                 // rounds completed since the iterate was (re)packed
+  bool valid = false;
+  void* opened[3 * PEER_MAX] = {};
+  int nopened = 0;
+};
+cudaError_t tile_sweeps_sharded(const GridDev& g, const ViState& vs, TileBuffers& tb, ViPeer& vp, long long nsweeps, bool want_res,
+                                cudaStream_t st);
 
 // counts kernel launches made through the launch_* wrappers
 extern thread_local long long g_launches;

@@ -43,6 +43,7 @@ constexpr int TMP = TMB / 4;        // 32-bit words
 template <typename T> struct TileK {
   int ld, np;          // leading dimension and size of the padded arrays
   int TJ, EJ, tiles_i;
+  int tj0;             // first tile column of this launch (multi-GPU column slabs; 0 otherwise)
   int goal_pi, goal_pj, goal_p;  // goal in padded coordinates
   T kc, a1, b1, a2;    // nu: x_a = kc + a1*n_a + b1*S;  a2 = a1*log2(e)
   T kc_lo, a1_lo;      // fp32: what rounding kc and a1 to float lost (a constant per-sweep bias is amplified by 1/(1-gamma))
@@ -263,7 +264,7 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
   T* bufB = bufA + EJ * TEI;
   uint32_t* msk0 = reinterpret_cast<uint32_t*>(bufB + EJ * TEI);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
-  const int ti = blockIdx.x % k.tiles_i, tj = blockIdx.x / k.tiles_i;
+  const int ti = blockIdx.x % k.tiles_i, tj = blockIdx.x / k.tiles_i + k.tj0;
   const int org = ti * TTI + ld * (tj * k.TJ);  // padded index of the tile's (row 0, column 0)
   const int moff = (ti * TTI) & 15;              // bytes the staged cell-byte box starts before row 0 (0 or 8)
   const uint32_t* msk = msk0 + (moff >> 2);
@@ -608,7 +609,7 @@ TilePlan choose_tile_plan(int H, int W, int precision, int kind, int num_sms, bo
 
 template <typename T> static TileK<T> make_tile_k(const GridDev& g, const ViState& vs, const TilePlan& pl) {
   TileK<T> k;
-  k.ld = pl.ld; k.np = (int)pl.np; k.TJ = pl.TJ; k.EJ = pl.EJ; k.tiles_i = pl.tiles_i;
+  k.ld = pl.ld; k.np = (int)pl.np; k.TJ = pl.TJ; k.EJ = pl.EJ; k.tiles_i = pl.tiles_i; k.tj0 = 0;
   k.goal_pi = g.goal % g.H + TKH; k.goal_pj = g.goal / g.H + TKH; k.goal_p = k.goal_pi + pl.ld * k.goal_pj;
   const double w_on = 1.0 * (1.0 - g.randomness) + g.randomness / NA, w_off = 0.0 * (1.0 - g.randomness) + g.randomness / NA;
   const double a1 = g.gamma * (w_on - w_off);
@@ -661,8 +662,9 @@ void tile_free(TileBuffers& tb) {
   const long long key = tb.tuned_key;
   const TilePlan plan = tb.tuned_plan;
   const bool pers = tb.tuned_persistent;
+  const bool sh = tb.sharded;
   tb = TileBuffers{};
-  tb.tuned_key = key; tb.tuned_plan = plan; tb.tuned_persistent = pers;
+  tb.tuned_key = key; tb.tuned_plan = plan; tb.tuned_persistent = pers; tb.sharded = sh;
 }
 
 template <typename T>
@@ -724,6 +726,10 @@ static cudaError_t tile_setup(const GridDev& g, const uint8_t* cell, const ViSta
 
 cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs, TileBuffers& tb, int num_sms, cudaStream_t st) {
   const long long key = (((long long)g.H * 65537 + g.W) * 4 + vs.precision * 2 + (vs.fast ? 1 : 0)) * 4 + vs.kind;
+  if (tb.sharded) {  // every rank must use the same shape: the model's multi-launch choice, nothing timed
+    const TilePlan pl = make_tile_plan(g.H, g.W, vs.precision, vs.kind, num_sms);
+    return tile_setup(g, cell, vs, tb, pl, false, st);
+  }
   const bool pinned = getenv("PIQL_TILE_TJ") || getenv("PIQL_TILE_NW") || getenv("PIQL_TILE_NO_TUNE");
   if (!pinned && tb.tuned_key == key) return tile_setup(g, cell, vs, tb, tb.tuned_plan, tb.tuned_persistent, st);
   bool persist = false;
@@ -775,8 +781,9 @@ static cudaError_t launch_tile_t(const GridDev& g, const ViState& vs, TileBuffer
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  const TileK<T> k = make_tile_k<T>(g, vs, tb.plan);
-  const unsigned grid = (unsigned)(tb.plan.tiles_i * tb.plan.tiles_j);
+  TileK<T> k = make_tile_k<T>(g, vs, tb.plan);
+  k.tj0 = tb.sharded ? tb.tj0 : 0;
+  const unsigned grid = (unsigned)(tb.plan.tiles_i * (tb.sharded ? tb.tj1 - tb.tj0 : tb.plan.tiles_j));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * tb.plan.nw); cfg.dynamicSmemBytes = tb.plan.smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -887,6 +894,76 @@ void tile_unpack(const GridDev& g, const ViState& vs, const TileBuffers& tb, cud
   if (vs.precision == 0) tile_unpack_kernel<double><<<nblk(g.n, 256), 256, 0, st>>>(pg, (const double*)tb.x[tb.cur], (double*)vs.x[vs.cur]);
   else tile_unpack_kernel<float><<<nblk(g.n, 256), 256, 0, st>>>(pg, (const float*)tb.x[tb.cur], (float*)vs.x[vs.cur]);
   g_launches++;
+}
+
+// ---- multi-GPU soft VI: column slabs of tiles, halo columns exchanged over NVLink peer memory ---------------------------
+// Every rank holds the whole padded array (the layout is replicated) but sweeps only the tile columns [tj0, tj1) it owns.
+// After a round of TILE_KH sweeps it pushes its first and last TILE_KH interior columns of the new iterate into the same
+// places of its left / right neighbour's array (their halo) with peer stores and raises the neighbour's counter; before a
+// round it waits until both neighbours have delivered the previous round.  Receiving round r-1 from a neighbour also means
+// the neighbour has finished reading the buffer that round r's push overwrites.  Jacobi + tiling-independent values make
+// the result bit-identical to the single-GPU solve for any number of ranks.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+halo_push_kernel(const T* __restrict__ local, T* __restrict__ left, T* __restrict__ right, int ld, int c0, int c1,
+                 unsigned* left_flag, unsigned* right_flag, unsigned epoch) {
+  const int n = TKH * ld;
+  if (left) for (int i = threadIdx.x; i < n; i += blockDim.x) left[(size_t)c0 * ld + i] = local[(size_t)c0 * ld + i];
+  if (right) for (int i = threadIdx.x; i < n; i += blockDim.x) right[(size_t)(c1 - TKH) * ld + i] = local[(size_t)(c1 - TKH) * ld + i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (left_flag) *(volatile unsigned*)left_flag = epoch;
+    if (right_flag) *(volatile unsigned*)right_flag = epoch;
+  }
+}
+__global__ void halo_wait_kernel(const unsigned* from_left, const unsigned* from_right, unsigned epoch, int* err) {
+  const unsigned long long t0 = globaltimer_ns_tile();
+  for (int side = 0; side < 2; side++) {
+    const volatile unsigned* f = side ? from_right : from_left;
+    if (!f) continue;
+    while (*f < epoch) {
+      if (globaltimer_ns_tile() - t0 > 10000000000ull) { *err = 2; return; }
+      __nanosleep(100);
+    }
+  }
+  __threadfence_system();
+}
+
+cudaError_t tile_sweeps_sharded(const GridDev& g, const ViState& vs, TileBuffers& tb, ViPeer& vp, long long nsweeps, bool want_res,
+                                cudaStream_t st) {
+  const int ld = tb.plan.ld;
+  const int c0 = TKH + tb.tj0 * tb.plan.TJ, c1 = TKH + tb.tj1 * tb.plan.TJ;  // padded columns of the owned interior
+  const bool has_l = vp.rank > 0, has_r = vp.rank < vp.world - 1;
+  while (nsweeps > 0) {
+    const int nsub = (int)std::min<long long>(nsweeps, TKH);
+    nsweeps -= nsub;
+    const bool res = want_res && nsweeps == 0;
+    if (vp.round > 0 && (has_l || has_r))
+      halo_wait_kernel<<<1, 1, 0, st>>>(has_l ? vp.own_flags + 0 : nullptr, has_r ? vp.own_flags + 1 : nullptr, (unsigned)vp.round, tb.d_err);
+    cudaError_t e;
+    if (vs.precision == 0) e = launch_tile_k<double, false>(g, vs, tb, nsub, res, st);
+    else if (vs.fast) e = launch_tile_k<float, true>(g, vs, tb, nsub, res, st);
+    else e = launch_tile_k<float, false>(g, vs, tb, nsub, res, st);
+    if (e != cudaSuccess) return e;
+    vp.round++;
+    const int cur = tb.cur;  // the buffer just written
+    // my first columns are the left neighbour's right halo (its counter "from right"), and vice versa
+    if (vs.precision == 0)
+      halo_push_kernel<double><<<1, 1024, 0, st>>>((const double*)tb.x[cur], has_l ? (double*)vp.x[cur][vp.rank - 1] : nullptr,
+                                                    has_r ? (double*)vp.x[cur][vp.rank + 1] : nullptr, ld, c0, c1,
+                                                    has_l ? vp.flags[vp.rank - 1] + 1 : nullptr, has_r ? vp.flags[vp.rank + 1] + 0 : nullptr,
+                                                    (unsigned)vp.round);
+    else
+      halo_push_kernel<float><<<1, 1024, 0, st>>>((const float*)tb.x[cur], has_l ? (float*)vp.x[cur][vp.rank - 1] : nullptr,
+                                                   has_r ? (float*)vp.x[cur][vp.rank + 1] : nullptr, ld, c0, c1,
+                                                   has_l ? vp.flags[vp.rank - 1] + 1 : nullptr, has_r ? vp.flags[vp.rank + 1] + 0 : nullptr,
+                                                   (unsigned)vp.round);
+    g_launches += 2;
+    if (res) launch_residual_final(tb.partial, tb.plan.tiles_i * (tb.tj1 - tb.tj0), vs.residual, st);
+  }
+  cudaError_t e = cudaMemcpyAsync(tb.err, tb.d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace piql

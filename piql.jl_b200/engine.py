@@ -237,6 +237,21 @@ class Engine:
         x = _cell(np.nan_to_num(np.asarray(x, dtype=np.float64)), self.H, self.W, "x")
         self._ck(self._lib.piql_vi_set_iterate(self._ctx, _pd(x)))
 
+    # multi-GPU soft VI (column slabs, halo exchange over NVLink peer memory)
+    def vi_shard_begin(self, rank, world):
+        h = K.ViShardHandles()
+        self._ck(self._lib.piql_vi_shard_begin(self._ctx, int(rank), int(world), C.byref(h)))
+        return bytes(h), (int(h.col0), int(h.col1))
+
+    def vi_shard_connect(self, blobs):
+        arr = (K.ViShardHandles * len(blobs))()
+        for r, b in enumerate(blobs):
+            C.memmove(C.addressof(arr[r]), b, C.sizeof(K.ViShardHandles))
+        self._ck(self._lib.piql_vi_shard_connect(self._ctx, arr))
+
+    def vi_shard_end(self):
+        self._ck(self._lib.piql_vi_shard_end(self._ctx))
+
     def vi_sweeps(self, sweeps):
         self._ck(self._lib.piql_vi_sweeps_dev(self._ctx, int(sweeps)))
 

@@ -94,3 +94,74 @@ def test_sharded_rollout_with_peer_and_nccl_exchange_matches_single_gpu(piql):
     assert got[0][1]["peer"][0][3] + got[1][1]["peer"][0][3] == int(st1.transitions)
     for a, b in zip(got[0][2], got[1][2]):
         assert np.array_equal(a, b)
+
+
+def _vi_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import piql_jl_b200 as piql
+    from piql_jl_b200 import distributed as pd
+    from conftest import random_gridworld
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda:%d" % rank))
+    walls, goal = random_gridworld((300, 420), 0.2, seed=17)
+    eng = piql.Engine(rank)
+    eng.load_grid(walls, goal, 0.03, 0.02, 0.2, 0.97)
+    x0 = np.asfortranarray(np.random.default_rng(5).normal(size=walls.shape))
+    V = np.asfortranarray(np.random.default_rng(6).normal(size=walls.shape) * 0.3)
+    out = {}
+    for kind, prec, kw in (("nu", "f64", {}), ("nu", "f32fast", {}), ("logz", "f64", dict(V=V, beta=0.6))):
+        x, sweeps, res = pd.solve_sharded(eng, kind, rank, world, precision=prec, tol=0.0, max_sweeps=37, check_every=10, x0=x0, **kw)
+        out[(kind, prec)] = (x, sweeps, res)
+    conv, sw, res = pd.solve_sharded(eng, "nu", rank, world, precision="f64", tol=1e-10, max_sweeps=100000, check_every=32)
+    out["converged"] = (conv, sw, res)
+    q.put((rank, out))
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs two GPUs on one box")
+def test_sharded_value_iteration_is_bit_identical_to_single_gpu(piql):
+    """North star: value-iteration results are bit-stable across GPU counts."""
+    import torch.multiprocessing as mp
+    from conftest import random_gridworld
+    world = 2
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_vi_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=240) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    walls, goal = random_gridworld((300, 420), 0.2, seed=17)
+    eng = piql.Engine(0)
+    eng.load_grid(walls, goal, 0.03, 0.02, 0.2, 0.97)
+    x0 = np.asfortranarray(np.random.default_rng(5).normal(size=walls.shape))
+    V = np.asfortranarray(np.random.default_rng(6).normal(size=walls.shape) * 0.3)
+    for kind, prec, kw in (("nu", "f64", {}), ("nu", "f32fast", {}), ("logz", "f64", dict(V=V, beta=0.6))):
+        eng.vi_prepare(kind, precision=prec, **kw)
+        eng.vi_set_iterate(x0)
+        for _ in range(3):
+            eng.vi_sweeps(10)
+        eng.vi_sweeps(7)
+        one, res1 = eng.vi_fetch()
+        for rank, out in got:
+            x, sweeps, res = out[(kind, prec)]
+            assert sweeps == 37
+            assert np.array_equal(np.nan_to_num(x).view(np.uint64), np.nan_to_num(one).view(np.uint64)), (kind, prec, rank)
+            assert abs(res - res1) <= 1e-9 * max(1.0, res1)
+    nu1, st = eng.solve_nu(tol=1e-10, check_every=32, max_sweeps=100000)
+    for rank, out in got:
+        conv, sw, res = out["converged"]
+        assert sw == st.sweeps and np.array_equal(np.nan_to_num(conv).view(np.uint64), np.nan_to_num(nu1).view(np.uint64))
+    eng.close()
