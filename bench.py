@@ -402,6 +402,38 @@ def run_ours(args, rank, world, local_rank):
                         "(includes the residual reduction on the last launch); f32fast = MUFU ex2/lg2; keys without a kind are nu")
         vi["setup_vlo"] = {"sweeps": int(vst.sweeps), "device_seconds": float(vst.device_seconds)}
 
+    # ---- soft-VI sweeps of ONE grid on all N GPUs (column slabs, halo exchange over NVLink peer memory) -------------
+    vi_sharded = None
+    if world > 1 and not args.no_vi:
+        vi_sharded = {}
+        for prec, nbytes in (("f32fast", 8), ("f64", 16)):
+            eng.vi_prepare("nu", precision=prec)
+            blob, cols = eng.vi_shard_begin(rank, world)
+            blobs = [None] * world
+            dist.all_gather_object(blobs, blob)
+            eng.vi_shard_connect(blobs)
+            barrier()
+            with torch.cuda.stream(stream):
+                eng.vi_sweeps(40)
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                eng.vi_sweeps(args.vi_sweeps)
+                b.record(stream)
+                barrier()
+            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda:%d" % local_rank)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t[0]) * 1e-3
+            sps = args.vi_sweeps / sec
+            gbs = nbytes * eng.nfree * sps / 1e9
+            vi_sharded[prec] = {"sweeps_per_s": sps, "us_per_sweep": 1e6 / sps, "state_backups_per_s": sps * eng.nfree,
+                                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak * world, "unit": "GB/s",
+                                             "frac": gbs / (peak * world), "bytes_per_state": nbytes}}
+            barrier()
+            eng.vi_shard_end()
+        vi_sharded["note"] = ("nu sweeps of the one %s grid split into %d column slabs; 4 sweeps per round, edge columns pushed to "
+                              "the neighbours over NVLink after every round; values bit-identical to the 1-GPU solve" % (name, world))
+
     # ---- CPU baseline beside it (rank 0, N = 1) ------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -435,7 +467,7 @@ def run_ours(args, rank, world, local_rank):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(name, args, world), "clocks": clocks, "exchange": exchange, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "vi": vi, "experiment": experiment,
+                "roofline": roofline, "cpu_baseline": cpu, "vi": vi, "vi_sharded": vi_sharded, "experiment": experiment,
                 "transitions_per_step": transitions / args.steps}
         print(json.dumps(line), flush=True)
     eng.close()

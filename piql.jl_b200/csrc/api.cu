@@ -1106,9 +1106,10 @@ int32_t piql_vi_shard_begin(piql_ctx* ctx, int32_t rank, int32_t world, piql_vi_
   ctx->tb.tj0 = (int)((long long)pl.tiles_j * rank / world);
   ctx->tb.tj1 = (int)((long long)pl.tiles_j * (rank + 1) / world);
   CK(tile_begin(ctx->g, ctx->d_cell, ctx->vs, ctx->tb, ctx->num_sms, st));  // packs the iterate in the shared shape
-  if (!vp.own_flags) CK(cudaMalloc((void**)&vp.own_flags, 2 * sizeof(unsigned)));
+  if (!vp.own_flags) CK(cudaMalloc((void**)&vp.own_flags, 4 * sizeof(unsigned)));
   CK(cudaStreamSynchronize(st));
-  CK(cudaMemset(vp.own_flags, 0, 2 * sizeof(unsigned)));
+  CK(cudaMemset(vp.own_flags, 0, 4 * sizeof(unsigned)));
+  vp.done = vp.own_flags + 2;
   vp.round = 0; vp.rank = rank; vp.world = world;
   CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->x0, ctx->tb.x[0]));
   CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->x1, ctx->tb.x[1]));

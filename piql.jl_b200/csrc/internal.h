@@ -197,7 +197,8 @@ struct ViPeer {
   int rank = 0, world = 0;
   void* x[2][PEER_MAX] = {};           // x[buffer][rank]
   unsigned* flags[PEER_MAX] = {};      // flags[r] on rank r: [0] rounds delivered by its left neighbour, [1] by its right one
-  unsigned* own_flags = nullptr;
+  unsigned* own_flags = nullptr;       // [0], [1]: counters the neighbours raise; [2]: blocks of my push kernel that are done
+  unsigned* done = nullptr;
   long long round = 0;                 // rounds completed since the iterate was (re)packed
   bool valid = false;
   void* opened[3 * PEER_MAX] = {};

@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "algebra.cuh"
@@ -904,15 +905,30 @@ void tile_unpack(const GridDev& g, const ViState& vs, const TileBuffers& tb, cud
 // the neighbour has finished reading the buffer that round r's push overwrites.  Jacobi + tiling-independent values make
 // the result bit-identical to the single-GPU solve for any number of ranks.
 template <typename T>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 halo_push_kernel(const T* __restrict__ local, T* __restrict__ left, T* __restrict__ right, int ld, int c0, int c1,
-                 unsigned* left_flag, unsigned* right_flag, unsigned epoch) {
-  const int n = TKH * ld;
-  if (left) for (int i = threadIdx.x; i < n; i += blockDim.x) left[(size_t)c0 * ld + i] = local[(size_t)c0 * ld + i];
-  if (right) for (int i = threadIdx.x; i < n; i += blockDim.x) right[(size_t)(c1 - TKH) * ld + i] = local[(size_t)(c1 - TKH) * ld + i];
+                 unsigned* left_flag, unsigned* right_flag, unsigned epoch, unsigned* done) {
+  __shared__ bool last;
+  const int n = TKH * ld / 4;  // 128-bit words per side (ld is a multiple of 32)
+  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  typedef typename std::conditional<sizeof(T) == 4, float4, double4>::type V4;
+  if (left) {
+    const V4* src = reinterpret_cast<const V4*>(local + (size_t)c0 * ld);
+    V4* dst = reinterpret_cast<V4*>(left + (size_t)c0 * ld);
+    for (int i = t0; i < n; i += stride) dst[i] = src[i];
+  }
+  if (right) {
+    const V4* src = reinterpret_cast<const V4*>(local + (size_t)(c1 - TKH) * ld);
+    V4* dst = reinterpret_cast<V4*>(right + (size_t)(c1 - TKH) * ld);
+    for (int i = t0; i < n; i += stride) dst[i] = src[i];
+  }
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x == 0) {  // every block's stores are fenced and counted: tell the neighbours
+    *done = 0u;
+    __threadfence_system();
     if (left_flag) *(volatile unsigned*)left_flag = epoch;
     if (right_flag) *(volatile unsigned*)right_flag = epoch;
   }
@@ -950,15 +966,15 @@ cudaError_t tile_sweeps_sharded(const GridDev& g, const ViState& vs, TileBuffers
     const int cur = tb.cur;  // the buffer just written
     // my first columns are the left neighbour's right halo (its counter "from right"), and vice versa
     if (vs.precision == 0)
-      halo_push_kernel<double><<<1, 1024, 0, st>>>((const double*)tb.x[cur], has_l ? (double*)vp.x[cur][vp.rank - 1] : nullptr,
+      halo_push_kernel<double><<<32, 256, 0, st>>>((const double*)tb.x[cur], has_l ? (double*)vp.x[cur][vp.rank - 1] : nullptr,
                                                     has_r ? (double*)vp.x[cur][vp.rank + 1] : nullptr, ld, c0, c1,
                                                     has_l ? vp.flags[vp.rank - 1] + 1 : nullptr, has_r ? vp.flags[vp.rank + 1] + 0 : nullptr,
-                                                    (unsigned)vp.round);
+                                                    (unsigned)vp.round, vp.done);
     else
-      halo_push_kernel<float><<<1, 1024, 0, st>>>((const float*)tb.x[cur], has_l ? (float*)vp.x[cur][vp.rank - 1] : nullptr,
+      halo_push_kernel<float><<<32, 256, 0, st>>>((const float*)tb.x[cur], has_l ? (float*)vp.x[cur][vp.rank - 1] : nullptr,
                                                    has_r ? (float*)vp.x[cur][vp.rank + 1] : nullptr, ld, c0, c1,
                                                    has_l ? vp.flags[vp.rank - 1] + 1 : nullptr, has_r ? vp.flags[vp.rank + 1] + 0 : nullptr,
-                                                   (unsigned)vp.round);
+                                                   (unsigned)vp.round, vp.done);
     g_launches += 2;
     if (res) launch_residual_final(tb.partial, tb.plan.tiles_i * (tb.tj1 - tb.tj0), vs.residual, st);
   }
