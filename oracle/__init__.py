@@ -209,7 +209,12 @@ def wall_unreachable(walls, goal_idx):
 
 
 def num_threads():
-    return int(lib().orc_num_threads())
+    """Host threads to use: the cores this process may run on.  (Not omp_get_max_threads: launchers such as torchrun export
+    OMP_NUM_THREADS=1 to every rank, and the OpenMP loops here take their thread count as an explicit argument anyway.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or int(lib().orc_num_threads()))
 
 
 def table_solve(tab, kind, V=None, nu=None, beta=1.0, reward_scale=1.0, tol=1e-12, max_sweeps=10 ** 7, x0=None):
