@@ -148,6 +148,15 @@ function mc_logz(ctx::Context, V; β = 1.0, npaths = 2^20, seed = 0, estimator =
     (logz = growable(ctx, logz_s), logz_sa = logz_sa, count = count, transitions = st.transitions)
 end
 
+# ---- the PIQL iteration itself: V <- V + log Z^/beta with log Z^ from rollouts, niter times on the device ----------------
+function mc_logz_updateV(ctx::Context, V; β = 1.0, npaths = 2^22, niter = 1, seed = 0, horizon = 2^20)
+    Vd = dense(ctx, V); out = similar(Vd); st = McStats()
+    o = McOpts(npaths, 0, seed, 0, 0, horizon, C_NULL, 0, C_NULL, 0)
+    GC.@preserve Vd out check(ctx, ccall((:piql_mc_update_v, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Cdouble, Ref{McOpts}, Int32, Ptr{Cdouble}, Ref{McStats}), ctx.ptr, Vd, β, o, niter, out, st))
+    growable(ctx, out; default = V.default)
+end
+
 # ---- the experiment protocol in two ccalls (scripts/experiments.jl:20-39; replaces the pmap over beta and over
 # ---- iterates of scripts/distributed_experiments.jl:26,28) ---------------------------------------------------
 function learning_traj_batch(ctx::Context, V0, βrange; n = 5, kw...)
