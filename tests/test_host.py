@@ -5,6 +5,7 @@ import ctypes
 import math
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -133,3 +134,25 @@ def test_host_path_sampler_mirrors_reference_draw_order(piql):
     steps = list(piql.path_transitions(ctrl, (3, 3), Q, rng, nsteps=20))
     assert len(steps) == 20 and rng.n_random == 40 and rng.n_int == 20
     assert len(piql.fitness_reward_estimate(ctrl, (3, 3), V, Q, rng, nsteps=20)) == 20
+
+
+def test_reference_arm_of_the_bench_runs_on_cpu_and_keeps_the_contract():
+    """bench.py --impl reference needs no GPU: one JSON line with the contract's keys from rank 0 (all host threads even
+    when a launcher exported OMP_NUM_THREADS=1, as torchrun does), nothing from the other ranks."""
+    import json
+    import subprocess
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "grid256", "--gpus", "2",
+           "--steps", "1", "--warmup", "0", "--ref-paths", "8192", "--setup-sweeps", "20"]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["n_gpus"] == 2
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    env["RANK"] = "1"
+    out1 = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert out1.returncode == 0 and out1.stdout.strip() == ""
