@@ -119,7 +119,7 @@ def solve_sharded(eng, kind, rank, world, V=None, nu=None, beta=1.0, reward_scal
     eng.vi_shard_connect(blobs)
     dist.barrier(group=group)
     sweeps, res = 0, float("inf")
-    dev = "cuda:%d" % eng.device
+    dev = "cuda:%d" % eng.device if dist.get_backend(group) == "nccl" else "cpu"
     while sweeps < max_sweeps:
         batch = min(check_every, max_sweeps - sweeps)
         eng.vi_sweeps(batch)

@@ -89,3 +89,84 @@ def test_lse_allreduce_matches_single_shard():
         assert np.allclose(lsa[ok], lsa_ref.ravel()[ok], rtol=1e-5, atol=2e-6)
     # every rank holds the same bits after the exchange
     assert np.array_equal(got[0][1], got[1][1]) and np.array_equal(got[0][2], got[1][2])
+
+
+class _FakeShardEngine:
+    """Stands in for piql.Engine in solve_sharded's host logic: every rank sweeps the whole grid with the oracle (so the
+    halo exchange is trivially right) but owns, and is asked for, only its slab of columns."""
+
+    def __init__(self, org, rank, world, W):
+        self.org, self.rank, self.world, self.W, self.device = org, rank, world, W, 0
+        self.calls = []
+
+    def vi_prepare(self, kind, **kw):
+        self.kind, self.kw = kind, {k: v for k, v in kw.items() if k in ("V", "nu", "beta", "reward_scale") and v is not None}
+        self.x = np.zeros((self.org.H, self.org.W), order="F")
+        self.res = float("inf")
+
+    def vi_set_iterate(self, x):
+        self.x = np.nan_to_num(np.asfortranarray(x))
+
+    def vi_shard_begin(self, rank, world):
+        c0, c1 = self.W * rank // world, self.W * (rank + 1) // world
+        self.cols = (c0, c1)
+        return b"blob%d" % rank, (c0, c1)
+
+    def vi_shard_connect(self, blobs):
+        assert blobs == [b"blob%d" % r for r in range(self.world)]
+        self.calls.append("connect")
+
+    def vi_sweeps(self, n):
+        for _ in range(n):
+            new, _d = self.org.sweep(self.kind, self.x, **self.kw)
+            c0, c1 = self.cols
+            mine = np.nan_to_num(new[:, c0:c1]) - np.nan_to_num(self.x[:, c0:c1])
+            self.res = float(np.abs(mine).sum())       # this rank's share of the stop rule
+            self.x = np.nan_to_num(new)
+
+    def vi_fetch(self, want_x=True):
+        out = self.x.copy()
+        out[self.org.walls != 0] = np.nan
+        return (out if want_x else None), self.res
+
+    def vi_shard_end(self):
+        self.calls.append("end")
+
+
+def _shard_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import piql_jl_b200  # noqa: F401
+    from piql_jl_b200.distributed import solve_sharded
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = Golden("r0_05g0_95")
+    eng = _FakeShardEngine(g.oracle(), rank, world, g.W)
+    x, sweeps, res = solve_sharded(eng, "nu", rank, world, tol=1e-9, max_sweeps=4000, check_every=16)
+    q.put((rank, x, sweeps, res, eng.calls))
+    dist.destroy_process_group()
+
+
+def test_sharded_solve_host_logic_stitches_slabs_and_sums_the_residual():
+    import torch.multiprocessing as mp
+    world = 2
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=180) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = Golden("r0_05g0_95")
+    for rank, x, sweeps, res, calls in got:
+        assert calls == ["connect", "end"] and sweeps % 16 == 0 and res < 1e-9
+        assert np.array_equal(np.isnan(x), g.walls != 0)
+        assert float(np.nanmax(np.abs(x - g.nu))) < 1e-8          # the reference's stored nu
+    assert got[0][2] == got[1][2] and np.array_equal(np.nan_to_num(got[0][1]), np.nan_to_num(got[1][1]))
