@@ -52,9 +52,9 @@ __device__ __forceinline__ void backup_cell(const K<T>& k, int s, unsigned ci, c
   } else if (KIND == KIND_NU) {
     nw = backup_nu(k, s, ci, nb);
   } else if (KIND == KIND_LOGZ) {
-    T A[NA];
-    load4(aux4, s, A);
-    nw = backup_logz(k, A, nb);
+    T ea[NA];
+    load4(aux4, s, ea);
+    nw = backup_logz(k, ea, __ldg(aux1 + s), nb);
   } else {
     T P[NA];
     load4(aux4, s, P);
@@ -204,6 +204,9 @@ resident_batch_kernel(K<T> k, int kind, const uint8_t* __restrict__ cell, const 
         if (kind == KIND_LOGZ) {
 #pragma unroll
           for (int a = 0; a < NA; a++) o4[a] = k.log_prior + k.beta * cv[a] + ((T)1 - k.beta) * (cv[a] - norm);
+          o1 = fmax(fmax(o4[0], o4[1]), fmax(o4[2], o4[3]));
+#pragma unroll
+          for (int a = 0; a < NA; a++) o4[a] = xexp(o4[a] - o1);
         } else {
           T nc, nnb[NA], cvn[NA];
           nc = (T)nu[s];
@@ -243,7 +246,7 @@ resident_batch_kernel(K<T> k, int kind, const uint8_t* __restrict__ cell, const 
         else if (kind == KIND_NU) nw = backup_nu(k, s, ci, nb);
         else {
           const T a4[NA] = {aux[s], aux[(size_t)n + s], aux[(size_t)2 * n + s], aux[(size_t)3 * n + s]};
-          nw = kind == KIND_LOGZ ? backup_logz(k, a4, nb) : backup_gap(k, a4, aux[(size_t)4 * n + s], nb);
+          nw = kind == KIND_LOGZ ? backup_logz(k, a4, aux[(size_t)4 * n + s], nb) : backup_gap(k, a4, aux[(size_t)4 * n + s], nb);
         }
         d += fabs((double)nw - (double)c);
         Y[s] = kind == KIND_LOGZ ? logaddexp((T)(-0.6931471805599453) + nw, (T)(-0.6931471805599453) + c) : nw;
@@ -317,6 +320,9 @@ prep_kernel(K<T> k, const uint8_t* __restrict__ cell, const T* __restrict__ V, c
     if (KIND == KIND_LOGZ) {
 #pragma unroll
       for (int a = 0; a < NA; a++) out4[a] = k.log_prior + k.beta * cv[a] + ((T)1 - k.beta) * (q[a] - norm);
+      out1 = fmax(fmax(out4[0], out4[1]), fmax(out4[2], out4[3]));   // stored as exp(A_a - max A) and max A
+#pragma unroll
+      for (int a = 0; a < NA; a++) out4[a] = xexp(out4[a] - out1);
     } else {
       T nc, nnb[NA], cvn[NA];
       gather(nu, s, k.H, ci, nc, nnb);
@@ -330,7 +336,7 @@ prep_kernel(K<T> k, const uint8_t* __restrict__ cell, const T* __restrict__ V, c
     }
   }
   store4(aux4, s, out4);
-  if (KIND == KIND_GAP) aux1[s] = out1;
+  aux1[s] = out1;
 }
 
 template <typename T>
@@ -391,7 +397,7 @@ static void prep_t(const GridDev& g, const uint8_t* cell, ViState& vs, const voi
   const K<T> k = make_k<T>(g, vs.reward_scale, vs.beta);
   const int nb = nblk(g.n, SWEEP_THREADS);
   if (vs.kind == KIND_LOGZ)
-    prep_kernel<T, KIND_LOGZ><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, (const T*)vs.V, (const T*)Q, nullptr, (T*)vs.aux4, nullptr);
+    prep_kernel<T, KIND_LOGZ><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, (const T*)vs.V, (const T*)Q, nullptr, (T*)vs.aux4, (T*)vs.aux1);
   else
     prep_kernel<T, KIND_GAP><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, (const T*)vs.V, (const T*)Q, (const T*)nu, (T*)vs.aux4, (T*)vs.aux1);
   g_launches++;
@@ -419,7 +425,7 @@ static void sweep_t(const GridDev& g, const uint8_t* cell, ViState& vs, bool wit
     case KIND_NU:
       sweep_kernel<T, KIND_NU><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, X, Y, nullptr, nullptr, tv, partial); break;
     case KIND_LOGZ:
-      sweep_kernel<T, KIND_LOGZ><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, X, Y, (const T*)vs.aux4, nullptr, tv, partial); break;
+      sweep_kernel<T, KIND_LOGZ><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, X, Y, (const T*)vs.aux4, (const T*)vs.aux1, tv, partial); break;
     default:
       sweep_kernel<T, KIND_GAP><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, X, Y, (const T*)vs.aux4, (const T*)vs.aux1, tv, partial); break;
   }
@@ -459,7 +465,7 @@ static void resident_t(const GridDev& g, const uint8_t* cell, ViState& vs, doubl
     case KIND_NU:
       resident_solve_kernel<T, KIND_NU><<<1, threads, smem, st>>>(k, cell, x0, xout, nullptr, nullptr, tv, tol, max_sweeps, dev_out); break;
     case KIND_LOGZ:
-      resident_solve_kernel<T, KIND_LOGZ><<<1, threads, smem, st>>>(k, cell, x0, xout, (const T*)vs.aux4, nullptr, tv, tol, max_sweeps, dev_out); break;
+      resident_solve_kernel<T, KIND_LOGZ><<<1, threads, smem, st>>>(k, cell, x0, xout, (const T*)vs.aux4, (const T*)vs.aux1, tv, tol, max_sweeps, dev_out); break;
     default:
       resident_solve_kernel<T, KIND_GAP><<<1, threads, smem, st>>>(k, cell, x0, xout, (const T*)vs.aux4, (const T*)vs.aux1, tv, tol, max_sweeps, dev_out); break;
   }

@@ -493,7 +493,7 @@ __global__ void tile_pack_mask_kernel(PadGeom g, const uint8_t* __restrict__ cel
   const int i = p % g.ld - TKH, j = p / g.ld - TKH;
   maskp[p] = (i >= 0 && i < g.H && j >= 0 && j < g.W) ? cell[i + g.H * j] : (uint8_t)(CELL_WALL | CELL_BLOCK_MASK);
 }
-// aux4 [cell][4] (+ aux1 [cell]) -> five planes.  logz: exp(A_a - max A), max A; gap: pi_a, D.
+// aux4 [cell][4] + aux1 [cell] -> five planes.  logz: exp(A_a - max A), max A (as prep_kernel stores them); gap: pi_a, D.
 template <typename T, int KIND>
 __global__ void tile_pack_aux_kernel(PadGeom g, const T* __restrict__ aux4, const T* __restrict__ aux1, T* __restrict__ auxp) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -505,12 +505,7 @@ __global__ void tile_pack_aux_kernel(PadGeom g, const T* __restrict__ aux4, cons
     const int s = i + g.H * j;
     T a[4];
     ldg4(aux4 + 4 * (size_t)s, a);
-    if (KIND == KIND_LOGZ) {
-      const T am = fmax(fmax(a[0], a[1]), fmax(a[2], a[3]));
-#pragma unroll
-      for (int q = 0; q < 4; q++) o[q] = xexp(a[q] - am);
-      o[4] = am;
-    } else {
+    {
 #pragma unroll
       for (int q = 0; q < 4; q++) o[q] = a[q];
       o[4] = aux1[s];
@@ -677,7 +672,7 @@ static void pack_t(const GridDev& g, const uint8_t* cell, const ViState& vs, Til
   tile_pack_mask_kernel<<<nb, 256, 0, st>>>(pg, cell, tb.mask);
   g_launches += 3;
   if (vs.kind == KIND_LOGZ) {
-    tile_pack_aux_kernel<T, KIND_LOGZ><<<nb, 256, 0, st>>>(pg, (const T*)vs.aux4, nullptr, (T*)tb.aux);
+    tile_pack_aux_kernel<T, KIND_LOGZ><<<nb, 256, 0, st>>>(pg, (const T*)vs.aux4, (const T*)vs.aux1, (T*)tb.aux);
     g_launches++;
   } else if (vs.kind == KIND_GAP) {
     tile_pack_aux_kernel<T, KIND_GAP><<<nb, 256, 0, st>>>(pg, (const T*)vs.aux4, (const T*)vs.aux1, (T*)tb.aux);
