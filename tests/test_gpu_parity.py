@@ -339,3 +339,21 @@ def test_error_codes(piql, golden01):
         eng.mc_logz(np.zeros((golden01.H, golden01.W)), npaths=10, starts=[10 ** 6])
     assert e.value.code == K.ERR_ARG
     eng.close()
+
+
+def test_config1_monte_carlo_protocol(engine):
+    """golden r=0.00 gamma=0.99 grid, 2^24 paths from s0 = (2,17), seeds {0,1,2}, V = V_lo and V = nu,
+    beta in {1, 0.18009...}: every estimate within 4 sigma of the exact log Z(s0)."""
+    g = Golden("r0_00g0_99")
+    load(engine, g)
+    n = 1 << 24
+    for V in (np.nan_to_num(g.V(7, 0)), np.nan_to_num(g.nu)):
+        for beta in (1.0, float(g.betas[5])):
+            exact, _ = engine.solve_logz(V, beta=beta)
+            for seed in (0, 1, 2):
+                sa, cnt, ls, st = engine.mc_logz(V, beta=beta, npaths=n, seed=seed, starts=[g.s0_idx])
+                logw, _ = engine.mc_records(n)
+                w = np.exp(logw.astype(np.float64) - logw.max())
+                sigma = w.std() / np.sqrt(n) / w.mean()
+                assert abs(ls[g.s0] - exact[g.s0]) < 4 * sigma + 2e-6, (beta, seed, ls[g.s0], exact[g.s0], sigma)
+                assert int(cnt.sum()) == n
