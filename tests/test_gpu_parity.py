@@ -357,3 +357,24 @@ def test_config1_monte_carlo_protocol(engine):
                 sigma = w.std() / np.sqrt(n) / w.mean()
                 assert abs(ls[g.s0] - exact[g.s0]) < 4 * sigma + 2e-6, (beta, seed, ls[g.s0], exact[g.s0], sigma)
                 assert int(cnt.sum()) == n
+
+
+@pytest.mark.parametrize("name", ["r0_01g0_99", "r0_05g0_95"])
+def test_config2_path_integral_vs_value_iteration_sweep(engine, name):
+    """for every beta of the stored experiment and the first two iterates, the path-integral estimate of
+    log Z(s0) against the value-iteration one (exact), and the resulting V_{k+1}(s0) against the reference's stored value."""
+    g = Golden(name)
+    load(engine, g)
+    n = 1 << 22
+    for b, beta in enumerate(float(x) for x in g.betas):
+        for k in (0, 1):
+            V = np.nan_to_num(g.V(b, k))
+            exact, _ = engine.solve_logz(V, beta=beta)
+            sa, cnt, ls, st = engine.mc_logz(V, beta=beta, npaths=n, seed=100 + 8 * k + b, starts=[g.s0_idx])
+            logw, _ = engine.mc_records(n)
+            w = np.exp(logw.astype(np.float64) - logw.max())
+            sigma = w.std() / np.sqrt(n) / w.mean()
+            assert abs(ls[g.s0] - exact[g.s0]) < 4 * sigma + 2e-6, (name, b, k, ls[g.s0], exact[g.s0], sigma)
+            # V_{k+1}(s0) = V_k(s0) + log Z(s0) / beta   (value_iteration.jl:119-124), against data/*.jld2
+            v_next = V[g.s0] + ls[g.s0] / beta
+            assert abs(v_next - g.V(b, k + 1)[g.s0]) < (4 * sigma + 2e-6) / beta + 1e-8, (name, b, k)
