@@ -378,3 +378,26 @@ def test_config2_path_integral_vs_value_iteration_sweep(engine, name):
             # V_{k+1}(s0) = V_k(s0) + log Z(s0) / beta   (value_iteration.jl:119-124), against data/*.jld2
             v_next = V[g.s0] + ls[g.s0] / beta
             assert abs(v_next - g.V(b, k + 1)[g.s0]) < (4 * sigma + 2e-6) / beta + 1e-8, (name, b, k)
+
+
+def test_config3_long_horizon_rollouts(engine):
+    """gamma = 0.9999.  Paths under the V_lo policy end at the goal long before the geometric horizon
+    (1e4): lengths average ~630 steps with a tail of thousands, log-weights span tens of nats -- the reduction must stay in
+    the log domain, and lanes are refilled as paths of very different length finish."""
+    g = Golden("r0_00g0_9999")
+    load(engine, g)
+    V = np.nan_to_num(g.V(7, 0))
+    n = 1 << 20
+    exact, _ = engine.solve_logz(V, beta=1.0)
+    sa, cnt, ls, st = engine.mc_logz(V, beta=1.0, npaths=n, seed=31, starts=[g.s0_idx])
+    logw, meta = engine.mc_records(n)
+    length = (meta >> 2).astype(np.int64)
+    assert 560 < length.mean() < 700 and 1500 < length.max() < 20000 and length.min() >= 0
+    assert int(length.sum()) == st.transitions
+    assert np.isfinite(logw).all() and logw.max() <= 1e-3 and -200 < logw.min() < -20
+    w = np.exp(logw.astype(np.float64) - logw.max())
+    sigma = w.std() / np.sqrt(n) / w.mean()
+    assert abs(ls[g.s0] - exact[g.s0]) < 4 * sigma + 2e-6, (ls[g.s0], exact[g.s0], sigma)
+    # a direct float64 log-mean-exp of the records agrees with the kernel's (max, sum, count) reduction
+    direct = logw.max() + np.log(np.mean(np.exp(logw.astype(np.float64) - logw.max())))
+    assert abs(ls[g.s0] - direct) < 1e-6
