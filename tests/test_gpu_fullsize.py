@@ -95,3 +95,31 @@ def test_rollout_conservation_determinism_and_known_answer(engine, big):
     free = walls == 0
     z = np.exp(ls[free])
     assert abs(z.mean() - 1.0) < 5e-3, z.mean()
+
+
+def test_config5_4096_grid_properties(engine):
+    """BASELINE config 5 (4096 x 4096, one GPU's share of the work): fp32-fast soft VI reaches a fixed point that one more
+    Float64 sweep barely moves and that respects the value bounds; rollouts conserve paths and are deterministic."""
+    import bench
+    walls, goal, params = bench.make_world("grid4096")
+    engine.load_grid(walls, goal, **params)
+    free = walls == 0
+    nu32, st = engine.solve_nu(tol=0.0, max_sweeps=2000, precision="f32fast")
+    assert st.kernel == 2 and np.array_equal(np.isnan(nu32), walls != 0) and nu32[goal] == 0.0
+    engine.vi_prepare("nu", precision="f64")
+    engine.vi_set_iterate(nu32)
+    engine.vi_sweeps(1)
+    x, res = engine.vi_fetch()
+    rel = np.abs(x[free] - nu32[free]) / np.maximum(1.0, np.abs(nu32[free]))
+    assert rel.max() < 2e-6, rel.max()              # fp32 fixed point: a Float64 sweep moves it by fp32 rounding only
+    lo = -params["step_cost"] / (1 - params["gamma"]) - 1e-5
+    assert lo <= np.nanmin(nu32) and np.nanmax(nu32) <= params["reward"] + np.log(4.0) / (1 - params["gamma"])
+    V = np.nan_to_num(nu32)
+    n = 1 << 24
+    sa, cnt, ls, st1 = engine.mc_logz(V, beta=1.0, npaths=n, seed=3, want=("count", "s"))
+    assert int(cnt.sum()) == n and 50 * n < st1.transitions < 101 * n
+    sa2, cnt2, ls2, _ = engine.mc_logz(V, beta=1.0, npaths=n, seed=3, want=("count", "s"))
+    assert np.array_equal(cnt, cnt2) and np.array_equal(np.nan_to_num(ls), np.nan_to_num(ls2))
+    started = cnt.reshape(walls.shape[1], walls.shape[0], 4).sum(axis=2).T > 0
+    z = np.exp(ls[started])
+    assert abs(z.mean() - 1.0) < 2e-2, z.mean()     # exact log Z = 0 at V = nu (one or two paths per cell here)
