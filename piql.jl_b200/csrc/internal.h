@@ -38,6 +38,22 @@ struct TilePlan {
   size_t smem;           // dynamic shared memory per CTA
   int ctas_per_sm;
 };
+// Halo exchange of the multi-GPU soft VI, carried by the tile kernel itself: the CTAs of the slab's first / last tile column
+// wait for the neighbour's counter before they stage their tile, and after the write-back also store their edge columns
+// into the neighbour's array and (the last of them) raise the neighbour's counter.  All null / 0 on one GPU.
+struct TileHalo {
+  const unsigned* in_left = nullptr;   // local counters the neighbours raise
+  const unsigned* in_right = nullptr;
+  unsigned wait_epoch = 0;             // 0: nothing to wait for (first round after packing)
+  void* out_left = nullptr;            // the neighbours' copies of the buffer this launch writes
+  void* out_right = nullptr;
+  unsigned* flag_left = nullptr;       // counters on the neighbours
+  unsigned* flag_right = nullptr;
+  unsigned* done = nullptr;            // local: edge CTAs that have pushed, [0] left, [1] right
+  unsigned post_epoch = 0;
+  int tj_first = -1, tj_last = -1;
+  int* err = nullptr;
+};
 struct TileBuffers {
   void* x[2] = {nullptr, nullptr};  // padded ping-pong iterate
   void* aux = nullptr;              // five padded planes (logz: exp(A_a - max A), max A; gap: pi_a, D)
@@ -61,6 +77,7 @@ struct TileBuffers {
   // multi-GPU column slabs: this rank sweeps tile columns [tj0, tj1) (piql_vi_shard_*)
   bool sharded = false;
   int tj0 = 0, tj1 = 0;
+  TileHalo halo;               // set per launch by tile_sweeps_sharded
   // shape found fastest on the device for the problem `tuned_key` (grid, precision, kind)
   long long tuned_key = -1;
   TilePlan tuned_plan{};

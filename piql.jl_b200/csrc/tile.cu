@@ -256,7 +256,7 @@ template <typename T, int KIND, bool FAST>
 __global__ void __launch_bounds__(512, sizeof(T) == 4 ? 2 : 1)
 tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmM,
                   int use_tma, const uint8_t* __restrict__ maskp, const T* __restrict__ X, T* __restrict__ Y,
-                  const T* __restrict__ aux, int nsub, int want_res, double* __restrict__ partial) {
+                  const T* __restrict__ aux, int nsub, int want_res, double* __restrict__ partial, const TileHalo halo) {
   extern __shared__ __align__(128) unsigned char tile_smem[];
   __shared__ double red[32];
   __shared__ __align__(8) unsigned long long mbar;
@@ -265,7 +265,9 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
   T* bufB = bufA + EJ * TEI;
   uint32_t* msk0 = reinterpret_cast<uint32_t*>(bufB + EJ * TEI);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
-  const int ti = blockIdx.x % k.tiles_i, tj = blockIdx.x / k.tiles_i + k.tj0;
+  // column slabs put their two edge tile columns first in launch order: their push is what the neighbours wait for
+  const int ti = blockIdx.x % k.tiles_i, tc = blockIdx.x / k.tiles_i;
+  const int tj = halo.tj_last < 0 ? tc + k.tj0 : tc == 0 ? halo.tj_first : tc == 1 ? halo.tj_last : halo.tj_first + tc - 1;
   const int org = ti * TTI + ld * (tj * k.TJ);  // padded index of the tile's (row 0, column 0)
   const int moff = (ti * TTI) & 15;              // bytes the staged cell-byte box starts before row 0 (0 or 8)
   const uint32_t* msk = msk0 + (moff >> 2);
@@ -274,6 +276,25 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
   // let the next one do the same, then wait for the previous grid's memory before the first global read.
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // multi-GPU column slabs: the tiles of the slab's edge columns read halo columns the neighbouring rank pushes
+  const bool edge_l = halo.out_left != nullptr && tj == halo.tj_first, edge_r = halo.out_right != nullptr && tj == halo.tj_last;
+  if (halo.wait_epoch && (edge_l || edge_r)) {
+    if (threadIdx.x == 0) {
+      const unsigned long long t0 = globaltimer_ns_tile();
+      for (int side = 0; side < 2; side++) {
+        const volatile unsigned* f = side ? halo.in_right : halo.in_left;
+        if (!f || !(side ? edge_r : edge_l)) continue;
+        while (*f < halo.wait_epoch) {
+          if (globaltimer_ns_tile() - t0 > 10000000000ull) { *halo.err = 2; break; }
+          __nanosleep(100);
+        }
+      }
+      __threadfence_system();
+      asm volatile("fence.proxy.async;" ::: "memory");  // the peer's stores, just acquired, before this thread's TMA reads
+    }
+    if (!use_tma) __syncthreads();
+  }
 
   // stage the tile (every access in bounds thanks to the ghost frame)
   if (use_tma) {
@@ -335,6 +356,10 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
         *reinterpret_cast<double2*>(Y + g) = make_double2((double)f[0], (double)f[1]);
         *reinterpret_cast<double2*>(Y + g + 2) = make_double2((double)f[2], (double)f[3]);
       }
+      // the slab's first / last TILE_KH interior columns are the neighbouring rank's halo: peer stores over NVLink
+      T* peer = (edge_l && jj < 2 * TKH) ? static_cast<T*>(halo.out_left)
+                                         : (edge_r && jj >= k.TJ) ? static_cast<T*>(halo.out_right) : nullptr;
+      if (peer) sts4(peer + g, f);
       if (want_res) {
         T p[4];
         lds4(dst + jj * TEI + 4 * lane, p);
@@ -348,6 +373,20 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
   if (want_res) {  // uniform
     const double s = block_sum(res, red);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  }
+  if (edge_l || edge_r) {  // block-uniform: the last edge CTA of a side to finish raises that neighbour's counter
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int side = 0; side < 2; side++) {
+        if (!(side ? edge_r : edge_l)) continue;
+        if (atomicAdd(halo.done + side, 1u) == (unsigned)k.tiles_i - 1u) {
+          halo.done[side] = 0u;
+          __threadfence_system();
+          *(volatile unsigned*)(side ? halo.flag_right : halo.flag_left) = halo.post_epoch;
+        }
+      }
+    }
   }
 }
 
@@ -791,7 +830,8 @@ static cudaError_t launch_tile_t(const GridDev& g, const ViState& vs, TileBuffer
   memcpy(&tmM, tb.tmm, sizeof(tmM));
   cudaError_t le = cudaLaunchKernelEx(&cfg, tile_sweep_kernel<T, KIND, FAST>, k, tmX, tmM, tb.use_tma ? 1 : 0,
                                       (const uint8_t*)tb.mask, (const T*)tb.x[tb.cur],
-                                      (T*)tb.x[tb.cur ^ 1], (const T*)tb.aux, nsub, want_res ? 1 : 0, tb.partial);
+                                      (T*)tb.x[tb.cur ^ 1], (const T*)tb.aux, nsub, want_res ? 1 : 0, tb.partial,
+                                      tb.sharded ? tb.halo : TileHalo());
   if (le != cudaSuccess) return le;
   g_launches++;
   tb.cur ^= 1;
@@ -894,83 +934,41 @@ void tile_unpack(const GridDev& g, const ViState& vs, const TileBuffers& tb, cud
 
 // ---- multi-GPU soft VI: column slabs of tiles, halo columns exchanged over NVLink peer memory ---------------------------
 // Every rank holds the whole padded array (the layout is replicated) but sweeps only the tile columns [tj0, tj1) it owns.
-// After a round of TILE_KH sweeps it pushes its first and last TILE_KH interior columns of the new iterate into the same
-// places of its left / right neighbour's array (their halo) with peer stores and raises the neighbour's counter; before a
-// round it waits until both neighbours have delivered the previous round.  Receiving round r-1 from a neighbour also means
-// the neighbour has finished reading the buffer that round r's push overwrites.  Jacobi + tiling-independent values make
+// The exchange rides in the tile kernel (TileHalo): the CTAs of the slab's first / last tile column store the first / last
+// TILE_KH interior columns of the new iterate also into the same places of the left / right neighbour's array (its halo)
+// with peer stores, and the last of them raises the neighbour's counter; in the next round those CTAs -- and only those --
+// wait for the neighbours' counters before they stage.  Receiving round r-1 from a neighbour also means the neighbour's
+// edge tiles have finished reading the buffer that round r's push overwrites (interior tiles never read the halo).  Jacobi + tiling-independent values make
 // the result bit-identical to the single-GPU solve for any number of ranks.
-template <typename T>
-__global__ void __launch_bounds__(256)
-halo_push_kernel(const T* __restrict__ local, T* __restrict__ left, T* __restrict__ right, int ld, int c0, int c1,
-                 unsigned* left_flag, unsigned* right_flag, unsigned epoch, unsigned* done) {
-  __shared__ bool last;
-  const int n = TKH * ld / 4;  // 128-bit words per side (ld is a multiple of 32)
-  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
-  typedef typename std::conditional<sizeof(T) == 4, float4, double4>::type V4;
-  if (left) {
-    const V4* src = reinterpret_cast<const V4*>(local + (size_t)c0 * ld);
-    V4* dst = reinterpret_cast<V4*>(left + (size_t)c0 * ld);
-    for (int i = t0; i < n; i += stride) dst[i] = src[i];
-  }
-  if (right) {
-    const V4* src = reinterpret_cast<const V4*>(local + (size_t)(c1 - TKH) * ld);
-    V4* dst = reinterpret_cast<V4*>(right + (size_t)(c1 - TKH) * ld);
-    for (int i = t0; i < n; i += stride) dst[i] = src[i];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (last && threadIdx.x == 0) {  // every block's stores are fenced and counted: tell the neighbours
-    *done = 0u;
-    __threadfence_system();
-    if (left_flag) *(volatile unsigned*)left_flag = epoch;
-    if (right_flag) *(volatile unsigned*)right_flag = epoch;
-  }
-}
-__global__ void halo_wait_kernel(const unsigned* from_left, const unsigned* from_right, unsigned epoch, int* err) {
-  const unsigned long long t0 = globaltimer_ns_tile();
-  for (int side = 0; side < 2; side++) {
-    const volatile unsigned* f = side ? from_right : from_left;
-    if (!f) continue;
-    while (*f < epoch) {
-      if (globaltimer_ns_tile() - t0 > 10000000000ull) { *err = 2; return; }
-      __nanosleep(100);
-    }
-  }
-  __threadfence_system();
-}
-
 cudaError_t tile_sweeps_sharded(const GridDev& g, const ViState& vs, TileBuffers& tb, ViPeer& vp, long long nsweeps, bool want_res,
                                 cudaStream_t st) {
-  const int ld = tb.plan.ld;
-  const int c0 = TKH + tb.tj0 * tb.plan.TJ, c1 = TKH + tb.tj1 * tb.plan.TJ;  // padded columns of the owned interior
   const bool has_l = vp.rank > 0, has_r = vp.rank < vp.world - 1;
   while (nsweeps > 0) {
     const int nsub = (int)std::min<long long>(nsweeps, TKH);
     nsweeps -= nsub;
     const bool res = want_res && nsweeps == 0;
-    if (vp.round > 0 && (has_l || has_r))
-      halo_wait_kernel<<<1, 1, 0, st>>>(has_l ? vp.own_flags + 0 : nullptr, has_r ? vp.own_flags + 1 : nullptr, (unsigned)vp.round, tb.d_err);
+    // one launch per round, as on one GPU: its edge CTAs wait for the neighbours' previous round and push this one
+    const int out = tb.cur ^ 1;
+    TileHalo h;
+    h.in_left = has_l ? vp.own_flags + 0 : nullptr;
+    h.in_right = has_r ? vp.own_flags + 1 : nullptr;
+    h.wait_epoch = (unsigned)vp.round;
+    h.out_left = has_l ? vp.x[out][vp.rank - 1] : nullptr;
+    h.out_right = has_r ? vp.x[out][vp.rank + 1] : nullptr;
+    // my first columns are the left neighbour's right halo (its counter "from right"), and vice versa
+    h.flag_left = has_l ? vp.flags[vp.rank - 1] + 1 : nullptr;
+    h.flag_right = has_r ? vp.flags[vp.rank + 1] + 0 : nullptr;
+    h.done = vp.done;
+    h.post_epoch = (unsigned)(vp.round + 1);
+    h.tj_first = tb.tj0; h.tj_last = tb.tj1 - 1;
+    h.err = tb.d_err;
+    tb.halo = h;
     cudaError_t e;
     if (vs.precision == 0) e = launch_tile_k<double, false>(g, vs, tb, nsub, res, st);
     else if (vs.fast) e = launch_tile_k<float, true>(g, vs, tb, nsub, res, st);
     else e = launch_tile_k<float, false>(g, vs, tb, nsub, res, st);
     if (e != cudaSuccess) return e;
     vp.round++;
-    const int cur = tb.cur;  // the buffer just written
-    // my first columns are the left neighbour's right halo (its counter "from right"), and vice versa
-    if (vs.precision == 0)
-      halo_push_kernel<double><<<32, 256, 0, st>>>((const double*)tb.x[cur], has_l ? (double*)vp.x[cur][vp.rank - 1] : nullptr,
-                                                    has_r ? (double*)vp.x[cur][vp.rank + 1] : nullptr, ld, c0, c1,
-                                                    has_l ? vp.flags[vp.rank - 1] + 1 : nullptr, has_r ? vp.flags[vp.rank + 1] + 0 : nullptr,
-                                                    (unsigned)vp.round, vp.done);
-    else
-      halo_push_kernel<float><<<32, 256, 0, st>>>((const float*)tb.x[cur], has_l ? (float*)vp.x[cur][vp.rank - 1] : nullptr,
-                                                   has_r ? (float*)vp.x[cur][vp.rank + 1] : nullptr, ld, c0, c1,
-                                                   has_l ? vp.flags[vp.rank - 1] + 1 : nullptr, has_r ? vp.flags[vp.rank + 1] + 0 : nullptr,
-                                                   (unsigned)vp.round, vp.done);
-    g_launches += 2;
     if (res) launch_residual_final(tb.partial, tb.plan.tiles_i * (tb.tj1 - tb.tj0), vs.residual, st);
   }
   cudaError_t e = cudaMemcpyAsync(tb.err, tb.d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
