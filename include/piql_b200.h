@@ -70,7 +70,7 @@ typedef struct {
   double device_seconds; /* CUDA-event time of the sweeps */
   int64_t backups;       /* state backups performed = sweeps * free cells */
   int32_t converged;
-  int32_t kernel;        /* 1 = single-CTA resident solver, 2 = tiled multi-sweep kernel (4 sweeps per launch), 3 = batched resident, 4 = table */
+  int32_t kernel;        /* 1 = single-CTA resident solver, 2 = tiled multi-sweep kernel (4 sweeps per launch), 3 = batched resident, 4 = table, 5 = one launch per sweep (linear-space Z on large grids) */
 } piql_solve_stats;
 
 enum { PIQL_EST_SAMPLED_STOP = 0 /* estimator A */, PIQL_EST_DISCOUNTED = 1 /* estimator B */ };
@@ -128,6 +128,15 @@ int32_t piql_solve_logz(piql_ctx* ctx, const double* V, const double* Q, double 
 /* logz_updateV(ctrl, V; β) = V + logz/β   src/value_iteration.jl:119-124.  logz_out optional. */
 int32_t piql_update_v(piql_ctx* ctx, const double* V, double beta, const piql_solve_opts* opts,
                       double* vnew_out, double* logz_out, piql_solve_stats* stats_out);
+/* generate_z(ctrl, V; β) and z_updateV(ctrl, V; β) = V + log(Z)/β   src/value_iteration.jl:23-59 over z_recursion
+ * src/PIQL.jl:109-115: the linear-space twin of the log Z solve (Z starts at 1, linear damping η = ½, stop rule on
+ * Σ|log new − log old|; the reference calls it "not numerically stable enough" and so it serves as a cross-check:
+ * log(Z) agrees with piql_solve_logz wherever exp does not under/overflow).  Swept by the per-cell kernels
+ * (stats.kernel 1 or 5).  Q and z_out optional as above. */
+int32_t piql_solve_z(piql_ctx* ctx, const double* V, const double* Q, double beta,
+                     const piql_solve_opts* opts, double* z_out, piql_solve_stats* stats_out);
+int32_t piql_z_update_v(piql_ctx* ctx, const double* V, double beta, const piql_solve_opts* opts,
+                        double* vnew_out, double* z_out, piql_solve_stats* stats_out);
 /* generate_optimality_gap(ctrl, V; ν)   src/value_iteration.jl:129-169 */
 int32_t piql_solve_gap(piql_ctx* ctx, const double* V, const double* Q, const double* nu,
                        const piql_solve_opts* opts, double* gap_out, piql_solve_stats* stats_out);
@@ -180,7 +189,7 @@ int32_t piql_table_mc_logz(piql_ctx* ctx, const double* V, double beta, const pi
                            uint64_t* count_sa_out, double* logz_s_out, piql_mc_stats* stats_out, float* cdf_out,
                            float* bf_out, float* cum_out);
 
-/* One Jacobi sweep from x_in (kind: 0 nu, 1 logz, 2 gap), for parity tests of the backup itself. */
+/* One Jacobi sweep from x_in (kind: 0 nu, 1 logz, 2 gap, 3 z), for parity tests of the backup itself. */
 int32_t piql_sweep_once(piql_ctx* ctx, int32_t kind, const double* V, const double* Q, const double* nu,
                         double beta, double reward_scale, int32_t precision, const double* x_in,
                         double* x_out, double* residual_out);

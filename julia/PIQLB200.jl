@@ -121,6 +121,21 @@ function logz_updateV(ctx::Context, V; β = 1.0, kw...)
         ctx.ptr, Vd, β, opts(; kw...), out, C_NULL, st))
     growable(ctx, out; default = V.default)
 end
+# the linear-space twins (src/value_iteration.jl:42-59); the reference's stop rule for these is 1e-9
+function generate_z(ctx::Context, V; β = 1.0, tol = 1e-9, kw...)
+    Vd = dense(ctx, V); out = similar(Vd); st = SolveStats()
+    GC.@preserve Vd out check(ctx, ccall((:piql_solve_z, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ref{SolveOpts}, Ptr{Cdouble}, Ref{SolveStats}),
+        ctx.ptr, Vd, C_NULL, β, opts(; tol, kw...), out, st))
+    growable(ctx, out; default = x -> 1.0)
+end
+function z_updateV(ctx::Context, V; β = 1.0, tol = 1e-9, kw...)
+    Vd = dense(ctx, V); out = similar(Vd); st = SolveStats()
+    GC.@preserve Vd out check(ctx, ccall((:piql_z_update_v, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Cdouble, Ref{SolveOpts}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{SolveStats}),
+        ctx.ptr, Vd, β, opts(; tol, kw...), out, C_NULL, st))
+    growable(ctx, out; default = V.default)
+end
 function generate_optimality_gap(ctx::Context, V; ν, kw...)
     Vd = dense(ctx, V); nd = dense(ctx, ν); out = similar(Vd); st = SolveStats()
     GC.@preserve Vd nd out check(ctx, ccall((:piql_solve_gap, LIB), Int32,

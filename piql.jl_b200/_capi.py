@@ -14,7 +14,7 @@ F64, F32, F32_FAST = 0, 1, 2
 PRECISIONS = {"f64": F64, "f32": F32, "f32fast": F32_FAST, F64: F64, F32: F32, F32_FAST: F32_FAST}
 EST_SAMPLED_STOP, EST_DISCOUNTED = 0, 1
 START_ALL_FREE, START_LIST = 0, 1
-KIND_NU, KIND_LOGZ, KIND_GAP = 0, 1, 2
+KIND_NU, KIND_LOGZ, KIND_GAP, KIND_Z = 0, 1, 2, 3
 
 
 class GridParams(C.Structure):
@@ -76,6 +76,8 @@ SYMBOLS = {
     "piql_solve_logz": (C.c_int32, [_P, _D, _D, C.c_double, C.POINTER(SolveOpts), _D, C.POINTER(SolveStats)]),
     "piql_update_v": (C.c_int32, [_P, _D, C.c_double, C.POINTER(SolveOpts), _D, _D, C.POINTER(SolveStats)]),
     "piql_solve_gap": (C.c_int32, [_P, _D, _D, _D, C.POINTER(SolveOpts), _D, C.POINTER(SolveStats)]),
+    "piql_solve_z": (C.c_int32, [_P, _D, _D, C.c_double, C.POINTER(SolveOpts), _D, C.POINTER(SolveStats)]),
+    "piql_z_update_v": (C.c_int32, [_P, _D, C.c_double, C.POINTER(SolveOpts), _D, _D, C.POINTER(SolveStats)]),
     "piql_sweep_once": (C.c_int32, [_P, C.c_int32, _D, _D, _D, C.c_double, C.c_double, C.c_int32, _D, _D, _D]),
     "piql_policy_table": (C.c_int32, [_P, _D, _D, C.c_double, C.POINTER(C.c_float)]),
     "piql_policy_table_set": (C.c_int32, [_P, C.POINTER(C.c_float), C.c_double]),

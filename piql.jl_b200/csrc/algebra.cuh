@@ -92,6 +92,16 @@ __device__ __forceinline__ T backup_logz(const K<T>& k, const T (&ea)[NA], T ama
   for (int a = 0; a < NA; a++) sum += ea[a] * (g1 * (k.w_on * e[a] + k.w_off * (esum - e[a])) + g0);
   return fmax(m, (T)0) + amax + xlog(sum);
 }
+// z_recursion (PIQL.jl:109-115), the linear-space form the reference keeps beside logz_recursion ("not numerically
+// stable enough" in its own words): Z_new = sum_a exp(A_a) * (gamma * sum_a' P(a'|a) Z(n_a') + 1 - gamma), with
+// eA_a = exp(A_a) stored by prep_kernel.
+template <typename T>
+__device__ __forceinline__ T backup_z(const K<T>& k, const T (&eA)[NA], const T (&nb)[NA]) {
+  T out = 0;
+#pragma unroll
+  for (int a = 0; a < NA; a++) out += eA[a] * (k.gamma * pa(k, a, nb) + (T)1 - k.gamma);
+  return out;
+}
 template <typename T>
 __device__ __forceinline__ T backup_gap(const K<T>& k, const T (&P)[NA], T D, const T (&nb)[NA]) {
   T out = D;  // D = sum_a pi_a (controlQ - controlV(nu)); gap term has no gamma (value_iteration.jl:165)

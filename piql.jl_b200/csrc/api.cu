@@ -180,7 +180,7 @@ int ensure_vi(piql_ctx* ctx) {
 int vi_prepare(piql_ctx* ctx, int kind, const double* V, const double* Q, const double* nu, double beta,
                double reward_scale, int precision) {
   NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded (call piql_grid_load first)");
-  NEED(kind >= 0 && kind <= 2, PIQL_ERR_ARG, "kind must be 0 (nu), 1 (logz) or 2 (gap)");
+  NEED(kind >= 0 && kind <= 3, PIQL_ERR_ARG, "kind must be 0 (nu), 1 (logz), 2 (gap) or 3 (z)");
   NEED(precision == PIQL_F64 || precision == PIQL_F32 || precision == PIQL_F32_FAST, PIQL_ERR_ARG,
        "precision must be PIQL_F64, PIQL_F32 or PIQL_F32_FAST");
   const bool fast = precision == PIQL_F32_FAST;
@@ -217,8 +217,9 @@ int vi_prepare(piql_ctx* ctx, int kind, const double* V, const double* Q, const 
     CK(cudaMemcpyAsync(ctx->d_in1, nu, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
     launch_convert_in(ctx->d_in1, ctx->d_nu, n, precision, st);
   }
-  launch_fill(vs.x[0], 0.0, n, precision, st);  // Growable default x -> 0.0   value_iteration.jl:79,109,146
-  launch_fill(vs.x[1], 0.0, n, precision, st);
+  const double x_default = kind == KIND_Z ? 1.0 : 0.0;  // Growable default x -> 0.0 (x -> 1.0 for Z)  value_iteration.jl:44,79,109,146
+  launch_fill(vs.x[0], x_default, n, precision, st);
+  launch_fill(vs.x[1], x_default, n, precision, st);
   launch_prep(ctx->g, ctx->d_cell, vs, dQ, ctx->d_nu, st);
   CK_LAST();
   ctx->vs_ready = true;
@@ -245,6 +246,21 @@ int vi_solve(piql_ctx* ctx, const piql_solve_opts* opts, double* out, piql_solve
     CK(cudaStreamSynchronize(st));
     sweeps = (long long)ctx->h_scalars[1];
     residual = ctx->h_scalars[2];
+  } else if (vs.kind == KIND_Z) {
+    // the linear-space cross-check has no tiled kernel: one launch per sweep, residual read back every check_every sweeps
+    kernel = 5;
+    const long long every = opts->check_every > 0 ? opts->check_every : 64;
+    while (sweeps < opts->max_sweeps) {
+      const long long batch = opts->max_sweeps - sweeps < every ? opts->max_sweeps - sweeps : every;
+      for (long long i = 0; i < batch; i++) launch_sweep(ctx->g, ctx->d_cell, vs, i == batch - 1, st);
+      CK_LAST();
+      sweeps += batch;
+      CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      residual = ctx->h_scalars[0];
+      if (!(residual == residual)) return fail(ctx, PIQL_ERR_CUDA, "soft-VI residual is NaN (diverged)");
+      if (tol > 0 && residual < tol) break;
+    }
   } else {
     kernel = 2;
     CK(tile_begin(ctx->g, ctx->d_cell, vs, ctx->tb, ctx->num_sms, st));
@@ -643,25 +659,38 @@ int32_t piql_solve_gap(piql_ctx* ctx, const double* V, const double* Q, const do
                        double* gap_out, piql_solve_stats* stats) {
   return solve_entry(ctx, KIND_GAP, V, Q, nu, 1.0, 1.0, opts, gap_out, stats);
 }
+int32_t piql_solve_z(piql_ctx* ctx, const double* V, const double* Q, double beta, const piql_solve_opts* opts,
+                     double* z_out, piql_solve_stats* stats) {
+  return solve_entry(ctx, KIND_Z, V, Q, nullptr, beta, 1.0, opts, z_out, stats);
+}
 
-int32_t piql_update_v(piql_ctx* ctx, const double* V, double beta, const piql_solve_opts* opts, double* vnew_out,
-                      double* logz_out, piql_solve_stats* stats) {
+static int update_v_entry(piql_ctx* ctx, int kind, const double* V, double beta, const piql_solve_opts* opts, double* vnew_out,
+                          double* logz_out, piql_solve_stats* stats) {
   if (!ctx) return PIQL_ERR_ARG;
   LaunchScope ls(ctx);
   NEED(opts != nullptr && vnew_out != nullptr, PIQL_ERR_ARG, "opts / output pointer is null");
   NEED(beta != 0.0, PIQL_ERR_ARG, "beta must be non-zero");
   CK(cudaSetDevice(ctx->device));
-  int rc = vi_prepare(ctx, KIND_LOGZ, V, nullptr, nullptr, beta, 1.0, opts->precision);
+  int rc = vi_prepare(ctx, kind, V, nullptr, nullptr, beta, 1.0, opts->precision);
   if (rc) return rc;
   rc = vi_solve(ctx, opts, logz_out, stats);
   if (rc && rc != PIQL_ERR_NOT_CONVERGED) return rc;
-  // V + logz/beta   value_iteration.jl:119-124 (d_in0 still holds the caller's V in double)
+  // V + logz/beta   value_iteration.jl:119-124, or V + log(Z)/beta  :53-59 (d_in0 still holds the caller's V in double)
   cudaStream_t st = ctx->stream;
-  launch_update_v(ctx->d_in0, ctx->vs.x[ctx->vs.cur], ctx->d_cell, beta, ctx->d_out, ctx->g.n, ctx->vs.precision, st);
+  launch_update_v(ctx->d_in0, ctx->vs.x[ctx->vs.cur], ctx->d_cell, beta, ctx->d_out, ctx->g.n, ctx->vs.precision, st,
+                  kind == KIND_Z);
   CK_LAST();
   CK(cudaMemcpyAsync(vnew_out, ctx->d_out, 8 * (size_t)ctx->g.n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return rc;
+}
+int32_t piql_update_v(piql_ctx* ctx, const double* V, double beta, const piql_solve_opts* opts, double* vnew_out,
+                      double* logz_out, piql_solve_stats* stats) {
+  return update_v_entry(ctx, KIND_LOGZ, V, beta, opts, vnew_out, logz_out, stats);
+}
+int32_t piql_z_update_v(piql_ctx* ctx, const double* V, double beta, const piql_solve_opts* opts, double* vnew_out,
+                        double* z_out, piql_solve_stats* stats) {
+  return update_v_entry(ctx, KIND_Z, V, beta, opts, vnew_out, z_out, stats);
 }
 
 // ---- batched entry points: the experiment protocol in two launches ------------------------------------------
@@ -1017,6 +1046,7 @@ int32_t piql_vi_prepare_dev(piql_ctx* ctx, int32_t kind, const double* V, const 
   if (!ctx) return PIQL_ERR_ARG;
   LaunchScope ls(ctx);
   CK(cudaSetDevice(ctx->device));
+  NEED(kind != KIND_Z, PIQL_ERR_ARG, "the device-resident sweep loop covers kinds 0..2 (use piql_solve_z for the linear-space recursion)");
   int rc = vi_prepare(ctx, kind, V, Q, nu, beta, reward_scale, precision);
   if (rc) return rc;
   if (ctx->g.n > RESIDENT_MAX_CELLS) CK(tile_begin(ctx->g, ctx->d_cell, ctx->vs, ctx->tb, ctx->num_sms, ctx->stream));
@@ -1025,6 +1055,7 @@ int32_t piql_vi_prepare_dev(piql_ctx* ctx, int32_t kind, const double* V, const 
 int32_t piql_vi_tile_plan(piql_ctx* ctx, int32_t kind, int32_t precision, int32_t* plan_out) {
   if (!ctx || !plan_out) return PIQL_ERR_ARG;
   NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded");
+  NEED(kind >= KIND_NU && kind <= KIND_GAP, PIQL_ERR_ARG, "kind must be 0 (nu), 1 (logz) or 2 (gap)");
   bool persistent = false;
   TilePlan pl = choose_tile_plan(ctx->g.H, ctx->g.W, precision == PIQL_F64 ? 0 : 1, kind, ctx->num_sms, &persistent);
   if (ctx->tb.active && ctx->vs.kind == kind && ctx->vs.precision == (precision == PIQL_F64 ? 0 : 1)) {

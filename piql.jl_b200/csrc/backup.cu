@@ -48,17 +48,26 @@ __device__ __forceinline__ void backup_cell(const K<T>& k, int s, unsigned ci, c
   gather(X, s, k.H, ci, c, nb);
   T nw;
   if (ci & CELL_GOAL) {
-    nw = term_value;  // terminal_condition: nu, gap -> 0; logz -> 0 - V(goal)
+    nw = term_value;  // terminal_condition: nu, gap -> 0; logz -> 0 - V(goal); Z -> exp(0 - V(goal))
   } else if (KIND == KIND_NU) {
     nw = backup_nu(k, s, ci, nb);
   } else if (KIND == KIND_LOGZ) {
     T ea[NA];
     load4(aux4, s, ea);
     nw = backup_logz(k, ea, __ldg(aux1 + s), nb);
+  } else if (KIND == KIND_Z) {
+    T eA[NA];
+    load4(aux4, s, eA);
+    nw = backup_z(k, eA, nb);
   } else {
     T P[NA];
     load4(aux4, s, P);
     nw = backup_gap(k, P, __ldg(aux1 + s), nb);
+  }
+  if (KIND == KIND_Z) {  // update_z!: diff += |log(new) - log(Z(s0))|, Z <- eta*new + (1-eta)*Z   value_iteration.jl:35-37
+    absdiff = fabs(log((double)nw) - log((double)c));
+    stored = (T)0.5 * nw + ((T)1 - (T)0.5) * c;
+    return;
   }
   absdiff = fabs((double)nw - (double)c);
   // eta = 0.5 damping of update_logz!: logaddexp(log(eta)+new, log(1-eta)+old)   value_iteration.jl:101-102
@@ -317,7 +326,10 @@ prep_kernel(K<T> k, const uint8_t* __restrict__ cell, const T* __restrict__ V, c
 #pragma unroll
     for (int a = 0; a < NA; a++) x[a] = k.log_prior + q[a];
     const T norm = lse4(x);  // Qnormalization   PIQL.jl:72-75
-    if (KIND == KIND_LOGZ) {
+    if (KIND == KIND_Z) {  // prior * exp(beta*controlV + (1-beta)*controlQ)   PIQL.jl:112
+#pragma unroll
+      for (int a = 0; a < NA; a++) out4[a] = (T)0.25 * xexp(k.beta * cv[a] + ((T)1 - k.beta) * (q[a] - norm));
+    } else if (KIND == KIND_LOGZ) {
 #pragma unroll
       for (int a = 0; a < NA; a++) out4[a] = k.log_prior + k.beta * cv[a] + ((T)1 - k.beta) * (q[a] - norm);
       out1 = fmax(fmax(out4[0], out4[1]), fmax(out4[2], out4[3]));   // stored as exp(A_a - max A) and max A
@@ -358,9 +370,10 @@ template <typename T> __global__ void fill_kernel(T* dst, T v, int n) {
 }
 template <typename T>
 __global__ void update_v_kernel(const double* __restrict__ V, const T* __restrict__ logz, const uint8_t* __restrict__ cell,
-                                double beta, double* __restrict__ out, int n) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;  // V(k) + logz(k)/beta   value_iteration.jl:121-122
-  if (s < n) out[s] = (cell[s] & CELL_WALL) ? CUDART_NAN : V[s] + (double)logz[s] / beta;
+                                double beta, double* __restrict__ out, int n, int linear) {
+  // V(k) + logz(k)/beta   value_iteration.jl:121-122;  linear: V(k) + log(Z(k))/beta   :55-57
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) out[s] = (cell[s] & CELL_WALL) ? CUDART_NAN : V[s] + (linear ? log((double)logz[s]) : (double)logz[s]) / beta;
 }
 
 // ---- host launchers ------------------------------------------------------------------------------
@@ -386,9 +399,9 @@ void launch_fill(void* dst, double value, int n, int precision, cudaStream_t st)
   g_launches++;
 }
 void launch_update_v(const double* V, const void* logz, const uint8_t* cell, double beta, double* out, int n,
-                     int precision, cudaStream_t st) {
-  if (precision == 0) update_v_kernel<double><<<nblk(n, 256), 256, 0, st>>>(V, (const double*)logz, cell, beta, out, n);
-  else update_v_kernel<float><<<nblk(n, 256), 256, 0, st>>>(V, (const float*)logz, cell, beta, out, n);
+                     int precision, cudaStream_t st, bool linear) {
+  if (precision == 0) update_v_kernel<double><<<nblk(n, 256), 256, 0, st>>>(V, (const double*)logz, cell, beta, out, n, linear);
+  else update_v_kernel<float><<<nblk(n, 256), 256, 0, st>>>(V, (const float*)logz, cell, beta, out, n, linear);
   g_launches++;
 }
 
@@ -398,6 +411,8 @@ static void prep_t(const GridDev& g, const uint8_t* cell, ViState& vs, const voi
   const int nb = nblk(g.n, SWEEP_THREADS);
   if (vs.kind == KIND_LOGZ)
     prep_kernel<T, KIND_LOGZ><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, (const T*)vs.V, (const T*)Q, nullptr, (T*)vs.aux4, (T*)vs.aux1);
+  else if (vs.kind == KIND_Z)
+    prep_kernel<T, KIND_Z><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, (const T*)vs.V, (const T*)Q, nullptr, (T*)vs.aux4, (T*)vs.aux1);
   else
     prep_kernel<T, KIND_GAP><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, (const T*)vs.V, (const T*)Q, (const T*)nu, (T*)vs.aux4, (T*)vs.aux1);
   g_launches++;
@@ -410,6 +425,7 @@ void launch_prep(const GridDev& g, const uint8_t* cell, ViState& vs, const void*
 
 // terminal cells: nu, gap -> 0; logz -> 0 - V(goal)   value_iteration.jl:66-67,93-94,133-134
 template <typename T> static T term_value_of(const ViState& vs) {
+  if (vs.kind == KIND_Z) return (T)exp(0.0 - vs.v_goal);  // value_iteration.jl:28
   return vs.kind == KIND_LOGZ ? (T)(0.0 - vs.v_goal) : (T)0;
 }
 
@@ -426,6 +442,8 @@ static void sweep_t(const GridDev& g, const uint8_t* cell, ViState& vs, bool wit
       sweep_kernel<T, KIND_NU><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, X, Y, nullptr, nullptr, tv, partial); break;
     case KIND_LOGZ:
       sweep_kernel<T, KIND_LOGZ><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, X, Y, (const T*)vs.aux4, (const T*)vs.aux1, tv, partial); break;
+    case KIND_Z:
+      sweep_kernel<T, KIND_Z><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, X, Y, (const T*)vs.aux4, (const T*)vs.aux1, tv, partial); break;
     default:
       sweep_kernel<T, KIND_GAP><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, X, Y, (const T*)vs.aux4, (const T*)vs.aux1, tv, partial); break;
   }
@@ -466,6 +484,8 @@ static void resident_t(const GridDev& g, const uint8_t* cell, ViState& vs, doubl
       resident_solve_kernel<T, KIND_NU><<<1, threads, smem, st>>>(k, cell, x0, xout, nullptr, nullptr, tv, tol, max_sweeps, dev_out); break;
     case KIND_LOGZ:
       resident_solve_kernel<T, KIND_LOGZ><<<1, threads, smem, st>>>(k, cell, x0, xout, (const T*)vs.aux4, (const T*)vs.aux1, tv, tol, max_sweeps, dev_out); break;
+    case KIND_Z:
+      resident_solve_kernel<T, KIND_Z><<<1, threads, smem, st>>>(k, cell, x0, xout, (const T*)vs.aux4, (const T*)vs.aux1, tv, tol, max_sweeps, dev_out); break;
     default:
       resident_solve_kernel<T, KIND_GAP><<<1, threads, smem, st>>>(k, cell, x0, xout, (const T*)vs.aux4, (const T*)vs.aux1, tv, tol, max_sweeps, dev_out); break;
   }
@@ -484,8 +504,8 @@ int configure_backup_kernels() {
   cudaError_t e = cudaSuccess;
 #define PIQL_SET(T, KND) \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(resident_solve_kernel<T, KND>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
-  PIQL_SET(double, KIND_NU) PIQL_SET(double, KIND_LOGZ) PIQL_SET(double, KIND_GAP)
-  PIQL_SET(float, KIND_NU) PIQL_SET(float, KIND_LOGZ) PIQL_SET(float, KIND_GAP)
+  PIQL_SET(double, KIND_NU) PIQL_SET(double, KIND_LOGZ) PIQL_SET(double, KIND_GAP) PIQL_SET(double, KIND_Z)
+  PIQL_SET(float, KIND_NU) PIQL_SET(float, KIND_LOGZ) PIQL_SET(float, KIND_GAP) PIQL_SET(float, KIND_Z)
 #undef PIQL_SET
   if (e == cudaSuccess) e = cudaFuncSetAttribute(resident_batch_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(resident_batch_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

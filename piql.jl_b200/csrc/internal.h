@@ -7,7 +7,9 @@
 
 namespace piql {
 
-enum Kind { KIND_NU = 0, KIND_LOGZ = 1, KIND_GAP = 2 };
+// KIND_Z: the reference's linear-space twin of KIND_LOGZ (update_z!, value_iteration.jl:23-40); swept by the plain
+// per-cell kernels only (resident solver or one launch per sweep), never by the tiled kernels.
+enum Kind { KIND_NU = 0, KIND_LOGZ = 1, KIND_GAP = 2, KIND_Z = 3 };
 
 // Device state of one soft-VI solve.  All value arrays hold n = H*W elements of the sweep
 // precision (float or double), column-major like the wall array.
@@ -107,8 +109,9 @@ void launch_sweep(const GridDev& g, const uint8_t* cell, ViState& vs, bool with_
 // Whole solve in one CTA (n <= RESIDENT_MAX_CELLS): returns through dev_out {sweeps, residual}.
 void launch_resident_solve(const GridDev& g, const uint8_t* cell, ViState& vs, double tol, long long max_sweeps,
                            double* dev_out /*2 doubles*/, cudaStream_t st);
+// linear: logz holds Z (z_updateV, value_iteration.jl:53-59) instead of log Z
 void launch_update_v(const double* V, const void* logz, const uint8_t* cell, double beta, double* out, int n,
-                     int precision, cudaStream_t st);
+                     int precision, cudaStream_t st, bool linear = false);
 size_t resident_smem_bytes(int n, int precision);
 // One CTA per problem (beta chain of logz_updateV solves, or single nu / gap solves), everything in shared memory.
 size_t resident_batch_smem_bytes(int n, int precision);

@@ -125,6 +125,26 @@ class Engine:
                  allow=(K.ERR_NOT_CONVERGED,) if allow_unconverged else ())
         return (out, logz, st) if want_logz else (out, st)
 
+    def solve_z(self, V, beta=1.0, Q=None, tol=1e-9, max_sweeps=10 ** 7, precision="f64", check_every=0,
+                allow_unconverged=False):
+        """generate_z (value_iteration.jl:42-51): the linear-space Z solve; the reference's stop rule is 1e-9."""
+        V, Q = _cell(V, self.H, self.W, "V"), _sa(Q, self.H, self.W, "Q")
+        out, st = self._out(), K.SolveStats()
+        o = self._opts(tol, max_sweeps, precision, check_every)
+        self._ck(self._lib.piql_solve_z(self._ctx, _pd(V), _pd(Q), float(beta), C.byref(o), _pd(out), C.byref(st)),
+                 allow=(K.ERR_NOT_CONVERGED,) if allow_unconverged else ())
+        return out, st
+
+    def z_update_v(self, V, beta=1.0, tol=1e-9, max_sweeps=10 ** 7, precision="f64", check_every=0,
+                   allow_unconverged=False):
+        """z_updateV (value_iteration.jl:53-59): V + log(Z)/beta."""
+        V = _cell(V, self.H, self.W, "V")
+        out, st = self._out(), K.SolveStats()
+        o = self._opts(tol, max_sweeps, precision, check_every)
+        self._ck(self._lib.piql_z_update_v(self._ctx, _pd(V), float(beta), C.byref(o), _pd(out), None, C.byref(st)),
+                 allow=(K.ERR_NOT_CONVERGED,) if allow_unconverged else ())
+        return out, st
+
     def solve_gap(self, V, nu, Q=None, tol=1e-12, max_sweeps=10 ** 7, precision="f64", check_every=0,
                   allow_unconverged=False):
         V, nu, Q = _cell(V, self.H, self.W, "V"), _cell(nu, self.H, self.W, "nu"), _sa(Q, self.H, self.W, "Q")
@@ -210,7 +230,7 @@ class Engine:
         return (sa, cnt, s, st, (cdf, bf, cum)) if want_tables else (sa, cnt, s, st)
 
     def sweep_once(self, kind, x, V=None, Q=None, nu=None, beta=1.0, reward_scale=1.0, precision="f64"):
-        kind = {"nu": K.KIND_NU, "logz": K.KIND_LOGZ, "gap": K.KIND_GAP}[kind]
+        kind = {"nu": K.KIND_NU, "logz": K.KIND_LOGZ, "gap": K.KIND_GAP, "z": K.KIND_Z}[kind]
         prec = K.PRECISIONS[precision]
         x = _cell(np.nan_to_num(np.asarray(x, dtype=np.float64)), self.H, self.W, "x")
         V, nu, Q = _cell(V, self.H, self.W, "V"), _cell(nu, self.H, self.W, "nu"), _sa(Q, self.H, self.W, "Q")

@@ -232,6 +232,30 @@ def logz_updateV(ctrl, V, beta=1.0, β=None, tol=1e-12, max_sweeps=10 ** 7, prec
     return (g, st) if return_stats else g
 
 
+def generate_z(ctrl, V, beta=1.0, β=None, Q=None, tol=1e-9, max_sweeps=10 ** 7, precision="f64", device=0,
+               return_stats=False):
+    """generate_z (src/value_iteration.jl:42-51): the linear-space twin of generate_logz, default x -> 1.0, stop rule
+    sum |log new - log old| < 1e-9.  Gridworld problems only (the reference never runs it on anything else)."""
+    beta = beta if β is None else β
+    if ctrl.grid is None:
+        raise NotImplementedError("generate_z is provided for gridworld problems; use generate_logz for tabulated ones")
+    eng = engine_for(ctrl, device)
+    out, st = eng.solve_z(_dense(V, eng), beta=beta, Q=Q, tol=tol, max_sweeps=max_sweeps, precision=precision)
+    g = Growable.from_dense(out, eng.walls, default=lambda x: 1.0)
+    return (g, st) if return_stats else g
+
+
+def z_updateV(ctrl, V, beta=1.0, β=None, tol=1e-9, max_sweeps=10 ** 7, precision="f64", device=0, return_stats=False):
+    """z_updateV (src/value_iteration.jl:53-59): V + log(Z)/beta."""
+    beta = beta if β is None else β
+    if ctrl.grid is None:
+        raise NotImplementedError("z_updateV is provided for gridworld problems; use logz_updateV for tabulated ones")
+    eng = engine_for(ctrl, device)
+    out, st = eng.z_update_v(_dense(V, eng), beta=beta, tol=tol, max_sweeps=max_sweeps, precision=precision)
+    g = Growable.from_dense(out, eng.walls, default=getattr(V, "default", lambda x: 0.0))
+    return (g, st) if return_stats else g
+
+
 def generate_optimality_gap(ctrl, V, nu=None, ν=None, Q=None, tol=1e-12, max_sweeps=10 ** 7, precision="f64", device=0,
                             return_stats=False):
     nu = nu if ν is None else ν

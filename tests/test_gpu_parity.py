@@ -63,6 +63,66 @@ def test_single_sweep_large_grid_generic_kernel(engine):
     assert nmax(out, ref) < 1e-13 and abs(d - dref) < 1e-9
 
 
+# ---- the linear-space twin: update_z! / generate_z / z_updateV (value_iteration.jl:23-59) -----------------------
+@pytest.mark.parametrize("precision,tol", [("f64", 1e-13), ("f32", 2e-6)])
+def test_linear_space_z_sweep_matches_oracle(engine, golden01, precision, tol):
+    g = golden01
+    org = load(engine, g)
+    x = np.asfortranarray(np.random.default_rng(4).uniform(0.2, 2.0, size=(g.H, g.W)))   # Z > 0
+    V = np.nan_to_num(g.V(7, 1))
+    ref, dref = org.sweep("z", x, V=V, beta=0.4)
+    out, d = engine.sweep_once("z", x, V=V, beta=0.4, precision=precision)
+    assert np.array_equal(np.isnan(out), g.walls != 0)
+    assert nmax(out, ref) < tol and abs(d - dref) < tol * 4000, (nmax(out, ref), d, dref)
+    Q = np.random.default_rng(5).normal(size=(g.H * g.W, 4)) * 0.2
+    if precision == "f64":
+        assert nmax(engine.sweep_once("z", x, V=V, Q=Q, beta=0.25)[0], org.sweep("z", x, V=V, Q=Q, beta=0.25)[0]) < 1e-13
+
+
+def test_generate_z_and_z_updateV(engine, golden01, piql):
+    g = golden01
+    org = load(engine, g)
+    V = np.nan_to_num(g.V(7, 0))
+    for beta in (1.0, 0.1800923121479524):
+        z, st = engine.solve_z(V, beta=beta)                       # the reference's stop rule: 1e-9 on sum |dlog Z|
+        ref, rst = org.solve("z", V=V, beta=beta, tol=1e-9)
+        assert st.kernel == 1 and st.converged and st.sweeps == rst.sweeps
+        assert nmax(z, ref) < 1e-12
+        logz, _ = engine.solve_logz(V, beta=beta)
+        assert nmax(np.log(z), logz) < 2e-9                        # the two forms of the same fixed point
+        v1, _ = engine.z_update_v(V, beta=beta)
+        free = g.walls == 0
+        assert nmax(v1[free], (V + np.log(ref) / beta)[free]) < 1e-10
+        assert nmax(v1, engine.update_v(V, beta=beta)[0]) < 2e-8   # z_updateV == logz_updateV up to the stop rules
+    # through the mirror of the reference interface
+    gw = piql.Gridworld(g.walls != 0, g.goal)
+    ctrl = piql.gridworld_ctrl(gw, randomness=g.params["randomness"], gamma=g.params["gamma"])
+    Vg = piql.Growable.from_dense(V, g.walls)
+    Z = piql.generate_z(ctrl, Vg, β=1.0)
+    assert Z.default(None) == 1.0 and abs(Z(g.s0) - ref_at(org, V, g)) < 1e-12
+    V1 = piql.z_updateV(ctrl, Vg, β=1.0)
+    assert abs(V1(g.s0) - (Vg(g.s0) + np.log(Z(g.s0)))) < 1e-12
+
+
+def ref_at(org, V, g):
+    z, _ = org.solve("z", V=V, beta=1.0, tol=1e-9)
+    return z[g.s0]
+
+
+def test_linear_space_z_on_a_large_grid(engine):
+    # > RESIDENT_MAX_CELLS: one launch per sweep (stats.kernel 5), stop rule checked every 32 sweeps
+    walls, goal = random_gridworld((100, 100), 0.2, seed=5)
+    engine.load_grid(walls, goal, 0.02, 0.02, 0.2, 0.95)
+    org = oracle.Grid(walls, goal, randomness=0.02, step_cost=0.02, reward=0.2, gamma=0.95)
+    V = np.nan_to_num(org.solve("nu", reward_scale=0.1, tol=1e-11, nthreads=8)[0])
+    z, st = engine.solve_z(V, beta=0.5, check_every=32)
+    assert st.kernel == 5 and st.converged and st.sweeps % 32 == 0
+    ref, _ = org.solve("z", V=V, beta=0.5, tol=1e-9, nthreads=8)
+    assert nmax(np.log(z), np.log(ref)) < 1e-8
+    with pytest.raises(Exception):
+        engine.vi_prepare("z", V=V)
+
+
 # ---- fixed points against the reference's stored results ---------------------------------------
 def test_nu_and_vlo_match_reference_data(engine, golden):
     g = golden
