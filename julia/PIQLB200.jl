@@ -194,6 +194,25 @@ function optimality_gap_batch(ctx::Context, Vs::Vector, ν; kw...)
     [growable(ctx, out[:, :, i]) for i in 1:m]
 end
 
+# ---- run_experiment[_distributed] (scripts/experiments.jl:20-39, scripts/distributed_experiments.jl:15-33) ------------
+# Returns the same NamedTuple of PIQL.Growable's the reference builds, so that `@save "data/<name>.jld2" out`
+# (scripts/distributed_experiments.jl:49-59) writes files of the layout data/*.jld2 have, and scripts/plotting.jl
+# (`out.traj`, `out.gap`, `out.s0`, `out.ν`, `out.randomness`; :46-89) reads GPU-produced results unchanged.
+function run_experiment(ctx::Context, gw; randomness = 0.01, γ = 0.99, starting_temp = 0.1, βrange = exp.(range(-6, 0, 8)), n = 5, kw...)
+    gwctrl = gridworld_ctrl(gw; randomness, γ)
+    load!(ctx, gwctrl, gw; randomness)
+    ν = generate_ν(ctx; kw...)
+    (_, furthest) = findmin(ν.dict)
+    V_lo = generate_ν(ctx; reward_scale = starting_temp, kw...)        # modify(gwctrl, reward_function = starting_temp * ...)
+    experiment = learning_traj_batch(ctx, V_lo, βrange; n, kw...)      # Dict(β => [V_lo, V_1, ..., V_n])
+    βs = collect(keys(experiment))
+    flat = reduce(vcat, [experiment[β] for β in βs])
+    gaps = optimality_gap_batch(ctx, flat, ν; kw...)
+    optimality_gap = Dict(β => gaps[(b-1)*(n+1)+1:b*(n+1)] for (b, β) in enumerate(βs))
+    return (ν = ν, traj = experiment, gap = optimality_gap, randomness = randomness, γ = γ, ctrl = gwctrl, s0 = furthest)
+end
+const run_experiment_distributed = run_experiment
+
 # ---- any other ControlProblem (e.g. binary_bandit_problem, src/Problems/BinaryBandit.jl): tabulate through the closures ----
 struct TableProblem
     nstates::Int64; nactions::Int32; row_ptr::Ptr{Int64}; succ::Ptr{Int32}; prob::Ptr{Cdouble}; reward::Ptr{Cdouble}
