@@ -222,6 +222,19 @@ int32_t piql_mc_logz(piql_ctx* ctx, const double* V, const double* Q, double bet
 int32_t piql_mc_update_v(piql_ctx* ctx, const double* V, double beta, const piql_mc_opts* opts, int32_t niter,
                          double* vnew_out, piql_mc_stats* stats_out);
 
+/* fitness_reward_estimate / direct_reward_estimate   src/path_functions.jl:34-50 over path_transitions :23-32, for
+ * opts->npaths paths at once: exactly nsteps sampled transitions per path under π_Q (the reference's walk has no stop
+ * rule and does not treat the goal specially; estimator / horizon in opts are ignored), and after every transition
+ *   fitness_out[p][t] = V(s0) + Σ_{τ≤t} fitness(s_τ, a_τ)
+ *   direct_out[p][t]  = V(s0) + Σ_{τ≤t} [reward_function(s_τ, a_τ, s'_τ) − kl_cost(s_τ)]      (sampled reward)
+ * in fp32 ([npaths][nsteps] each).  The reference file does not load as written (`ctrl.reward`, a missing `return out`);
+ * these are the evident intent, as the oracle restates them.  Uniforms: the estimator's contract (word 1 of a step, the
+ * stop test, is drawn and unused).  Optional outputs: triples_out [npaths][nsteps][3] (s, a, s'); table_out (32 B per
+ * cell, the β = 1 sampler records) and kl_out (one float per cell) -- what the kernel read, for bit-exact checks.
+ * Replaces the current policy table: call piql_policy_table again before piql_mc_rollout_dev. */
+int32_t piql_path_estimates(piql_ctx* ctx, const double* V, const double* Q, const piql_mc_opts* opts, int32_t nsteps,
+                            float* fitness_out, float* direct_out, int32_t* triples_out, float* table_out, float* kl_out);
+
 /* Debug export for bit-exact trajectory parity: the (s, a, s') triples of each path (int32 cell
  * indices, -1 padded, [npaths][max_steps][3]) and the per-path record: logw (float) and
  * meta = a0 | (len << 2).  Uses the current policy table. */

@@ -163,6 +163,22 @@ function mc_logz(ctx::Context, V; β = 1.0, npaths = 2^20, seed = 0, estimator =
     (logz = growable(ctx, logz_s), logz_sa = logz_sa, count = count, transitions = st.transitions)
 end
 
+# ---- fitness_reward_estimate / direct_reward_estimate (src/path_functions.jl:34-50) for npaths paths at once --------
+# returns (fitness, direct): nsteps x npaths Float32 matrices of running totals (column p = path p), Q = the V-determined
+# Q-function; s0 a CartesianIndex, a vector of them, or nothing for every free cell
+function path_estimates(ctx::Context, V; s0 = nothing, npaths = 2^16, nsteps = 20, seed = 0)
+    Vd = dense(ctx, V); H = size(ctx.walls, 1)
+    cells = s0 === nothing ? Int32[] : Int32[(c[1] - 1) + H * (c[2] - 1) for c in (s0 isa CartesianIndex ? [s0] : s0)]
+    fit = Matrix{Float32}(undef, nsteps, npaths); dir = similar(fit)
+    GC.@preserve cells Vd fit dir begin
+        o = McOpts(npaths, 0, seed, 0, isempty(cells) ? 0 : 1, nsteps, isempty(cells) ? C_NULL : pointer(cells), length(cells), C_NULL, 0)
+        check(ctx, ccall((:piql_path_estimates, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{McOpts}, Int32, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Int32}, Ptr{Cfloat}, Ptr{Cfloat}),
+            ctx.ptr, Vd, C_NULL, o, nsteps, fit, dir, C_NULL, C_NULL, C_NULL))
+    end
+    (fitness = fit, direct = dir)
+end
+
 # ---- the PIQL iteration itself: V <- V + log Z^/beta with log Z^ from rollouts, niter times on the device ----------------
 function mc_logz_updateV(ctx::Context, V; β = 1.0, npaths = 2^22, niter = 1, seed = 0, horizon = 2^20)
     Vd = dense(ctx, V); out = similar(Vd); st = McStats()

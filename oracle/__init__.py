@@ -160,6 +160,45 @@ class Grid:
                           _p(meta, C.c_uint32), _p(trace, C.c_int32), C.c_int64(trace_steps), C.c_int(nthreads))
         return (logw, meta, trace) if trace_steps else (logw, meta)
 
+    def kl_table(self, V, Q=None):
+        """kl_cost per cell (path_functions.jl:17-20), rounded once to float like the sampler's records."""
+        out = np.zeros(self.H * self.W, dtype=np.float32)
+        for s in self.free_cells():
+            out[s] = self.kl_cost(V, int(s), Q=Q)
+        return out
+
+    def path_estimates(self, table, kl, V, starts, npaths, nsteps=20, path0=0, seed=0, injected=None, trace=False):
+        """fitness_reward_estimate / direct_reward_estimate (path_functions.jl:34-50) on the fp32 records:
+        running totals fit[npaths, nsteps], dir[npaths, nsteps] (+ the (s, a, s') triples)."""
+        starts = np.ascontiguousarray(starts, dtype=np.int32)
+        table = np.ascontiguousarray(table, dtype=np.float32)
+        kl = np.ascontiguousarray(kl, dtype=np.float32)
+        V = _f(np.nan_to_num(np.asarray(V, dtype=np.float64)))
+        fit = np.empty((npaths, nsteps), dtype=np.float32)
+        dr = np.empty((npaths, nsteps), dtype=np.float32)
+        inj_steps = 0
+        if injected is not None:
+            injected = np.ascontiguousarray(injected, dtype=np.float32)
+            assert injected.shape[0] == npaths and injected.shape[1] >= nsteps and injected.shape[2] == 4
+            inj_steps = injected.shape[1]
+        tr = np.empty((npaths, nsteps, 3), dtype=np.int32) if trace else None
+        lib().orc_path_estimates(C.c_int64(self.H), C.c_int64(self.goal_idx), _p(table, C.c_float), _p(kl, C.c_float),
+                                 _p(V, C.c_double), C.c_double(self.randomness), C.c_double(self.step_cost),
+                                 C.c_double(self.reward), C.c_int64(nsteps), C.c_int64(path0), C.c_int64(npaths),
+                                 _p(starts, C.c_int32), C.c_int64(len(starts)), C.c_uint64(seed), _p(injected, C.c_float),
+                                 C.c_int64(inj_steps), _p(fit, C.c_float), _p(dr, C.c_float), _p(tr, C.c_int32))
+        return (fit, dr, tr) if trace else (fit, dr)
+
+    def path_estimates_f64(self, V, triples, Q=None):
+        """The same totals in Float64 through the reference's closures, along given (s, a, s') triples of ONE path."""
+        V, Q = _f(np.nan_to_num(np.asarray(V, dtype=np.float64))), _q(Q)
+        triples = np.ascontiguousarray(triples, dtype=np.int32)
+        n = triples.shape[0]
+        fit, dr = np.empty(n), np.empty(n)
+        lib().orc_path_estimates_f64(*self._args(1.0), _p(V, C.c_double), _p(Q, C.c_double), _p(triples, C.c_int32),
+                                     C.c_int64(n), _p(fit, C.c_double), _p(dr, C.c_double))
+        return fit, dr
+
     def rollout_f64(self, V, start, injected, beta=1.0, Q=None, stop_rule=True, reward_scale=1.0):
         V, Q = _f(V), _q(Q)
         injected = np.ascontiguousarray(injected, dtype=np.float64)

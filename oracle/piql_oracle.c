@@ -535,6 +535,71 @@ int orc_rollout(int64_t H, int64_t goal, const float *table, double gamma, doubl
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------
+ * fitness_reward_estimate / direct_reward_estimate   path_functions.jl:34-50 over path_transitions :23-32
+ * (as evidently intended: the file does not load as written -- `ctrl.reward` for ctrl.reward_function, `return out`
+ * of an undefined name in the generator, no return of the running totals).  Exactly nsteps transitions per path, no
+ * stop rule, the goal is not special.  After each transition:
+ *   fit[t] = V(s0) + sum fitness(s,a)            dir[t] = V(s0) + sum [reward_function(s,a,s') - kl_cost(s)]
+ * fp32 version (what the CUDA kernel must reproduce bit-for-bit): reads the fp32 policy records of beta = 1
+ * (rec[4+a] = fitness) and an fp32 kl_cost per cell, sums in float in the order below.
+ * ---------------------------------------------------------------------------------- */
+int orc_path_estimates(int64_t H, int64_t goal, const float *table, const float *kl, const double *V,
+                       double randomness, double step_cost, double reward, int64_t nsteps, int64_t path0,
+                       int64_t npaths, const int32_t *starts, int64_t nstarts, uint64_t seed, const float *inj,
+                       int64_t inj_steps, float *fit, float *dir, int32_t *trace) {
+  const float rho = (float)randomness, rg = (float)reward, rs = (float)(-step_cost);
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  const int64_t off[4] = {1, -1, H, -H};
+  for (int64_t q = 0; q < npaths; q++) {
+    int64_t p = path0 + q;
+    int64_t s = starts[p % nstarts];
+    float tf = (float)V[s], td = tf;
+    for (int64_t t = 0; t < nsteps; t++) {
+      float u[4];
+      if (inj) memcpy(u, inj + ((size_t)q * inj_steps + t) * 4, sizeof u);
+      else {
+        uint32_t ctr[4] = {(uint32_t)t, 0u, (uint32_t)p, (uint32_t)((uint64_t)p >> 32)}, r[4];
+        orc_philox4x32_10(ctr, key, r);
+        for (int i = 0; i < 4; i++) u[i] = u01(r[i]);
+      }
+      const float *rec = table + 8 * s;
+      uint32_t mask; memcpy(&mask, rec + 3, 4);
+      int a = 0;
+      while (rec[a] < u[0] && a < 3) a++;                        /* choose_action :12-15 */
+      int as = (int)(4.0f * u[3]); if (as > 3) as = 3;
+      int aa = (u[2] < rho) ? as : a;                            /* propagator  GridWorld.jl:113-115 */
+      int64_t s1 = ((mask >> aa) & 1u) ? s : s + off[aa];
+      tf = tf + rec[4 + a];                                      /* total += fitness(ctrl,V,Q,s,a)  :38 */
+      float rw = (s1 == goal) ? rg : rs;                         /* reward_function  GridWorld.jl:116 */
+      td = td + (rw - kl[s]);                                    /* total += reward - kl_cost  :47 */
+      fit[q * nsteps + t] = tf;
+      dir[q * nsteps + t] = td;
+      if (trace) { int32_t *tr = trace + (q * nsteps + t) * 3; tr[0] = (int32_t)s; tr[1] = a; tr[2] = (int32_t)s1; }
+      s = s1;
+    }
+  }
+  return 0;
+}
+
+/* The same two estimates evaluated the reference's way -- Float64, every fitness / kl_cost / reward_function call
+ * through the closures -- along a GIVEN sequence of (s, a, s') triples: pins the fp32 tables against the algebra. */
+int orc_path_estimates_f64(int64_t H, int64_t W, const uint8_t *walls, int64_t goal, double randomness,
+                           double step_cost, double reward, double gamma, double reward_scale, const double *V,
+                           const double *Qtab, const int32_t *triples, int64_t nsteps, double *fit, double *dir) {
+  orc_grid g = {H, W, walls, goal, randomness, step_cost, reward, gamma, reward_scale};
+  orc_q q = {&g, dense_fn, (void *)V, Qtab};
+  double tf = V[triples[0]], td = tf;
+  for (int64_t t = 0; t < nsteps; t++) {
+    int64_t s = triples[3 * t], s1 = triples[3 * t + 2];
+    int a = triples[3 * t + 1];
+    tf += fitness(&q, s, a);
+    td += reward_fn(&g, s1) - orc_kl_cost(H, W, walls, goal, randomness, step_cost, reward, gamma, reward_scale, V, Qtab, s);
+    fit[t] = tf; dir[t] = td;
+  }
+  return 0;
+}
+
 /* Faithful fp64 sampler: choose_action + propagator exactly as the reference evaluates them
  * (weights from action_probability in Float64, t = u*sum(w), walk cw < t), for one path with
  * injected uniforms.  Used to show the fp32-table sampler takes the same actions. */

@@ -20,6 +20,6 @@ from .gridworld import (ControlProblem, Gridworld, gridworld_ctrl, make_gridworl
 from .tables import (BanditState, ProblemTable, bandit_state_iterator, binary_bandit_problem, reachable, tabulate_problem,
                      update)
 from .solvers import (Growable, McResult, Qnormalization, action_probability, average_reward, choose_action,
-                      controlQ, controlV, engine_for, fitness, fitness_reward_estimate, generate_logz, generate_nu,
+                      controlQ, controlV, direct_reward_estimate, engine_for, fitness, fitness_reward_estimate, generate_logz, generate_nu,
                       generate_optimality_gap, generate_optimality_gap_batch, generate_z, generate_ν, kl_cost, learning_traj, learning_traj_batch, logz_updateV, mc_logz, mc_logz_updateV,
-                      path_transitions, run_experiment, run_experiment_distributed, z_updateV)
+                      path_estimates, path_transitions, run_experiment, run_experiment_distributed, z_updateV)

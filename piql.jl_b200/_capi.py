@@ -85,6 +85,8 @@ SYMBOLS = {
                                  C.POINTER(McStats)]),
     "piql_trace_paths": (C.c_int32, [_P, C.POINTER(McOpts), C.c_int64, C.POINTER(C.c_int32),
                                      C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    "piql_path_estimates": (C.c_int32, [_P, _D, _D, C.POINTER(McOpts), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "piql_mc_reset_dev": (C.c_int32, [_P, C.POINTER(McOpts)]),
     "piql_mc_rollout_dev": (C.c_int32, [_P, C.POINTER(McOpts)]),
     "piql_mc_stats_dev": (C.c_int32, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),

@@ -471,7 +471,7 @@ int mc_finalize(piql_ctx* ctx, double* logz_sa, uint64_t* count_sa, double* logz
   return PIQL_OK;
 }
 
-int build_table(piql_ctx* ctx, const double* V, const double* Q, double beta) {
+int build_table(piql_ctx* ctx, const double* V, const double* Q, double beta, float* kl_dev = nullptr) {
   NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded (call piql_grid_load first)");
   NEED(V != nullptr, PIQL_ERR_ARG, "V is null");
   NEED(beta == beta, PIQL_ERR_ARG, "beta is NaN");
@@ -483,7 +483,7 @@ int build_table(piql_ctx* ctx, const double* V, const double* Q, double beta) {
   NEED(vg == vg, PIQL_ERR_ARG, "V(goal) is NaN");
   CK(cudaMemcpyAsync(ctx->d_in0, V, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
   if (Q) CK(cudaMemcpyAsync(ctx->d_in4, Q, 32 * (size_t)n, cudaMemcpyHostToDevice, st));
-  launch_policy_table(ctx->g, ctx->d_cell, ctx->d_in0, Q ? ctx->d_in4 : nullptr, beta, 1.0, ctx->d_table, st);
+  launch_policy_table(ctx->g, ctx->d_cell, ctx->d_in0, Q ? ctx->d_in4 : nullptr, beta, 1.0, ctx->d_table, st, kl_dev);
   CK_LAST();
   ctx->v_goal = vg;
   ctx->has_table = true;
@@ -1308,6 +1308,66 @@ int32_t piql_trace_paths(piql_ctx* ctx, const piql_mc_opts* opts, int64_t max_st
   }
   cudaFree(d_trace);
   return rc;
+}
+
+int32_t piql_path_estimates(piql_ctx* ctx, const double* V, const double* Q, const piql_mc_opts* opts, int32_t nsteps,
+                            float* fitness_out, float* direct_out, int32_t* triples_out, float* table_out, float* kl_out) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded (call piql_grid_load first)");
+  int rc = mc_check_opts(ctx, opts);
+  if (rc) return rc;
+  NEED(nsteps > 0, PIQL_ERR_ARG, "nsteps must be positive");
+  NEED(fitness_out && direct_out, PIQL_ERR_ARG, "fitness_out / direct_out is null");
+  NEED(opts->npaths * (long long)nsteps < (1LL << 28), PIQL_ERR_ARG, "too many running totals (npaths*nsteps must be < 2^28)");
+  NEED(!opts->injected || opts->injected_steps >= nsteps, PIQL_ERR_ARG, "injected_steps must cover nsteps");
+  NEED(V != nullptr, PIQL_ERR_ARG, "V is null");
+  rc = mc_setup_slots(ctx, opts);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  const int n = ctx->g.n;
+  const size_t nt = (size_t)opts->npaths * (size_t)nsteps;
+  float *d_kl = nullptr, *d_fit = nullptr;
+  int* d_tr = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_kl, 4 * (size_t)n);
+  if (e == cudaSuccess) {
+    // beta = 1: the record's weight column is fitness(s,a) itself; kl_cost per cell beside it
+    rc = build_table(ctx, V, Q, 1.0, d_kl);
+    ctx->has_table = false;  // not the sampler's table of whatever beta the caller asked for earlier
+    if (rc) { cudaFree(d_kl); return rc; }
+  }
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_fit, 8 * (nt ? nt : 1));
+  if (e == cudaSuccess && triples_out) e = cudaMalloc((void**)&d_tr, 12 * (nt ? nt : 1));
+  const float* inj_dev = nullptr;
+  if (e == cudaSuccess && opts->injected) {
+    const size_t nf = (size_t)opts->npaths * (size_t)opts->injected_steps * 4;
+    e = grow(ctx->d_inj, ctx->inj_cap, nf);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_inj, opts->injected, 4 * nf, cudaMemcpyHostToDevice, st);
+    inj_dev = ctx->d_inj;
+  }
+  if (e == cudaSuccess) {
+    PathEstArgs a{};  // d_in0 still holds the caller's V in double
+    a.table = ctx->d_table; a.kl = d_kl; a.V = ctx->d_in0;
+    a.starts = ctx->d_starts; a.nstarts = ctx->nstarts; a.path0 = opts->path0; a.npaths = opts->npaths;
+    a.nsteps = nsteps; a.H = ctx->g.H; a.goal = ctx->g.goal;
+    a.rho = (float)ctx->g.randomness; a.rho_k = (uint32_t)std::ceil((double)a.rho * 16777216.0);
+    a.rwd_goal = (float)ctx->g.reward; a.rwd_step = (float)(-ctx->g.step_cost);
+    a.keys = philox_expand((uint32_t)opts->seed, (uint32_t)(opts->seed >> 32));
+    a.injected = inj_dev; a.injected_steps = opts->injected_steps;
+    a.fit = d_fit; a.dir = d_fit + nt; a.trace = d_tr;
+    launch_path_estimates(a, ctx->num_sms, st);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(fitness_out, d_fit, 4 * nt, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(direct_out, d_fit + nt, 4 * nt, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && triples_out) e = cudaMemcpyAsync(triples_out, d_tr, 12 * nt, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && table_out) e = cudaMemcpyAsync(table_out, ctx->d_table, 32 * (size_t)n, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && kl_out) e = cudaMemcpyAsync(kl_out, d_kl, 4 * (size_t)n, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  for (void* p : {(void*)d_kl, (void*)d_fit, (void*)d_tr}) if (p) cudaFree(p);
+  if (e != cudaSuccess) return fail(ctx, PIQL_ERR_CUDA, std::string("piql_path_estimates: ") + cudaGetErrorString(e));
+  return PIQL_OK;
 }
 
 int32_t piql_mc_reset_dev(piql_ctx* ctx, const piql_mc_opts* opts) {

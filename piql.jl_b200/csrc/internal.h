@@ -142,8 +142,26 @@ struct RolloutArgs {
   int* trace;            // optional [npaths][trace_steps][3]
   long long trace_steps;
 };
+// kl_out (optional): kl_cost(ctrl, s, Q) per cell, path_functions.jl:17-20
 void launch_policy_table(const GridDev& g, const uint8_t* cell, const double* V, const double* Q, double beta,
-                         double reward_scale, float4* table, cudaStream_t st);
+                         double reward_scale, float4* table, cudaStream_t st, float* kl_out = nullptr);
+struct PathEstArgs {
+  const float4* table;   // policy records built with beta = 1 (bf = fitness)
+  const float* kl;       // kl_cost per cell
+  const double* V;       // the caller's V (double, device): V(s0) opens both totals
+  const int* starts;
+  long long nstarts, path0, npaths;
+  int nsteps, H, goal;
+  float rho, rwd_goal, rwd_step;
+  uint32_t rho_k;
+  PhiloxKeys keys;
+  const float* injected;
+  long long injected_steps;
+  float* fit;            // [npaths][nsteps]
+  float* dir;            // [npaths][nsteps]
+  int* trace;            // optional [npaths][nsteps][3]
+};
+void launch_path_estimates(const PathEstArgs& a, int num_sms, cudaStream_t st);
 void launch_rollout(const RolloutArgs& a, int num_sms, cudaStream_t st);
 // Reduce records into (max, sum, count)[nstarts*4], merged into the accumulators; adds the
 // transition count to *transitions.

@@ -21,11 +21,13 @@ namespace piql {
 // Computed in double from the caller's V (and Q) and rounded once to float, like the oracle.
 __global__ void __launch_bounds__(256)
 policy_table_kernel(GridDev g, double reward_scale, double beta, const uint8_t* __restrict__ cell,
-                    const double* __restrict__ V, const double* __restrict__ Q, float4* __restrict__ table) {
+                    const double* __restrict__ V, const double* __restrict__ Q, float4* __restrict__ table,
+                    float* __restrict__ kl_out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= g.n) return;
   const unsigned ci = cell[s];
   float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+  float kl = 0.f;
   if (!(ci & CELL_WALL)) {
     const double w_on = 1.0 * (1.0 - g.randomness) + g.randomness / NA;
     const double w_off = 0.0 * (1.0 - g.randomness) + g.randomness / NA;
@@ -65,14 +67,82 @@ policy_table_kernel(GridDev g, double reward_scale, double beta, const uint8_t* 
     }
     r0 = make_float4(cdf[0], cdf[1], cdf[2], __uint_as_float(ci & CELL_BLOCK_MASK));
     r1 = make_float4(bf[0], bf[1], bf[2], bf[3]);
+    if (kl_out) {  // kl_cost(ctrl, s, Q) = sum_a xlogx(p_a) - xlogy(p_a, prior)   path_functions.jl:17-20
+      double acc = 0.0;
+#pragma unroll
+      for (int a = 0; a < NA; a++) acc += (w[a] == 0.0 ? 0.0 : w[a] * log(w[a])) - (w[a] == 0.0 ? 0.0 : w[a] * log(1.0 / NA));
+      kl = (float)acc;
+    }
   }
   table[2 * (size_t)s] = r0;
   table[2 * (size_t)s + 1] = r1;
+  if (kl_out) kl_out[s] = kl;
 }
 
 void launch_policy_table(const GridDev& g, const uint8_t* cell, const double* V, const double* Q, double beta,
-                         double reward_scale, float4* table, cudaStream_t st) {
-  policy_table_kernel<<<(g.n + 255) / 256, 256, 0, st>>>(g, reward_scale, beta, cell, V, Q, table);
+                         double reward_scale, float4* table, cudaStream_t st, float* kl_out) {
+  policy_table_kernel<<<(g.n + 255) / 256, 256, 0, st>>>(g, reward_scale, beta, cell, V, Q, table, kl_out);
+  g_launches++;
+}
+
+// ---- the reference's own path statistics ---------------------------------------------------------------
+// fitness_reward_estimate / direct_reward_estimate (src/path_functions.jl:34-50) over path_transitions (:23-32): exactly
+// nsteps sampled transitions per path -- no stop rule and no terminal handling, the walk goes on through the goal as the
+// reference's does -- and after every transition the running totals
+//   fit[t] = V(s0) + sum_{tau<=t} fitness(s_tau, a_tau)
+//   dir[t] = V(s0) + sum_{tau<=t} [reward_function(s_tau, a_tau, s'_tau) - kl_cost(s_tau)]       (sampled reward)
+// One path per thread (all paths have the same length, so there is nothing to refill); the per-step record is the
+// sampler's 32-byte record built with beta = 1 plus one float of kl_cost per cell; fp32 running sums in the order
+// written here, which the oracle repeats.  Uniform contract as the estimator's (word 1, the stop test, is drawn and unused).
+template <bool INJ>
+__global__ void __launch_bounds__(256)
+path_estimates_kernel(const PathEstArgs p) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < p.npaths; q += stride) {
+    const unsigned long long gp = (unsigned long long)(p.path0 + q);
+    int s = __ldg(p.starts + (long long)(gp % (unsigned long long)p.nstarts));
+    float tf = (float)p.V[s], td = tf;
+    float* fo = p.fit + (size_t)q * p.nsteps;
+    float* go = p.dir + (size_t)q * p.nsteps;
+    for (int t = 0; t < p.nsteps; t++) {
+      const float4 r0 = __ldg(p.table + 2 * (size_t)s), r1 = __ldg(p.table + 2 * (size_t)s + 1);
+      const float kl = __ldg(p.kl + s);
+      float u0;
+      bool slip;
+      int aslip;
+      if (INJ) {
+        const float4 u = *reinterpret_cast<const float4*>(p.injected + ((size_t)q * (size_t)p.injected_steps + t) * 4);
+        u0 = u.x; slip = u.z < p.rho; aslip = min((int)(4.0f * u.w), 3);
+      } else {
+        const uint4 r = philox4x32_10(p.keys, (uint32_t)t, 0u, (uint32_t)gp, (uint32_t)(gp >> 32));
+        u0 = u01(r.x); slip = (r.z >> 8) < p.rho_k; aslip = (int)(r.w >> 30);
+      }
+      const bool b0 = r0.x < u0, b1 = r0.y < u0, b2 = r0.z < u0;  // choose_action: the cw < t walk
+      const int a = (int)b0 + (int)b1 + (int)b2;
+      float bf = r1.x;
+      bf = b0 ? r1.y : bf; bf = b1 ? r1.z : bf; bf = b2 ? r1.w : bf;
+      const int aa = slip ? aslip : a;                             // propagator   GridWorld.jl:113-115
+      const unsigned blocked = (__float_as_uint(r0.w) >> aa) & 1u;
+      int d = (aa & 2) ? p.H : 1;
+      d = (aa & 1) ? -d : d;
+      const int s1 = blocked ? s : s + d;
+      tf = __fadd_rn(tf, bf);
+      const float rw = s1 == p.goal ? p.rwd_goal : p.rwd_step;     // reward_function(s, a, s')   GridWorld.jl:116
+      td = __fadd_rn(td, __fsub_rn(rw, kl));
+      fo[t] = tf;
+      go[t] = td;
+      if (p.trace) { int* tr = p.trace + ((size_t)q * p.nsteps + t) * 3; tr[0] = s; tr[1] = a; tr[2] = s1; }
+      s = s1;
+    }
+  }
+}
+
+void launch_path_estimates(const PathEstArgs& a, int num_sms, cudaStream_t st) {
+  if (a.npaths <= 0) return;
+  const long long want = (a.npaths + 255) / 256, cap = (long long)num_sms * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  if (a.injected) path_estimates_kernel<true><<<grid, 256, 0, st>>>(a);
+  else path_estimates_kernel<false><<<grid, 256, 0, st>>>(a);
   g_launches++;
 }
 

@@ -345,6 +345,26 @@ class Engine:
                                             meta.ctypes.data_as(C.POINTER(C.c_uint32))))
         return tr, logw, meta
 
+    def path_estimates(self, V, npaths, nsteps=20, Q=None, want_trace=False, want_tables=False, **kw):
+        """fitness_reward_estimate / direct_reward_estimate (path_functions.jl:34-50) for npaths paths of nsteps
+        transitions: running totals fit[npaths, nsteps], dir[npaths, nsteps] (float32)."""
+        V, Q = _cell(V, self.H, self.W, "V"), _sa(Q, self.H, self.W, "Q")
+        o, _keep = self._mc_opts(npaths, **kw)
+        fit = np.empty((npaths, nsteps), dtype=np.float32)
+        dr = np.empty((npaths, nsteps), dtype=np.float32)
+        tr = np.empty((npaths, nsteps, 3), dtype=np.int32) if want_trace else None
+        tab = np.empty((self.H * self.W, 8), dtype=np.float32) if want_tables else None
+        kl = np.empty(self.H * self.W, dtype=np.float32) if want_tables else None
+        pf = lambda a, t=C.c_float: None if a is None else a.ctypes.data_as(C.POINTER(t))
+        self._ck(self._lib.piql_path_estimates(self._ctx, _pd(V), _pd(Q), C.byref(o), int(nsteps), pf(fit), pf(dr),
+                                               pf(tr, C.c_int32), pf(tab), pf(kl)))
+        out = [fit, dr]
+        if want_trace:
+            out.append(tr)
+        if want_tables:
+            out += [tab, kl]
+        return tuple(out)
+
     # device-resident pieces (bench, multi-GPU)
     def mc_reset(self, starts=None):
         o, _keep = self._mc_opts(0, starts=starts)

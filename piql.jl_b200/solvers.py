@@ -165,6 +165,29 @@ def fitness_reward_estimate(ctrl, s0, V, Q, rng, nsteps=20):
     return out
 
 
+def direct_reward_estimate(ctrl, s0, V, Q, rng, nsteps=20):
+    """Running V(s0) + sum_t [reward_function(s_t, a_t, s'_t) - kl_cost(s_t)] along one path   path_functions.jl:43-50
+    (the reference writes ctrl.reward, a field that does not exist; reward_function is meant)"""
+    total, out = V(s0), []
+    for (s, a, ss) in path_transitions(ctrl, s0, Q, rng, nsteps=nsteps):
+        total += ctrl.reward_function(s, a, ss) - kl_cost(ctrl, s, Q)
+        out.append(total)
+    return out
+
+
+def path_estimates(ctrl, V, s0=None, npaths=1 << 16, nsteps=20, seed=0, device=0):
+    """Both path estimates for npaths paths at once on the GPU (piql_path_estimates), Q = the V-determined Q-function
+    (s, a) -> controlV(ctrl, V, s, a) as everywhere in the reference's scripts.  s0: one start state, a list of them
+    (path p starts at s0[p % len]) or None for every free cell.  Returns (fitness[npaths, nsteps], direct[npaths, nsteps])."""
+    eng = engine_for(ctrl, device)
+    starts = None
+    if s0 is not None:
+        lst = [s0] if isinstance(s0[0], (int, np.integer)) else list(s0)
+        starts = [int(i) + eng.H * int(j) for (i, j) in lst]
+    fit, dr = eng.path_estimates(_dense(V, eng), npaths, nsteps=nsteps, seed=seed, starts=starts)
+    return fit, dr
+
+
 # ---- problems that are not the implicit gridworld: tabulate through the closures, solve on the table ABI ---------
 _tables = {}
 

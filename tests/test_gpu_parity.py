@@ -226,6 +226,61 @@ def test_fp32_sweeps_within_1e5_relative(engine, golden01):
     assert rel.max() < 1e-4, rel.max()
 
 
+# ---- the reference's own path statistics: fitness_reward_estimate / direct_reward_estimate --------------------
+@pytest.mark.parametrize("injected", [False, True])
+def test_path_estimates_bit_exact(engine, golden, injected):
+    g = golden
+    org = load(engine, g)
+    V = np.nan_to_num(g.V(5, 2))
+    npaths, nsteps = 3000, 20                                         # path_transitions' nsteps = 20
+    starts = [g.s0_idx, g.goal[0] + g.H * g.goal[1], int(org.free_cells()[7])]   # also a path that starts on the goal
+    inj = np.random.default_rng(8).random((npaths, nsteps, 4), dtype=np.float32) if injected else None
+    fit, dr, tr, tab, kl = engine.path_estimates(V, npaths, nsteps=nsteps, want_trace=True, want_tables=True,
+                                                 seed=11, path0=5, starts=starts, injected=inj)
+    # what the kernel read: the beta = 1 records and kl_cost per cell, against the oracle's Float64 evaluation
+    ref_tab, ref_kl = org.policy_table(V, beta=1.0), org.kl_table(V)
+    ulp = np.abs(tab.view(np.int32).astype(np.int64) - ref_tab.view(np.int32).astype(np.int64))
+    ulp[:, 3] = 0
+    assert ulp[np.abs(ref_tab) > 1e-30].max() <= 2 and np.abs(kl - ref_kl).max() < 1e-7
+    # same records, same uniforms: identical trajectories and identical fp32 running totals
+    rfit, rdr, rtr = org.path_estimates(tab, kl, V, starts, npaths, nsteps=nsteps, path0=5, seed=11, injected=inj, trace=True)
+    assert np.array_equal(tr, rtr)
+    assert np.array_equal(fit.view(np.uint32), rfit.view(np.uint32))
+    assert np.array_equal(dr.view(np.uint32), rdr.view(np.uint32))
+    # ... and they are the Float64 estimates the reference's closures give along those paths
+    for p in (0, 1, 2, 17, npaths - 1):
+        f64, d64 = org.path_estimates_f64(V, tr[p])
+        assert np.abs(fit[p] - f64).max() < 1e-5 and np.abs(dr[p] - d64).max() < 1e-5
+    # the walk goes on through the goal (no terminal handling in path_transitions)
+    assert tr[2, 0, 0] == starts[(5 + 2) % 3] == starts[1] and (tr[:, 1:, 0] == tr[:, :-1, 2]).all()
+
+
+def test_path_estimates_known_answers(engine, golden01, piql):
+    g = golden01
+    load(engine, g)
+    nu = np.nan_to_num(g.nu)
+    # at V = nu the V-determined policy is optimal and fitness vanishes identically: the fitness total stays at nu(s0)
+    fit, dr = engine.path_estimates(nu, 4096, nsteps=20, seed=1, starts=[g.s0_idx])
+    assert np.abs(fit - np.float32(nu[g.s0])).max() < 2e-5
+    # ... while the direct (sampled-reward) totals are unbiased for the same quantity only through gamma-discounting,
+    # which this undiscounted 20-step walk does not apply: they drift down by about step_cost + KL per step
+    assert dr[:, -1].mean() < dr[:, 0].mean() < nu[g.s0] + 1e-3
+    # the host-side generator mirrors give the same totals along the same path
+    gw = piql.Gridworld(g.walls != 0, g.goal)
+    ctrl = piql.gridworld_ctrl(gw, randomness=g.params["randomness"], gamma=g.params["gamma"])
+    V = piql.Growable.from_dense(np.nan_to_num(g.V(7, 1)), g.walls)
+    f2, d2, tr = engine.path_estimates(np.nan_to_num(g.V(7, 1)), 4, nsteps=20, seed=2, starts=[g.s0_idx], want_trace=True)
+    Q = lambda s, a: piql.controlV(ctrl, V, s, a)
+    tf = td = V(g.s0)
+    for t in range(20):
+        s, a, ss = (int(tr[0, t, 0]) % g.H, int(tr[0, t, 0]) // g.H), int(tr[0, t, 1]), (int(tr[0, t, 2]) % g.H, int(tr[0, t, 2]) // g.H)
+        tf += piql.fitness(ctrl, V, Q, s, a)
+        td += ctrl.reward_function(s, a, ss) - piql.kl_cost(ctrl, s, Q)
+        assert abs(tf - f2[0, t]) < 1e-5 and abs(td - d2[0, t]) < 1e-5
+    fit3, dr3 = piql.path_estimates(ctrl, V, s0=g.s0, npaths=4, seed=2)
+    assert np.array_equal(fit3, f2) and np.array_equal(dr3, d2)
+
+
 # ---- policy table and trajectories -----------------------------------------------------------------
 def test_policy_table_matches_oracle(engine, golden01):
     g = golden01

@@ -157,3 +157,20 @@ def test_flood_fill_matches_host_generator():
     from piql_jl_b200 import gridworld as gwmod
     mask = gwmod.get_reachable(raw, goal)
     assert np.array_equal(walled != 0, ~mask) and nreach == mask.sum()
+
+
+def test_path_estimates_restate_the_reference(golden01):
+    # fitness_reward_estimate / direct_reward_estimate (path_functions.jl:34-50): fp32 records against the Float64 closures
+    g = golden01
+    org = g.oracle()
+    V = np.nan_to_num(g.V(7, 1))
+    tab, kl = org.policy_table(V, beta=1.0), org.kl_table(V)
+    fit, dr, tr = org.path_estimates(tab, kl, V, [g.s0_idx], 64, nsteps=20, seed=3, trace=True)
+    for p in range(0, 64, 9):
+        f64, d64 = org.path_estimates_f64(V, tr[p])
+        assert np.abs(fit[p] - f64).max() < 2e-6 and np.abs(dr[p] - d64).max() < 2e-6
+    assert (tr[:, 1:, 0] == tr[:, :-1, 2]).all() and (tr[:, 0, 0] == g.s0_idx).all()
+    # V = nu: fitness of the V-determined policy vanishes, the fitness total never moves
+    nu = np.nan_to_num(g.nu)
+    fit, _ = org.path_estimates(org.policy_table(nu, beta=1.0), org.kl_table(nu), nu, [g.s0_idx], 256, nsteps=20, seed=4)
+    assert np.abs(fit - np.float32(nu[g.s0])).max() < 2e-5
