@@ -20,18 +20,18 @@ end
 struct SolveOpts           # piql_solve_opts
     tol::Cdouble
     max_sweeps::Int64
-    precision::Int32       # 0 = Float64, 1 = Float32
+    precision::Int32       # 0 = Float64, 1 = Float32, 2 = Float32 with MUFU ex2/lg2 (tiled kernel)
     check_every::Int32
 end
-mutable struct SolveStats  # piql_solve_stats
-    sweeps::Int64
+struct SolveStats          # piql_solve_stats (immutable and isbits: a Vector{SolveStats} is the C array the batched
+    sweeps::Int64          # entry points fill, a Ref{SolveStats} the single struct)
     residual::Cdouble
     device_seconds::Cdouble
     backups::Int64
     converged::Int32
     kernel::Int32
-    SolveStats() = new(0, 0.0, 0.0, 0, 0, 0)
 end
+SolveStats() = SolveStats(0, 0.0, 0.0, 0, 0, 0)
 struct McOpts              # piql_mc_opts
     npaths::Int64
     path0::Int64
@@ -44,13 +44,13 @@ struct McOpts              # piql_mc_opts
     injected::Ptr{Cfloat}
     injected_steps::Int64
 end
-mutable struct McStats     # piql_mc_stats
+struct McStats             # piql_mc_stats
     transitions::UInt64
     paths::UInt64
     device_seconds::Cdouble
     rollout_seconds::Cdouble
-    McStats() = new(0, 0, 0.0, 0.0)
 end
+McStats() = McStats(0, 0, 0.0, 0.0)
 
 mutable struct Context
     ptr::Ptr{Cvoid}
@@ -102,20 +102,20 @@ opts(; tol = 1e-12, max_sweeps = 10^7, precision = 0, check_every = 0) = SolveOp
 
 # ---- PIQL's solver entry points (src/value_iteration.jl) -----------------------------------------------
 function generate_ν(ctx::Context; reward_scale = 1.0, kw...)
-    out = Matrix{Float64}(undef, size(ctx.walls)); st = SolveStats()
+    out = Matrix{Float64}(undef, size(ctx.walls)); st = Ref(SolveStats())
     GC.@preserve out check(ctx, ccall((:piql_solve_nu, LIB), Int32,
         (Ptr{Cvoid}, Cdouble, Ref{SolveOpts}, Ptr{Cdouble}, Ref{SolveStats}), ctx.ptr, reward_scale, opts(; kw...), out, st))
     growable(ctx, out)
 end
 function generate_logz(ctx::Context, V; β = 1.0, kw...)
-    Vd = dense(ctx, V); out = similar(Vd); st = SolveStats()
+    Vd = dense(ctx, V); out = similar(Vd); st = Ref(SolveStats())
     GC.@preserve Vd out check(ctx, ccall((:piql_solve_logz, LIB), Int32,
         (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ref{SolveOpts}, Ptr{Cdouble}, Ref{SolveStats}),
         ctx.ptr, Vd, C_NULL, β, opts(; kw...), out, st))
     growable(ctx, out)
 end
 function logz_updateV(ctx::Context, V; β = 1.0, kw...)
-    Vd = dense(ctx, V); out = similar(Vd); st = SolveStats()
+    Vd = dense(ctx, V); out = similar(Vd); st = Ref(SolveStats())
     GC.@preserve Vd out check(ctx, ccall((:piql_update_v, LIB), Int32,
         (Ptr{Cvoid}, Ptr{Cdouble}, Cdouble, Ref{SolveOpts}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{SolveStats}),
         ctx.ptr, Vd, β, opts(; kw...), out, C_NULL, st))
@@ -123,21 +123,21 @@ function logz_updateV(ctx::Context, V; β = 1.0, kw...)
 end
 # the linear-space twins (src/value_iteration.jl:42-59); the reference's stop rule for these is 1e-9
 function generate_z(ctx::Context, V; β = 1.0, tol = 1e-9, kw...)
-    Vd = dense(ctx, V); out = similar(Vd); st = SolveStats()
+    Vd = dense(ctx, V); out = similar(Vd); st = Ref(SolveStats())
     GC.@preserve Vd out check(ctx, ccall((:piql_solve_z, LIB), Int32,
         (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ref{SolveOpts}, Ptr{Cdouble}, Ref{SolveStats}),
         ctx.ptr, Vd, C_NULL, β, opts(; tol, kw...), out, st))
     growable(ctx, out; default = x -> 1.0)
 end
 function z_updateV(ctx::Context, V; β = 1.0, tol = 1e-9, kw...)
-    Vd = dense(ctx, V); out = similar(Vd); st = SolveStats()
+    Vd = dense(ctx, V); out = similar(Vd); st = Ref(SolveStats())
     GC.@preserve Vd out check(ctx, ccall((:piql_z_update_v, LIB), Int32,
         (Ptr{Cvoid}, Ptr{Cdouble}, Cdouble, Ref{SolveOpts}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{SolveStats}),
         ctx.ptr, Vd, β, opts(; tol, kw...), out, C_NULL, st))
     growable(ctx, out; default = V.default)
 end
 function generate_optimality_gap(ctx::Context, V; ν, kw...)
-    Vd = dense(ctx, V); nd = dense(ctx, ν); out = similar(Vd); st = SolveStats()
+    Vd = dense(ctx, V); nd = dense(ctx, ν); out = similar(Vd); st = Ref(SolveStats())
     GC.@preserve Vd nd out check(ctx, ccall((:piql_solve_gap, LIB), Int32,
         (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{SolveOpts}, Ptr{Cdouble}, Ref{SolveStats}),
         ctx.ptr, Vd, C_NULL, nd, opts(; kw...), out, st))
@@ -152,7 +152,7 @@ function mc_logz(ctx::Context, V; β = 1.0, npaths = 2^20, seed = 0, estimator =
     Vd = dense(ctx, V)
     logz_sa = Array{Float64}(undef, 4, size(ctx.walls)...)      # Q-like layout: action fastest
     count = Array{UInt64}(undef, 4, size(ctx.walls)...)
-    logz_s = similar(Vd); st = McStats()
+    logz_s = similar(Vd); st = Ref(McStats())
     GC.@preserve cells Vd logz_sa count logz_s begin
         o = McOpts(npaths, 0, seed, estimator, isempty(cells) ? 0 : 1, horizon,
                    isempty(cells) ? C_NULL : pointer(cells), length(cells), C_NULL, 0)
@@ -160,7 +160,7 @@ function mc_logz(ctx::Context, V; β = 1.0, npaths = 2^20, seed = 0, estimator =
             (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ref{McOpts}, Ptr{Cdouble}, Ptr{UInt64}, Ptr{Cdouble}, Ref{McStats}),
             ctx.ptr, Vd, C_NULL, β, o, logz_sa, count, logz_s, st))
     end
-    (logz = growable(ctx, logz_s), logz_sa = logz_sa, count = count, transitions = st.transitions)
+    (logz = growable(ctx, logz_s), logz_sa = logz_sa, count = count, transitions = st[].transitions)
 end
 
 # ---- fitness_reward_estimate / direct_reward_estimate (src/path_functions.jl:34-50) for npaths paths at once --------
@@ -181,7 +181,7 @@ end
 
 # ---- the PIQL iteration itself: V <- V + log Z^/beta with log Z^ from rollouts, niter times on the device ----------------
 function mc_logz_updateV(ctx::Context, V; β = 1.0, npaths = 2^22, niter = 1, seed = 0, horizon = 2^20)
-    Vd = dense(ctx, V); out = similar(Vd); st = McStats()
+    Vd = dense(ctx, V); out = similar(Vd); st = Ref(McStats())
     o = McOpts(npaths, 0, seed, 0, 0, horizon, C_NULL, 0, C_NULL, 0)
     GC.@preserve Vd out check(ctx, ccall((:piql_mc_update_v, LIB), Int32,
         (Ptr{Cvoid}, Ptr{Cdouble}, Cdouble, Ref{McOpts}, Int32, Ptr{Cdouble}, Ref{McStats}), ctx.ptr, Vd, β, o, niter, out, st))
@@ -262,7 +262,7 @@ function load_table!(ctx::Context, ctrl::ControlProblem; roots = [ctrl.initial_s
 end
 function table_solve(ctx::Context, states, kind; V = nothing, ν = nothing, β = 1.0, reward_scale = 1.0, kw...)
     Vd = V === nothing ? C_NULL : Float64[V(s) for s in states]; nd = ν === nothing ? C_NULL : Float64[ν(s) for s in states]
-    out = Vector{Float64}(undef, length(states)); st = SolveStats()
+    out = Vector{Float64}(undef, length(states)); st = Ref(SolveStats())
     GC.@preserve Vd nd out check(ctx, ccall((:piql_table_solve, LIB), Int32,
         (Ptr{Cvoid}, Int32, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cdouble, Ref{SolveOpts}, Ptr{Cdouble}, Ref{SolveStats}),
         ctx.ptr, kind, Vd, nd, β, reward_scale, opts(; kw...), out, st))

@@ -212,13 +212,16 @@ __device__ __forceinline__ void tile_strip(const TileK<T>& k, const T* __restric
   sts4(dst + jj * TEI + 4 * lane, out);
 }
 
-// One Jacobi sweep of the staged tile, src -> dst (columns 1 .. EJ-2; all 128 rows); the caller puts a CTA barrier after it.
+// Jacobi sweep number `sub` (0-based) of the staged tile, src -> dst, all 128 rows; the caller puts a CTA barrier after it.
+// src holds sweep `sub` of the round in columns sub .. EJ-1-sub only (the valid region loses one ring per sweep), so the
+// columns worth computing are 1+sub .. EJ-2-sub: the trapezoid, not the rectangle.  What lies outside keeps older values
+// that no kept cell ever reads.
 template <typename T, int KIND, bool FAST>
 __device__ __forceinline__ void tile_subsweep(const TileK<T>& k, const T* __restrict__ src, T* __restrict__ dst,
                                               const uint32_t* __restrict__ msk, const T* __restrict__ aux, int org, int lane,
-                                              int warp, int NW) {
+                                              int warp, int NW, int sub) {
 #pragma unroll 2
-  for (int jj = 1 + warp; jj < k.EJ - 1; jj += NW) tile_strip<T, KIND, FAST>(k, src, dst, msk, aux, org, lane, jj);
+  for (int jj = 1 + sub + warp; jj < k.EJ - 1 - sub; jj += NW) tile_strip<T, KIND, FAST>(k, src, dst, msk, aux, org, lane, jj);
 }
 
 // The goal (terminal value) and, for nu, its four neighbours (a step into the goal earns the reward, so the
@@ -334,7 +337,7 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
   T* src = bufA;
   T* dst = bufB;
   for (int sub = 0; sub < nsub; sub++) {
-    tile_subsweep<T, KIND, FAST>(k, src, dst, msk, aux, org, lane, warp, NW);
+    tile_subsweep<T, KIND, FAST>(k, src, dst, msk, aux, org, lane, warp, NW, sub);
     __syncthreads();
     if (near_goal) {  // block-uniform: the tile(s) around the goal redo those cells after every sweep
       tile_goal_fixup<T, KIND, FAST>(k, src, dst, msk, gi, gj);
@@ -470,7 +473,7 @@ tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, c
     __syncthreads();
     src = bufA; dst = bufB;
     for (int sub = 0; sub < nsub; sub++) {
-      tile_subsweep<T, KIND, FAST>(k, src, dst, msk, aux, org, lane, warp, NW);
+      tile_subsweep<T, KIND, FAST>(k, src, dst, msk, aux, org, lane, warp, NW, sub);
       __syncthreads();
       if (near_goal) {
         tile_goal_fixup<T, KIND, FAST>(k, src, dst, msk, gi, gj);
@@ -569,7 +572,8 @@ static size_t tile_smem_bytes(int EJ, int precision) {
 // Candidate tile shapes (TJ interior columns, nw warps per CTA), cheapest first by a small cost model in SM cycles per
 // round of TILE_KH sweeps.  Measured on B200 (fp32 nu): an SM retires one 128-cell warp-strip (~140 instructions) per
 // ~61 cycles when ~32 warps are resident, and a warp needs ~1700 cycles per strip however few warps share the SM.
-//   multi-launch: waves of c CTAs per SM, each the slower of c*cols*61 and rounds*1700, plus a fixed cost per wave
+//   multi-launch: waves of c CTAs per SM, each the slower of c*strips*61 and rounds*1700 (strips and rounds summed over
+//                 the TILE_KH sweeps of a launch: sweep `sub` computes cols - 2*sub columns), plus a fixed cost per wave
 //                 (launch, staging, tail);
 //   persistent:   every tile resident at once (tiles <= SMs x CTAs per SM); everybody advances at the pace of the
 //                 busiest SM, c*rounds*nw*61 with at least 24 resident warps.
@@ -600,20 +604,26 @@ static std::vector<PlanCand> enumerate_plans(int H, int W, int precision, int ki
       if (ctas < 1) continue;
       const int tiles_j = (W + TJ - 1) / TJ;
       const long long tiles = (long long)tiles_i * tiles_j;
-      const int rounds = (cols + nw - 1) / nw;
+      // sweep `sub` of a round computes the cols - 2*sub columns of the trapezoid (tile_subsweep)
+      int rounds = 0, strips = 0;
+      for (int sub = 0; sub < TKH; sub++) {
+        const int cs = std::max(cols - 2 * sub, 0);
+        rounds += (cs + nw - 1) / nw;
+        strips += cs;
+      }
       const long long slots = (long long)num_sms * ctas;
       double cost = 0.0;
       if (persistent) {
         if (tiles > slots) continue;
         const int c = (int)((tiles + num_sms - 1) / num_sms);
         if (c * nw < 24 && !(env_tj || env_nw)) continue;
-        cost = TKH * (double)c * rounds * nw * strip_issue + 3000.0;
+        cost = (double)c * rounds * nw * strip_issue + 3000.0;
       } else {
         long long left = tiles;
         while (left > 0) {
           const long long now = std::min(left, slots);
           const int c = (int)((now + num_sms - 1) / num_sms);
-          cost += wave_fixed + TKH * std::max(c * cols * strip_issue, rounds * strip_latency);
+          cost += wave_fixed + std::max(c * strips * strip_issue, rounds * strip_latency);
           left -= now;
         }
       }
