@@ -82,8 +82,8 @@ typedef struct {
   uint64_t seed;         /* Philox4x32-10 key; counter = (step, 0, path id lo, path id hi) */
   int32_t estimator;     /* PIQL_EST_* */
   int32_t start_mode;    /* PIQL_START_* */
-  int64_t horizon;       /* step cap per path (estimator B: the truncation horizon) */
-  const int32_t* starts; /* PIQL_START_LIST: cell indices; path p starts at starts[p mod nstarts] */
+  int64_t horizon;       /* step cap per path, in [1, 2^30) (estimator B: the truncation horizon) */
+  const int32_t* starts; /* PIQL_START_LIST: free (non-wall) cell indices; path p starts at starts[p mod nstarts] */
   int64_t nstarts;
   const float* injected; /* optional [npaths][injected_steps][4] uniforms replacing Philox */
   int64_t injected_steps;

@@ -303,12 +303,15 @@ int mc_check_opts(piql_ctx* ctx, const piql_mc_opts* o) {
   NEED(o != nullptr, PIQL_ERR_ARG, "mc opts is null");
   NEED(o->npaths >= 0 && o->path0 >= 0, PIQL_ERR_ARG, "npaths and path0 must be non-negative");
   NEED(o->estimator == 0 || o->estimator == 1, PIQL_ERR_ARG, "estimator must be 0 (sampled stop) or 1 (discounted)");
-  NEED(o->horizon > 0, PIQL_ERR_ARG, "horizon must be positive");
+  NEED(o->horizon > 0 && o->horizon < (1LL << 30), PIQL_ERR_ARG, "horizon must lie in [1, 2^30) (a path record keeps its length in 30 bits)");
   NEED(o->start_mode == PIQL_START_ALL_FREE || o->start_mode == PIQL_START_LIST, PIQL_ERR_ARG, "bad start_mode");
   if (o->start_mode == PIQL_START_LIST) {
     NEED(o->starts != nullptr && o->nstarts > 0, PIQL_ERR_ARG, "start list is empty");
-    for (long long i = 0; i < o->nstarts; i++)
+    for (long long i = 0; i < o->nstarts; i++) {
       NEED(o->starts[i] >= 0 && o->starts[i] < ctx->g.n, PIQL_ERR_ARG, "start cell out of range");
+      // initial_state never yields a wall (draw_not_wall, GridWorld.jl:54-61), and a wall cell has no policy record
+      NEED(!ctx->h_walls_nan(o->starts[i]), PIQL_ERR_ARG, "start cell is a wall");
+    }
   }
   if (o->injected) NEED(o->injected_steps > 0, PIQL_ERR_ARG, "injected_steps must be positive");
   return PIQL_OK;
@@ -322,7 +325,6 @@ int mc_setup_slots(piql_ctx* ctx, const piql_mc_opts* o) {
     ctx->nstarts = ctx->nfree;
   } else {
     CK(grow(ctx->d_starts_own, ctx->starts_own_cap, o->nstarts));
-    // reject wall cells: a path cannot start inside a wall
     CK(cudaMemcpyAsync(ctx->d_starts_own, o->starts, 4 * (size_t)o->nstarts, cudaMemcpyHostToDevice, st));
     ctx->d_starts = ctx->d_starts_own;
     ctx->nstarts = o->nstarts;
