@@ -269,6 +269,47 @@ function table_solve(ctx::Context, states, kind; V = nothing, ν = nothing, β =
     Growable(Dict(s => out[i] for (i, s) in enumerate(states)), x -> 0.0)
 end
 
+# logz_updateV / Monte-Carlo log Z on the tabulated problem (states as returned by load_table!)
+function table_logz_updateV(ctx::Context, states, V; β = 1.0, kw...)
+    Vd = Float64[V(s) for s in states]; out = similar(Vd); st = Ref(SolveStats())
+    GC.@preserve Vd out check(ctx, ccall((:piql_table_update_v, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Cdouble, Ref{SolveOpts}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{SolveStats}),
+        ctx.ptr, Vd, β, opts(; kw...), out, C_NULL, st))
+    Growable(Dict(s => out[i] for (i, s) in enumerate(states)), V.default)
+end
+function table_mc_logz(ctx::Context, states, nactions, V; β = 1.0, npaths = 2^20, seed = 0, horizon = 2^20, roots = Int[])
+    Vd = Float64[V(s) for s in states]; ns = length(states); cells = Int32.(roots)           # roots: 0-based state indices
+    logz_sa = Matrix{Float64}(undef, nactions, ns); count = Matrix{UInt64}(undef, nactions, ns); logz_s = Vector{Float64}(undef, ns)
+    st = Ref(McStats())
+    GC.@preserve cells Vd logz_sa count logz_s begin
+        o = McOpts(npaths, 0, seed, 0, isempty(cells) ? 0 : 1, horizon, isempty(cells) ? C_NULL : pointer(cells), length(cells), C_NULL, 0)
+        check(ctx, ccall((:piql_table_mc_logz, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Cdouble}, Cdouble, Ref{McOpts}, Ptr{Cdouble}, Ptr{UInt64}, Ptr{Cdouble}, Ref{McStats}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}),
+            ctx.ptr, Vd, β, o, logz_sa, count, logz_s, st, C_NULL, C_NULL, C_NULL))
+    end
+    (logz = Growable(Dict(s => logz_s[i] for (i, s) in enumerate(states)), x -> 0.0), logz_sa = logz_sa, count = count,
+     transitions = st[].transitions)
+end
+
+# ---- sharded rollouts: one worker process per GPU rolls out its block of path ids [path0, path0 + npaths) and keeps the
+# ---- statistics on the device until they are exchanged (next section) and finalised -----------------------------------
+function policy_table!(ctx::Context, V; β = 1.0)
+    Vd = dense(ctx, V)
+    GC.@preserve Vd check(ctx, ccall((:piql_policy_table, LIB), Int32, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cfloat}),
+        ctx.ptr, Vd, C_NULL, β, C_NULL))
+end
+all_free(npaths, path0, seed, horizon) = McOpts(npaths, path0, seed, 0, 0, horizon, C_NULL, 0, C_NULL, 0)
+mc_reset!(ctx::Context) = check(ctx, ccall((:piql_mc_reset_dev, LIB), Int32, (Ptr{Cvoid}, Ref{McOpts}), ctx.ptr, all_free(0, 0, 0, 1)))
+mc_rollout!(ctx::Context; npaths, path0 = 0, seed = 0, horizon = 2^20) =
+    check(ctx, ccall((:piql_mc_rollout_dev, LIB), Int32, (Ptr{Cvoid}, Ref{McOpts}), ctx.ptr, all_free(npaths, path0, seed, horizon)))
+function mc_finalize(ctx::Context)
+    logz_sa = Array{Float64}(undef, 4, size(ctx.walls)...); count = Array{UInt64}(undef, 4, size(ctx.walls)...)
+    logz_s = Matrix{Float64}(undef, size(ctx.walls)); st = Ref(McStats())
+    GC.@preserve logz_sa count logz_s check(ctx, ccall((:piql_mc_finalize, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{UInt64}, Ptr{Cdouble}, Ref{McStats}), ctx.ptr, logz_sa, count, logz_s, st))
+    (logz = growable(ctx, logz_s), logz_sa = logz_sa, count = count, transitions = st[].transitions)
+end
+
 # ---- multi-GPU exchange over NVLink peer memory: one worker process per GPU (replaces addprocs/pmap/@spawn,
 # ---- scripts/distributed_experiments.jl:3,26,28,43-46).  The handle blobs travel over Distributed.jl itself.
 struct PeerHandles; lse_max::NTuple{64,UInt8}; lse_sum::NTuple{64,UInt8}; count::NTuple{64,UInt8}; flags::NTuple{64,UInt8}; n::Int64; end
