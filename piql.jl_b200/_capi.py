@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpiql_b200.so")
+# PIQL_B200_LIB names another build of the same library (the Julia shim honours the same variable)
+LIB_PATH = os.environ.get("PIQL_B200_LIB") or os.path.join(_HERE, "lib", "libpiql_b200.so")
 
 OK, ERR_ARG, ERR_STATE, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_NOT_CONVERGED = range(7)
 F64, F32, F32_FAST = 0, 1, 2

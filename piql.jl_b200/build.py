@@ -19,14 +19,16 @@ def needs_build():
     return any(os.path.getmtime(f) > t for f in SRC + HDR)
 
 
-def build(force=False, verbose=False):
-    if not (force or needs_build()):
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: an experimental variant (tools/vi_ab.py) built beside the product library, selected with PIQL_B200_LIB."""
+    if out is None and not (force or needs_build()):
         return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    out = out or OUT
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + SRC + ["-o", OUT]
+    cmd = [nvcc] + FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + SRC + ["-o", out]
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

