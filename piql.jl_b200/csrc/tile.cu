@@ -240,9 +240,7 @@ __device__ __forceinline__ void tile_strip(const TileK<T>& k, const T* __restric
                                      f2(nb[3][r], nb[3][r + 1]));
       out[r] = o.x; out[r + 1] = o.y;
     }
-    sts4(dst + jj * TEI + 4 * lane, out);
-    return;
-  }
+  } else {
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     const uint32_t b = mk >> (8 * r);
@@ -257,6 +255,7 @@ __device__ __forceinline__ void tile_strip(const TileK<T>& k, const T* __restric
     else if (KIND == KIND_LOGZ) o = logz_cell<T, FAST>(k, c, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
     else o = gap_cell<T>(k, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
     out[r] = o;
+  }
   }
   sts4(dst + jj * TEI + 4 * lane, out);
 }
@@ -641,7 +640,9 @@ static std::vector<PlanCand> enumerate_plans(int H, int W, int precision, int ki
   const char* env_nw = getenv("PIQL_TILE_NW");
   // registers per thread of the instantiation that will run (48 .. 64 in fp32, 110 .. 128 in Float64): they, the shared
   // memory of a tile and the 2048-thread limit decide how many CTAs share an SM
-  const int regs = tile_kernel_regs(precision, kind, fast, persistent);
+  // (Float64 is ranked at its __launch_bounds__ cap of 128: two resident CTAs of 8-9 warps, which 110 registers would
+  // allow, measured 40 % slower at 4098^2 than one CTA of 16 warps -- and the sharded solve runs the model's first choice untimed)
+  const int regs = precision == 0 ? 128 : tile_kernel_regs(precision, kind, fast, persistent);
   const double strip_issue = 61.0, strip_latency = 1700.0, wave_fixed = 8000.0;
   for (int nw = 4; nw <= 16; nw++) {
     if (env_nw && atoi(env_nw) != nw) continue;
