@@ -188,6 +188,25 @@ __device__ __forceinline__ T logz_cell(const TileK<T>& k, T c, T n0, T n1, T n2,
     return damp_half<T, FAST>(nw, c);
   }
 }
+// The fast fp32 form of the same recursion, relative to the cell's own value c instead of the neighbour maximum:
+//   Z_new / e^c = sum_a e^(A_a) * (gamma * sum_a' P(a'|a) e^(n_a' - c) + (1 - gamma) e^(-c)),   stored = c + log(1/2 + 1/2 Z_new / e^c)
+// (the eta = 1/2 damping fused as above).  Six MUFU per cell instead of seven -- the XU pipe bounds these sweeps -- and no sign
+// cases; EA_a = e^(A_a) comes from the packed constant planes (tile_pack_aux_kernel folds max A in for this mode).  The sum is
+// ~1 at the fixed point whatever the magnitude of c, so e^(-c) cannot overflow the products there; the exponents are clamped
+// at 2^126 so that a wild warm start stays finite and the damped iteration recovers.
+#ifndef PIQL_LOGZ_OWN_SHIFT
+#define PIQL_LOGZ_OWN_SHIFT 1
+#endif
+__device__ __forceinline__ float logz_cell_fast_own(const TileK<float>& k, float c, float n0, float n1, float n2, float n3,
+                                                    float EA0, float EA1, float EA2, float EA3) {
+  const float l2e = 1.44269504088896f, tc = -c * l2e;
+  const float u0 = ex2_approx(fminf(fmaf(n0, l2e, tc), 126.f)), u1 = ex2_approx(fminf(fmaf(n1, l2e, tc), 126.f));
+  const float u2 = ex2_approx(fminf(fmaf(n2, l2e, tc), 126.f)), u3 = ex2_approx(fminf(fmaf(n3, l2e, tc), 126.f));
+  const float h = ex2_approx(fminf(tc, 126.f));
+  const float base = fmaf(k.gamma * k.w_off, (u0 + u1) + (u2 + u3), k.omg * h), gd = k.gamma * k.dw;
+  const float sum = (EA0 * fmaf(gd, u0, base) + EA1 * fmaf(gd, u1, base)) + (EA2 * fmaf(gd, u2, base) + EA3 * fmaf(gd, u3, base));
+  return fmaf(0.693147180559945f, lg2_approx(fmaf(0.5f, sum, 0.5f)), c);
+}
 // gap: D + sum_a pi_a * pa(s,a,gap), no discount on the gap term   value_iteration.jl:165
 template <typename T>
 __device__ __forceinline__ T gap_cell(const TileK<T>& k, T n0, T n1, T n2, T n3, T p0, T p1, T p2, T p3, T D) {
@@ -220,7 +239,7 @@ __device__ __forceinline__ void tile_strip(const TileK<T>& k, const T* __restric
   if (KIND != KIND_NU) {
     const int sidx = org + jj * k.ld + 4 * lane;
 #pragma unroll
-    for (int pl = 0; pl < 5; pl++) ldg4(aux + (size_t)pl * k.np + sidx, ax[pl]);
+    for (int pl = 0; pl < ((PIQL_LOGZ_OWN_SHIFT && KIND == KIND_LOGZ && FAST) ? 4 : 5); pl++) ldg4(aux + (size_t)pl * k.np + sidx, ax[pl]);
   }
   if constexpr (PIQL_TILE_PACKED && KIND == KIND_NU && FAST && sizeof(T) == 4) {
     // rows (0,1) and (2,3) as packed pairs
@@ -252,6 +271,7 @@ __device__ __forceinline__ void tile_strip(const TileK<T>& k, const T* __restric
     const T n3 = (b & 8u) ? c : L[r];
     T o;
     if (KIND == KIND_NU) o = nu_cell<T, FAST>(k, n0, n1, n2, n3);
+    else if constexpr (PIQL_LOGZ_OWN_SHIFT && KIND == KIND_LOGZ && FAST) o = logz_cell_fast_own(k, c, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r]);
     else if (KIND == KIND_LOGZ) o = logz_cell<T, FAST>(k, c, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
     else o = gap_cell<T>(k, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
     out[r] = o;
@@ -585,7 +605,8 @@ __global__ void tile_pack_mask_kernel(PadGeom g, const uint8_t* __restrict__ cel
 }
 // aux4 [cell][4] + aux1 [cell] -> five planes.  logz: exp(A_a - max A), max A (as prep_kernel stores them); gap: pi_a, D.
 template <typename T, int KIND>
-__global__ void tile_pack_aux_kernel(PadGeom g, const T* __restrict__ aux4, const T* __restrict__ aux1, T* __restrict__ auxp) {
+__global__ void tile_pack_aux_kernel(PadGeom g, const T* __restrict__ aux4, const T* __restrict__ aux1, T* __restrict__ auxp,
+                                     int fold_max) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int np = g.ld * g.Wp;
   if (p >= np) return;
@@ -599,6 +620,11 @@ __global__ void tile_pack_aux_kernel(PadGeom g, const T* __restrict__ aux4, cons
 #pragma unroll
       for (int q = 0; q < 4; q++) o[q] = a[q];
       o[4] = aux1[s];
+      if (fold_max) {  // fast fp32 log Z: planes 0..3 hold exp(A_a) = exp(A_a - max A) * exp(max A)
+        const T em = (T)exp((double)o[4]);
+#pragma unroll
+        for (int q = 0; q < 4; q++) o[q] *= em;
+      }
     }
   }
 #pragma unroll
@@ -774,10 +800,11 @@ static void pack_t(const GridDev& g, const uint8_t* cell, const ViState& vs, Til
   tile_pack_mask_kernel<<<nb, 256, 0, st>>>(pg, cell, tb.mask);
   g_launches += 3;
   if (vs.kind == KIND_LOGZ) {
-    tile_pack_aux_kernel<T, KIND_LOGZ><<<nb, 256, 0, st>>>(pg, (const T*)vs.aux4, (const T*)vs.aux1, (T*)tb.aux);
+    tile_pack_aux_kernel<T, KIND_LOGZ><<<nb, 256, 0, st>>>(pg, (const T*)vs.aux4, (const T*)vs.aux1, (T*)tb.aux,
+                                                           (PIQL_LOGZ_OWN_SHIFT && vs.fast) ? 1 : 0);
     g_launches++;
   } else if (vs.kind == KIND_GAP) {
-    tile_pack_aux_kernel<T, KIND_GAP><<<nb, 256, 0, st>>>(pg, (const T*)vs.aux4, (const T*)vs.aux1, (T*)tb.aux);
+    tile_pack_aux_kernel<T, KIND_GAP><<<nb, 256, 0, st>>>(pg, (const T*)vs.aux4, (const T*)vs.aux1, (T*)tb.aux, 0);
     g_launches++;
   }
 }
