@@ -80,10 +80,13 @@ struct TileBuffers {
   bool sharded = false;
   int tj0 = 0, tj1 = 0;
   TileHalo halo;               // set per launch by tile_sweeps_sharded
-  // shape found fastest on the device for the problem `tuned_key` (grid, precision, kind)
-  long long tuned_key = -1;
-  TilePlan tuned_plan{};
-  bool tuned_persistent = false;
+  // shapes found fastest on the device, one per problem key (grid, precision, kind): a context that alternates between
+  // nu / log Z / gap solves or precisions on one grid times each of them once
+  static constexpr int TUNED_MAX = 24;
+  int ntuned = 0, tuned_next = 0;
+  long long tuned_key[TUNED_MAX] = {};
+  TilePlan tuned_plan[TUNED_MAX] = {};
+  bool tuned_persistent[TUNED_MAX] = {};
 };
 TilePlan make_tile_plan(int H, int W, int precision, int kind, bool fast, int num_sms);
 TilePlan choose_tile_plan(int H, int W, int precision, int kind, bool fast, int num_sms, bool* persistent);

@@ -783,12 +783,13 @@ static bool encode_tile_map(void* out, void* base, CUtensorMapDataType dt, size_
 void tile_free(TileBuffers& tb) {
   for (void* p : {tb.x[0], tb.x[1], tb.aux, (void*)tb.mask, (void*)tb.partial, (void*)tb.flags, (void*)tb.d_err}) if (p) cudaFree(p);
   if (tb.err) cudaFreeHost(tb.err);
-  const long long key = tb.tuned_key;
-  const TilePlan plan = tb.tuned_plan;
-  const bool pers = tb.tuned_persistent;
-  const bool sh = tb.sharded;
+  const TileBuffers keep = tb;  // the tuning results and the sharded flag survive a re-allocation
   tb = TileBuffers{};
-  tb.tuned_key = key; tb.tuned_plan = plan; tb.tuned_persistent = pers; tb.sharded = sh;
+  tb.ntuned = keep.ntuned; tb.tuned_next = keep.tuned_next;
+  for (int i = 0; i < keep.ntuned; i++) {
+    tb.tuned_key[i] = keep.tuned_key[i]; tb.tuned_plan[i] = keep.tuned_plan[i]; tb.tuned_persistent[i] = keep.tuned_persistent[i];
+  }
+  tb.sharded = keep.sharded;
 }
 
 template <typename T>
@@ -856,7 +857,9 @@ cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs,
     return tile_setup(g, cell, vs, tb, pl, false, st);
   }
   const bool pinned = getenv("PIQL_TILE_TJ") || getenv("PIQL_TILE_NW") || getenv("PIQL_TILE_NO_TUNE");
-  if (!pinned && tb.tuned_key == key) return tile_setup(g, cell, vs, tb, tb.tuned_plan, tb.tuned_persistent, st);
+  if (!pinned)
+    for (int i = 0; i < tb.ntuned; i++)
+      if (tb.tuned_key[i] == key) return tile_setup(g, cell, vs, tb, tb.tuned_plan[i], tb.tuned_persistent[i], st);
   bool persist = false;
   const TilePlan model = choose_tile_plan(g.H, g.W, vs.precision, vs.kind, vs.fast, num_sms, &persist);
   if (pinned) return tile_setup(g, cell, vs, tb, model, persist, st);
@@ -877,11 +880,14 @@ cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs,
   double best = 1e300;
   Try chosen{model, persist};
   const long long probe = 8 * TKH;
+  // Short probes (small grids: 0.1 ms) are noisy and are repeated; once a probe lasts more than half a millisecond one
+  // measurement per shape is enough, and all a first solve should pay (tuning stays near a tenth of a solve to tolerance).
+  int reps = 2;
   for (const Try& t : tries) {
     if ((err = tile_setup(g, cell, vs, tb, t.plan, t.persist, st)) != cudaSuccess) break;
     if ((err = tile_sweeps(g, vs, tb, 2 * TKH, false, st)) != cudaSuccess) break;
     float ms = 1e30f;
-    for (int rep = 0; rep < 2 && err == cudaSuccess; rep++) {  // the faster of two probes: a probe lasts 0.1 .. 1 ms
+    for (int rep = 0; rep < reps && err == cudaSuccess; rep++) {
       cudaEventRecord(e0, st);
       if ((err = tile_sweeps(g, vs, tb, probe, false, st)) != cudaSuccess) break;
       cudaEventRecord(e1, st);
@@ -889,6 +895,7 @@ cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs,
       float m1 = 0.f;
       cudaEventElapsedTime(&m1, e0, e1);
       ms = std::min(ms, m1);
+      if (m1 > 0.5f) reps = 1;
     }
     if (err != cudaSuccess) break;
     if (tb.err && *tb.err) { err = cudaErrorLaunchTimeout; break; }
@@ -897,7 +904,8 @@ cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs,
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   if (err != cudaSuccess) return err;
-  tb.tuned_key = key; tb.tuned_plan = chosen.plan; tb.tuned_persistent = chosen.persist;
+  const int slot = tb.ntuned < TileBuffers::TUNED_MAX ? tb.ntuned++ : (tb.tuned_next++ % TileBuffers::TUNED_MAX);
+  tb.tuned_key[slot] = key; tb.tuned_plan[slot] = chosen.plan; tb.tuned_persistent[slot] = chosen.persist;
   return tile_setup(g, cell, vs, tb, chosen.plan, chosen.persist, st);  // re-pack: the probes advanced the iterate
 }
 
