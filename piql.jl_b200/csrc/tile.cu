@@ -193,16 +193,17 @@ __device__ __forceinline__ T logz_cell(const TileK<T>& k, T c, T n0, T n1, T n2,
 // (the eta = 1/2 damping fused as above).  Six MUFU per cell instead of seven -- the XU pipe bounds these sweeps -- and no sign
 // cases; EA_a = e^(A_a) comes from the packed constant planes (tile_pack_aux_kernel folds max A in for this mode).  The sum is
 // ~1 at the fixed point whatever the magnitude of c, so e^(-c) cannot overflow the products there; the exponents are clamped
-// at 2^126 so that a wild warm start stays finite and the damped iteration recovers.
+// at 2^100 (four of them still add up far below FLT_MAX) so that a wild warm start stays finite and the damped iteration recovers.
+// The clamp cannot bite at a fixed point: Z(s) >= (1 - gamma) sum_a e^(A_a), so -c <= -log(1 - gamma) - max_a A_a, a few tens at most.
 #ifndef PIQL_LOGZ_OWN_SHIFT
 #define PIQL_LOGZ_OWN_SHIFT 1
 #endif
 __device__ __forceinline__ float logz_cell_fast_own(const TileK<float>& k, float c, float n0, float n1, float n2, float n3,
                                                     float EA0, float EA1, float EA2, float EA3) {
   const float l2e = 1.44269504088896f, tc = -c * l2e;
-  const float u0 = ex2_approx(fminf(fmaf(n0, l2e, tc), 126.f)), u1 = ex2_approx(fminf(fmaf(n1, l2e, tc), 126.f));
-  const float u2 = ex2_approx(fminf(fmaf(n2, l2e, tc), 126.f)), u3 = ex2_approx(fminf(fmaf(n3, l2e, tc), 126.f));
-  const float h = ex2_approx(fminf(tc, 126.f));
+  const float u0 = ex2_approx(fminf(fmaf(n0, l2e, tc), 100.f)), u1 = ex2_approx(fminf(fmaf(n1, l2e, tc), 100.f));
+  const float u2 = ex2_approx(fminf(fmaf(n2, l2e, tc), 100.f)), u3 = ex2_approx(fminf(fmaf(n3, l2e, tc), 100.f));
+  const float h = ex2_approx(fminf(tc, 100.f));
   const float base = fmaf(k.gamma * k.w_off, (u0 + u1) + (u2 + u3), k.omg * h), gd = k.gamma * k.dw;
   const float sum = (EA0 * fmaf(gd, u0, base) + EA1 * fmaf(gd, u1, base)) + (EA2 * fmaf(gd, u2, base) + EA3 * fmaf(gd, u3, base));
   return fmaf(0.693147180559945f, lg2_approx(fmaf(0.5f, sum, 0.5f)), c);
