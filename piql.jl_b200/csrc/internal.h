@@ -30,7 +30,10 @@ struct ViState {
 };
 
 // tile.cu: temporally blocked sweeps on a padded copy of the iterate ---------------------------
-constexpr int TILE_KH = 4;  // halo width = Jacobi sweeps per launch
+#ifndef PIQL_TILE_KH
+#define PIQL_TILE_KH 4  // a multiple of 4 (tools/vi_ab.py builds other depths for timing)
+#endif
+constexpr int TILE_KH = PIQL_TILE_KH;  // halo width = Jacobi sweeps per launch
 struct TilePlan {
   int TJ, EJ;            // interior / staged columns per tile (EJ = TJ + 2*TILE_KH); rows are 120 / 128
   int tiles_i, tiles_j;

@@ -2,7 +2,11 @@
 """A/B timing of compile-time variants of the soft-VI kernels.
     build (CPU box):  python tools/vi_ab.py build NAME -DPIQL_TILE_UNROLL=3 ...   -> tools/probe/variants/libpiql_NAME.so
     time  (GPU box):  python tools/vi_ab.py time [grid1024|grid4096 ...]          -> us/sweep of every variant + the product build
-Each timing runs in its own process with PIQL_B200_LIB pointing at the variant."""
+Each timing runs in its own process with PIQL_B200_LIB pointing at the variant.
+Switches the sources honour: PIQL_TILE_UNROLL (columns a warp interleaves, default 1), PIQL_TILE_PACKED (FADD2/FFMA2 nu cell, 1),
+PIQL_LOGZ_OWN_SHIFT (6-MUFU log Z cell, 1), PIQL_TILE_KH (sweeps per launch = ghost depth, a multiple of 4, default 4 -- deeper
+blocking for the 10^6-cell grids has been built but not timed yet; run the tiled tests against the variant first:
+PIQL_B200_LIB=tools/probe/variants/libpiql_kh8.so pytest tests/test_gpu_tiled.py -m gpu)."""
 import glob
 import json
 import os
