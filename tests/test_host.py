@@ -88,6 +88,22 @@ def test_closures_agree_with_the_oracle_algebra(piql):
         assert np.allclose([0.7 * piql.fitness(ctrl, Vf, Q, s, a) for a in range(4)], tab[idx, 4:], atol=1e-7)
         assert abs(piql.kl_cost(ctrl, s, Q) - org.kl_cost(np.nan_to_num(V), idx)) < 1e-12
         assert piql.kl_cost(ctrl, s, Q) > 0                         # test/runtests.jl:39
+    # the goal cell's own record (only path_transitions, which walks on through the goal, reads it): a blocked move out of
+    # the goal stays in the goal and earns the reward -- reward_function looks at s' alone   GridWorld.jl:116
+    w2 = np.ones((3, 4), dtype=np.uint8, order="F")
+    w2[1, 1:3] = 0
+    gw2 = piql.Gridworld(w2 != 0, (1, 2))
+    ctrl2 = piql.gridworld_ctrl(gw2, randomness=0.1, gamma=0.9)
+    org2 = oracle.Grid(w2, (1, 2), randomness=0.1, gamma=0.9)
+    V2 = 0.5 * np.nan_to_num(org2.solve("nu")[0])
+    Vf2 = piql.Growable.from_dense(np.where(w2 != 0, np.nan, V2), w2)
+    Q2 = lambda s, a: piql.controlV(ctrl2, Vf2, s, a)
+    tab2 = org2.policy_table(V2, beta=0.7)
+    for s in ((1, 1), (1, 2)):
+        idx = s[0] + 3 * s[1]
+        p = [piql.action_probability(ctrl2, Q2, s, a) for a in range(4)]
+        assert np.allclose(np.cumsum(p)[:3], tab2[idx, :3], atol=2e-7)
+        assert np.allclose([0.7 * piql.fitness(ctrl2, Vf2, Q2, s, a) for a in range(4)], tab2[idx, 4:], atol=1e-7)
     # logpropagatorexp == log(propagator_average(exp f))
     f = lambda s: 0.3 * s[0] - 0.1 * s[1]
     s = piql.state_iterator(gw)[3]
