@@ -174,3 +174,36 @@ def test_path_estimates_restate_the_reference(golden01):
     nu = np.nan_to_num(g.nu)
     fit, _ = org.path_estimates(org.policy_table(nu, beta=1.0), org.kl_table(nu), nu, [g.s0_idx], 256, nsteps=20, seed=4)
     assert np.abs(fit - np.float32(nu[g.s0])).max() < 2e-5
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_restatements_agree_on_random_gridworlds(seed):
+    """The oracle's independent restatements of one recursion -- the faithful one (hash-map Growable that discovers the
+    states from a start cell, shuffled Gauss-Seidel, closure-style nested recomputation) and the dense Jacobi one that
+    the stored data/*.jld2 pin -- agree on random small problems over the whole parameter range, including goals that
+    touch walls, randomness 0 and 1 and short horizons."""
+    from conftest import random_gridworld
+    rng = np.random.default_rng(100 + seed)
+    size = (int(rng.integers(3, 9)), int(rng.integers(3, 9)))
+    walls, goal = random_gridworld(size, float(rng.choice([0.0, 0.15, 0.3])), seed=200 + seed)
+    params = dict(randomness=float(rng.choice([0.0, 0.03, 0.5, 1.0])), gamma=float(rng.choice([0.5, 0.9, 0.99])),
+                  reward_scale=float(rng.choice([0.2, 1.0])))
+    org = oracle.Grid(walls, goal, **params)
+    free = org.free_cells()
+    start = int(free[int(rng.integers(len(free)))])
+    nu_j, _ = org.solve("nu", mode="jacobi")
+    nu_f, st = org.solve("nu", mode="faithful", start=start, seed=seed)
+    assert st.nstates == len(free)                      # every free cell reaches the goal, so discovery finds them all
+    assert np.array_equal(np.isnan(nu_j), walls != 0) and nmax(nu_j, nu_f) < 1e-9
+    assert nu_j[goal] == 0.0
+    V = np.nan_to_num(org.solve("nu", reward_scale=0.3)[0])
+    beta = float(rng.choice([0.05, 0.5, 1.0]))
+    lz_j, _ = org.solve("logz", V=V, beta=beta)
+    lz_f, _ = org.solve("logz", V=V, beta=beta, mode="faithful", start=start, seed=seed + 1)
+    assert nmax(lz_j, lz_f) < 1e-9 and abs(lz_j[goal] + V[goal]) < 1e-11
+    gap_j, _ = org.solve("gap", V=V, nu=np.nan_to_num(nu_j))
+    gap_g, _ = org.solve("gap", V=V, nu=np.nan_to_num(nu_j), mode="gauss_seidel", seed=seed)
+    assert nmax(gap_j, gap_g) < 1e-8 and np.nanmin(gap_j) > -1e-9   # nu is the optimum: the gap of any policy is >= 0
+    # one backup of the converged iterate is the iterate (the sweep and the solver share no loop)
+    again, diff = org.sweep("nu", np.nan_to_num(nu_j))
+    assert diff < 1e-10 and nmax(again, nu_j) < 1e-11
