@@ -262,21 +262,21 @@ __device__ __forceinline__ void tile_strip(const TileK<T>& k, const T* __restric
     }
   } else {
 #pragma unroll
-  for (int r = 0; r < 4; r++) {
-    const uint32_t b = mk >> (8 * r);
-    const T c = v[r];
-    // f(take_step(s,a)): the neighbour, or the cell itself when a wall blocks the move  GridWorld.jl:29-32
-    const T n0 = (b & 1u) ? c : (r < 3 ? v[r < 3 ? r + 1 : 3] : dn);
-    const T n1 = (b & 2u) ? c : (r > 0 ? v[r > 0 ? r - 1 : 0] : up);
-    const T n2 = (b & 4u) ? c : R[r];
-    const T n3 = (b & 8u) ? c : L[r];
-    T o;
-    if (KIND == KIND_NU) o = nu_cell<T, FAST>(k, n0, n1, n2, n3);
-    else if constexpr (PIQL_LOGZ_OWN_SHIFT && KIND == KIND_LOGZ && FAST) o = logz_cell_fast_own(k, c, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r]);
-    else if (KIND == KIND_LOGZ) o = logz_cell<T, FAST>(k, c, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
-    else o = gap_cell<T>(k, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
-    out[r] = o;
-  }
+    for (int r = 0; r < 4; r++) {
+      const uint32_t b = mk >> (8 * r);
+      const T c = v[r];
+      // f(take_step(s,a)): the neighbour, or the cell itself when a wall blocks the move  GridWorld.jl:29-32
+      const T n0 = (b & 1u) ? c : (r < 3 ? v[r < 3 ? r + 1 : 3] : dn);
+      const T n1 = (b & 2u) ? c : (r > 0 ? v[r > 0 ? r - 1 : 0] : up);
+      const T n2 = (b & 4u) ? c : R[r];
+      const T n3 = (b & 8u) ? c : L[r];
+      T o;
+      if (KIND == KIND_NU) o = nu_cell<T, FAST>(k, n0, n1, n2, n3);
+      else if constexpr (PIQL_LOGZ_OWN_SHIFT && KIND == KIND_LOGZ && FAST) o = logz_cell_fast_own(k, c, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r]);
+      else if (KIND == KIND_LOGZ) o = logz_cell<T, FAST>(k, c, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
+      else o = gap_cell<T>(k, n0, n1, n2, n3, ax[0][r], ax[1][r], ax[2][r], ax[3][r], ax[4][r]);
+      out[r] = o;
+    }
   }
   sts4(dst + jj * TEI + 4 * lane, out);
 }
