@@ -208,6 +208,77 @@ def run_golden_experiment(device, with_cpu=True, name="r0_01g0_99"):
     return out
 
 
+def run_extra(name, fn):
+    """The sections after the headline (sweep rates, CPU baseline, golden experiment) must not be able to lose the line."""
+    try:
+        return fn()
+    except Exception as e:  # reported in the line instead
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
+def vi_section(args, eng, stream, V, peak, vst):
+    """Soft-VI sweep rates on the loaded grid (rank 0): nu in three precisions, log Z and gap in fast fp32, the ground-truth solve."""
+    import torch
+    vi = {}
+    cases = [("nu", "f32fast", 8, {}), ("nu", "f32", 8, {}), ("nu", "f64", 16, {}),
+             ("logz", "f32fast", 12, dict(V=V, beta=BETA)), ("gap", "f32fast", 16, dict(V=V, nu=V))]
+    for kind, prec, nbytes, kw in cases:
+        eng.vi_prepare(kind, reward_scale=1.0, precision=prec, **kw)
+        with torch.cuda.stream(stream):
+            eng.vi_sweeps(20)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            eng.vi_sweeps(args.vi_sweeps)
+            b.record(stream)
+            torch.cuda.synchronize()
+        sec = a.elapsed_time(b) * 1e-3
+        sps = args.vi_sweeps / sec
+        gbs = nbytes * eng.nfree * sps / 1e9
+        key = prec if kind == "nu" else "%s_%s" % (kind, prec)
+        if key == "f32fast":
+            vi["tile_plan"] = eng.vi_tile_plan("nu", "f32fast")   # the shape the library timed fastest on this device
+        vi[key] = {"sweeps_per_s": sps, "state_backups_per_s": sps * eng.nfree, "us_per_sweep": 1e6 / sps,
+                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                "bytes_per_state": nbytes, "traffic": None}}
+    # the ground-truth solve itself (config 4: "soft VI ground truth on 1 B200"), host buffers in and out
+    solves = {}
+    for prec, tol in (("f64", 1e-9), ("f32fast", 0.05)):
+        t0 = time.perf_counter()
+        _nu, sst = eng.solve_nu(tol=tol, max_sweeps=20000, precision=prec, allow_unconverged=True)
+        solves[prec] = {"tol_sum_abs_delta": tol, "sweeps": int(sst.sweeps), "converged": bool(sst.converged),
+                        "seconds": time.perf_counter() - t0, "device_seconds": float(sst.device_seconds)}
+    vi["solve_nu"] = solves
+    vi["kernel"] = ("tile_sweep_kernel<T,KIND,FAST>: 4 Jacobi sweeps per launch on 128 x (TJ+8) shared-memory tiles "
+                    "(includes the residual reduction on the last launch); f32fast = MUFU ex2/lg2; keys without a kind are nu")
+    vi["setup_vlo"] = {"sweeps": int(vst.sweeps), "device_seconds": float(vst.device_seconds)}
+    return vi
+
+
+def cpu_section(args, eng, walls, goal, params, V, vi):
+    """The oracle on the box's host cores beside the GPU numbers (rank 0, N = 1): a bounded sample of the same step."""
+    import oracle
+    org = oracle.Grid(walls, goal, **params)
+    threads = oracle.num_threads()
+    table = eng.policy_table(V, beta=BETA)        # same fp32 table the GPU read
+    free = org.free_cells()
+    sample = args.ref_paths
+    org.rollout(table, V[goal], free, 1 << 14, seed=MC_SEED, nthreads=threads)
+    t0 = time.perf_counter()
+    lw, meta = org.rollout(table, V[goal], free, sample, path0=0, seed=MC_SEED, nthreads=threads)
+    mxo, smo, cno, tr = oracle.reduce_paths(lw, meta, len(free), path0=0)
+    dt = time.perf_counter() - t0
+    cpu = {"value": tr / dt, "unit": "transitions/s", "cores": threads, "kind": "port",
+           "sample": "first %d paths of the step (%.2e transitions), oracle/piql_oracle.c with OpenMP over paths"
+                     % (sample, tr)}
+    if vi is not None:
+        t0 = time.perf_counter()
+        org.nu_jacobi_dense(3, nthreads=threads)
+        vi["cpu_baseline"] = {"sweeps_per_s": 3 / (time.perf_counter() - t0), "cores": threads, "kind": "port",
+                              "sample": "3 dense OpenMP Jacobi sweeps (f64)"}
+    return cpu
+
+
 def workload_config(name, args, world):
     w = WORKLOADS[name]
     return {"workload": "synthetic %dx%d gridworld (BASELINE config %s), density %.1f, randomness %.2f, gamma %.2f, beta %.0f, "
@@ -372,39 +443,7 @@ def run_ours(args, rank, world, local_rank):
     # algorithmic bytes per state per sweep: nu 2 x sizeof(T), logz 3 x, gap 4 x
     vi = None
     if rank == 0 and not args.no_vi:
-        vi = {}
-        cases = [("nu", "f32fast", 8, {}), ("nu", "f32", 8, {}), ("nu", "f64", 16, {}),
-                 ("logz", "f32fast", 12, dict(V=V, beta=BETA)), ("gap", "f32fast", 16, dict(V=V, nu=V))]
-        for kind, prec, nbytes, kw in cases:
-            eng.vi_prepare(kind, reward_scale=1.0, precision=prec, **kw)
-            with torch.cuda.stream(stream):
-                eng.vi_sweeps(20)
-                torch.cuda.synchronize()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream)
-                eng.vi_sweeps(args.vi_sweeps)
-                b.record(stream)
-                torch.cuda.synchronize()
-            sec = a.elapsed_time(b) * 1e-3
-            sps = args.vi_sweeps / sec
-            gbs = nbytes * eng.nfree * sps / 1e9
-            key = prec if kind == "nu" else "%s_%s" % (kind, prec)
-            if key == "f32fast":
-                vi["tile_plan"] = eng.vi_tile_plan("nu", "f32fast")   # the shape the library timed fastest on this device
-            vi[key] = {"sweeps_per_s": sps, "state_backups_per_s": sps * eng.nfree, "us_per_sweep": 1e6 / sps,
-                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                                    "bytes_per_state": nbytes, "traffic": None}}
-        # the ground-truth solve itself (config 4: "soft VI ground truth on 1 B200"), host buffers in and out
-        solves = {}
-        for prec, tol in (("f64", 1e-9), ("f32fast", 0.05)):
-            t0 = time.perf_counter()
-            _nu, sst = eng.solve_nu(tol=tol, max_sweeps=20000, precision=prec, allow_unconverged=True)
-            solves[prec] = {"tol_sum_abs_delta": tol, "sweeps": int(sst.sweeps), "converged": bool(sst.converged),
-                            "seconds": time.perf_counter() - t0, "device_seconds": float(sst.device_seconds)}
-        vi["solve_nu"] = solves
-        vi["kernel"] = ("tile_sweep_kernel<T,KIND,FAST>: 4 Jacobi sweeps per launch on 128 x (TJ+8) shared-memory tiles "
-                        "(includes the residual reduction on the last launch); f32fast = MUFU ex2/lg2; keys without a kind are nu")
-        vi["setup_vlo"] = {"sweeps": int(vst.sweeps), "device_seconds": float(vst.device_seconds)}
+        vi = run_extra("vi", lambda: vi_section(args, eng, stream, V, peak, vst))
 
     # ---- soft-VI sweeps of ONE grid on all N GPUs (column slabs, halo exchange over NVLink peer memory) -------------
     vi_sharded = None
@@ -441,30 +480,12 @@ def run_ours(args, rank, world, local_rank):
     # ---- CPU baseline beside it (rank 0, N = 1) ------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        import oracle
-        org = oracle.Grid(walls, goal, **params)
-        threads = oracle.num_threads()
-        table = eng.policy_table(V, beta=BETA)        # same fp32 table the GPU read
-        free = org.free_cells()
-        sample = args.ref_paths
-        org.rollout(table, V[goal], free, 1 << 14, seed=MC_SEED, nthreads=threads)
-        t0 = time.perf_counter()
-        lw, meta = org.rollout(table, V[goal], free, sample, path0=0, seed=MC_SEED, nthreads=threads)
-        mxo, smo, cno, tr = oracle.reduce_paths(lw, meta, len(free), path0=0)
-        dt = time.perf_counter() - t0
-        cpu = {"value": tr / dt, "unit": "transitions/s", "cores": threads, "kind": "port",
-               "sample": "first %d paths of the step (%.2e transitions), oracle/piql_oracle.c with OpenMP over paths"
-                         % (sample, tr)}
-        if vi is not None:
-            t0 = time.perf_counter()
-            org.nu_jacobi_dense(3, nthreads=threads)
-            vi["cpu_baseline"] = {"sweeps_per_s": 3 / (time.perf_counter() - t0), "cores": threads, "kind": "port",
-                                  "sample": "3 dense OpenMP Jacobi sweeps (f64)"}
+        cpu = run_extra("cpu_baseline", lambda: cpu_section(args, eng, walls, goal, params, V, vi))
 
     # ---- the reference's own experiment (BASELINE configs 1-3: golden 20x20 grid) through the batched calls ------
     experiment = None
     if rank == 0 and world == 1 and not args.no_exp:
-        experiment = run_golden_experiment(local_rank, with_cpu=not args.no_cpu)
+        experiment = run_extra("experiment", lambda: run_golden_experiment(local_rank, with_cpu=not args.no_cpu))
 
     if rank == 0:
         line = {"metric": "sampled transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world,
