@@ -456,6 +456,13 @@ def run_ours(args, rank, world, local_rank):
             dist.all_gather_object(blobs, blob)
             eng.vi_shard_connect(blobs)
             barrier()
+            # two rounds first: a halo wait that timed out on any rank (bounded at 10 s per launch in the kernel) must not
+            # be repeated for the hundred launches of the timed run
+            if not pd.sharded_sweeps_ok(eng, sweeps=8):
+                vi_sharded[prec] = {"error": "a halo wait timed out on some rank; timed run skipped"}
+                barrier()
+                eng.vi_shard_end()
+                continue
             with torch.cuda.stream(stream):
                 eng.vi_sweeps(40)
                 barrier()

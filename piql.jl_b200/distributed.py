@@ -139,3 +139,21 @@ def solve_sharded(eng, kind, rank, world, V=None, nu=None, beta=1.0, reward_scal
     dist.barrier(group=group)     # nobody unmaps while a neighbour may still push
     eng.vi_shard_end()
     return out, sweeps, res
+
+
+def sharded_sweeps_ok(eng, sweeps=8, group=None):
+    """A few sharded soft-VI sweeps as a canary: True on every rank iff no rank's halo wait timed out (a rank whose kernel
+    gave up waiting for a neighbour reports it through vi_fetch).  Every rank makes the same collective call whatever happened
+    locally, so the ranks stay in step and can all skip a long timed run together."""
+    import torch
+    import torch.distributed as dist
+    ok = 1.0
+    try:
+        eng.vi_sweeps(sweeps)
+        eng.vi_fetch(want_x=False)
+    except Exception:
+        ok = 0.0
+    dev = "cuda:%d" % eng.device if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([ok], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return float(t[0]) > 0.5

@@ -170,3 +170,48 @@ def test_sharded_solve_host_logic_stitches_slabs_and_sums_the_residual():
         assert np.array_equal(np.isnan(x), g.walls != 0)
         assert float(np.nanmax(np.abs(x - g.nu))) < 1e-8          # the reference's stored nu
     assert got[0][2] == got[1][2] and np.array_equal(np.nan_to_num(got[0][1]), np.nan_to_num(got[1][1]))
+
+
+def _canary_worker(rank, world, port, bad_rank, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import piql_jl_b200  # noqa: F401
+    from piql_jl_b200.distributed import sharded_sweeps_ok
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Eng:
+        device = 0
+        swept = 0
+
+        def vi_sweeps(self, n):
+            self.swept += n
+
+        def vi_fetch(self, want_x=True):
+            if rank == bad_rank:
+                raise RuntimeError("a soft-VI kernel timed out waiting for a neighbouring tile or rank")
+            return None, 0.0
+    eng = Eng()
+    q.put((rank, sharded_sweeps_ok(eng, sweeps=8), eng.swept))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bad_rank", [-1, 1])
+def test_sharded_canary_agrees_on_every_rank(bad_rank):
+    """bench.py runs a few sharded sweeps before the long timed run: if any rank's halo wait timed out, all ranks skip it."""
+    import torch.multiprocessing as mp
+    world = 2
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_canary_worker, args=(r, world, port, bad_rank, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=180) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [g[1] for g in got] == [bad_rank < 0] * world and all(g[2] == 8 for g in got)
