@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -54,6 +55,9 @@ struct piql_ctx {
 
   // Monte-Carlo
   float4* d_table = nullptr;
+#if PIQL_ROLL_TILED
+  float4* d_table_tiled = nullptr;  // the same records in 8 x 8 blocks of cells, for the production rollout kernel (large grids)
+#endif
   bool has_table = false;
   double v_goal = 0.0;
   float* d_logw = nullptr;
@@ -355,6 +359,10 @@ int mc_reset(piql_ctx* ctx, const piql_mc_opts* o) {
 RolloutArgs make_rollout_args(piql_ctx* ctx, const piql_mc_opts* o) {
   RolloutArgs a{};
   a.table = ctx->d_table;
+#if PIQL_ROLL_TILED
+  a.table_tiled = ctx->d_table_tiled;
+  a.W = ctx->g.W;
+#endif
   a.table_bytes = 32LL * ctx->g.n;
   a.goal = ctx->g.goal; a.H = ctx->g.H;
   a.gamma = (float)ctx->g.gamma; a.rho = (float)ctx->g.randomness; a.vgoal = (float)ctx->v_goal;
@@ -486,6 +494,9 @@ int build_table(piql_ctx* ctx, const double* V, const double* Q, double beta, fl
   CK(cudaMemcpyAsync(ctx->d_in0, V, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
   if (Q) CK(cudaMemcpyAsync(ctx->d_in4, Q, 32 * (size_t)n, cudaMemcpyHostToDevice, st));
   launch_policy_table(ctx->g, ctx->d_cell, ctx->d_in0, Q ? ctx->d_in4 : nullptr, beta, 1.0, ctx->d_table, st, kl_dev);
+#if PIQL_ROLL_TILED
+  if (ctx->d_table_tiled) launch_table_tile(ctx->d_table, ctx->d_table_tiled, ctx->g.H, ctx->g.W, st);
+#endif
   CK_LAST();
   ctx->v_goal = vg;
   ctx->has_table = true;
@@ -557,6 +568,9 @@ int32_t piql_destroy(piql_ctx* ctx) {
                   (void*)ctx->acc_cnt, (void*)ctx->d_scratch, (void*)ctx->d_transitions, (void*)ctx->d_inj,
                   (void*)ctx->d_scalars})
     if (p) cudaFree(p);
+#if PIQL_ROLL_TILED
+  if (ctx->d_table_tiled) cudaFree(ctx->d_table_tiled);
+#endif
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
   if (ctx->h_transitions) cudaFreeHost(ctx->h_transitions);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -613,6 +627,12 @@ int32_t piql_grid_load(piql_ctx* ctx, const uint8_t* walls, int64_t H, int64_t W
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_cell, (size_t)n);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_free, sizeof(int) * (size_t)(nfree ? nfree : 1));
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_table, 32 * (size_t)n);
+#if PIQL_ROLL_TILED
+  if (ctx->d_table_tiled) cudaFree(ctx->d_table_tiled);
+  ctx->d_table_tiled = nullptr;
+  if (e == cudaSuccess && n >= ROLL_TILED_MIN_CELLS && H < 65536 && W < 65536 && getenv("PIQL_ROLL_NO_TILED") == nullptr)
+    e = cudaMalloc((void**)&ctx->d_table_tiled, 32 * (size_t)roll_tiled_records((int)H, (int)W));
+#endif
   if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_walls, walls, (size_t)n, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_free, h_free, sizeof(int) * (size_t)nfree, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) {
@@ -1205,6 +1225,9 @@ int32_t piql_policy_table_set(piql_ctx* ctx, const float* table, double v_goal) 
   NEED(table != nullptr, PIQL_ERR_ARG, "table is null");
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(ctx->d_table, table, 32 * (size_t)ctx->g.n, cudaMemcpyHostToDevice, ctx->stream));
+#if PIQL_ROLL_TILED
+  if (ctx->d_table_tiled) launch_table_tile(ctx->d_table, ctx->d_table_tiled, ctx->g.H, ctx->g.W, ctx->stream);
+#endif
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->v_goal = v_goal;
   ctx->has_table = true;
@@ -1258,6 +1281,9 @@ int32_t piql_mc_update_v(piql_ctx* ctx, const double* V, double beta, const piql
     CK(cudaStreamSynchronize(st));
     ctx->v_goal = ctx->h_scalars[4];
     launch_policy_table(ctx->g, ctx->d_cell, ctx->d_in1, nullptr, beta, 1.0, ctx->d_table, st);
+#if PIQL_ROLL_TILED
+    if (ctx->d_table_tiled) launch_table_tile(ctx->d_table, ctx->d_table_tiled, ctx->g.H, ctx->g.W, st);
+#endif
     ctx->has_table = true;
     rc = mc_reset(ctx, &o);
     if (rc) return rc;

@@ -128,6 +128,19 @@ int configure_backup_kernels();
 void launch_residual_final(const double* partial, int nblocks, double* out, cudaStream_t st);
 
 // rollout.cu --------------------------------------------------------------------------------
+// PIQL_ROLL_TILED (build-time experiment, default off): the production rollout kernel reads a second copy of the policy
+// records laid out in 8 x 8 blocks of cells (2 KB per block) instead of whole columns.  On grids whose table does not fit
+// L2 a step to the left or right then stays within a DRAM page or two instead of jumping H * 32 bytes (131 KB at 4098^2),
+// where the kernel is bound by random 32-byte reads (DRAM 3.0 of 6.5 TB/s, load latency 1.6 us under load).  The
+// cell-order table stays the ABI's and every other kernel's.
+#ifndef PIQL_ROLL_TILED
+#define PIQL_ROLL_TILED 0
+#endif
+#if PIQL_ROLL_TILED
+constexpr long long ROLL_TILED_MIN_CELLS = 4LL << 20;  // below that the table lives in L2 and the extra address arithmetic only costs
+inline long long roll_tiled_records(int H, int W) { return 64LL * ((H + 7) / 8) * ((W + 7) / 8); }
+void launch_table_tile(const float4* table, float4* tiled, int H, int W, cudaStream_t st);
+#endif
 struct RolloutArgs {
   const float4* table;   // 2 x float4 per cell
   long long table_bytes; // 32 * cells
@@ -147,6 +160,10 @@ struct RolloutArgs {
   uint32_t* meta;        // [npaths]
   int* trace;            // optional [npaths][trace_steps][3]
   long long trace_steps;
+#if PIQL_ROLL_TILED
+  const float4* table_tiled;  // nullptr: cell order only
+  int W;
+#endif
 };
 // kl_out (optional): kl_cost(ctrl, s, Q) per cell, path_functions.jl:17-20
 void launch_policy_table(const GridDev& g, const uint8_t* cell, const double* V, const double* Q, double beta,
