@@ -172,3 +172,16 @@ def test_reference_arm_of_the_bench_runs_on_cpu_and_keeps_the_contract():
     env["RANK"] = "1"
     out1 = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert out1.returncode == 0 and out1.stdout.strip() == ""
+
+
+def test_library_path_override_fails_loudly_when_missing(tmp_path):
+    """PIQL_B200_LIB selects another build of the library (the Julia shim reads the same variable); a path that does not
+    exist is an import error naming it, never a silent fallback to anything else."""
+    import subprocess
+    missing = str(tmp_path / "libpiql_nowhere.so")
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import piql_jl_b200 as piql\n"
+            "try:\n    piql._capi.load()\nexcept ImportError as e:\n    print('IMPORTERROR', e)\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PIQL_B200_LIB=missing), capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0 and "IMPORTERROR" in r.stdout and missing in r.stdout, (r.stdout, r.stderr[-300:])
