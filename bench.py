@@ -114,6 +114,19 @@ def pinned(shape, dtype, order="C"):
 
 
 # ------------------------------------------------------------------------------------------------
+def sample_starts(free, path0, sample):
+    """Start list for a bounded sample of consecutive path ids [path0, path0 + sample): the step's paths start at
+    free[p % nfree]; a sample shorter than the free-cell cycle touches only `sample` consecutive slots of it, so the CPU
+    arm reduces into those (a rotation keeps slot = p % nstarts) instead of initialising all 4 x nfree buckets per step."""
+    nfree = len(free)
+    if sample >= nfree:
+        return free
+    p = path0 + np.arange(sample, dtype=np.int64)
+    starts = np.empty(sample, dtype=np.int32)
+    starts[p % sample] = free[p % nfree]
+    return starts
+
+
 def run_reference(args, rank, world):
     """The reference's algorithm on the host cores: the C restatement (oracle/), all threads."""
     if rank != 0:
@@ -123,12 +136,13 @@ def run_reference(args, rank, world):
     walls, goal, params = make_world(name)
     org = oracle.Grid(walls, goal, **params)
     threads = oracle.num_threads()
-    # V_lo as in the GPU arm, but the CPU cannot afford 1000 dense sweeps of the 4096^2 grid inside a bounded run: 64 there
-    # (the rollout cost per transition does not depend on how converged V is; path lengths are set by gamma)
+    # V_lo as in the GPU arm (VLO_SWEEPS dense Jacobi sweeps); at 4096^2 the host needs ~0.4 s per sweep on 8 cores, so the
+    # bounded run builds it from 64 sweeps there: the policy away from the goal is the same near-uniform one either way and
+    # the path-length distribution (set by gamma) and the cost per transition do not depend on how converged V is
     ref_sweeps = min(args.setup_sweeps, 64) if name == "grid4096" else args.setup_sweeps
     V, _ = org.nu_jacobi_dense(ref_sweeps, reward_scale=VLO_SCALE, nthreads=threads)
     V = np.nan_to_num(V)
-    table = org.policy_table(V, beta=BETA)
+    table = org.policy_table(V, beta=BETA, nthreads=threads)
     free = org.free_cells()
     sample = args.ref_paths
     vgoal = V[goal]
@@ -136,8 +150,9 @@ def run_reference(args, rank, world):
 
     def step():
         nonlocal done
-        lw, meta = org.rollout(table, vgoal, free, sample, path0=done, seed=MC_SEED, nthreads=threads)
-        mx, sm, cnt, tr = oracle.reduce_paths(lw, meta, len(free), path0=done)
+        starts = sample_starts(free, done, sample)
+        lw, meta = org.rollout(table, vgoal, starts, sample, path0=done, seed=MC_SEED, nthreads=threads)
+        mx, sm, cnt, tr = oracle.reduce_paths(lw, meta, len(starts), path0=done)
         done += sample
         return tr
     for _ in range(args.warmup):
@@ -146,17 +161,23 @@ def run_reference(args, rank, world):
     transitions = sum(step() for _ in range(args.steps))
     dt = time.perf_counter() - t0
     value = transitions / dt
+    cfg = workload_config(name, args, world)
+    cfg["paths_per_step"] = int(sample)
+    cfg["sharding"] = "one host process, %d threads" % threads
+    cfg["v_lo_sweeps"] = int(ref_sweeps)
+    cfg["sample"] = ("each step rolls out %d consecutive path ids of the GPU arm's %d-path step and reduces them into the "
+                     "(start cell, action) buckets they touch" % (sample, WORKLOADS[name]["paths"]))
     line = {
         "impl": "reference", "metric": "sampled transitions/sec", "value": value, "unit": "transitions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(name, args, world),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": threads, "kind": "port",
                          "sample": "%d paths per step (of the %d-path step per GPU), oracle/piql_oracle.c with OpenMP over paths, V_lo from "
                                    "%d Jacobi sweeps; Julia is not installed, so the reference itself cannot run"
                                    % (sample, WORKLOADS[name]["paths"], ref_sweeps)},
         "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "transitions_per_step": transitions / args.steps,
     }
     print(json.dumps(line), flush=True)
 
@@ -216,7 +237,17 @@ def run_extra(name, fn):
         return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
-def vi_section(args, eng, stream, V, peak, vst):
+def vi_traffic(name, key):
+    """ncu DRAM bytes (read + write) of one launch of the tiled sweep kernel, from profiles/vi_traffic.json
+    ({"grid1024:f32fast": {"bytes": ..., "sweeps_per_launch": 4}, ...}); None when that case has not been captured."""
+    path = os.path.join(ROOT, "profiles", "vi_traffic.json")
+    try:
+        return json.load(open(path)).get("%s:%s" % (name, key))
+    except Exception:
+        return None
+
+
+def vi_section(args, eng, stream, V, peak, vst, name=None):
     """Soft-VI sweep rates on the loaded grid (rank 0): nu in three precisions, log Z and gap in fast fp32, the ground-truth solve."""
     import torch
     vi = {}
@@ -238,9 +269,17 @@ def vi_section(args, eng, stream, V, peak, vst):
         key = prec if kind == "nu" else "%s_%s" % (kind, prec)
         if key == "f32fast":
             vi["tile_plan"] = eng.vi_tile_plan("nu", "f32fast")   # the shape the library timed fastest on this device
+        plan = eng.vi_tile_plan(kind, prec)
+        kh = max(int(plan.get("sweeps_per_round", 4)), 1)
+        tr = vi_traffic(name, key)
         vi[key] = {"sweeps_per_s": sps, "state_backups_per_s": sps * eng.nfree, "us_per_sweep": 1e6 / sps,
                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                                "bytes_per_state": nbytes, "traffic": None}}
+                                "bytes_per_state": nbytes, "sweeps_per_launch": kh,
+                                "algorithmic_bytes_per_launch": nbytes * eng.nfree * kh,
+                                "avg_launch_us": kh * 1e6 / sps,
+                                "traffic": None if tr is None else tr.get("bytes"),
+                                "traffic_note": None if tr is None else tr.get("note")},
+                   "tile_plan": plan}
     # the ground-truth solve itself (config 4: "soft VI ground truth on 1 B200"), host buffers in and out
     solves = {}
     for prec, tol in (("f64", 1e-9), ("f32fast", 0.05)):
@@ -255,18 +294,86 @@ def vi_section(args, eng, stream, V, peak, vst):
     return vi
 
 
-def cpu_section(args, eng, walls, goal, params, V, vi):
+class OracleSide:
+    """The CPU oracle on this rank's problem, reading the policy table the GPU built (test infrastructure: the checker and the
+    cpu_baseline leg, never the thing measured)."""
+
+    def __init__(self, eng, walls, goal, params, V, threads=None, table=None):
+        import oracle
+        self.oracle = oracle
+        self.org = oracle.Grid(walls, goal, **params)
+        self.threads = threads or oracle.num_threads()
+        self.table = eng.policy_table(V, beta=BETA) if table is None else table   # the fp32 table the GPU read
+        self.free = self.org.free_cells()
+        self.vgoal = float(V[goal])
+
+    def records(self, path0, n):
+        return self.org.rollout(self.table, self.vgoal, self.free, n, path0=path0, seed=MC_SEED, nthreads=self.threads)
+
+    def slot_stats(self, slots, id0, id1):
+        """(max, sum, count)[len(slots), 4] and log Z^(s0, a0) over the path ids of [id0, id1) that start in the given slots."""
+        nfree = len(self.free)
+        lw, me, owner = [], [], []
+        for k, sl in enumerate(slots):
+            first = id0 + ((int(sl) - id0) % nfree)
+            for pid in range(first, id1, nfree):
+                a, b = self.org.rollout(self.table, self.vgoal, self.free[sl:sl + 1], 1, path0=pid, seed=MC_SEED)
+                lw.append(a[0]); me.append(b[0]); owner.append(k)
+        lw, me, owner = np.array(lw, dtype=np.float32), np.array(me, dtype=np.uint32), np.array(owner)
+        # reduce_paths buckets by (path0 + q) % nstarts: feed it one slot's records at a time
+        mx = np.full((len(slots), 4), -np.inf); sm = np.zeros((len(slots), 4)); cn = np.zeros((len(slots), 4), dtype=np.uint64)
+        for k in range(len(slots)):
+            sel = owner == k
+            if sel.any():
+                m1, s1, c1, _tr = self.oracle.reduce_paths(lw[sel], me[sel], 1)
+                mx[k], sm[k], cn[k] = m1[0], s1[0], c1[0]
+        lsa, _ls = self.oracle.logz_from_stats(mx, sm, cn)
+        return cn, lsa, len(lw)
+
+
+def parity_section(args, eng, osd, last_path0, last_count, step_id0, step_id1, world, sample):
+    """Driver-run parity of the production launch: the first `sample` per-path records of the LAST TIMED rollout launch
+    against the oracle, bit for bit, and the accumulators the step left on this rank (after the exchange at N > 1: the
+    reduction over all ranks' shards of the step's path ids [step_id0, step_id1)) for a sample of start slots."""
+    from piql_jl_b200 import distributed as pd
+    import torch
+    n = int(min(sample, last_count))
+    logw, meta = eng.mc_records(n)
+    lw, me = osd.records(last_path0, n)
+    rec_ok = bool(np.array_equal(meta, me) and np.array_equal(logw.view(np.uint32), lw.view(np.uint32)))
+    nfree = len(osd.free)
+    slots = np.unique(np.random.default_rng(7).integers(0, nfree, size=args.parity_slots))
+    m, sm, c = pd.stats_tensors(eng)
+    idx = torch.as_tensor((slots[:, None] * 4 + np.arange(4)[None, :]).ravel(), device=m.device)
+    gm = m[idx].cpu().numpy().astype(np.float64).reshape(-1, 4)
+    gs = sm[idx].cpu().numpy().astype(np.float64).reshape(-1, 4)
+    gc = c[idx].cpu().numpy().astype(np.int64).reshape(-1, 4)
+    cn, lsa, npaths = osd.slot_stats(slots, step_id0, step_id1)
+    cnt_ok = bool(np.array_equal(gc, cn.astype(np.int64)))
+    ok = cn > 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        glsa = gm + np.log(gs) - np.log(gc.astype(np.float64))
+    err = float(np.max(np.abs(glsa[ok] - lsa[ok]))) if ok.any() else 0.0
+    return {"records_bit_exact": rec_ok, "paths": n,
+            "records_of": "first %d records of the last timed launch of rollout_kernel<0,false,false,STAGED=false> (path ids from %d) "
+                          "against oracle.rollout on the GPU's table: log-weight bits, first action, length" % (n, last_path0),
+            "accumulator_counts_exact": cnt_ok, "accumulator_logz_max_abs_err": err, "accumulator_logz_ok": bool(err < 1e-5),
+            "accumulator_slots": int(len(slots)), "accumulator_paths": int(npaths),
+            "accumulators_of": "the step's (max, sum, count) accumulators on this rank%s for %d random start slots against "
+                               "oracle.reduce_paths over every path id of the step that starts there"
+                               % (" after the exchange (all ranks' shards)" if world > 1 else "", len(slots))}
+
+
+def cpu_section(args, osd, vi):
     """The oracle on the box's host cores beside the GPU numbers (rank 0, N = 1): a bounded sample of the same step."""
-    import oracle
-    org = oracle.Grid(walls, goal, **params)
-    threads = oracle.num_threads()
-    table = eng.policy_table(V, beta=BETA)        # same fp32 table the GPU read
-    free = org.free_cells()
+    oracle, org, threads = osd.oracle, osd.org, osd.threads
+    free = osd.free
     sample = args.ref_paths
-    org.rollout(table, V[goal], free, 1 << 14, seed=MC_SEED, nthreads=threads)
+    starts = sample_starts(free, 0, sample)
+    org.rollout(osd.table, osd.vgoal, free, 1 << 14, seed=MC_SEED, nthreads=threads)
     t0 = time.perf_counter()
-    lw, meta = org.rollout(table, V[goal], free, sample, path0=0, seed=MC_SEED, nthreads=threads)
-    mxo, smo, cno, tr = oracle.reduce_paths(lw, meta, len(free), path0=0)
+    lw, meta = org.rollout(osd.table, osd.vgoal, starts, sample, path0=0, seed=MC_SEED, nthreads=threads)
+    mxo, smo, cno, tr = oracle.reduce_paths(lw, meta, len(starts), path0=0)
     dt = time.perf_counter() - t0
     cpu = {"value": tr / dt, "unit": "transitions/s", "cores": threads, "kind": "port",
            "sample": "first %d paths of the step (%.2e transitions), oracle/piql_oracle.c with OpenMP over paths"
@@ -277,6 +384,82 @@ def cpu_section(args, eng, walls, goal, params, V, vi):
         vi["cpu_baseline"] = {"sweeps_per_s": 3 / (time.perf_counter() - t0), "cores": threads, "kind": "port",
                               "sample": "3 dense OpenMP Jacobi sweeps (f64)"}
     return cpu
+
+
+def grid4096_section(args, eng, stream):
+    """The config-5 workload on ONE GPU (N = 1 runs only): the same-config anchor of the 1 -> 8 scaling curve, whose N > 1
+    lines run 4096^2 while the N = 1 headline is config 4 (1024^2)."""
+    import torch
+    name = "grid4096"
+    walls, goal, params = make_world(name)
+    eng.load_grid(walls, goal, **params)
+    V, _ = eng.solve_nu(reward_scale=VLO_SCALE, tol=0.0, max_sweeps=args.setup_sweeps)
+    eng.policy_table(np.nan_to_num(V), beta=BETA, download=False)
+    P = WORKLOADS[name]["paths"]
+    steps, k = max(2, min(args.steps, 4)), [0]
+
+    def step():
+        eng.mc_reset()
+        eng.mc_rollout(P, path0=k[0] * P, seed=MC_SEED)
+        k[0] += 1
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        eng.mc_timing()
+        tr0 = eng.mc_transitions_total()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(steps):
+            step()
+        b.record(stream)
+        torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    tr = eng.mc_transitions_total() - tr0
+    roll_s, red_s, nl = eng.mc_timing()
+    peak, _src = measured_peak()
+    alg = 32.0 * tr + 8.0 * P * steps
+    return {"value": tr / (ms * 1e-3), "unit": "transitions/s", "steps": steps, "warmup": 3, "ms_per_step": ms / steps,
+            "config": workload_config(name, args, 1),
+            "roofline": rollout_roofline(name, alg / roll_s / 1e9 if roll_s > 0 else 0.0, peak, nl, roll_s, red_s, tr),
+            "note": "same workload as the N > 1 lines (BASELINE config 5) on one GPU, no exchange: divide an N-GPU `value` by "
+                    "N x this for the same-config weak-scaling efficiency"}
+
+
+ROLL_LIMITER = {
+    "grid1024": ("issue/ALU", "the 34 MB policy table stays in L2/L1 (DRAM traffic is ~0.3 % of the algorithmic bytes): the kernel is bound "
+                              "by instruction issue and the integer pipe (Philox4x32-10: 20 IMAD.WIDE + 20 LOP3 per step), not by HBM; "
+                              "`achieved` is the algorithmic byte rate, comparable across grids, not DRAM traffic"),
+    "grid4096": ("hbm", "the 537 MB table is read as random 32-byte sectors: dependent-load latency (long scoreboard) at the DRAM "
+                        "rate `traffic` / launch time; L2 absorbs the rest of the algorithmic bytes"),
+}
+
+
+def rollout_roofline(name, achieved, peak, nl, roll_s, red_s, tr_local, peak_src=None, paths_per_launch=None):
+    traffic = prof = None
+    tpath = os.path.join(ROOT, "profiles", "rollout_traffic.json")
+    # the ncu capture is one launch of the workload's own size: it says nothing about other launch sizes
+    if os.path.exists(tpath) and paths_per_launch in (None, WORKLOADS.get(name, {}).get("paths")):
+        try:
+            t = json.load(open(tpath))
+            traffic, prof = t.get(name), t.get("_pipes", {}).get(name)
+        except Exception:
+            traffic = None
+    bound, why = ROLL_LIMITER.get(name, ("hbm", ""))
+    launch_ms = 1e3 * roll_s / max(nl, 1)
+    out = {"bound": bound, "kernel": "rollout_kernel<0,false,false,STAGED=false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+           "frac": achieved / peak, "traffic": traffic, "bytes_per_transition": 32, "bytes_per_path": 8, "launches": nl,
+           "avg_launch_ms": launch_ms, "reduce_share": red_s / max(roll_s + red_s, 1e-12),
+           "transitions_per_s_kernel": tr_local / roll_s if roll_s > 0 else 0.0, "limiter": why}
+    if traffic and launch_ms > 0:
+        # ncu DRAM bytes of one full-size launch over the live launch time of this run
+        out["dram_gbs"] = traffic / (launch_ms * 1e-3) / 1e9
+        out["dram_frac_of_peak"] = out["dram_gbs"] / peak
+    if prof:
+        out["ncu_pipes"] = prof
+    if peak_src:
+        out["peak_source"] = peak_src
+    return out
 
 
 def workload_config(name, args, world):
@@ -372,18 +555,28 @@ def run_ours(args, rank, world, local_rank):
     p0, cnt = pd.shard_range(P, rank, world)
     alg_bytes = 32.0 * tr_local + 8.0 * cnt * args.steps
     achieved = alg_bytes / roll_s / 1e9 if roll_s > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "rollout_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(name)
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "rollout_kernel<0,false,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_transition": 32, "bytes_per_path": 8, "launches": nl,
-                "avg_launch_ms": 1e3 * roll_s / max(nl, 1), "reduce_share": red_s / max(roll_s + red_s, 1e-12),
-                "transitions_per_s_kernel": tr_local / roll_s if roll_s > 0 else 0.0}
+    roofline = rollout_roofline(name, achieved, peak, nl, roll_s, red_s, tr_local, peak_src, paths_per_launch=cnt)
+
+    # ---- parity of the launch just timed, against the oracle (every rank checks its own shard) -------------------
+    parity = None
+    osd = None
+    if not args.no_parity:
+        import oracle
+        def _parity():
+            nonlocal osd
+            osd = OracleSide(eng, walls, goal, params, V, threads=max(1, oracle.num_threads() // world))
+            last = step_no[0] - 1
+            chunk = 1 << 28                                  # the library's records per launch (MAX_RECORDS_PER_LAUNCH)
+            off = ((cnt - 1) // chunk) * chunk if cnt > 0 else 0
+            return parity_section(args, eng, osd, last * P + p0 + off, cnt - off, last * P, (last + 1) * P, world,
+                                  args.parity_paths if world == 1 else max(args.parity_paths // world, 1 << 16))
+        parity = run_extra("parity", _parity)
+        if world > 1:
+            flags = [parity.get("records_bit_exact", False), parity.get("accumulator_counts_exact", False), parity.get("accumulator_logz_ok", False)]
+            t = torch.tensor([1.0 if f else 0.0 for f in flags], dtype=torch.float64, device="cuda:%d" % local_rank)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            parity["all_ranks"] = {"records_bit_exact": bool(t[0] > 0.5), "accumulator_counts_exact": bool(t[1] > 0.5),
+                                   "accumulator_logz_ok": bool(t[2] > 0.5), "ranks": world}
     exchange = None
     if world > 1:
         # the exchange alone: ranks aligned by a barrier first, so no rank waits for a slower rollout
@@ -443,12 +636,34 @@ def run_ours(args, rank, world, local_rank):
     # algorithmic bytes per state per sweep: nu 2 x sizeof(T), logz 3 x, gap 4 x
     vi = None
     if rank == 0 and not args.no_vi:
-        vi = run_extra("vi", lambda: vi_section(args, eng, stream, V, peak, vst))
+        vi = run_extra("vi", lambda: vi_section(args, eng, stream, V, peak, vst, name))
 
     # ---- soft-VI sweeps of ONE grid on all N GPUs (column slabs, halo exchange over NVLink peer memory) -------------
     vi_sharded = None
     if world > 1 and not args.no_vi:
         vi_sharded = {}
+        if not args.no_parity:
+            # north star: value-iteration results are bit-stable across GPU counts -- 37 sharded sweeps from a random iterate
+            # against the same 37 sweeps on rank 0's GPU alone
+            def _vi_bits():
+                x0 = np.asfortranarray(np.random.default_rng(5).normal(size=(H, W)))
+                one = None
+                if rank == 0:
+                    eng.vi_prepare("nu", precision="f32fast")
+                    eng.vi_set_iterate(x0)
+                    eng.vi_sweeps(37)
+                    one, _r = eng.vi_fetch()
+                x, sweeps, _res = pd.solve_sharded(eng, "nu", rank, world, precision="f32fast", tol=0.0, max_sweeps=37, check_every=10, x0=x0)
+                same = True
+                if rank == 0:
+                    same = bool(np.array_equal(np.nan_to_num(x).view(np.uint64), np.nan_to_num(one).view(np.uint64)))
+                t = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device="cuda:%d" % local_rank)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                return {"vi_sharded_bit_identical": bool(t[0] > 0.5), "sweeps": int(sweeps), "kind": "nu", "precision": "f32fast",
+                        "what": "assembled slabs of %d GPUs vs the single-GPU iterate, every bit" % world}
+            vb = run_extra("vi_bits", _vi_bits)
+            if parity is not None:
+                parity["vi_sharded"] = vb
         for prec, nbytes in (("f32fast", 8), ("f64", 16)):
             eng.vi_prepare("nu", precision=prec)
             blob, cols = eng.vi_shard_begin(rank, world)
@@ -487,19 +702,27 @@ def run_ours(args, rank, world, local_rank):
     # ---- CPU baseline beside it (rank 0, N = 1) ------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = run_extra("cpu_baseline", lambda: cpu_section(args, eng, walls, goal, params, V, vi))
+        def _cpu():
+            return cpu_section(args, osd or OracleSide(eng, walls, goal, params, V), vi)
+        cpu = run_extra("cpu_baseline", _cpu)
 
     # ---- the reference's own experiment (BASELINE configs 1-3: golden 20x20 grid) through the batched calls ------
     experiment = None
     if rank == 0 and world == 1 and not args.no_exp:
         experiment = run_extra("experiment", lambda: run_golden_experiment(local_rank, with_cpu=not args.no_cpu))
 
+    # ---- the config-5 workload on this one GPU: same-config anchor of the scaling curve (last: it reloads the grid) ----
+    g4096 = None
+    if rank == 0 and world == 1 and name == "grid1024" and not args.no_4096:
+        g4096 = run_extra("rollout_grid4096", lambda: grid4096_section(args, eng, stream))
+
     if rank == 0:
         line = {"metric": "sampled transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(name, args, world), "clocks": clocks, "exchange": exchange, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "vi": vi, "vi_sharded": vi_sharded, "experiment": experiment,
+                "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "vi": vi, "vi_sharded": vi_sharded, "experiment": experiment,
+                "rollout_grid4096": g4096,
                 "transitions_per_step": transitions / args.steps}
         print(json.dumps(line), flush=True)
     eng.close()
@@ -521,6 +744,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-vi", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed launch's records and accumulators")
+    ap.add_argument("--no-4096", action="store_true", help="N = 1: skip the config-5 (4096^2) single-GPU rate")
+    ap.add_argument("--parity-paths", type=int, default=1 << 20, help="records of the last timed launch compared with the oracle")
+    ap.add_argument("--parity-slots", type=int, default=64, help="start slots whose accumulators are compared with the oracle")
     ap.add_argument("--no-exp", action="store_true", help="skip the golden-grid experiment (2 nu + 40 logz_updateV + 48 gap solves)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -133,9 +133,10 @@ class Grid:
         return lib().orc_kl_cost(*self._args(reward_scale), _p(V, C.c_double), _p(Q, C.c_double), C.c_int64(s))
 
     # ---- sampling ----------------------------------------------------------------------
-    def policy_table(self, V, beta=1.0, Q=None, reward_scale=1.0):
+    def policy_table(self, V, beta=1.0, Q=None, reward_scale=1.0, nthreads=1):
         V, Q = _f(V), _q(Q)
         tab = np.zeros((self.H * self.W, 8), dtype=np.float32)
+        lib().orc_set_table_threads(C.c_int(nthreads))
         lib().orc_policy_table(*self._args(reward_scale), _p(V, C.c_double), _p(Q, C.c_double),
                                C.c_double(beta), _p(tab, C.c_float))
         return tab

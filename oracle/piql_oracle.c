@@ -415,12 +415,17 @@ double orc_kl_cost(int64_t H, int64_t W, const uint8_t *walls, int64_t goal, dou
  *   [4..7] float  beta * fitness(s,a)
  * w_a = action_probability(ctrl,Q,s,a)  (choose_action, path_functions.jl:12-15)
  * ---------------------------------------------------------------------------------- */
+static int orc_table_threads_ = 1; /* cells are independent: the full-size test grids build their table on all cores */
+void orc_set_table_threads(int n) { orc_table_threads_ = n > 0 ? n : 1; }
 int orc_policy_table(int64_t H, int64_t W, const uint8_t *walls, int64_t goal, double randomness,
                      double step_cost, double reward, double gamma, double reward_scale, const double *V,
                      const double *Qtab, double beta, float *table) {
   orc_grid g = {H, W, walls, goal, randomness, step_cost, reward, gamma, reward_scale};
   orc_q q = {&g, dense_fn, (void *)V, Qtab};
   memset(table, 0, sizeof(float) * 8 * H * W);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 4096) num_threads(orc_table_threads_)
+#endif
   for (int64_t s = 0; s < H * W; s++) {
     if (walls[s]) continue;
     double w[NA], sum = 0.0, cw = 0.0;
@@ -479,7 +484,10 @@ int orc_rollout(int64_t H, int64_t goal, const float *table, double gamma, doubl
                 const int32_t *starts, int64_t nstarts, uint64_t seed, const float *inj,
                 int64_t inj_steps, float *logw_out, uint32_t *meta_out, int32_t *trace,
                 int64_t trace_steps, int nthreads) {
-  const float gam = (float)gamma, rho = (float)randomness, vgoal = (float)Vgoal;
+  /* the stop and slip tests compare the (float) uniform with the Float64 gamma / randomness of the problem, as the
+   * reference's rand() < randomness does (GridWorld.jl:114): for u = k 2^-24 that is k >= ceil(gamma 2^24) exactly */
+  const double gam = gamma, rho = randomness;
+  const float vgoal = (float)Vgoal;
   const float lgam = (float)log(gamma), l1mg = (float)log(1 - gamma);
   const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   const int64_t off[4] = {1, -1, H, -H};
@@ -516,12 +524,12 @@ int orc_rollout(int64_t H, int64_t goal, const float *table, double gamma, doubl
       logw += rec[4 + a];
       if (t == 0) a0 = (uint32_t)a;
       if (estimator == 0) {
-        if (u[1] >= gam) { t++; break; }
+        if ((double)u[1] >= gam) { t++; break; }
       } else {
         acc = logaddexpf_(acc, ((float)t * lgam + l1mg) + logw);
       }
       int as = (int)(4.0f * u[3]); if (as > 3) as = 3;
-      int aa = (u[2] < rho) ? as : a;
+      int aa = ((double)u[2] < rho) ? as : a;
       int64_t s1 = ((mask >> aa) & 1u) ? s : s + off[aa];
       if (trace && t < trace_steps) {
         int32_t *tr = trace + ((size_t)q * trace_steps + t) * 3;
@@ -548,7 +556,8 @@ int orc_path_estimates(int64_t H, int64_t goal, const float *table, const float 
                        double randomness, double step_cost, double reward, int64_t nsteps, int64_t path0,
                        int64_t npaths, const int32_t *starts, int64_t nstarts, uint64_t seed, const float *inj,
                        int64_t inj_steps, float *fit, float *dir, int32_t *trace) {
-  const float rho = (float)randomness, rg = (float)reward, rs = (float)(-step_cost);
+  const double rho = randomness;
+  const float rg = (float)reward, rs = (float)(-step_cost);
   const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   const int64_t off[4] = {1, -1, H, -H};
   for (int64_t q = 0; q < npaths; q++) {
@@ -568,7 +577,7 @@ int orc_path_estimates(int64_t H, int64_t goal, const float *table, const float 
       int a = 0;
       while (rec[a] < u[0] && a < 3) a++;                        /* choose_action :12-15 */
       int as = (int)(4.0f * u[3]); if (as > 3) as = 3;
-      int aa = (u[2] < rho) ? as : a;                            /* propagator  GridWorld.jl:113-115 */
+      int aa = ((double)u[2] < rho) ? as : a;                    /* propagator  GridWorld.jl:113-115 */
       int64_t s1 = ((mask >> aa) & 1u) ? s : s + off[aa];
       tf = tf + rec[4 + a];                                      /* total += fitness(ctrl,V,Q,s,a)  :38 */
       float rw = (s1 == goal) ? rg : rs;                         /* reward_function  GridWorld.jl:116 */
@@ -839,7 +848,7 @@ int orc_table_rollout(int64_t ns, int na, const int64_t *ptr, const int32_t *suc
                       int64_t nstarts, int64_t path0, int64_t npaths, uint64_t seed, int64_t horizon, float *logw_out,
                       uint32_t *meta_out) {
   (void)ns;
-  const float gam = (float)gamma;
+  const double gam = gamma;
   for (int64_t q = 0; q < npaths; q++) {
     const uint64_t gp = (uint64_t)(path0 + q);
     int64_t s = starts ? starts[gp % (uint64_t)nstarts] : (int64_t)(gp % (uint64_t)nstarts);
@@ -856,7 +865,7 @@ int orc_table_rollout(int64_t ns, int na, const int64_t *ptr, const int32_t *suc
       while (a < na - 1 && cdf[s * na + a] < u0) a++;
       logw = logw + bf[s * na + a];
       if (t == 0) a0 = (uint32_t)a;
-      if (u1 >= gam) break;
+      if ((double)u1 >= gam) break;
       int64_t e = ptr[s * na + a];
       const int64_t last = ptr[s * na + a + 1] - 1;
       while (e < last && cum[e] < u2) e++;

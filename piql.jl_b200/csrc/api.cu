@@ -60,9 +60,11 @@ struct piql_ctx {
 #endif
   bool has_table = false;
   double v_goal = 0.0;
-  float* d_logw = nullptr;
-  uint32_t* d_meta = nullptr;
+  uint2* d_rec = nullptr;        // per-path records of the last rollout launch {log-weight bits, a0 | len << 2}
   long long rec_cap = 0;
+  float* d_logw = nullptr;       // split copies: the table path's records; de-interleaved d_rec for piql_mc_records
+  uint32_t* d_meta = nullptr;
+  long long split_cap = 0;
   int* d_starts = nullptr;       // current slot list (points at d_free or d_starts_own)
   int* d_starts_own = nullptr;
   long long starts_own_cap = 0;
@@ -303,6 +305,18 @@ int vi_solve(piql_ctx* ctx, const piql_solve_opts* opts, double* out, piql_solve
   return PIQL_OK;
 }
 
+// Separate log-weight / meta arrays of n entries (the table sampler's records; the split view of d_rec for the host).
+int ensure_split(piql_ctx* ctx, long long n) {
+  if (n <= ctx->split_cap) return PIQL_OK;
+  if (ctx->d_logw) cudaFree(ctx->d_logw);
+  if (ctx->d_meta) cudaFree(ctx->d_meta);
+  ctx->d_logw = nullptr; ctx->d_meta = nullptr; ctx->split_cap = 0;
+  CK(cudaMalloc((void**)&ctx->d_logw, 4 * (size_t)n));
+  CK(cudaMalloc((void**)&ctx->d_meta, 4 * (size_t)n));
+  ctx->split_cap = n;
+  return PIQL_OK;
+}
+
 int mc_check_opts(piql_ctx* ctx, const piql_mc_opts* o) {
   NEED(o != nullptr, PIQL_ERR_ARG, "mc opts is null");
   NEED(o->npaths >= 0 && o->path0 >= 0, PIQL_ERR_ARG, "npaths and path0 must be non-negative");
@@ -365,12 +379,14 @@ RolloutArgs make_rollout_args(piql_ctx* ctx, const piql_mc_opts* o) {
 #endif
   a.table_bytes = 32LL * ctx->g.n;
   a.goal = ctx->g.goal; a.H = ctx->g.H;
-  a.gamma = (float)ctx->g.gamma; a.rho = (float)ctx->g.randomness; a.vgoal = (float)ctx->v_goal;
+  a.gamma = ctx->g.gamma; a.rho = ctx->g.randomness; a.vgoal = (float)ctx->v_goal;
   a.lgam = (float)std::log(ctx->g.gamma); a.l1mg = (float)std::log(1.0 - ctx->g.gamma);
-  // integer forms of `u >= gamma` / `u < randomness` for u = k * 2^-24: a.gamma and a.rho are floats in [0,1], so their
-  // products with 2^24 are exact and k >= gamma*2^24 <=> k >= ceil(gamma*2^24), k < rho*2^24 <=> k < ceil(rho*2^24)
-  a.gamma_k = (uint32_t)std::ceil((double)a.gamma * 16777216.0);
-  a.rho_k = (uint32_t)std::ceil((double)a.rho * 16777216.0);
+  // integer forms of `u >= gamma` / `u < randomness` for u = k * 2^-24 against the problem's Float64 gamma / randomness
+  // (products with 2^24 are exact in double): k >= gamma*2^24 <=> k >= ceil(gamma*2^24), k < rho*2^24 <=> k < ceil(rho*2^24).
+  // Taking the thresholds from the float-rounded gamma instead would move the sampled stop probability 1 - gamma by up to
+  // 2^-25, e.g. 1.00017e-4 instead of 1e-4 at gamma = 0.9999.
+  a.gamma_k = (uint32_t)std::ceil(a.gamma * 16777216.0);
+  a.rho_k = (uint32_t)std::ceil(a.rho * 16777216.0);
   a.estimator = o->estimator; a.horizon = o->horizon;
   a.starts = ctx->d_starts; a.nstarts = ctx->nstarts;
   a.keys = philox_expand((uint32_t)o->seed, (uint32_t)(o->seed >> 32));
@@ -382,14 +398,7 @@ int mc_rollout(piql_ctx* ctx, const piql_mc_opts* o, int* trace_dev, long long t
   NEED(ctx->has_table, PIQL_ERR_STATE, "no policy table (call piql_policy_table or piql_mc_logz first)");
   cudaStream_t st = ctx->stream;
   const long long chunk = o->npaths < MAX_RECORDS_PER_LAUNCH ? o->npaths : MAX_RECORDS_PER_LAUNCH;
-  if (chunk > ctx->rec_cap) {
-    if (ctx->d_logw) cudaFree(ctx->d_logw);
-    if (ctx->d_meta) cudaFree(ctx->d_meta);
-    ctx->d_logw = nullptr; ctx->d_meta = nullptr; ctx->rec_cap = 0;
-    CK(cudaMalloc((void**)&ctx->d_logw, 4 * (size_t)chunk));
-    CK(cudaMalloc((void**)&ctx->d_meta, 4 * (size_t)chunk));
-    ctx->rec_cap = chunk;
-  }
+  CK(grow(ctx->d_rec, ctx->rec_cap, chunk));
   const size_t sf = reduce_scratch_floats(chunk, ctx->nstarts);
   CK(grow(ctx->d_scratch, ctx->scratch_cap, sf ? sf : 1));
   const float* inj_dev = nullptr;
@@ -402,7 +411,7 @@ int mc_rollout(piql_ctx* ctx, const piql_mc_opts* o, int* trace_dev, long long t
   }
   RolloutArgs a = make_rollout_args(ctx, o);
   a.injected = inj_dev; a.injected_steps = o->injected_steps;
-  a.logw = ctx->d_logw; a.meta = ctx->d_meta;
+  a.rec = ctx->d_rec;
   a.trace = trace_dev; a.trace_steps = trace_steps;
   for (long long done = 0; done < o->npaths; done += chunk) {
     a.path0 = o->path0 + done;
@@ -418,7 +427,7 @@ int mc_rollout(piql_ctx* ctx, const piql_mc_opts* o, int* trace_dev, long long t
     }
     launch_rollout(a, ctx->num_sms, st);
     if (timed) CK(cudaEventRecord(ctx->tev[ctx->tev_used + 1], st));
-    launch_reduce(ctx->d_logw, ctx->d_meta, a.path0, a.npaths, ctx->nstarts, ctx->acc_max, ctx->acc_sum, ctx->acc_cnt,
+    launch_reduce(ctx->d_rec, a.path0, a.npaths, ctx->nstarts, ctx->acc_max, ctx->acc_sum, ctx->acc_cnt,
                   ctx->d_scratch, ctx->scratch_cap, ctx->d_transitions, ctx->num_sms, st);
     if (timed) {
       CK(cudaEventRecord(ctx->tev[ctx->tev_used + 2], st));
@@ -539,8 +548,7 @@ int32_t piql_create(piql_ctx** ctx_out, int32_t device_id) {
        cudaMallocHost((void**)&ctx->h_scalars, 64) == cudaSuccess &&
        cudaMalloc((void**)&ctx->d_transitions, 16) == cudaSuccess &&
        cudaMemset(ctx->d_transitions, 0, 16) == cudaSuccess &&
-       cudaMallocHost((void**)&ctx->h_transitions, 16) == cudaSuccess && configure_backup_kernels() == 0 &&
-       configure_rollout_kernels() == 0;
+       cudaMallocHost((void**)&ctx->h_transitions, 16) == cudaSuccess && configure_backup_kernels() == 0;
   if (!ok) {
     cudaGetLastError();
     delete ctx;
@@ -563,7 +571,7 @@ int32_t piql_destroy(piql_ctx* ctx) {
   if (ctx->peer.done) cudaFree(ctx->peer.done);
   if (ctx->peer.err) cudaFreeHost(ctx->peer.err);
   free_vi(ctx);
-  for (void* p : {(void*)ctx->d_walls, (void*)ctx->d_cell, (void*)ctx->d_free, (void*)ctx->d_table, (void*)ctx->d_logw,
+  for (void* p : {(void*)ctx->d_walls, (void*)ctx->d_cell, (void*)ctx->d_free, (void*)ctx->d_table, (void*)ctx->d_rec, (void*)ctx->d_logw,
                   (void*)ctx->d_meta, (void*)ctx->d_starts_own, (void*)ctx->acc_max, (void*)ctx->acc_sum,
                   (void*)ctx->acc_cnt, (void*)ctx->d_scratch, (void*)ctx->d_transitions, (void*)ctx->d_inj,
                   (void*)ctx->d_scalars})
@@ -972,13 +980,9 @@ int32_t piql_table_mc_logz(piql_ctx* ctx, const double* V, double beta, const pi
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const long long rows = t.ns * t.na, nstarts = o->start_mode == PIQL_START_LIST ? o->nstarts : t.ns, nb = nstarts * t.na;
-  if (o->npaths > ctx->rec_cap) {
-    if (ctx->d_logw) cudaFree(ctx->d_logw);
-    if (ctx->d_meta) cudaFree(ctx->d_meta);
-    ctx->d_logw = nullptr; ctx->d_meta = nullptr; ctx->rec_cap = 0;
-    CK(cudaMalloc((void**)&ctx->d_logw, 4 * (size_t)(o->npaths ? o->npaths : 1)));
-    CK(cudaMalloc((void**)&ctx->d_meta, 4 * (size_t)(o->npaths ? o->npaths : 1)));
-    ctx->rec_cap = o->npaths ? o->npaths : 1;
+  {
+    int rc2 = ensure_split(ctx, o->npaths ? o->npaths : 1);
+    if (rc2) return rc2;
   }
   std::vector<void*> tmp;
   auto dev = [&](size_t bytes, void** p) -> cudaError_t {
@@ -1329,8 +1333,12 @@ int32_t piql_trace_paths(piql_ctx* ctx, const piql_mc_opts* opts, int64_t max_st
   rc = e == cudaSuccess ? mc_rollout(ctx, opts, d_trace, max_steps) : fail(ctx, PIQL_ERR_CUDA, cudaGetErrorString(e));
   if (rc == PIQL_OK) {
     e = cudaMemcpyAsync(triples_out, d_trace, 4 * nt, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && logw_out) e = cudaMemcpyAsync(logw_out, ctx->d_logw, 4 * (size_t)opts->npaths, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && meta_out) e = cudaMemcpyAsync(meta_out, ctx->d_meta, 4 * (size_t)opts->npaths, cudaMemcpyDeviceToHost, ctx->stream);
+    if (logw_out || meta_out) {
+      rc = ensure_split(ctx, opts->npaths ? opts->npaths : 1);
+      if (rc == PIQL_OK) launch_split_records(ctx->d_rec, opts->npaths, ctx->d_logw, ctx->d_meta, ctx->stream);
+    }
+    if (rc == PIQL_OK && e == cudaSuccess && logw_out) e = cudaMemcpyAsync(logw_out, ctx->d_logw, 4 * (size_t)opts->npaths, cudaMemcpyDeviceToHost, ctx->stream);
+    if (rc == PIQL_OK && e == cudaSuccess && meta_out) e = cudaMemcpyAsync(meta_out, ctx->d_meta, 4 * (size_t)opts->npaths, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = fail(ctx, PIQL_ERR_CUDA, cudaGetErrorString(e));
   }
@@ -1379,7 +1387,7 @@ int32_t piql_path_estimates(piql_ctx* ctx, const double* V, const double* Q, con
     a.table = ctx->d_table; a.kl = d_kl; a.V = ctx->d_in0;
     a.starts = ctx->d_starts; a.nstarts = ctx->nstarts; a.path0 = opts->path0; a.npaths = opts->npaths;
     a.nsteps = nsteps; a.H = ctx->g.H; a.goal = ctx->g.goal;
-    a.rho = (float)ctx->g.randomness; a.rho_k = (uint32_t)std::ceil((double)a.rho * 16777216.0);
+    a.rho = ctx->g.randomness; a.rho_k = (uint32_t)std::ceil(a.rho * 16777216.0);
     a.rwd_goal = (float)ctx->g.reward; a.rwd_step = (float)(-ctx->g.step_cost);
     a.keys = philox_expand((uint32_t)opts->seed, (uint32_t)(opts->seed >> 32));
     a.injected = inj_dev; a.injected_steps = opts->injected_steps;
@@ -1538,6 +1546,13 @@ int32_t piql_mc_records(piql_ctx* ctx, float* logw_out, uint32_t* meta_out, int6
   if (!ctx) return PIQL_ERR_ARG;
   NEED(n >= 0 && n <= ctx->rec_cap, PIQL_ERR_ARG, "more records requested than the last rollout produced");
   CK(cudaSetDevice(ctx->device));
+  LaunchScope ls(ctx);
+  {
+    int rc = ensure_split(ctx, n ? n : 1);
+    if (rc) return rc;
+  }
+  launch_split_records(ctx->d_rec, n, ctx->d_logw, ctx->d_meta, ctx->stream);
+  CK_LAST();
   if (logw_out) CK(cudaMemcpyAsync(logw_out, ctx->d_logw, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   if (meta_out) CK(cudaMemcpyAsync(meta_out, ctx->d_meta, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

@@ -146,8 +146,9 @@ struct RolloutArgs {
   long long table_bytes; // 32 * cells
   int goal;
   int H;
-  float gamma, rho, vgoal, lgam, l1mg;
-  uint32_t gamma_k, rho_k;  // ceil(gamma * 2^24), ceil(randomness * 2^24): thresholds on the 24-bit integers behind the uniforms
+  double gamma, rho;        // the problem's Float64 gamma and randomness: injected uniforms are compared with them as doubles
+  float vgoal, lgam, l1mg;
+  uint32_t gamma_k, rho_k;  // ceil(gamma * 2^24), ceil(randomness * 2^24): the same tests on the 24-bit integers behind the Philox uniforms
   int estimator;
   long long horizon;
   long long path0, npaths;
@@ -156,8 +157,7 @@ struct RolloutArgs {
   PhiloxKeys keys;       // round keys of Philox4x32-10 for (seed lo, seed hi)
   const float* injected;
   long long injected_steps;
-  float* logw;           // [npaths]
-  uint32_t* meta;        // [npaths]
+  uint2* rec;            // [npaths] per-path records {log-weight bits, a0 | len << 2}: one 8-byte store per finished path
   int* trace;            // optional [npaths][trace_steps][3]
   long long trace_steps;
 #if PIQL_ROLL_TILED
@@ -175,7 +175,8 @@ struct PathEstArgs {
   const int* starts;
   long long nstarts, path0, npaths;
   int nsteps, H, goal;
-  float rho, rwd_goal, rwd_step;
+  double rho;
+  float rwd_goal, rwd_step;
   uint32_t rho_k;
   PhiloxKeys keys;
   const float* injected;
@@ -188,10 +189,12 @@ void launch_path_estimates(const PathEstArgs& a, int num_sms, cudaStream_t st);
 void launch_rollout(const RolloutArgs& a, int num_sms, cudaStream_t st);
 // Reduce records into (max, sum, count)[nstarts*4], merged into the accumulators; adds the
 // transition count to *transitions.
-void launch_reduce(const float* logw, const uint32_t* meta, long long path0, long long npaths, long long nstarts,
+void launch_reduce(const uint2* rec, long long path0, long long npaths, long long nstarts,
                    float* acc_max, float* acc_sum, uint32_t* acc_cnt, float* scratch, size_t scratch_floats,
                    unsigned long long* transitions, int num_sms, cudaStream_t st);
 size_t reduce_scratch_floats(long long npaths, long long nstarts);
+// De-interleaves the first n records into separate log-weight / meta arrays (piql_mc_records, piql_trace_paths).
+void launch_split_records(const uint2* rec, long long n, float* logw, uint32_t* meta, cudaStream_t st);
 void launch_mc_reset(float* acc_max, float* acc_sum, uint32_t* acc_cnt, long long n, cudaStream_t st);
 void launch_fold_counter(unsigned long long* counters, cudaStream_t st);
 void launch_mc_rescale(float* acc_max, float* acc_sum, const float* gmax, long long n, cudaStream_t st);
@@ -202,7 +205,6 @@ void launch_mc_finalize(const float* acc_max, const float* acc_sum, const uint32
 void launch_fill_f64(double* dst, double v, long long n, cudaStream_t st);
 void launch_mc_apply_update(const float* acc_max, const float* acc_sum, const uint32_t* acc_cnt, const int* starts,
                             long long nstarts, double beta, double* V, cudaStream_t st);
-int configure_rollout_kernels();
 
 // table.cu: soft VI on a tabulated ControlProblem (CSR over (state, action)) -------------------------
 struct TableDev {

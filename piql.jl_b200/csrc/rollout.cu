@@ -8,7 +8,7 @@
 //     Z(s) = E_{a~pi_Q}[ exp(beta fitness(s,a)) (gamma E_{s'} Z(s') + 1 - gamma) ],  Z(goal) = exp(-V(goal)).
 //
 // Data layout: one 32-byte record per cell {c0,c1,c2,mask | bf0..bf3} = exactly one DRAM/L2
-// sector per sampled transition; one 8-byte record per finished path {logw, a0|len<<2}.
+// sector per sampled transition; one 8-byte record per finished path {logw, a0|len<<2}, written with one 64-bit store.
 // One trajectory per thread; a warp owns a contiguous range of path ids and refills finished
 // lanes warp-synchronously (ballot + popc), so path -> lane assignment is deterministic.
 #include <cstdlib>
@@ -114,7 +114,7 @@ path_estimates_kernel(const PathEstArgs p) {
       int aslip;
       if (INJ) {
         const float4 u = *reinterpret_cast<const float4*>(p.injected + ((size_t)q * (size_t)p.injected_steps + t) * 4);
-        u0 = u.x; slip = u.z < p.rho; aslip = min((int)(4.0f * u.w), 3);
+        u0 = u.x; slip = (double)u.z < p.rho; aslip = min((int)(4.0f * u.w), 3);
       } else {
         const uint4 r = philox4x32_10(p.keys, (uint32_t)t, 0u, (uint32_t)gp, (uint32_t)(gp >> 32));
         u0 = u01(r.x); slip = (r.z >> 8) < p.rho_k; aslip = (int)(r.w >> 30);
@@ -222,7 +222,7 @@ rollout_kernel(const RolloutArgs p) {
 #else
   const int H = p.H, goal = p.goal;
 #endif
-  const float gam = p.gamma, rho = p.rho;
+  const double gam = p.gamma, rho = p.rho;  // injected uniforms only (the Philox path tests the 24-bit integers)
 
   bool active = false;
   uint32_t q = 0;             // path index within the warp's range
@@ -249,11 +249,15 @@ rollout_kernel(const RolloutArgs p) {
         t = 0; a0 = 0; logw = 0.f; acc = -CUDART_INF_F;
         active = true;
       }
-      const uint32_t handed = __popc(need);
-      next += handed;
-      slot_next += handed;
-      if (nstarts >= 32u) { if (slot_next >= nstarts) slot_next -= nstarts; }
-      else slot_next %= nstarts;
+      // saturating: once the warp's range is handed out, `next` stays at wcount however long the last lanes walk on
+      // (estimator B with a long horizon would otherwise wrap the 32-bit counter and hand finished paths out again)
+      if (next < wcount) {
+        const uint32_t handed = min((uint32_t)__popc(need), wcount - next);
+        next += handed;
+        slot_next += handed;
+        if (nstarts >= 32u) { if (slot_next >= nstarts) slot_next -= nstarts; }
+        else slot_next %= nstarts;
+      }
       if (!__any_sync(FULL, active)) break;
     }
     if (active) {
@@ -291,12 +295,12 @@ rollout_kernel(const RolloutArgs p) {
           const float4 u = *reinterpret_cast<const float4*>(
               p.injected + (((size_t)wbase + q) * (size_t)p.injected_steps + t) * 4);
           u0 = u.x;
-          stop = u.y >= gam;
-          slip = u.z < rho;
+          stop = (double)u.y >= gam;
+          slip = (double)u.z < rho;
           aslip = min((int)(4.0f * u.w), 3);
         } else {
-          // u = k * 2^-24 with the 24-bit integer k = word >> 8, so the float tests u >= gamma and u < randomness are
-          // exactly k >= ceil(gamma * 2^24) and k < ceil(randomness * 2^24)
+          // u = k * 2^-24 with the 24-bit integer k = word >> 8, so the tests u >= gamma and u < randomness (against the
+          // problem's Float64 gamma / randomness) are exactly k >= ceil(gamma * 2^24) and k < ceil(randomness * 2^24)
           const uint4 r = philox4x32_10(p.keys, t, 0u, plo, phi);
           u0 = u01(r.x);
           stop = (r.y >> 8) >= p.gamma_k;
@@ -334,9 +338,8 @@ rollout_kernel(const RolloutArgs p) {
         }
       }
       if (done) {
-        const size_t o = (size_t)wbase + q;
-        p.logw[o] = (EST == 0) ? logw : acc;
-        p.meta[o] = a0 | (t << 2);
+        // the path's statistics leave in one 8-byte store (STG.64)
+        p.rec[(size_t)wbase + q] = make_uint2(__float_as_uint((EST == 0) ? logw : acc), a0 | (t << 2));
         active = false;
       }
     }
@@ -396,7 +399,7 @@ struct Lse {
 // Regime "many start slots": one thread per slot walks that slot's records (stride nstarts), so
 // consecutive threads read consecutive records; no cross-thread combine is needed at all.
 __global__ void __launch_bounds__(256)
-reduce_by_slot_kernel(const float* __restrict__ logw, const uint32_t* __restrict__ meta, long long path0,
+reduce_by_slot_kernel(const uint2* __restrict__ rec, long long path0,
                       long long npaths, long long nstarts, float* __restrict__ acc_max, float* __restrict__ acc_sum,
                       uint32_t* __restrict__ acc_cnt, unsigned long long* __restrict__ transitions) {
   __shared__ unsigned long long red[32];
@@ -409,8 +412,9 @@ reduce_by_slot_kernel(const float* __restrict__ logw, const uint32_t* __restrict
     // first local index q with (path0 + q) % nstarts == slot
     long long q = (slot - path0 % nstarts + nstarts) % nstarts;
     for (; q < npaths; q += nstarts) {
-      const float x = logw[q];
-      const uint32_t me = meta[q];
+      const uint2 rc = __ldg(rec + q);
+      const float x = __uint_as_float(rc.x);
+      const uint32_t me = rc.y;
       tr += me >> 2;
       const uint32_t a = me & 3u;
 #pragma unroll
@@ -433,7 +437,7 @@ reduce_by_slot_kernel(const float* __restrict__ logw, const uint32_t* __restrict
 // then block-level combine of (max, sum, count) per action, one partial per block, merged in a
 // fixed order by reduce_merge_kernel.
 __global__ void __launch_bounds__(256)
-reduce_block_kernel(const float* __restrict__ logw, const uint32_t* __restrict__ meta, long long path0,
+reduce_block_kernel(const uint2* __restrict__ rec, long long path0,
                     long long npaths, long long nstarts, float* __restrict__ part /*[slot][chunk][a][3]*/,
                     unsigned long long* __restrict__ transitions) {
   __shared__ float sm_m[NA][8];
@@ -451,8 +455,9 @@ reduce_block_kernel(const float* __restrict__ logw, const uint32_t* __restrict__
   unsigned long long tr = 0;
   for (long long j = jb + threadIdx.x; j < je; j += blockDim.x) {
     const long long q = q0 + j * nstarts;
-    const float x = logw[q];
-    const uint32_t me = meta[q];
+    const uint2 rc = __ldg(rec + q);
+    const float x = __uint_as_float(rc.x);
+    const uint32_t me = rc.y;
     tr += me >> 2;
     const uint32_t a = me & 3u;
 #pragma unroll
@@ -513,12 +518,12 @@ size_t reduce_scratch_floats(long long npaths, long long nstarts) {
   if (nstarts > REDUCE_FEW_SLOTS) return 0;
   return (size_t)nstarts * reduce_chunks(npaths, nstarts, 148) * NA * 3;
 }
-void launch_reduce(const float* logw, const uint32_t* meta, long long path0, long long npaths, long long nstarts,
+void launch_reduce(const uint2* rec, long long path0, long long npaths, long long nstarts,
                    float* acc_max, float* acc_sum, uint32_t* acc_cnt, float* scratch, size_t scratch_floats,
                    unsigned long long* transitions, int num_sms, cudaStream_t st) {
   if (npaths <= 0) return;
   if (nstarts > REDUCE_FEW_SLOTS) {
-    reduce_by_slot_kernel<<<(unsigned)((nstarts + 255) / 256), 256, 0, st>>>(logw, meta, path0, npaths, nstarts, acc_max,
+    reduce_by_slot_kernel<<<(unsigned)((nstarts + 255) / 256), 256, 0, st>>>(rec, path0, npaths, nstarts, acc_max,
                                                                              acc_sum, acc_cnt, transitions);
     g_launches++;
   } else {
@@ -526,10 +531,24 @@ void launch_reduce(const float* logw, const uint32_t* meta, long long path0, lon
     const int chunks = reduce_chunks(npaths, nstarts, 148);
     (void)scratch_floats;
     dim3 grid(chunks, (unsigned)nstarts);
-    reduce_block_kernel<<<grid, 256, 0, st>>>(logw, meta, path0, npaths, nstarts, scratch, transitions);
+    reduce_block_kernel<<<grid, 256, 0, st>>>(rec, path0, npaths, nstarts, scratch, transitions);
     reduce_merge_kernel<<<(unsigned)((nstarts * NA + 127) / 128), 128, 0, st>>>(scratch, chunks, nstarts, acc_max, acc_sum, acc_cnt);
     g_launches += 2;
   }
+}
+
+__global__ void split_records_kernel(const uint2* __restrict__ rec, long long n, float* __restrict__ logw,
+                                     uint32_t* __restrict__ meta) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint2 r = rec[i];
+  if (logw) logw[i] = __uint_as_float(r.x);
+  if (meta) meta[i] = r.y;
+}
+void launch_split_records(const uint2* rec, long long n, float* logw, uint32_t* meta, cudaStream_t st) {
+  if (n <= 0) return;
+  split_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, n, logw, meta);
+  g_launches++;
 }
 
 // ---- accumulator maintenance -----------------------------------------------------------------------
@@ -634,7 +653,5 @@ void launch_fill_f64(double* dst, double v, long long n, cudaStream_t st) {
   fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, v, n);
   g_launches++;
 }
-
-int configure_rollout_kernels() { return 0; }
 
 }  // namespace piql

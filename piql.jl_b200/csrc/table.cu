@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) table_rollout_kernel(const TableRollArgs 
         t = 0; a0 = 0; logw = 0.f;
         active = true;
       }
-      next += __popc(need);
+      next = min(next + (uint32_t)__popc(need), wcount);  // saturating: the counter must not wrap while the last lanes walk on
       if (!__any_sync(FULL, active)) break;
     }
     if (active) {
@@ -335,7 +335,7 @@ void launch_table_rollout(const TableDev& t, const float* cdf, const float* bf, 
   if (npaths <= 0) return;
   TableRollArgs a{};
   a.t = t; a.cdf = cdf; a.bf = bf; a.cum = cum; a.vterm = vterm;
-  a.gamma_k = (uint32_t)ceil((double)(float)gamma * 16777216.0);
+  a.gamma_k = (uint32_t)ceil(gamma * 16777216.0);  // u1 >= gamma against the Float64 gamma, for u1 = k 2^-24
   a.horizon = horizon; a.path0 = path0; a.npaths = npaths; a.starts = starts; a.nstarts = nstarts;
   a.keys = philox_expand((uint32_t)seed, (uint32_t)(seed >> 32));
   a.logw = logw; a.meta = meta;
