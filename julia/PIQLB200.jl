@@ -8,6 +8,10 @@ module PIQLB200
 
 using PIQL
 import PIQL: Growable, ControlProblem
+# extended below with methods on ControlProblem, so that the reference's own call sites -- generate_ν(ctrl),
+# generate_logz(ctrl, V; β), logz_updateV(ctrl, V; β), generate_optimality_gap(ctrl, V; ν) in scripts/experiments.jl:10-39,
+# scripts/distributed_experiments.jl:5-33 and test/runtests.jl:10-20 -- run on the GPU unchanged after `using PIQL, PIQLB200`
+import PIQL: generate_ν, generate_logz, logz_updateV, generate_z, z_updateV, generate_optimality_gap
 
 const LIB = get(ENV, "PIQL_B200_LIB", joinpath(@__DIR__, "..", "piql.jl_b200", "lib", "libpiql_b200.so"))
 
@@ -55,11 +59,13 @@ McStats() = McStats(0, 0, 0.0, 0.0)
 mutable struct Context
     ptr::Ptr{Cvoid}
     walls::Array{Bool,2}
+    key::Any        # what is loaded on the device: the tabulated problem's identity (context_for)
+    states::Any     # tabulated (non-grid) problems: the discovered states, in table order
     function Context(device::Integer = 0)
         ref = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:piql_create, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32), ref, device)
         rc == 0 || error("piql_create failed with status $rc (no CPU fallback)")
-        ctx = new(ref[], Array{Bool}(undef, 0, 0))
+        ctx = new(ref[], Array{Bool}(undef, 0, 0), nothing, nothing)
         finalizer(c -> ccall((:piql_destroy, LIB), Int32, (Ptr{Cvoid},), c.ptr), ctx)
     end
 end
@@ -144,6 +150,82 @@ function generate_optimality_gap(ctx::Context, V; ν, kw...)
     growable(ctx, out)
 end
 
+# ---- the reference's own signatures: methods on ControlProblem (src/value_iteration.jl:42,54,77,107,119,144) ----------
+# A ControlProblem is a struct of closures.  gridworld_ctrl's closures capture everything piql_grid_load needs
+# (src/Problems/GridWorld.jl:96-121: `pa` captures walls and randomness, `s -> s == gw.goal` captures gw), and Julia exposes
+# captured variables as fields of the closure object -- the same fields JLD2 serialised into data/*.jld2.  So the problem is
+# recognised and tabulated from `ctrl` alone, a context per device is kept in a registry, and the grid is (re)loaded only
+# when the tabulated problem changes (content hash of the wall array, goal, the four parameters): the mirror of
+# solvers.engine_for on the Python side.  A reward_function replaced through modify() (scripts/experiments.jl:26,
+# test/runtests.jl:7-8) keeps the captured gridworld and is probed by tabulate.  Any other ControlProblem (the bandit)
+# goes through the sparse-table entry points.
+const CONTEXTS = Dict{Int,Context}()
+const DEVICE = Ref(0)              # PIQLB200.DEVICE[] = k selects the GPU the ControlProblem methods use
+
+function gridworld_of(ctrl::ControlProblem)
+    tc, pa = ctrl.terminal_condition, ctrl.propagator_average
+    (hasfield(typeof(tc), :gw) && hasfield(typeof(pa), :walls) && hasfield(typeof(pa), :randomness)) || return nothing
+    gw = getfield(tc, :gw)
+    getfield(pa, :walls) === gw.walls || return nothing
+    return (gw, Float64(getfield(pa, :randomness)))
+end
+
+function context_for(ctrl::ControlProblem)
+    ctx = get!(() -> Context(DEVICE[]), CONTEXTS, DEVICE[])
+    g = gridworld_of(ctrl)
+    if g === nothing                  # not the implicit gridworld: tabulate through the closures (bandit, user problems)
+        key = (:table, objectid(ctrl))
+        if ctx.key != key
+            ctx.states = load_table!(ctx, ctrl)
+            ctx.key = key
+        end
+        return ctx
+    end
+    gw, randomness = g
+    t = tabulate(ctrl, gw; randomness)
+    key = (:grid, hash(gw.walls), size(gw.walls), Tuple(t.goal), t.params)
+    if ctx.key != key
+        load!(ctx, ctrl, gw; randomness)
+        ctx.key = key; ctx.states = nothing
+    end
+    return ctx
+end
+on_table(ctx::Context) = ctx.states !== nothing
+
+function generate_ν(ctrl::ControlProblem; kw...)
+    ctx = context_for(ctrl)
+    on_table(ctx) ? table_solve(ctx, ctx.states, 0; kw...) : generate_ν(ctx; kw...)
+end
+function generate_logz(ctrl::ControlProblem, V; β = 1.0, kw...)
+    ctx = context_for(ctrl)
+    on_table(ctx) ? table_solve(ctx, ctx.states, 1; V, β, kw...) : generate_logz(ctx, V; β, kw...)
+end
+function logz_updateV(ctrl::ControlProblem, V; β = 1.0, kw...)
+    ctx = context_for(ctrl)
+    on_table(ctx) ? table_logz_updateV(ctx, ctx.states, V; β, kw...) : logz_updateV(ctx, V; β, kw...)
+end
+function generate_z(ctrl::ControlProblem, V; β = 1.0, kw...)
+    ctx = context_for(ctrl)
+    on_table(ctx) && error("generate_z: the linear-space cross-check exists for gridworld problems only")
+    generate_z(ctx, V; β, kw...)
+end
+function z_updateV(ctrl::ControlProblem, V; β = 1.0, kw...)
+    ctx = context_for(ctrl)
+    on_table(ctx) && error("z_updateV: the linear-space cross-check exists for gridworld problems only")
+    z_updateV(ctx, V; β, kw...)
+end
+function generate_optimality_gap(ctrl::ControlProblem, V; ν = generate_ν(ctrl), kw...)
+    ctx = context_for(ctrl)
+    on_table(ctx) ? table_solve(ctx, ctx.states, 2; V, ν, kw...) : generate_optimality_gap(ctx, V; ν, kw...)
+end
+# new entry points of the hot path with the same calling convention
+mc_logz(ctrl::ControlProblem, V; kw...) = mc_logz(context_for(ctrl), V; kw...)
+mc_logz_updateV(ctrl::ControlProblem, V; kw...) = mc_logz_updateV(context_for(ctrl), V; kw...)
+path_estimates(ctrl::ControlProblem, V; kw...) = path_estimates(context_for(ctrl), V; kw...)
+
+# run_experiment(gw; ...) exactly as scripts/experiments.jl:20-39 spells it, batched on the device
+run_experiment(gw; kw...) = run_experiment(get!(() -> Context(DEVICE[]), CONTEXTS, DEVICE[]), gw; kw...)
+
 # ---- Monte-Carlo estimate of generate_logz's fixed point (replaces src/path_functions.jl:12-41) ----
 function mc_logz(ctx::Context, V; β = 1.0, npaths = 2^20, seed = 0, estimator = 0, horizon = 2^20,
                  starts::Vector{CartesianIndex{2}} = CartesianIndex{2}[])
@@ -217,6 +299,7 @@ end
 function run_experiment(ctx::Context, gw; randomness = 0.01, γ = 0.99, starting_temp = 0.1, βrange = exp.(range(-6, 0, 8)), n = 5, kw...)
     gwctrl = gridworld_ctrl(gw; randomness, γ)
     load!(ctx, gwctrl, gw; randomness)
+    ctx.key = nothing; ctx.states = nothing      # loaded outside the registry: the next context_for reloads
     ν = generate_ν(ctx; kw...)
     (_, furthest) = findmin(ν.dict)
     V_lo = generate_ν(ctx; reward_scale = starting_temp, kw...)        # modify(gwctrl, reward_function = starting_temp * ...)

@@ -10,9 +10,10 @@ The directory name carries a dot, so import it through the `piql_jl_b200` shim a
 
 Layout: csrc/ (CUDA kernels + the C ABI of include/piql_b200.h), lib/ (the built shared library),
 _capi.py (ctypes binding), engine.py (one context per GPU), gridworld.py and solvers.py (the
-host-side mirror of the reference interface), build.py.
+host-side mirror of the reference interface), jld2.py (writer of the reference's result files), build.py.
 """
 from . import _capi
+from . import jld2
 from ._capi import PiqlError
 from .engine import Engine
 from .gridworld import (ControlProblem, Gridworld, gridworld_ctrl, make_gridworld, make_walls, modify,

@@ -55,9 +55,6 @@ struct piql_ctx {
 
   // Monte-Carlo
   float4* d_table = nullptr;
-#if PIQL_ROLL_TILED
-  float4* d_table_tiled = nullptr;  // the same records in 8 x 8 blocks of cells, for the production rollout kernel (large grids)
-#endif
   bool has_table = false;
   double v_goal = 0.0;
   uint2* d_rec = nullptr;        // per-path records of the last rollout launch {log-weight bits, a0 | len << 2}
@@ -65,6 +62,7 @@ struct piql_ctx {
   float* d_logw = nullptr;       // split copies: the table path's records; de-interleaved d_rec for piql_mc_records
   uint32_t* d_meta = nullptr;
   long long split_cap = 0;
+  bool records_split = false;    // the last rollout was the table sampler's: d_logw / d_meta already hold its records
   int* d_starts = nullptr;       // current slot list (points at d_free or d_starts_own)
   int* d_starts_own = nullptr;
   long long starts_own_cap = 0;
@@ -226,7 +224,8 @@ int vi_prepare(piql_ctx* ctx, int kind, const double* V, const double* Q, const 
   const double x_default = kind == KIND_Z ? 1.0 : 0.0;  // Growable default x -> 0.0 (x -> 1.0 for Z)  value_iteration.jl:44,79,109,146
   launch_fill(vs.x[0], x_default, n, precision, st);
   launch_fill(vs.x[1], x_default, n, precision, st);
-  launch_prep(ctx->g, ctx->d_cell, vs, dQ, ctx->d_nu, st);
+  // per-cell constants from the Float64 uploads (d_in0 = V, d_in4 = Q, d_in1 = nu), rounded once to the sweep precision
+  launch_prep(ctx->g, ctx->d_cell, vs, ctx->d_in0, dQ ? ctx->d_in4 : nullptr, ctx->d_in1, st);
   CK_LAST();
   ctx->vs_ready = true;
   ctx->vi_sweeps_done = 0;
@@ -284,6 +283,8 @@ int vi_solve(piql_ctx* ctx, const piql_solve_opts* opts, double* out, piql_solve
     tile_unpack(ctx->g, vs, ctx->tb, st);
     CK_LAST();
     CK(cudaStreamSynchronize(st));
+    NEED(!(ctx->tb.err && *ctx->tb.err == 4), PIQL_ERR_UNSUPPORTED,
+         "PIQL_F32_FAST log Z sweeps work on Z = exp(log Z), which left the float range (|log Z| beyond ~87): use PIQL_F32 or PIQL_F64");
     NEED(!(ctx->tb.err && *ctx->tb.err), PIQL_ERR_CUDA, "the persistent sweep kernel timed out waiting for a neighbouring tile");
   }
   CK(cudaEventRecord(ctx->ev1, st));
@@ -373,10 +374,6 @@ int mc_reset(piql_ctx* ctx, const piql_mc_opts* o) {
 RolloutArgs make_rollout_args(piql_ctx* ctx, const piql_mc_opts* o) {
   RolloutArgs a{};
   a.table = ctx->d_table;
-#if PIQL_ROLL_TILED
-  a.table_tiled = ctx->d_table_tiled;
-  a.W = ctx->g.W;
-#endif
   a.table_bytes = 32LL * ctx->g.n;
   a.goal = ctx->g.goal; a.H = ctx->g.H;
   a.gamma = ctx->g.gamma; a.rho = ctx->g.randomness; a.vgoal = (float)ctx->v_goal;
@@ -399,6 +396,7 @@ int mc_rollout(piql_ctx* ctx, const piql_mc_opts* o, int* trace_dev, long long t
   cudaStream_t st = ctx->stream;
   const long long chunk = o->npaths < MAX_RECORDS_PER_LAUNCH ? o->npaths : MAX_RECORDS_PER_LAUNCH;
   CK(grow(ctx->d_rec, ctx->rec_cap, chunk));
+  ctx->records_split = false;
   const size_t sf = reduce_scratch_floats(chunk, ctx->nstarts);
   CK(grow(ctx->d_scratch, ctx->scratch_cap, sf ? sf : 1));
   const float* inj_dev = nullptr;
@@ -503,9 +501,6 @@ int build_table(piql_ctx* ctx, const double* V, const double* Q, double beta, fl
   CK(cudaMemcpyAsync(ctx->d_in0, V, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
   if (Q) CK(cudaMemcpyAsync(ctx->d_in4, Q, 32 * (size_t)n, cudaMemcpyHostToDevice, st));
   launch_policy_table(ctx->g, ctx->d_cell, ctx->d_in0, Q ? ctx->d_in4 : nullptr, beta, 1.0, ctx->d_table, st, kl_dev);
-#if PIQL_ROLL_TILED
-  if (ctx->d_table_tiled) launch_table_tile(ctx->d_table, ctx->d_table_tiled, ctx->g.H, ctx->g.W, st);
-#endif
   CK_LAST();
   ctx->v_goal = vg;
   ctx->has_table = true;
@@ -576,9 +571,6 @@ int32_t piql_destroy(piql_ctx* ctx) {
                   (void*)ctx->acc_cnt, (void*)ctx->d_scratch, (void*)ctx->d_transitions, (void*)ctx->d_inj,
                   (void*)ctx->d_scalars})
     if (p) cudaFree(p);
-#if PIQL_ROLL_TILED
-  if (ctx->d_table_tiled) cudaFree(ctx->d_table_tiled);
-#endif
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
   if (ctx->h_transitions) cudaFreeHost(ctx->h_transitions);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -635,12 +627,6 @@ int32_t piql_grid_load(piql_ctx* ctx, const uint8_t* walls, int64_t H, int64_t W
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_cell, (size_t)n);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_free, sizeof(int) * (size_t)(nfree ? nfree : 1));
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_table, 32 * (size_t)n);
-#if PIQL_ROLL_TILED
-  if (ctx->d_table_tiled) cudaFree(ctx->d_table_tiled);
-  ctx->d_table_tiled = nullptr;
-  if (e == cudaSuccess && n >= ROLL_TILED_MIN_CELLS && H < 65536 && W < 65536 && getenv("PIQL_ROLL_NO_TILED") == nullptr)
-    e = cudaMalloc((void**)&ctx->d_table_tiled, 32 * (size_t)roll_tiled_records((int)H, (int)W));
-#endif
   if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_walls, walls, (size_t)n, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_free, h_free, sizeof(int) * (size_t)nfree, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) {
@@ -983,6 +969,7 @@ int32_t piql_table_mc_logz(piql_ctx* ctx, const double* V, double beta, const pi
   {
     int rc2 = ensure_split(ctx, o->npaths ? o->npaths : 1);
     if (rc2) return rc2;
+    ctx->records_split = true;
   }
   std::vector<void*> tmp;
   auto dev = [&](size_t bytes, void** p) -> cudaError_t {
@@ -1089,7 +1076,7 @@ int32_t piql_vi_tile_plan(piql_ctx* ctx, int32_t kind, int32_t precision, int32_
     persistent = ctx->tb.persistent;
   }
   plan_out[0] = pl.TJ; plan_out[1] = pl.nw; plan_out[2] = pl.tiles_i; plan_out[3] = pl.tiles_j;
-  plan_out[4] = pl.ctas_per_sm; plan_out[5] = (int32_t)pl.smem; plan_out[6] = TILE_KH; plan_out[7] = persistent ? 1 : 0;
+  plan_out[4] = pl.ctas_per_sm; plan_out[5] = (int32_t)pl.smem; plan_out[6] = pl.kh; plan_out[7] = (persistent ? 1 : 0) | (pl.planes << 1);
   return PIQL_OK;
 }
 int32_t piql_vi_set_iterate(piql_ctx* ctx, const double* x) {
@@ -1141,6 +1128,8 @@ int32_t piql_vi_fetch(piql_ctx* ctx, double* x_out, double* residual_out) {
   }
   CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  NEED(!(ctx->tb.err && *ctx->tb.err == 4), PIQL_ERR_UNSUPPORTED,
+       "PIQL_F32_FAST log Z sweeps work on Z = exp(log Z), which left the float range (|log Z| beyond ~87): use PIQL_F32 or PIQL_F64");
   NEED(!(ctx->tb.err && *ctx->tb.err), PIQL_ERR_CUDA, "a soft-VI kernel timed out waiting for a neighbouring tile or rank");
   if (residual_out) *residual_out = ctx->h_scalars[0];
   return PIQL_OK;
@@ -1229,9 +1218,6 @@ int32_t piql_policy_table_set(piql_ctx* ctx, const float* table, double v_goal) 
   NEED(table != nullptr, PIQL_ERR_ARG, "table is null");
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(ctx->d_table, table, 32 * (size_t)ctx->g.n, cudaMemcpyHostToDevice, ctx->stream));
-#if PIQL_ROLL_TILED
-  if (ctx->d_table_tiled) launch_table_tile(ctx->d_table, ctx->d_table_tiled, ctx->g.H, ctx->g.W, ctx->stream);
-#endif
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->v_goal = v_goal;
   ctx->has_table = true;
@@ -1285,9 +1271,6 @@ int32_t piql_mc_update_v(piql_ctx* ctx, const double* V, double beta, const piql
     CK(cudaStreamSynchronize(st));
     ctx->v_goal = ctx->h_scalars[4];
     launch_policy_table(ctx->g, ctx->d_cell, ctx->d_in1, nullptr, beta, 1.0, ctx->d_table, st);
-#if PIQL_ROLL_TILED
-    if (ctx->d_table_tiled) launch_table_tile(ctx->d_table, ctx->d_table_tiled, ctx->g.H, ctx->g.W, st);
-#endif
     ctx->has_table = true;
     rc = mc_reset(ctx, &o);
     if (rc) return rc;
@@ -1544,15 +1527,16 @@ int32_t piql_mc_transitions_total(piql_ctx* ctx, uint64_t* total_out) {
 }
 int32_t piql_mc_records(piql_ctx* ctx, float* logw_out, uint32_t* meta_out, int64_t n) {
   if (!ctx) return PIQL_ERR_ARG;
-  NEED(n >= 0 && n <= ctx->rec_cap, PIQL_ERR_ARG, "more records requested than the last rollout produced");
+  NEED(n >= 0 && n <= (ctx->records_split ? ctx->split_cap : ctx->rec_cap), PIQL_ERR_ARG,
+       "more records requested than the last rollout produced");
   CK(cudaSetDevice(ctx->device));
   LaunchScope ls(ctx);
-  {
+  if (!ctx->records_split) {  // the grid sampler keeps {log-weight, meta} interleaved: split them for the host
     int rc = ensure_split(ctx, n ? n : 1);
     if (rc) return rc;
+    launch_split_records(ctx->d_rec, n, ctx->d_logw, ctx->d_meta, ctx->stream);
+    CK_LAST();
   }
-  launch_split_records(ctx->d_rec, n, ctx->d_logw, ctx->d_meta, ctx->stream);
-  CK_LAST();
   if (logw_out) CK(cudaMemcpyAsync(logw_out, ctx->d_logw, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   if (meta_out) CK(cudaMemcpyAsync(meta_out, ctx->d_meta, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

@@ -304,10 +304,14 @@ void launch_resident_batch(const GridDev& g, const uint8_t* cell, int kind, int 
 }
 
 // Per-cell constants of the logz / gap sweeps.
-template <typename T, int KIND>
+// Always evaluated in double from the caller's Float64 V / Q / nu and rounded ONCE to the sweep precision: the constants are
+// per-cell inputs of every sweep, so a rounding pattern shared by all cells (fp32 log 1/4, fp32 gamma ...) would act as a
+// bias the recursion amplifies by 1/(1-gamma) -- measured 2e-5 relative on log Z at beta = 0.2 with fp32 constants.
+template <typename TO, int KIND>
 __global__ void __launch_bounds__(SWEEP_THREADS)
-prep_kernel(K<T> k, const uint8_t* __restrict__ cell, const T* __restrict__ V, const T* __restrict__ Q,
-            const T* __restrict__ nu, T* __restrict__ aux4, T* __restrict__ aux1) {
+prep_kernel(K<double> k, const uint8_t* __restrict__ cell, const double* __restrict__ V, const double* __restrict__ Q,
+            const double* __restrict__ nu, TO* __restrict__ aux4o, TO* __restrict__ aux1o) {
+  typedef double T;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= k.n) return;
   const unsigned ci = cell[s];
@@ -347,8 +351,11 @@ prep_kernel(K<T> k, const uint8_t* __restrict__ cell, const T* __restrict__ V, c
       }
     }
   }
-  store4(aux4, s, out4);
-  aux1[s] = out1;
+  TO o4[NA];
+#pragma unroll
+  for (int a = 0; a < NA; a++) o4[a] = (TO)out4[a];
+  store4(aux4o, s, o4);
+  aux1o[s] = (TO)out1;
 }
 
 template <typename T>
@@ -406,21 +413,24 @@ void launch_update_v(const double* V, const void* logz, const uint8_t* cell, dou
 }
 
 template <typename T>
-static void prep_t(const GridDev& g, const uint8_t* cell, ViState& vs, const void* Q, const void* nu, cudaStream_t st) {
-  const K<T> k = make_k<T>(g, vs.reward_scale, vs.beta);
+static void prep_t(const GridDev& g, const uint8_t* cell, ViState& vs, const double* V, const double* Q, const double* nu,
+                   cudaStream_t st) {
+  const K<double> k = make_k<double>(g, vs.reward_scale, vs.beta);
   const int nb = nblk(g.n, SWEEP_THREADS);
   if (vs.kind == KIND_LOGZ)
-    prep_kernel<T, KIND_LOGZ><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, (const T*)vs.V, (const T*)Q, nullptr, (T*)vs.aux4, (T*)vs.aux1);
+    prep_kernel<T, KIND_LOGZ><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, V, Q, nullptr, (T*)vs.aux4, (T*)vs.aux1);
   else if (vs.kind == KIND_Z)
-    prep_kernel<T, KIND_Z><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, (const T*)vs.V, (const T*)Q, nullptr, (T*)vs.aux4, (T*)vs.aux1);
+    prep_kernel<T, KIND_Z><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, V, Q, nullptr, (T*)vs.aux4, (T*)vs.aux1);
   else
-    prep_kernel<T, KIND_GAP><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, (const T*)vs.V, (const T*)Q, (const T*)nu, (T*)vs.aux4, (T*)vs.aux1);
+    prep_kernel<T, KIND_GAP><<<nb, SWEEP_THREADS, 0, st>>>(k, cell, V, Q, nu, (T*)vs.aux4, (T*)vs.aux1);
   g_launches++;
 }
-void launch_prep(const GridDev& g, const uint8_t* cell, ViState& vs, const void* Q, const void* nu, cudaStream_t st) {
+// V, Q (nullable), nu: the caller's Float64 arrays on the device (NaN at walls is fine: wall cells are never read)
+void launch_prep(const GridDev& g, const uint8_t* cell, ViState& vs, const double* V, const double* Q, const double* nu,
+                 cudaStream_t st) {
   if (vs.kind == KIND_NU) return;
-  if (vs.precision == 0) prep_t<double>(g, cell, vs, Q, nu, st);
-  else prep_t<float>(g, cell, vs, Q, nu, st);
+  if (vs.precision == 0) prep_t<double>(g, cell, vs, V, Q, nu, st);
+  else prep_t<float>(g, cell, vs, V, Q, nu, st);
 }
 
 // terminal cells: nu, gap -> 0; logz -> 0 - V(goal)   value_iteration.jl:66-67,93-94,133-134

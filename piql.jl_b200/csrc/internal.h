@@ -30,12 +30,11 @@ struct ViState {
 };
 
 // tile.cu: temporally blocked sweeps on a padded copy of the iterate ---------------------------
-#ifndef PIQL_TILE_KH
-#define PIQL_TILE_KH 4  // a multiple of 4 (tools/vi_ab.py builds other depths for timing)
-#endif
-constexpr int TILE_KH = PIQL_TILE_KH;  // halo width = Jacobi sweeps per launch
+constexpr int TILE_KH_MAX = 8;  // deepest temporal blocking (sweeps per round = ghost depth of the padded layout): 4 or 8 per plan
 struct TilePlan {
-  int TJ, EJ;            // interior / staged columns per tile (EJ = TJ + 2*TILE_KH); rows are 120 / 128
+  int TJ, EJ;            // interior / staged columns per tile (EJ = TJ + 2*kh); rows are 128 - 2*kh / 128
+  int kh;                // Jacobi sweeps per round = halo width = ghost frame of the padded layout (4 or 8)
+  int planes;            // constant planes staged in shared memory per round (fast fp32 log Z: 4, gap: 5), 0: read from global
   int tiles_i, tiles_j;
   int nw;                // warps per CTA
   int ld, Wp;            // padded leading dimension and column count
@@ -72,6 +71,7 @@ struct TileBuffers {
   // CUtensorMap descriptors (opaque here) of x[0], x[1] and mask: boxes of 128 x EJ elements for the TMA staging
   alignas(64) unsigned char tmx[2][128] = {};
   alignas(64) unsigned char tmm[128] = {};
+  alignas(64) unsigned char tmp[128] = {};  // 3-D map over the constant planes (fast fp32 log Z / gap: planes staged per round)
   bool use_tma = false;
   // persistent variant (all tiles resident at once): one cooperative launch per batch of sweeps
   bool persistent = false;
@@ -109,7 +109,8 @@ void launch_convert_in(const double* src, void* dst, int n, int precision, cudaS
 void launch_convert_out(const void* src, const uint8_t* cell, double* dst, int n, int precision, cudaStream_t st);
 void launch_fill(void* dst, double value, int n, int precision, cudaStream_t st);
 // Precompute the per-cell constants of the logz / gap sweeps from V (and Q, nu).
-void launch_prep(const GridDev& g, const uint8_t* cell, ViState& vs, const void* Q, const void* nu, cudaStream_t st);
+void launch_prep(const GridDev& g, const uint8_t* cell, ViState& vs, const double* V, const double* Q, const double* nu,
+                 cudaStream_t st);
 // One Jacobi sweep x[cur] -> x[cur^1]; with_residual: also per-block partials + final sum.
 void launch_sweep(const GridDev& g, const uint8_t* cell, ViState& vs, bool with_residual, cudaStream_t st);
 // Whole solve in one CTA (n <= RESIDENT_MAX_CELLS): returns through dev_out {sweeps, residual}.
@@ -128,19 +129,6 @@ int configure_backup_kernels();
 void launch_residual_final(const double* partial, int nblocks, double* out, cudaStream_t st);
 
 // rollout.cu --------------------------------------------------------------------------------
-// PIQL_ROLL_TILED (build-time experiment, default off): the production rollout kernel reads a second copy of the policy
-// records laid out in 8 x 8 blocks of cells (2 KB per block) instead of whole columns.  On grids whose table does not fit
-// L2 a step to the left or right then stays within a DRAM page or two instead of jumping H * 32 bytes (131 KB at 4098^2),
-// where the kernel is bound by random 32-byte reads (DRAM 3.0 of 6.5 TB/s, load latency 1.6 us under load).  The
-// cell-order table stays the ABI's and every other kernel's.
-#ifndef PIQL_ROLL_TILED
-#define PIQL_ROLL_TILED 0
-#endif
-#if PIQL_ROLL_TILED
-constexpr long long ROLL_TILED_MIN_CELLS = 4LL << 20;  // below that the table lives in L2 and the extra address arithmetic only costs
-inline long long roll_tiled_records(int H, int W) { return 64LL * ((H + 7) / 8) * ((W + 7) / 8); }
-void launch_table_tile(const float4* table, float4* tiled, int H, int W, cudaStream_t st);
-#endif
 struct RolloutArgs {
   const float4* table;   // 2 x float4 per cell
   long long table_bytes; // 32 * cells
@@ -160,10 +148,6 @@ struct RolloutArgs {
   uint2* rec;            // [npaths] per-path records {log-weight bits, a0 | len << 2}: one 8-byte store per finished path
   int* trace;            // optional [npaths][trace_steps][3]
   long long trace_steps;
-#if PIQL_ROLL_TILED
-  const float4* table_tiled;  // nullptr: cell order only
-  int W;
-#endif
 };
 // kl_out (optional): kl_cost(ctrl, s, Q) per cell, path_functions.jl:17-20
 void launch_policy_table(const GridDev& g, const uint8_t* cell, const double* V, const double* Q, double beta,

@@ -161,32 +161,11 @@ constexpr int ROLL_THREADS = 256;
 // by one bulk asynchronous copy per CTA and every step reads its record with two LDS.128 instead of a global load.
 constexpr size_t ROLL_STAGE_MAX_BYTES = 24 * 1024;  // x 8 resident CTAs per SM
 
-#if PIQL_ROLL_TILED
-// cell-order records -> 8 x 8 blocks: record (i, j) at ((j / 8) * ceil(H / 8) + i / 8) * 64 + (j % 8) * 8 + i % 8
-__device__ __forceinline__ uint32_t tiled_record(uint32_t i, uint32_t j, uint32_t Hb) {
-  return (((j >> 3) * Hb + (i >> 3)) << 6) | ((j & 7u) << 3) | (i & 7u);
-}
-__global__ void __launch_bounds__(256) table_tile_kernel(const float4* __restrict__ table, float4* __restrict__ tiled, int H, int W) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= H * W) return;
-  const uint32_t r = tiled_record((uint32_t)(s % H), (uint32_t)(s / H), (uint32_t)((H + 7) >> 3));
-  tiled[2 * (size_t)r] = table[2 * (size_t)s];
-  tiled[2 * (size_t)r + 1] = table[2 * (size_t)s + 1];
-}
-void launch_table_tile(const float4* table, float4* tiled, int H, int W, cudaStream_t st) {
-  table_tile_kernel<<<(unsigned)(((long long)H * W + 255) / 256), 256, 0, st>>>(table, tiled, H, W);
-  g_launches++;
-}
-#define ROLL_TPARAM , bool TILED
-#define ROLL_TARG(x) , x
-#else
-#define ROLL_TPARAM
-#define ROLL_TARG(x)
-#endif
 
-// (TILED, PIQL_ROLL_TILED builds only: the state is the key i | j << 16 instead of the cell index, a move adds 1 or 65536,
-// and the record address is computed from the key.)
-template <int EST, bool INJ, bool TRACE, bool STAGED ROLL_TPARAM>
+// Tried and dropped (measured on B200, profiles/r2_roll_tiled_check.txt): a second copy of the records in 8 x 8 blocks of
+// cells so that a horizontal step stays within a DRAM page -- bit-identical records, 12 % slower at 4098^2 (1.51e11 against
+// 1.71e11 transitions/s): the extra address arithmetic costs issue slots and the sector traffic does not change.
+template <int EST, bool INJ, bool TRACE, bool STAGED>
 __global__ void __launch_bounds__(ROLL_THREADS)
 rollout_kernel(const RolloutArgs p) {
   extern __shared__ __align__(128) unsigned char roll_smem[];
@@ -216,12 +195,7 @@ rollout_kernel(const RolloutArgs p) {
   uint32_t slot_next = (uint32_t)(gbase % (unsigned long long)p.nstarts);
   uint32_t next = 0;  // paths of this warp handed out so far
   const uint32_t hor = (uint32_t)min(INJ ? min(p.horizon, p.injected_steps) : p.horizon, 0xffffffffLL);
-#if PIQL_ROLL_TILED
-  const int H = TILED ? 65536 : p.H, goal = TILED ? (p.goal % p.H) | ((p.goal / p.H) << 16) : p.goal;
-  const uint32_t Hb = (uint32_t)(p.H + 7) >> 3;
-#else
   const int H = p.H, goal = p.goal;
-#endif
   const double gam = p.gamma, rho = p.rho;  // injected uniforms only (the Philox path tests the 24-bit integers)
 
   bool active = false;
@@ -243,9 +217,6 @@ rollout_kernel(const RolloutArgs p) {
         if (nstarts >= 32u) { if (slot >= nstarts) slot -= nstarts; }
         else slot %= nstarts;
         s = __ldg(p.starts + slot);
-#if PIQL_ROLL_TILED
-        if (TILED) s = (s % p.H) | ((s / p.H) << 16);
-#endif
         t = 0; a0 = 0; logw = 0.f; acc = -CUDART_INF_F;
         active = true;
       }
@@ -278,12 +249,7 @@ rollout_kernel(const RolloutArgs p) {
           r0 = stab[2 * s];
           r1 = stab[2 * s + 1];
         } else {
-#if PIQL_ROLL_TILED
-          const float4* rec = TILED ? p.table_tiled + 2 * (size_t)tiled_record((uint32_t)s & 0xffffu, (uint32_t)s >> 16, Hb)
-                                    : p.table + 2 * (size_t)s;
-#else
           const float4* rec = p.table + 2 * (size_t)s;
-#endif
           asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                        : "=f"(r0.x), "=f"(r0.y), "=f"(r0.z), "=f"(r0.w), "=f"(r1.x), "=f"(r1.y), "=f"(r1.z), "=f"(r1.w)
                        : "l"(rec));
@@ -353,17 +319,12 @@ void launch_rollout(const RolloutArgs& a, int num_sms, cudaStream_t st) {
   long long cap = (long long)num_sms * 8;
   const int grid = (int)(want < cap ? want : cap);
   const bool inj = a.injected != nullptr, tr = a.trace != nullptr;
-#define PIQL_ROLL(E, I, T) rollout_kernel<E, I, T, false ROLL_TARG(false)><<<grid, ROLL_THREADS, 0, st>>>(a)
+#define PIQL_ROLL(E, I, T) rollout_kernel<E, I, T, false><<<grid, ROLL_THREADS, 0, st>>>(a)
   static const bool no_stage = getenv("PIQL_ROLL_NO_STAGE") != nullptr;  // A/B timing only
   if (!no_stage && !inj && !tr && a.table_bytes > 0 && a.table_bytes <= (long long)ROLL_STAGE_MAX_BYTES) {
     // reference-scale tables: staged in shared memory
-    if (a.estimator == 0) rollout_kernel<0, false, false, true ROLL_TARG(false)><<<grid, ROLL_THREADS, (size_t)a.table_bytes, st>>>(a);
-    else rollout_kernel<1, false, false, true ROLL_TARG(false)><<<grid, ROLL_THREADS, (size_t)a.table_bytes, st>>>(a);
-#if PIQL_ROLL_TILED
-  } else if (a.table_tiled && !inj && !tr) {
-    if (a.estimator == 0) rollout_kernel<0, false, false, false, true><<<grid, ROLL_THREADS, 0, st>>>(a);
-    else rollout_kernel<1, false, false, false, true><<<grid, ROLL_THREADS, 0, st>>>(a);
-#endif
+    if (a.estimator == 0) rollout_kernel<0, false, false, true><<<grid, ROLL_THREADS, (size_t)a.table_bytes, st>>>(a);
+    else rollout_kernel<1, false, false, true><<<grid, ROLL_THREADS, (size_t)a.table_bytes, st>>>(a);
   } else if (a.estimator == 0) {
     if (inj) { if (tr) PIQL_ROLL(0, true, true); else PIQL_ROLL(0, true, false); }
     else { if (tr) PIQL_ROLL(0, false, true); else PIQL_ROLL(0, false, false); }

@@ -36,9 +36,7 @@ namespace piql {
 #define PIQL_TILE_UNROLL 1  // columns of a sub-sweep a warp interleaves; measured on B200: 1 beats 2, 3 and 4 by 3-6 % on every kind and precision
 #endif
 constexpr int TILE_UNROLL = PIQL_TILE_UNROLL;
-constexpr int TKH = TILE_KH;
 constexpr int TEI = 128;            // rows of the shared-memory tile: 32 lanes x 4-cell strips
-constexpr int TTI = TEI - 2 * TKH;  // interior rows per tile
 // Cell bytes of a staged column: 128 + 16.  A TMA box must start on a 16-byte boundary and a tile starts at byte
 // 120*ti of the byte array, so the box starts up to 8 bytes early and the kernel indexes past that offset.
 constexpr int TMB = TEI + 16;       // bytes
@@ -48,6 +46,7 @@ constexpr int TMP = TMB / 4;        // 32-bit words
 template <typename T> struct TileK {
   int ld, np;          // leading dimension and size of the padded arrays
   int TJ, EJ, tiles_i;
+  int kh, tti;         // sweeps per round = ghost depth (4 or 8); interior rows per tile = 128 - 2 * kh
   int tj0;             // first tile column of this launch (multi-GPU column slabs; 0 otherwise)
   int goal_pi, goal_pj, goal_p;  // goal in padded coordinates
   T kc, a1, b1, a2;    // nu: x_a = kc + a1*n_a + b1*S;  a2 = a1*log2(e)
@@ -107,6 +106,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
                ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
 // ---- per-cell backups on the four (already wall-resolved) neighbour values ----------------------------
 // nu: logsumexp_a[log 1/4 + gamma*pa(s,a,nu) + rbar] with pa = w_off*S + dw*n_a and rbar = -step_cost away
 // from the goal, i.e. kc + b1*S + a1*max + log sum_a exp(a1*(n_a - max)).
@@ -151,6 +155,13 @@ __device__ __forceinline__ float2 nu_cell_fast2(const TileK<float>& k, float2 n0
   const float2 hi = __ffma2_rn(f2(0.693147180559945f), lg2_2(sum), __ffma2_rn(f2(k.b1), S, __ffma2_rn(f2(k.a1), m, f2(k.kc))));
   return __fadd2_rn(hi, __ffma2_rn(f2(k.a1_lo), m, f2(k.kc_lo)));
 }
+
+constexpr int TILE_ERR_RANGE = 4;  // *err: a fast fp32 linear-domain sweep left the float range
+// Tried and dropped (measured on B200, profiles/r2_vi_experiments.txt): nu in the exponent domain -- E = e^(a1 nu) kept beside nu
+// in shared memory so that a sweep needs 2 MUFU per cell (lg2 of sum_a E(n_a), ex2 of the new value) instead of 4 and no
+// maximum network.  Same instruction count (the 32 wall selects of a strip double), twice the shared memory per tile, and
+// the exponentials lose the accuracy that arguments near zero give the maximum-shifted form: 3.74 against 3.23 us per sweep
+// at 1026^2, 37.4 against 26.2 at 4098^2, and a uniform 1.4e-5 relative bias of the fixed point (the shifted form: 3e-6).
 
 // eta = 1/2 damping of update_logz!: logaddexp(log(1/2) + new, log(1/2) + old)   value_iteration.jl:101-102
 template <typename T, bool FAST> __device__ __forceinline__ T damp_half(T nw, T c) {
@@ -208,6 +219,38 @@ __device__ __forceinline__ float logz_cell_fast_own(const TileK<float>& k, float
   const float sum = (EA0 * fmaf(gd, u0, base) + EA1 * fmaf(gd, u1, base)) + (EA2 * fmaf(gd, u2, base) + EA3 * fmaf(gd, u3, base));
   return fmaf(0.693147180559945f, lg2_approx(fmaf(0.5f, sum, 0.5f)), c);
 }
+// ---- fast fp32 log Z in the linear domain ----------------------------------------------------------------------------
+// With Z = e^(logZ) the recursion is linear, Z_new = sum_a e^(A_a) (gamma sum_a' P(a'|a) Z(n_a') + 1 - gamma), and so is the
+// reference's eta = 1/2 damping: log(1/2 e^new + 1/2 e^old) is the log of 1/2 Z_new + 1/2 Z_old (value_iteration.jl:101-102).
+// Exchanging the two sums, sum_a e^(A_a) sum_a' P(a'|a) Z(n_a') = sum_a' M_a' Z(n_a') with M_a' = w_off sum_a e^(A_a) + dw e^(A_a'),
+//     Z_stored = 1/2 Z + sum_a' G_a' Z(n_a') + C,      G_a' = 1/2 gamma M_a',   C = 1/2 (1 - gamma) sum_a e^(A_a):
+// five FMAs per cell on four constant planes (C follows from them), NO transcendental at all in a sweep (the log-domain forms need 6-7 MUFU per
+// cell on the pipe that bounds them) and no scalar constants whose fp32 rounding would act as a 1/(1-gamma)-amplified
+// bias: the planes are computed in double and rounded once per cell.  All terms are positive, so nothing cancels.  The
+// padded iterate holds Z for the whole solve (packing exponentiates, unpacking takes the log, the stop rule compares logs);
+// the values do not depend on the tiling or the GPU count.  Range: e^(logZ) must stay a normal float, |logZ| < ~87, checked
+// at the write-back (TILE_ERR_RANGE; PIQL_F32 / PIQL_F64 keep the log-domain form).
+#ifndef PIQL_LOGZ_ZDOM
+#define PIQL_LOGZ_ZDOM 1
+#endif
+template <typename T, int KIND, bool FAST> constexpr bool kZDom = PIQL_LOGZ_ZDOM && KIND == KIND_LOGZ && FAST && sizeof(T) == 4;
+// The two linear fast fp32 sweeps (log Z in the linear domain, gap) are FMA chains on per-cell constant planes; read from
+// global memory in every sub-sweep the planes make them L2-bandwidth bound (4-5 planes x 4 B per cell and sweep, ~10 TB/s
+// L2 -> SM at 4098^2).  So the planes of a tile are staged in shared memory beside the iterate, once per round (TMA, one 3-D
+// box per plane; once per launch in the persistent kernel): global traffic per cell and round falls from 4 x 16..20 B to
+// 16..20 B.  log Z needs only its four G planes: sum_a' G_a' = 1/2 gamma sum_a e^(A_a), so C = (1 - gamma) / gamma * sum_a' G_a'.
+#ifndef PIQL_TILE_PLANES
+#define PIQL_TILE_PLANES 1
+#endif
+template <typename T, int KIND, bool FAST, bool PL>  // PL: the plan stages the planes (TilePlan::planes > 0)
+constexpr int kPlanes = !(PL && PIQL_TILE_PLANES && FAST && sizeof(T) == 4) ? 0 : kZDom<T, KIND, FAST> ? 4 : KIND == KIND_GAP ? 5 : 0;
+__device__ __forceinline__ float2 logz_cell_lin2(float2 c, float2 z0, float2 z1, float2 z2, float2 z3, float2 G0, float2 G1,
+                                                 float2 G2, float2 G3, float kappa) {
+  // C = kappa * (G0 + G1 + G2 + G3), kappa = (1 - gamma) / gamma (C is ~1 % of the result: kappa's rounding is harmless)
+  const float2 C = __fmul2_rn(f2(kappa), __fadd2_rn(__fadd2_rn(G0, G1), __fadd2_rn(G2, G3)));
+  return __ffma2_rn(G0, z0, __ffma2_rn(G1, z1, __ffma2_rn(G2, z2, __ffma2_rn(G3, z3, __ffma2_rn(f2(0.5f), c, C)))));
+}
+
 // gap: D + sum_a pi_a * pa(s,a,gap), no discount on the gap term   value_iteration.jl:165
 template <typename T>
 __device__ __forceinline__ T gap_cell(const TileK<T>& k, T n0, T n1, T n2, T n3, T p0, T p1, T p2, T p3, T D) {
@@ -217,6 +260,11 @@ __device__ __forceinline__ T gap_cell(const TileK<T>& k, T n0, T n1, T n2, T n3,
 
 // |new - old| of the reference's stop rule from the two last iterates.  logz stores the damped value:
 // stored = log(1/2 e^new + 1/2 e^old)  =>  new - old = log(2 e^(stored-old) - 1).
+// ... and in the linear domain: Z_stored = 1/2 Z_new + 1/2 Z_old  =>  new - old = log((2 Z_stored - Z_old) / Z_old).
+__device__ __forceinline__ double sweep_diff_z(double stored, double old) {
+  const double r = (2.0 * stored - old) / old;
+  return r > 0.0 ? fabs(log(r)) : CUDART_INF;
+}
 template <int KIND> __device__ __forceinline__ double sweep_diff(double stored, double old) {
   const double d = stored - old;
   if (KIND != KIND_LOGZ) return fabs(d);
@@ -226,7 +274,7 @@ template <int KIND> __device__ __forceinline__ double sweep_diff(double stored, 
 
 // One column of one Jacobi sweep of the staged tile: lane l recomputes rows 4l .. 4l+3 of column jj from src into dst,
 // every cell by the generic formula (the goal and its neighbours are redone by tile_goal_fixup).
-template <typename T, int KIND, bool FAST>
+template <typename T, int KIND, bool FAST, bool PL>
 __device__ __forceinline__ void tile_strip(const TileK<T>& k, const T* __restrict__ src, T* __restrict__ dst,
                                            const uint32_t* __restrict__ msk, const T* __restrict__ aux, int org, int lane, int jj) {
   T v[4], L[4], R[4], out[4];
@@ -237,12 +285,35 @@ __device__ __forceinline__ void tile_strip(const TileK<T>& k, const T* __restric
   // rows 0 and 127 have no vertical neighbour in the tile: they are halo, any value will do
   const T up = __shfl_up_sync(FULL, v[3], 1), dn = __shfl_down_sync(FULL, v[0], 1);
   T ax[5][4];
-  if (KIND != KIND_NU) {
+  if constexpr (kPlanes<T, KIND, FAST, PL> > 0) {
+    // the tile's planes sit behind the ping-pong pair in shared memory (aux points at them)
+#pragma unroll
+    for (int pl = 0; pl < kPlanes<T, KIND, FAST, PL>; pl++) lds4(aux + (pl * k.EJ + jj) * TEI + 4 * lane, ax[pl]);
+  } else if (KIND != KIND_NU) {
     const int sidx = org + jj * k.ld + 4 * lane;
 #pragma unroll
-    for (int pl = 0; pl < ((PIQL_LOGZ_OWN_SHIFT && KIND == KIND_LOGZ && FAST) ? 4 : 5); pl++) ldg4(aux + (size_t)pl * k.np + sidx, ax[pl]);
+    for (int pl = 0; pl < ((kZDom<T, KIND, FAST> || (PIQL_LOGZ_OWN_SHIFT && KIND == KIND_LOGZ && FAST)) ? 4 : 5); pl++)
+      ldg4(aux + (size_t)pl * k.np + sidx, ax[pl]);
   }
-  if constexpr (PIQL_TILE_PACKED && KIND == KIND_NU && FAST && sizeof(T) == 4) {
+  if constexpr (kZDom<T, KIND, FAST>) {
+    float nb[4][4];  // [action][row]
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const uint32_t b = mk >> (8 * r);
+      const float c = v[r];
+      nb[0][r] = (b & 1u) ? c : (r < 3 ? v[r < 3 ? r + 1 : 3] : dn);
+      nb[1][r] = (b & 2u) ? c : (r > 0 ? v[r > 0 ? r - 1 : 0] : up);
+      nb[2][r] = (b & 4u) ? c : R[r];
+      nb[3][r] = (b & 8u) ? c : L[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r += 2) {
+      const float2 o = logz_cell_lin2(f2(v[r], v[r + 1]), f2(nb[0][r], nb[0][r + 1]), f2(nb[1][r], nb[1][r + 1]),
+                                      f2(nb[2][r], nb[2][r + 1]), f2(nb[3][r], nb[3][r + 1]), f2(ax[0][r], ax[0][r + 1]),
+                                      f2(ax[1][r], ax[1][r + 1]), f2(ax[2][r], ax[2][r + 1]), f2(ax[3][r], ax[3][r + 1]), k.omg);
+      out[r] = o.x; out[r + 1] = o.y;
+    }
+  } else if constexpr (PIQL_TILE_PACKED && KIND == KIND_NU && FAST && sizeof(T) == 4) {
     // rows (0,1) and (2,3) as packed pairs
     float nb[4][4];  // [action][row]
 #pragma unroll
@@ -285,12 +356,12 @@ __device__ __forceinline__ void tile_strip(const TileK<T>& k, const T* __restric
 // src holds sweep `sub` of the round in columns sub .. EJ-1-sub only (the valid region loses one ring per sweep), so the
 // columns worth computing are 1+sub .. EJ-2-sub: the trapezoid, not the rectangle.  What lies outside keeps older values
 // that no kept cell ever reads.
-template <typename T, int KIND, bool FAST>
+template <typename T, int KIND, bool FAST, bool PL>
 __device__ __forceinline__ void tile_subsweep(const TileK<T>& k, const T* __restrict__ src, T* __restrict__ dst,
                                               const uint32_t* __restrict__ msk, const T* __restrict__ aux, int org, int lane,
                                               int warp, int NW, int sub) {
 #pragma unroll TILE_UNROLL
-  for (int jj = 1 + sub + warp; jj < k.EJ - 1 - sub; jj += NW) tile_strip<T, KIND, FAST>(k, src, dst, msk, aux, org, lane, jj);
+  for (int jj = 1 + sub + warp; jj < k.EJ - 1 - sub; jj += NW) tile_strip<T, KIND, FAST, PL>(k, src, dst, msk, aux, org, lane, jj);
 }
 
 // The goal (terminal value) and, for nu, its four neighbours (a step into the goal earns the reward, so the
@@ -307,7 +378,8 @@ __device__ __noinline__ void tile_goal_fixup(const TileK<T>& k, const T* __restr
   T o;
   if (t == 0) {
     // terminal_condition: nu, gap -> 0; logz -> 0 - V(goal), damped like every other state
-    o = (KIND == KIND_LOGZ) ? damp_half<T, FAST>(k.term, c) : k.term;
+    if constexpr (kZDom<T, KIND, FAST>) o = (T)0.5 * k.term + (T)0.5 * c;  // linear domain: term = e^(-V(goal))
+    else o = (KIND == KIND_LOGZ) ? damp_half<T, FAST>(k.term, c) : k.term;
   } else {
     if (b & CELL_WALL) return;
     // rows 0 / 127 have no vertical neighbour in the tile; they are halo (never kept), any value will do
@@ -322,26 +394,38 @@ __device__ __noinline__ void tile_goal_fixup(const TileK<T>& k, const T* __restr
   dst[j * TEI + i] = o;
 }
 
+// linear-domain log Z: Z at a free cell must be a normal positive float (else the sweep left its range)
+template <typename T> __device__ __forceinline__ bool strip_not_normal(const T (&f)[4], uint32_t mk) {
+  bool bad = false;
+#pragma unroll
+  for (int r = 0; r < 4; r++) bad |= !((mk >> (8 * r)) & CELL_WALL) && !((double)f[r] >= 1.1754944e-38 && (double)f[r] <= 3.0e38);
+  return bad;
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------------
 // grid = tiles_i * tiles_j CTAs of NW warps; dynamic shared memory = EJ * (2 * 128 * sizeof(T) + 144) bytes.
-template <typename T, int KIND, bool FAST>
+template <typename T, int KIND, bool FAST, bool PL>
 __global__ void __launch_bounds__(512, sizeof(T) == 4 ? 2 : 1)
 tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmM,
-                  int use_tma, const uint8_t* __restrict__ maskp, const T* __restrict__ X, T* __restrict__ Y,
-                  const T* __restrict__ aux, int nsub, int want_res, double* __restrict__ partial, const TileHalo halo) {
+                  const __grid_constant__ CUtensorMap tmP, int use_tma, const uint8_t* __restrict__ maskp, const T* __restrict__ X,
+                  T* __restrict__ Y, const T* __restrict__ auxg, int nsub, int want_res, double* __restrict__ partial,
+                  const TileHalo halo) {
   extern __shared__ __align__(128) unsigned char tile_smem[];
   __shared__ double red[32];
   __shared__ __align__(8) unsigned long long mbar;
   const int EJ = k.EJ, ld = k.ld;
+  constexpr int NP = kPlanes<T, KIND, FAST, PL>;
   T* bufA = reinterpret_cast<T*>(tile_smem);
   T* bufB = bufA + EJ * TEI;
-  uint32_t* msk0 = reinterpret_cast<uint32_t*>(bufB + EJ * TEI);
+  T* planes = bufB + EJ * TEI;  // NP constant planes of the tile (fast fp32 log Z / gap)
+  uint32_t* msk0 = reinterpret_cast<uint32_t*>(planes + NP * EJ * TEI);
+  const T* aux = NP > 0 ? planes : auxg;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
   // column slabs put their two edge tile columns first in launch order: their push is what the neighbours wait for
   const int ti = blockIdx.x % k.tiles_i, tc = blockIdx.x / k.tiles_i;
   const int tj = halo.tj_last < 0 ? tc + k.tj0 : tc == 0 ? halo.tj_first : tc == 1 ? halo.tj_last : halo.tj_first + tc - 1;
-  const int org = ti * TTI + ld * (tj * k.TJ);  // padded index of the tile's (row 0, column 0)
-  const int moff = (ti * TTI) & 15;              // bytes the staged cell-byte box starts before row 0 (0 or 8)
+  const int org = ti * k.tti + ld * (tj * k.TJ);  // padded index of the tile's (row 0, column 0)
+  const int moff = (ti * k.tti) & 15;              // bytes the staged cell-byte box starts before row 0 (0 or 8)
   const uint32_t* msk = msk0 + (moff >> 2);
 
   // Programmatic dependent launch: this grid may be scheduled while the previous launch (which wrote X) drains;
@@ -374,9 +458,11 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
     // or a register on the copy, and the whole tile is in flight at once
     if (threadIdx.x == 0) {
       mbar_init(&mbar, 1);
-      mbar_expect_tx(&mbar, (unsigned)(EJ * (TEI * sizeof(T) + TMB)));
-      tma_load_2d(bufA, &tmX, ti * TTI, tj * k.TJ, &mbar);
-      tma_load_2d(msk0, &tmM, ti * TTI - moff, tj * k.TJ, &mbar);  // rows past the array's end are zero-filled
+      mbar_expect_tx(&mbar, (unsigned)(EJ * ((1 + NP) * TEI * sizeof(T) + TMB)));
+      tma_load_2d(bufA, &tmX, ti * k.tti, tj * k.TJ, &mbar);
+      tma_load_2d(msk0, &tmM, ti * k.tti - moff, tj * k.TJ, &mbar);  // rows past the array's end are zero-filled
+#pragma unroll
+      for (int q = 0; q < NP; q++) tma_load_3d(planes + q * EJ * TEI, &tmP, ti * k.tti, tj * k.TJ, q, &mbar);
     }
     __syncthreads();  // the barrier word is initialised before anyone polls it
     mbar_wait(&mbar, 0);
@@ -395,18 +481,23 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
       sts4(bufA + jj * TEI + 4 * lane, v);
       if (jj == 0 || jj == EJ - 1) sts4(bufB + jj * TEI + 4 * lane, v);
       msk0[jj * TMP + (moff >> 2) + lane] = __ldg(reinterpret_cast<const uint32_t*>(maskp + g));
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        ldg4(auxg + (size_t)q * k.np + g, v);
+        sts4(planes + (q * EJ + jj) * TEI + 4 * lane, v);
+      }
     }
   }
   __syncthreads();
 
   // is the goal (or one of its neighbours) inside this tile?  block-uniform
-  const int gi = k.goal_pi - ti * TTI, gj = k.goal_pj - tj * k.TJ;
+  const int gi = k.goal_pi - ti * k.tti, gj = k.goal_pj - tj * k.TJ;
   const bool near_goal = gi >= -1 && gi <= TEI && gj >= -1 && gj <= EJ;
 
   T* src = bufA;
   T* dst = bufB;
   for (int sub = 0; sub < nsub; sub++) {
-    tile_subsweep<T, KIND, FAST>(k, src, dst, msk, aux, org, lane, warp, NW, sub);
+    tile_subsweep<T, KIND, FAST, PL>(k, src, dst, msk, aux, org, lane, warp, NW, sub);
     __syncthreads();
     if (near_goal) {  // block-uniform: the tile(s) around the goal redo those cells after every sweep
       tile_goal_fixup<T, KIND, FAST>(k, src, dst, msk, gi, gj);
@@ -417,10 +508,12 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
 
   // write the interior back (src: last iterate, dst: the one before); residual of the last sweep
   double res = 0.0;
-  if (lane >= TKH / 4 && lane < 32 - TKH / 4) {
-    for (int jj = TKH + warp; jj < TKH + k.TJ; jj += NW) {
+  bool bad = false;
+  if (lane >= k.kh / 4 && lane < 32 - k.kh / 4) {
+    for (int jj = k.kh + warp; jj < k.kh + k.TJ; jj += NW) {
       T f[4];
       lds4(src + jj * TEI + 4 * lane, f);
+      if constexpr (kZDom<T, KIND, FAST>) bad |= strip_not_normal(f, msk[jj * TMP + lane]);
       const int g = org + jj * ld + 4 * lane;
       if (sizeof(T) == 4) {
         *reinterpret_cast<float4*>(Y + g) = make_float4((float)f[0], (float)f[1], (float)f[2], (float)f[3]);
@@ -429,7 +522,7 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
         *reinterpret_cast<double2*>(Y + g + 2) = make_double2((double)f[2], (double)f[3]);
       }
       // the slab's first / last TILE_KH interior columns are the neighbouring rank's halo: peer stores over NVLink
-      T* peer = (edge_l && jj < 2 * TKH) ? static_cast<T*>(halo.out_left)
+      T* peer = (edge_l && jj < 2 * k.kh) ? static_cast<T*>(halo.out_left)
                                          : (edge_r && jj >= k.TJ) ? static_cast<T*>(halo.out_right) : nullptr;
       if (peer) sts4(peer + g, f);
       if (want_res) {
@@ -438,10 +531,12 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
         const uint32_t mk = msk[jj * TMP + lane];
 #pragma unroll
         for (int r = 0; r < 4; r++)
-          if (!((mk >> (8 * r)) & CELL_WALL)) res += sweep_diff<KIND>((double)f[r], (double)p[r]);
+          if (!((mk >> (8 * r)) & CELL_WALL))
+            res += kZDom<T, KIND, FAST> ? sweep_diff_z((double)f[r], (double)p[r]) : sweep_diff<KIND>((double)f[r], (double)p[r]);
       }
     }
   }
+  if (kZDom<T, KIND, FAST> && bad) *halo.err = TILE_ERR_RANGE;
   if (want_res) {  // uniform
     const double s = block_sum(res, red);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
@@ -478,10 +573,11 @@ __device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <typename T, int KIND, bool FAST>
+template <typename T, int KIND, bool FAST, bool PL>
 __global__ void __launch_bounds__(512, sizeof(T) == 4 ? 2 : 1)
 tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmM, T* __restrict__ XA, T* __restrict__ XB, const T* __restrict__ aux,
+                    const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmP, T* __restrict__ XA,
+                    T* __restrict__ XB, const T* __restrict__ auxg,
                     int nrounds, int nsub_last, int want_res, double* __restrict__ partial, unsigned* __restrict__ flags,
                     int tiles_j, int* __restrict__ err) {
   extern __shared__ __align__(128) unsigned char tile_smem[];
@@ -489,15 +585,18 @@ tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, c
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ int s_abort;
   const int EJ = k.EJ, ld = k.ld;
+  constexpr int NP = kPlanes<T, KIND, FAST, PL>;
   T* bufA = reinterpret_cast<T*>(tile_smem);
   T* bufB = bufA + EJ * TEI;
-  uint32_t* msk0 = reinterpret_cast<uint32_t*>(bufB + EJ * TEI);
+  T* planes = bufB + EJ * TEI;
+  uint32_t* msk0 = reinterpret_cast<uint32_t*>(planes + NP * EJ * TEI);
+  const T* aux = NP > 0 ? planes : auxg;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
   const int ti = blockIdx.x % k.tiles_i, tj = blockIdx.x / k.tiles_i;
-  const int org = ti * TTI + ld * (tj * k.TJ);
-  const int moff = (ti * TTI) & 15;
+  const int org = ti * k.tti + ld * (tj * k.TJ);
+  const int moff = (ti * k.tti) & 15;
   const uint32_t* msk = msk0 + (moff >> 2);
-  const int gi = k.goal_pi - ti * TTI, gj = k.goal_pj - tj * k.TJ;
+  const int gi = k.goal_pi - ti * k.tti, gj = k.goal_pj - tj * k.TJ;
   const bool near_goal = gi >= -1 && gi <= TEI && gj >= -1 && gj <= EJ;
 
   if (threadIdx.x == 0) mbar_init(&mbar, 1);
@@ -505,7 +604,7 @@ tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, c
   T* src = bufA;
   T* dst = bufB;
   for (int r = 0; r < nrounds; r++) {
-    const int nsub = r == nrounds - 1 ? nsub_last : TKH;
+    const int nsub = r == nrounds - 1 ? nsub_last : k.kh;
     const T* Xin = (r & 1) ? XB : XA;
     T* Xout = (r & 1) ? XA : XB;
     // neighbours (8-connected: a 4-deep halo reaches into the diagonal tiles) have finished round r-1
@@ -516,7 +615,8 @@ tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, c
         const unsigned* f = flags + ni + k.tiles_i * nj;
         const unsigned long long t0 = globaltimer_ns_tile();
         while (ld_acquire_gpu(f) < (unsigned)r) {
-          if (globaltimer_ns_tile() - t0 > 5000000000ull || *(volatile int*)err) { *err = 1; break; }
+          if (*(volatile int*)err) break;  // somebody else gave up (or left the linear-domain range): so do we
+          if (globaltimer_ns_tile() - t0 > 5000000000ull) { *err = 1; break; }
         }
       }
     }
@@ -528,9 +628,13 @@ tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, c
       // order this CTA's earlier generic-proxy accesses of the buffers, and the neighbours' global writes just
       // acquired, before the TMA engine (async proxy) overwrites / reads them
       asm volatile("fence.proxy.async;" ::: "memory");
-      mbar_expect_tx(&mbar, (unsigned)(EJ * TEI * sizeof(T) + (r == 0 ? EJ * TMB : 0)));
-      tma_load_2d(bufA, (r & 1) ? &tmB : &tmA, ti * TTI, tj * k.TJ, &mbar);
-      if (r == 0) tma_load_2d(msk0, &tmM, ti * TTI - moff, tj * k.TJ, &mbar);  // the cell bytes stay for all rounds
+      mbar_expect_tx(&mbar, (unsigned)(EJ * TEI * sizeof(T) + (r == 0 ? EJ * (TMB + NP * TEI * sizeof(T)) : 0)));
+      tma_load_2d(bufA, (r & 1) ? &tmB : &tmA, ti * k.tti, tj * k.TJ, &mbar);
+      if (r == 0) {  // the cell bytes and the constant planes stay for all rounds
+        tma_load_2d(msk0, &tmM, ti * k.tti - moff, tj * k.TJ, &mbar);
+#pragma unroll
+        for (int q = 0; q < NP; q++) tma_load_3d(planes + q * EJ * TEI, &tmP, ti * k.tti, tj * k.TJ, q, &mbar);
+      }
     }
     mbar_wait(&mbar, r & 1);
     if (warp < 2) {  // the outermost columns are never recomputed: keep both ping-pong copies defined
@@ -539,10 +643,10 @@ tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, c
       lds4(bufA + jj * TEI + 4 * lane, v);
       sts4(bufB + jj * TEI + 4 * lane, v);
     }
-    __syncthreads();
+      __syncthreads();
     src = bufA; dst = bufB;
     for (int sub = 0; sub < nsub; sub++) {
-      tile_subsweep<T, KIND, FAST>(k, src, dst, msk, aux, org, lane, warp, NW, sub);
+      tile_subsweep<T, KIND, FAST, PL>(k, src, dst, msk, aux, org, lane, warp, NW, sub);
       __syncthreads();
       if (near_goal) {
         tile_goal_fixup<T, KIND, FAST>(k, src, dst, msk, gi, gj);
@@ -551,10 +655,11 @@ tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, c
       T* t = src; src = dst; dst = t;
     }
     (void)Xin;
-    if (lane >= TKH / 4 && lane < 32 - TKH / 4) {
-      for (int jj = TKH + warp; jj < TKH + k.TJ; jj += NW) {
+    if (lane >= k.kh / 4 && lane < 32 - k.kh / 4) {
+      for (int jj = k.kh + warp; jj < k.kh + k.TJ; jj += NW) {
         T f[4];
         lds4(src + jj * TEI + 4 * lane, f);
+        if constexpr (kZDom<T, KIND, FAST>) { if (strip_not_normal(f, msk[jj * TMP + lane])) *err = TILE_ERR_RANGE; }
         const int g = org + jj * ld + 4 * lane;
         if (sizeof(T) == 4) {
           *reinterpret_cast<float4*>(Xout + g) = make_float4((float)f[0], (float)f[1], (float)f[2], (float)f[3]);
@@ -571,15 +676,16 @@ tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, c
   // residual of the last sweep (src: last iterate, dst: the one before)
   if (want_res) {
     double res = 0.0;
-    if (lane >= TKH / 4 && lane < 32 - TKH / 4) {
-      for (int jj = TKH + warp; jj < TKH + k.TJ; jj += NW) {
+    if (lane >= k.kh / 4 && lane < 32 - k.kh / 4) {
+      for (int jj = k.kh + warp; jj < k.kh + k.TJ; jj += NW) {
         T f[4], p[4];
         lds4(src + jj * TEI + 4 * lane, f);
         lds4(dst + jj * TEI + 4 * lane, p);
         const uint32_t mk = msk[jj * TMP + lane];
 #pragma unroll
         for (int q = 0; q < 4; q++)
-          if (!((mk >> (8 * q)) & CELL_WALL)) res += sweep_diff<KIND>((double)f[q], (double)p[q]);
+          if (!((mk >> (8 * q)) & CELL_WALL))
+            res += kZDom<T, KIND, FAST> ? sweep_diff_z((double)f[q], (double)p[q]) : sweep_diff<KIND>((double)f[q], (double)p[q]);
       }
     }
     const double s = block_sum(res, red);
@@ -588,30 +694,62 @@ tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, c
 }
 
 // ---- packing between the dense H x W arrays of the ABI side and the padded tile layout -------------------
+static bool tile_zdom(int precision, int kind, bool fast) { return PIQL_LOGZ_ZDOM && precision != 0 && fast && kind == KIND_LOGZ; }
 struct PadGeom {
-  int H, W, ld, Wp;
+  int H, W, ld, Wp, kh;
 };
+// zdom: the padded iterate is kept in the linear domain (fast fp32 log Z): Z = e^(log Z) on the way in, the log on the way out
 template <typename T>
-__global__ void tile_pack_kernel(PadGeom g, const T* __restrict__ dense, T* __restrict__ padded) {
+__global__ void tile_pack_kernel(PadGeom g, const T* __restrict__ dense, T* __restrict__ padded, int zdom) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.ld * g.Wp) return;
-  const int i = p % g.ld - TKH, j = p / g.ld - TKH;
-  padded[p] = (i >= 0 && i < g.H && j >= 0 && j < g.W) ? dense[i + g.H * j] : (T)0;
+  const int i = p % g.ld - g.kh, j = p / g.ld - g.kh;
+  T v = (i >= 0 && i < g.H && j >= 0 && j < g.W) ? dense[i + g.H * j] : (T)0;
+  if (zdom) v = (T)exp((double)v);
+  padded[p] = v;
 }
 __global__ void tile_pack_mask_kernel(PadGeom g, const uint8_t* __restrict__ cell, uint8_t* __restrict__ maskp) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.ld * g.Wp) return;
-  const int i = p % g.ld - TKH, j = p / g.ld - TKH;
+  const int i = p % g.ld - g.kh, j = p / g.ld - g.kh;
   maskp[p] = (i >= 0 && i < g.H && j >= 0 && j < g.W) ? cell[i + g.H * j] : (uint8_t)(CELL_WALL | CELL_BLOCK_MASK);
 }
 // aux4 [cell][4] + aux1 [cell] -> five planes.  logz: exp(A_a - max A), max A (as prep_kernel stores them); gap: pi_a, D.
+// Constants of the linear-domain log Z sweep (logz_cell_lin2): G_a' = 1/2 gamma (w_off sum_a e^(A_a) + dw e^(A_a')) and
+// C = 1/2 (1 - gamma) sum_a e^(A_a), in double from exp(A_a - max A) and max A, rounded once.
+struct ZPlaneK {
+  double gamma, w_off, dw;
+};
+template <typename T>
+__global__ void tile_pack_zplanes_kernel(PadGeom g, ZPlaneK zk, const T* __restrict__ aux4, const T* __restrict__ aux1,
+                                         T* __restrict__ auxp) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int np = g.ld * g.Wp;
+  if (p >= np) return;
+  const int i = p % g.ld - g.kh, j = p / g.ld - g.kh;
+  double o[5] = {0, 0, 0, 0, 0};
+  if (i >= 0 && i < g.H && j >= 0 && j < g.W) {
+    const int s = i + g.H * j;
+    T a[4];
+    ldg4(aux4 + 4 * (size_t)s, a);
+    const double em = exp((double)aux1[s]);
+    double ea[4], sum = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) { ea[q] = (double)a[q] * em; sum += ea[q]; }
+#pragma unroll
+    for (int q = 0; q < 4; q++) o[q] = 0.5 * zk.gamma * (zk.w_off * sum + zk.dw * ea[q]);
+    // (C = 1/2 (1 - gamma) sum = (1 - gamma) / gamma * sum_q o[q] is rebuilt in the sweep: plane 4 stays empty)
+  }
+#pragma unroll
+  for (int q = 0; q < 5; q++) auxp[(size_t)q * np + p] = (T)o[q];
+}
 template <typename T, int KIND>
 __global__ void tile_pack_aux_kernel(PadGeom g, const T* __restrict__ aux4, const T* __restrict__ aux1, T* __restrict__ auxp,
                                      int fold_max) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int np = g.ld * g.Wp;
   if (p >= np) return;
-  const int i = p % g.ld - TKH, j = p / g.ld - TKH;
+  const int i = p % g.ld - g.kh, j = p / g.ld - g.kh;
   T o[5] = {0, 0, 0, 0, 0};
   if (i >= 0 && i < g.H && j >= 0 && j < g.W) {
     const int s = i + g.H * j;
@@ -632,16 +770,21 @@ __global__ void tile_pack_aux_kernel(PadGeom g, const T* __restrict__ aux4, cons
   for (int q = 0; q < 5; q++) auxp[(size_t)q * np + p] = o[q];
 }
 template <typename T>
-__global__ void tile_unpack_kernel(PadGeom g, const T* __restrict__ padded, T* __restrict__ dense) {
+__global__ void tile_unpack_kernel(PadGeom g, const T* __restrict__ padded, T* __restrict__ dense, int zdom) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= g.H * g.W) return;
   const int i = s % g.H, j = s / g.H;
-  dense[s] = padded[(i + TKH) + g.ld * (j + TKH)];
+  const T v = padded[(i + g.kh) + g.ld * (j + g.kh)];
+  dense[s] = zdom ? (T)log((double)v) : v;
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
-static size_t tile_smem_bytes(int EJ, int precision) {
-  return (size_t)EJ * (2 * TEI * (precision == 0 ? 8 : 4) + TMB);
+static int tile_planes(int precision, int kind, bool fast) {  // constant planes the linear fast fp32 sweeps can keep in shared memory
+  if (!(PIQL_TILE_PLANES && precision != 0 && fast)) return 0;
+  return kind == KIND_GAP ? 5 : tile_zdom(precision, kind, fast) ? 4 : 0;
+}
+static size_t tile_smem_bytes(int EJ, int precision, int planes) {
+  return (size_t)EJ * ((2 + planes) * TEI * (precision == 0 ? 8 : 4) + TMB);
 }
 
 // Candidate tile shapes (TJ interior columns, nw warps per CTA), cheapest first by a small cost model in SM cycles per
@@ -654,14 +797,18 @@ static size_t tile_smem_bytes(int EJ, int precision) {
 //                 busiest SM, c*rounds*nw*61 with at least 24 resident warps.
 // The model only ranks; tile_begin times the leading candidates on the device and keeps the fastest.
 // PIQL_TILE_TJ / PIQL_TILE_NW pin the shape (tests, tuning sweeps).
-constexpr size_t TUNE_CANDIDATES = 12;  // shapes of each kind (persistent, multi-launch) tile_begin times on the device
+constexpr size_t TUNE_CANDIDATES = 8;  // shapes of each variant (persistent / multi-launch x depth x planes) tile_begin times on the device
 struct PlanCand {
   double cost;
   TilePlan plan;
 };
 static int tile_kernel_regs(int precision, int kind, bool fast, bool persistent);
-static std::vector<PlanCand> enumerate_plans(int H, int W, int precision, int kind, bool fast, int num_sms, bool persistent) {
+// One variant: kh sweeps per round (ghost depth 4 or 8) and `planes` constant planes staged in shared memory (0: read from
+// global memory in every sub-sweep).  Costs are per sweep, so variants can be compared.
+static std::vector<PlanCand> enumerate_plans(int H, int W, int precision, int kind, bool fast, int num_sms, bool persistent,
+                                             int kh = 4, int planes = 0) {
   std::vector<PlanCand> out;
+  const int TKH = kh, TTI = TEI - 2 * kh;
   const int tiles_i = (H + TTI - 1) / TTI;
   const char* env_tj = getenv("PIQL_TILE_TJ");
   const char* env_nw = getenv("PIQL_TILE_NW");
@@ -676,7 +823,7 @@ static std::vector<PlanCand> enumerate_plans(int H, int W, int precision, int ki
     for (int TJ = 8; TJ <= 120; TJ++) {
       if (env_tj && atoi(env_tj) != TJ) continue;
       const int EJ = TJ + 2 * TKH, cols = EJ - 2;
-      const size_t smem = tile_smem_bytes(EJ, precision);
+      const size_t smem = tile_smem_bytes(EJ, precision, planes);
       if (smem > 200 * 1024) continue;
       int ctas = (int)((227 * 1024) / (smem + 1024));
       ctas = std::min(ctas, std::min(2048 / (32 * nw), 65536 / (regs * 32 * nw)));
@@ -712,7 +859,8 @@ static std::vector<PlanCand> enumerate_plans(int H, int W, int precision, int ki
       p.ld = ((tiles_i * TTI + 2 * TKH + 31) / 32) * 32;
       p.Wp = tiles_j * TJ + 2 * TKH;
       p.np = (long long)p.ld * p.Wp;
-      out.push_back({cost, p});
+      p.kh = kh; p.planes = planes;
+      out.push_back({cost / kh, p});
     }
   }
   std::stable_sort(out.begin(), out.end(), [](const PlanCand& a, const PlanCand& b) {
@@ -720,14 +868,26 @@ static std::vector<PlanCand> enumerate_plans(int H, int W, int precision, int ki
   });
   return out;
 }
+// The variant an untimed plan uses: 4 sweeps per round, planes from global memory, unless the environment pins another
+// (PIQL_TILE_KH = 4 | 8, PIQL_TILE_PLANES_MODE = 0 | 1; tests and tuning sweeps).
+static void env_variant(int precision, int kind, bool fast, int& kh, int& planes) {
+  const char* env_kh = getenv("PIQL_TILE_KH");
+  const char* env_pm = getenv("PIQL_TILE_PLANES_MODE");
+  kh = env_kh && atoi(env_kh) == 8 ? 8 : 4;
+  planes = env_pm && atoi(env_pm) == 1 ? tile_planes(precision, kind, fast) : 0;
+}
 TilePlan make_tile_plan(int H, int W, int precision, int kind, bool fast, int num_sms) {
-  const std::vector<PlanCand> c = enumerate_plans(H, W, precision, kind, fast, num_sms, false);
+  int kh, planes;
+  env_variant(precision, kind, fast, kh, planes);
+  const std::vector<PlanCand> c = enumerate_plans(H, W, precision, kind, fast, num_sms, false, kh, planes);
   return c.empty() ? TilePlan{} : c[0].plan;
 }
 // The model's choice: the persistent shape when every tile can be resident at once, else the multi-launch one.
 TilePlan choose_tile_plan(int H, int W, int precision, int kind, bool fast, int num_sms, bool* persistent) {
+  int kh, planes;
+  env_variant(precision, kind, fast, kh, planes);
   const bool allow = getenv("PIQL_TILE_NO_PERSIST") == nullptr && getenv("PIQL_TILE_NO_TMA") == nullptr;
-  const std::vector<PlanCand> pp = allow ? enumerate_plans(H, W, precision, kind, fast, num_sms, true) : std::vector<PlanCand>();
+  const std::vector<PlanCand> pp = allow ? enumerate_plans(H, W, precision, kind, fast, num_sms, true, kh, planes) : std::vector<PlanCand>();
   if (persistent) *persistent = !pp.empty();
   return pp.empty() ? make_tile_plan(H, W, precision, kind, fast, num_sms) : pp[0].plan;
 }
@@ -735,7 +895,8 @@ TilePlan choose_tile_plan(int H, int W, int precision, int kind, bool fast, int 
 template <typename T> static TileK<T> make_tile_k(const GridDev& g, const ViState& vs, const TilePlan& pl) {
   TileK<T> k;
   k.ld = pl.ld; k.np = (int)pl.np; k.TJ = pl.TJ; k.EJ = pl.EJ; k.tiles_i = pl.tiles_i; k.tj0 = 0;
-  k.goal_pi = g.goal % g.H + TKH; k.goal_pj = g.goal / g.H + TKH; k.goal_p = k.goal_pi + pl.ld * k.goal_pj;
+  k.kh = pl.kh; k.tti = TEI - 2 * pl.kh;
+  k.goal_pi = g.goal % g.H + pl.kh; k.goal_pj = g.goal / g.H + pl.kh; k.goal_p = k.goal_pi + pl.ld * k.goal_pj;
   const double w_on = 1.0 * (1.0 - g.randomness) + g.randomness / NA, w_off = 0.0 * (1.0 - g.randomness) + g.randomness / NA;
   const double a1 = g.gamma * (w_on - w_off);
   const double kc = log(1.0 / NA) + vs.reward_scale * -g.step_cost;
@@ -744,6 +905,10 @@ template <typename T> static TileK<T> make_tile_k(const GridDev& g, const ViStat
   k.w_off = (T)w_off; k.dw = (T)(w_on - w_off);
   k.gamma = (T)g.gamma; k.omg = (T)(1.0 - g.gamma);
   k.term = vs.kind == KIND_LOGZ ? (T)(0.0 - vs.v_goal) : (T)0;
+  if (sizeof(T) == 4 && tile_zdom(vs.precision, vs.kind, vs.fast)) {
+    k.term = (T)exp(0.0 - vs.v_goal);          // Z(goal) = e^(-V(goal))
+    k.omg = (T)((1.0 - g.gamma) / g.gamma);    // kappa of logz_cell_lin2
+  }
   k.k = make_k<T>(g, vs.reward_scale, vs.beta);
   k.k.H = pl.ld; k.k.n = (int)pl.np; k.k.goal = k.goal_p;
   return k;
@@ -781,6 +946,18 @@ static bool encode_tile_map(void* out, void* base, CUtensorMapDataType dt, size_
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 3-D map over the padded constant planes (ld x Wp x 5), box = 128 x EJ x 1
+static bool encode_plane_map(void* out, void* base, const TilePlan& pl) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t gdim[3] = {(cuuint64_t)pl.ld, (cuuint64_t)pl.Wp, 5};
+  const cuuint64_t gstride[2] = {(cuuint64_t)pl.ld * 4, (cuuint64_t)pl.np * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)TEI, (cuuint32_t)pl.EJ, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 void tile_free(TileBuffers& tb) {
   for (void* p : {tb.x[0], tb.x[1], tb.aux, (void*)tb.mask, (void*)tb.partial, (void*)tb.flags, (void*)tb.d_err}) if (p) cudaFree(p);
   if (tb.err) cudaFreeHost(tb.err);
@@ -795,13 +972,19 @@ void tile_free(TileBuffers& tb) {
 
 template <typename T>
 static void pack_t(const GridDev& g, const uint8_t* cell, const ViState& vs, TileBuffers& tb, cudaStream_t st) {
-  const PadGeom pg{g.H, g.W, tb.plan.ld, tb.plan.Wp};
+  const PadGeom pg{g.H, g.W, tb.plan.ld, tb.plan.Wp, tb.plan.kh};
   const unsigned nb = nblk(tb.plan.np, 256);
-  tile_pack_kernel<T><<<nb, 256, 0, st>>>(pg, (const T*)vs.x[vs.cur], (T*)tb.x[0]);
-  tile_pack_kernel<T><<<nb, 256, 0, st>>>(pg, (const T*)vs.x[vs.cur], (T*)tb.x[1]);
+  const int zdom = tile_zdom(vs.precision, vs.kind, vs.fast) ? 1 : 0;
+  tile_pack_kernel<T><<<nb, 256, 0, st>>>(pg, (const T*)vs.x[vs.cur], (T*)tb.x[0], zdom);
+  tile_pack_kernel<T><<<nb, 256, 0, st>>>(pg, (const T*)vs.x[vs.cur], (T*)tb.x[1], zdom);
   tile_pack_mask_kernel<<<nb, 256, 0, st>>>(pg, cell, tb.mask);
   g_launches += 3;
-  if (vs.kind == KIND_LOGZ) {
+  if (zdom) {
+    const double w_on = 1.0 * (1.0 - g.randomness) + g.randomness / NA, w_off = 0.0 * (1.0 - g.randomness) + g.randomness / NA;
+    tile_pack_zplanes_kernel<T><<<nb, 256, 0, st>>>(pg, ZPlaneK{g.gamma, w_off, w_on - w_off}, (const T*)vs.aux4, (const T*)vs.aux1,
+                                                    (T*)tb.aux);
+    g_launches++;
+  } else if (vs.kind == KIND_LOGZ) {
     tile_pack_aux_kernel<T, KIND_LOGZ><<<nb, 256, 0, st>>>(pg, (const T*)vs.aux4, (const T*)vs.aux1, (T*)tb.aux,
                                                            (PIQL_LOGZ_OWN_SHIFT && vs.fast) ? 1 : 0);
     g_launches++;
@@ -839,11 +1022,16 @@ static cudaError_t tile_setup(const GridDev& g, const uint8_t* cell, const ViSta
   }
   tb.plan = pl;
   tb.cur = 0;
+  // a new solve starts with a clean error word (timed-out waits, exponent-domain range)
+  if (cudaMemsetAsync(tb.d_err, 0, sizeof(int), st) != cudaSuccess ||
+      cudaMemcpyAsync(tb.err, tb.d_err, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+    return cudaGetLastError();
   static_assert(sizeof(CUtensorMap) == 128, "descriptor size");
   const CUtensorMapDataType dt = vs.precision == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   tb.use_tma = getenv("PIQL_TILE_NO_TMA") == nullptr && encode_tile_map(tb.tmx[0], tb.x[0], dt, e, pl) &&
                encode_tile_map(tb.tmx[1], tb.x[1], dt, e, pl) &&
-               encode_tile_map(tb.tmm, tb.mask, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, pl, TMB);
+               encode_tile_map(tb.tmm, tb.mask, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, pl, TMB) &&
+               (pl.planes == 0 || encode_plane_map(tb.tmp, tb.aux, pl));
   tb.persistent = persist && tb.use_tma;
   if (vs.precision == 0) pack_t<double>(g, cell, vs, tb, st);
   else pack_t<float>(g, cell, vs, tb, st);
@@ -864,29 +1052,41 @@ cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs,
   bool persist = false;
   const TilePlan model = choose_tile_plan(g.H, g.W, vs.precision, vs.kind, vs.fast, num_sms, &persist);
   if (pinned) return tile_setup(g, cell, vs, tb, model, persist, st);
-  // time the leading candidates of both kinds on the device (a few launches each) and keep the fastest for this problem
+  // time the leading candidates of every variant on the device (a few launches each) and keep the fastest for this problem:
+  // persistent / one launch per round, 4 or 8 sweeps per round (PIQL_TILE_KH pins it), constant planes in shared memory or
+  // read from global memory (the two linear fast fp32 sweeps; PIQL_TILE_PLANES_MODE = 0 / 1 pins it)
   struct Try { TilePlan plan; bool persist; };
   std::vector<Try> tries;
   const bool allow_p = getenv("PIQL_TILE_NO_PERSIST") == nullptr && getenv("PIQL_TILE_NO_TMA") == nullptr;
-  if (allow_p) {
-    const std::vector<PlanCand> pp = enumerate_plans(g.H, g.W, vs.precision, vs.kind, vs.fast, num_sms, true);
-    for (size_t i = 0; i < pp.size() && i < TUNE_CANDIDATES; i++) tries.push_back({pp[i].plan, true});
+  const char* env_kh = getenv("PIQL_TILE_KH");
+  const char* env_pm = getenv("PIQL_TILE_PLANES_MODE");
+  const int npl = tile_planes(vs.precision, vs.kind, vs.fast);
+  for (int kh = 4; kh <= TILE_KH_MAX; kh += 4) {
+    if (env_kh && atoi(env_kh) != kh) continue;
+    for (int pm = 0; pm < (npl > 0 ? 2 : 1); pm++) {
+      if (env_pm && atoi(env_pm) != pm) continue;
+      const int planes = pm ? npl : 0;
+      if (allow_p) {
+        const std::vector<PlanCand> pp = enumerate_plans(g.H, g.W, vs.precision, vs.kind, vs.fast, num_sms, true, kh, planes);
+        for (size_t i = 0; i < pp.size() && i < TUNE_CANDIDATES; i++) tries.push_back({pp[i].plan, true});
+      }
+      const std::vector<PlanCand> mm = enumerate_plans(g.H, g.W, vs.precision, vs.kind, vs.fast, num_sms, false, kh, planes);
+      for (size_t i = 0; i < mm.size() && i < TUNE_CANDIDATES; i++) tries.push_back({mm[i].plan, false});
+    }
   }
-  const std::vector<PlanCand> mm = enumerate_plans(g.H, g.W, vs.precision, vs.kind, vs.fast, num_sms, false);
-  for (size_t i = 0; i < mm.size() && i < TUNE_CANDIDATES; i++) tries.push_back({mm[i].plan, false});
   cudaEvent_t e0, e1;
   cudaError_t err = cudaEventCreate(&e0);
   if (err != cudaSuccess) return err;
   if ((err = cudaEventCreate(&e1)) != cudaSuccess) { cudaEventDestroy(e0); return err; }
   double best = 1e300;
   Try chosen{model, persist};
-  const long long probe = 8 * TKH;
+  const long long probe = 32;
   // Short probes (small grids: 0.1 ms) are noisy and are repeated; once a probe lasts more than half a millisecond one
   // measurement per shape is enough, and all a first solve should pay (tuning stays near a tenth of a solve to tolerance).
   int reps = 2;
   for (const Try& t : tries) {
     if ((err = tile_setup(g, cell, vs, tb, t.plan, t.persist, st)) != cudaSuccess) break;
-    if ((err = tile_sweeps(g, vs, tb, 2 * TKH, false, st)) != cudaSuccess) break;
+    if ((err = tile_sweeps(g, vs, tb, 2 * t.plan.kh, false, st)) != cudaSuccess) break;
     float ms = 1e30f;
     for (int rep = 0; rep < reps && err == cudaSuccess; rep++) {
       cudaEventRecord(e0, st);
@@ -910,13 +1110,13 @@ cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs,
   return tile_setup(g, cell, vs, tb, chosen.plan, chosen.persist, st);  // re-pack: the probes advanced the iterate
 }
 
-template <typename T, int KIND, bool FAST>
+template <typename T, int KIND, bool FAST, bool PL>
 static cudaError_t launch_tile_t(const GridDev& g, const ViState& vs, TileBuffers& tb, int nsub, bool want_res, cudaStream_t st) {
   static bool configured[64] = {};  // shared-memory opt-in, once per instantiation and device
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(tile_sweep_kernel<T, KIND, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tile_sweep_kernel<T, KIND, FAST, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
@@ -929,13 +1129,15 @@ static cudaError_t launch_tile_t(const GridDev& g, const ViState& vs, TileBuffer
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  CUtensorMap tmX, tmM;
+  CUtensorMap tmX, tmM, tmP;
   memcpy(&tmX, tb.tmx[tb.cur], sizeof(tmX));
   memcpy(&tmM, tb.tmm, sizeof(tmM));
-  cudaError_t le = cudaLaunchKernelEx(&cfg, tile_sweep_kernel<T, KIND, FAST>, k, tmX, tmM, tb.use_tma ? 1 : 0,
+  memcpy(&tmP, tb.tmp, sizeof(tmP));
+  TileHalo halo = tb.sharded ? tb.halo : TileHalo();
+  halo.err = tb.d_err;  // also where a linear-domain sweep reports that it left the float range
+  cudaError_t le = cudaLaunchKernelEx(&cfg, tile_sweep_kernel<T, KIND, FAST, PL>, k, tmX, tmM, tmP, tb.use_tma ? 1 : 0,
                                       (const uint8_t*)tb.mask, (const T*)tb.x[tb.cur],
-                                      (T*)tb.x[tb.cur ^ 1], (const T*)tb.aux, nsub, want_res ? 1 : 0, tb.partial,
-                                      tb.sharded ? tb.halo : TileHalo());
+                                      (T*)tb.x[tb.cur ^ 1], (const T*)tb.aux, nsub, want_res ? 1 : 0, tb.partial, halo);
   if (le != cudaSuccess) return le;
   g_launches++;
   tb.cur ^= 1;
@@ -944,19 +1146,20 @@ static cudaError_t launch_tile_t(const GridDev& g, const ViState& vs, TileBuffer
 
 // All rounds of nsweeps sweeps in one cooperative launch (tb.persistent).  cudaErrorCooperativeLaunchTooLarge means the
 // occupancy estimate of the plan was optimistic for this instantiation: the caller falls back to one launch per round.
-template <typename T, int KIND, bool FAST>
+template <typename T, int KIND, bool FAST, bool PL>
 static cudaError_t launch_persist_t(const GridDev& g, const ViState& vs, TileBuffers& tb, long long nsweeps, bool want_res,
                                     cudaStream_t st) {
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(tile_persist_kernel<T, KIND, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tile_persist_kernel<T, KIND, FAST, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const TileK<T> k = make_tile_k<T>(g, vs, tb.plan);
   const unsigned grid = (unsigned)(tb.plan.tiles_i * tb.plan.tiles_j);
+  const int TKH = tb.plan.kh;
   const int nrounds = (int)((nsweeps + TKH - 1) / TKH), nsub_last = (int)(nsweeps - (long long)(nrounds - 1) * TKH);
   cudaError_t e = cudaMemsetAsync(tb.flags, 0, sizeof(unsigned) * grid, st);
   if (e != cudaSuccess) return e;
@@ -966,11 +1169,12 @@ static cudaError_t launch_persist_t(const GridDev& g, const ViState& vs, TileBuf
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  CUtensorMap tmA, tmB, tmM;
+  CUtensorMap tmA, tmB, tmM, tmP;
   memcpy(&tmA, tb.tmx[tb.cur], sizeof(tmA));
   memcpy(&tmB, tb.tmx[tb.cur ^ 1], sizeof(tmB));
   memcpy(&tmM, tb.tmm, sizeof(tmM));
-  e = cudaLaunchKernelEx(&cfg, tile_persist_kernel<T, KIND, FAST>, k, tmA, tmB, tmM, (T*)tb.x[tb.cur], (T*)tb.x[tb.cur ^ 1],
+  memcpy(&tmP, tb.tmp, sizeof(tmP));
+  e = cudaLaunchKernelEx(&cfg, tile_persist_kernel<T, KIND, FAST, PL>, k, tmA, tmB, tmM, tmP, (T*)tb.x[tb.cur], (T*)tb.x[tb.cur ^ 1],
                          (const T*)tb.aux, nrounds, nsub_last, want_res ? 1 : 0, tb.partial, tb.flags, tb.plan.tiles_j, tb.d_err);
   if (e != cudaSuccess) return e;
   e = cudaMemcpyAsync(tb.err, tb.d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -979,22 +1183,33 @@ static cudaError_t launch_persist_t(const GridDev& g, const ViState& vs, TileBuf
   tb.cur = (tb.cur + nrounds) & 1;
   return cudaSuccess;
 }
+// PL = true exists for the two linear fast fp32 sweeps only (the plan asks for it through TilePlan::planes)
 template <typename T, bool FAST>
 static cudaError_t launch_persist_k(const GridDev& g, const ViState& vs, TileBuffers& tb, long long nsweeps, bool want_res,
                                     cudaStream_t st) {
+  const bool pl = tb.plan.planes > 0;
   switch (vs.kind) {
-    case KIND_NU: return launch_persist_t<T, KIND_NU, FAST>(g, vs, tb, nsweeps, want_res, st);
-    case KIND_LOGZ: return launch_persist_t<T, KIND_LOGZ, FAST>(g, vs, tb, nsweeps, want_res, st);
-    default: return launch_persist_t<T, KIND_GAP, FAST>(g, vs, tb, nsweeps, want_res, st);
+    case KIND_NU: return launch_persist_t<T, KIND_NU, FAST, false>(g, vs, tb, nsweeps, want_res, st);
+    case KIND_LOGZ:
+      if constexpr (FAST) { if (pl) return launch_persist_t<T, KIND_LOGZ, FAST, true>(g, vs, tb, nsweeps, want_res, st); }
+      return launch_persist_t<T, KIND_LOGZ, FAST, false>(g, vs, tb, nsweeps, want_res, st);
+    default:
+      if constexpr (FAST) { if (pl) return launch_persist_t<T, KIND_GAP, FAST, true>(g, vs, tb, nsweeps, want_res, st); }
+      return launch_persist_t<T, KIND_GAP, FAST, false>(g, vs, tb, nsweeps, want_res, st);
   }
 }
 
 template <typename T, bool FAST>
 static cudaError_t launch_tile_k(const GridDev& g, const ViState& vs, TileBuffers& tb, int nsub, bool want_res, cudaStream_t st) {
+  const bool pl = tb.plan.planes > 0;
   switch (vs.kind) {
-    case KIND_NU: return launch_tile_t<T, KIND_NU, FAST>(g, vs, tb, nsub, want_res, st);
-    case KIND_LOGZ: return launch_tile_t<T, KIND_LOGZ, FAST>(g, vs, tb, nsub, want_res, st);
-    default: return launch_tile_t<T, KIND_GAP, FAST>(g, vs, tb, nsub, want_res, st);
+    case KIND_NU: return launch_tile_t<T, KIND_NU, FAST, false>(g, vs, tb, nsub, want_res, st);
+    case KIND_LOGZ:
+      if constexpr (FAST) { if (pl) return launch_tile_t<T, KIND_LOGZ, FAST, true>(g, vs, tb, nsub, want_res, st); }
+      return launch_tile_t<T, KIND_LOGZ, FAST, false>(g, vs, tb, nsub, want_res, st);
+    default:
+      if constexpr (FAST) { if (pl) return launch_tile_t<T, KIND_GAP, FAST, true>(g, vs, tb, nsub, want_res, st); }
+      return launch_tile_t<T, KIND_GAP, FAST, false>(g, vs, tb, nsub, want_res, st);
   }
 }
 
@@ -1005,8 +1220,8 @@ template <typename T, int KIND, bool FAST> static int regs_of(bool persistent) {
   int& c = cache[persistent ? 1 : 0];
   if (c == 0) {
     cudaFuncAttributes a;
-    cudaError_t e = persistent ? cudaFuncGetAttributes(&a, tile_persist_kernel<T, KIND, FAST>)
-                               : cudaFuncGetAttributes(&a, tile_sweep_kernel<T, KIND, FAST>);
+    cudaError_t e = persistent ? cudaFuncGetAttributes(&a, tile_persist_kernel<T, KIND, FAST, false>)
+                               : cudaFuncGetAttributes(&a, tile_sweep_kernel<T, KIND, FAST, false>);
     if (e == cudaSuccess && a.numRegs > 0) c = ((a.numRegs + 7) / 8) * 8;  // allocation granularity: 8 per thread
     else { cudaGetLastError(); c = sizeof(T) == 4 ? 64 : 128; }
   }
@@ -1026,6 +1241,7 @@ static int tile_kernel_regs(int precision, int kind, bool fast, bool persistent)
 
 // nsweeps Jacobi sweeps in ceil(nsweeps / TILE_KH) launches; the residual of the last sweep lands in vs.residual.
 cudaError_t tile_sweeps(const GridDev& g, const ViState& vs, TileBuffers& tb, long long nsweeps, bool want_res, cudaStream_t st) {
+  const int TKH = tb.plan.kh;
   if (tb.persistent && nsweeps > TKH) {
     if (tb.err && *tb.err) return cudaErrorLaunchTimeout;  // an earlier persistent launch gave up waiting for a neighbour
     cudaError_t e;
@@ -1051,14 +1267,19 @@ cudaError_t tile_sweeps(const GridDev& g, const ViState& vs, TileBuffers& tb, lo
     if (e != cudaSuccess) return e;
     if (res) launch_residual_final(tb.partial, tb.plan.tiles_i * tb.plan.tiles_j, vs.residual, st);
   }
+  if (tile_zdom(vs.precision, vs.kind, vs.fast)) {  // the range word travels with the batch (read after the next sync)
+    cudaError_t e = cudaMemcpyAsync(tb.err, tb.d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+  }
   return cudaGetLastError();
 }
 
 // Copies the current iterate back into the dense array vs.x[vs.cur].
 void tile_unpack(const GridDev& g, const ViState& vs, const TileBuffers& tb, cudaStream_t st) {
-  const PadGeom pg{g.H, g.W, tb.plan.ld, tb.plan.Wp};
-  if (vs.precision == 0) tile_unpack_kernel<double><<<nblk(g.n, 256), 256, 0, st>>>(pg, (const double*)tb.x[tb.cur], (double*)vs.x[vs.cur]);
-  else tile_unpack_kernel<float><<<nblk(g.n, 256), 256, 0, st>>>(pg, (const float*)tb.x[tb.cur], (float*)vs.x[vs.cur]);
+  const PadGeom pg{g.H, g.W, tb.plan.ld, tb.plan.Wp, tb.plan.kh};
+  const int zdom = tile_zdom(vs.precision, vs.kind, vs.fast) ? 1 : 0;
+  if (vs.precision == 0) tile_unpack_kernel<double><<<nblk(g.n, 256), 256, 0, st>>>(pg, (const double*)tb.x[tb.cur], (double*)vs.x[vs.cur], 0);
+  else tile_unpack_kernel<float><<<nblk(g.n, 256), 256, 0, st>>>(pg, (const float*)tb.x[tb.cur], (float*)vs.x[vs.cur], zdom);
   g_launches++;
 }
 
@@ -1073,6 +1294,7 @@ void tile_unpack(const GridDev& g, const ViState& vs, const TileBuffers& tb, cud
 cudaError_t tile_sweeps_sharded(const GridDev& g, const ViState& vs, TileBuffers& tb, ViPeer& vp, long long nsweeps, bool want_res,
                                 cudaStream_t st) {
   const bool has_l = vp.rank > 0, has_r = vp.rank < vp.world - 1;
+  const int TKH = tb.plan.kh;
   while (nsweeps > 0) {
     const int nsub = (int)std::min<long long>(nsweeps, TKH);
     nsweeps -= nsub;

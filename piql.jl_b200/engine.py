@@ -251,7 +251,9 @@ class Engine:
         out = (C.c_int32 * 8)()
         self._ck(self._lib.piql_vi_tile_plan(self._ctx, {"nu": K.KIND_NU, "logz": K.KIND_LOGZ, "gap": K.KIND_GAP}[kind],
                                              K.PRECISIONS[precision], out))
-        return dict(zip(("TJ", "warps", "tiles_i", "tiles_j", "ctas_per_sm", "smem", "sweeps_per_round", "persistent"), list(out)))
+        d = dict(zip(("TJ", "warps", "tiles_i", "tiles_j", "ctas_per_sm", "smem", "sweeps_per_round", "persistent"), list(out)))
+        d["planes_in_smem"], d["persistent"] = d["persistent"] >> 1, d["persistent"] & 1
+        return d
 
     def vi_set_iterate(self, x):
         x = _cell(np.nan_to_num(np.asarray(x, dtype=np.float64)), self.H, self.W, "x")

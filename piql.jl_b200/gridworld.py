@@ -161,8 +161,12 @@ class GridTable:
     gamma: float
 
     def key(self):
-        return (self.walls.ctypes.data, self.walls.shape, self.goal, self.randomness, self.step_cost, self.reward,
-                self.gamma)
+        """Identity of the tabulated problem: a content hash of the wall bytes (not their address -- tabulate() copies the
+        wall array on every call, and a caller may edit walls in place) plus goal and parameters.  An unchanged problem is
+        loaded on the device once, a changed one always reloaded (solvers.engine_for)."""
+        import hashlib
+        digest = hashlib.blake2b(np.ascontiguousarray(self.walls.T).data, digest_size=16).hexdigest()
+        return (digest, self.walls.shape, self.goal, self.randomness, self.step_cost, self.reward, self.gamma)
 
 
 def tabulate(ctrl, probes=64):

@@ -34,10 +34,10 @@ def engine_for(ctrl, device=0):
     eng = _engines.get(device)
     if eng is None:
         eng = _engines[device] = Engine(device)
-    if eng.grid_key != tab.key():
+    key = tab.key()
+    if eng.grid_key != key:
         eng.load_grid(tab.walls, tab.goal, tab.randomness, tab.step_cost, tab.reward, tab.gamma)
-        eng.grid_key = tab.key()
-        eng._tab = tab  # keeps the wall array alive so the key's address stays unique
+        eng.grid_key = key
     return eng
 
 

@@ -124,3 +124,52 @@ def test_fp32_tiled_fixed_points_within_1e5_relative(engine, precision, bar):
     rel = np.abs(l32[free] - l64[free]) / np.maximum(1.0, np.abs(l64[free]))
     print(precision, "logz rel err max %.2e mean %.2e" % (rel.max(), rel.mean()))
     assert rel.max() < bar, rel.max()
+
+
+def test_fast_logz_reports_when_it_leaves_the_float_range(engine, piql):
+    """PIQL_F32_FAST log Z sweeps iterate on Z = exp(log Z) (linear domain, no transcendentals in a sweep): an iterate beyond
+    the float exponent range must be reported (PIQL_ERR_UNSUPPORTED), never returned as inf / NaN; the next solve on the context
+    starts clean, an underflowing start recovers (the 1 - gamma term is positive), and PIQL_F32 has no such limit."""
+    walls, goal = world((150, 70), 11)
+    engine.load_grid(walls, goal, **PARAMS)
+    V = np.asfortranarray(np.random.default_rng(2).normal(size=walls.shape) * 0.3)
+    free = walls == 0
+    engine.vi_prepare("logz", precision="f32fast", V=V, beta=0.7)
+    engine.vi_set_iterate(np.asfortranarray(np.full(walls.shape, 400.0)))
+    engine.vi_sweeps(4)
+    with pytest.raises(piql.PiqlError) as e:
+        engine.vi_fetch()
+    assert e.value.code == piql._capi.ERR_UNSUPPORTED
+    out, _ = gpu_sweeps(engine, "logz", np.full(walls.shape, 400.0), 4, precision="f32", V=V, beta=0.7)
+    assert np.isfinite(out[free]).all()
+    ref, _ = oracle_sweeps(oracle.Grid(walls, goal, **PARAMS), "logz", np.full(walls.shape, -400.0), 6, V=V, beta=0.7)
+    out, _ = gpu_sweeps(engine, "logz", np.full(walls.shape, -400.0), 6, precision="f32fast", V=V, beta=0.7)
+    assert np.isfinite(out[free]).all() and nmax(out, ref) < 1e-4
+
+
+def test_values_do_not_depend_on_depth_or_plane_staging(engine):
+    """The plan variants the library times -- 4 or 8 sweeps per round, constant planes in shared memory or read from global
+    memory -- are schedules of the same per-cell Jacobi update: every bit must agree, for every kind and precision."""
+    walls, goal = world((200, 180), 21)
+    engine.load_grid(walls, goal, **PARAMS)
+    rng = np.random.default_rng(1)
+    x0 = np.asfortranarray(rng.normal(size=walls.shape) * 0.5)
+    V = np.asfortranarray(rng.normal(size=walls.shape) * 0.3)
+    nu = np.asfortranarray(rng.normal(size=walls.shape) * 0.3)
+    cases = [("nu", {}, ("f64", "f32", "f32fast")), ("logz", dict(V=V, beta=0.6), ("f64", "f32fast")), ("gap", dict(V=V, nu=nu), ("f32", "f32fast"))]
+    try:
+        os.environ["PIQL_TILE_TJ"], os.environ["PIQL_TILE_NW"] = "26", "8"
+        for kind, kw, precs in cases:
+            for prec in precs:
+                outs = []
+                for kh, pm in (("4", "0"), ("8", "0"), ("4", "1"), ("8", "1")):
+                    os.environ["PIQL_TILE_KH"], os.environ["PIQL_TILE_PLANES_MODE"] = kh, pm
+                    out, _ = gpu_sweeps(engine, kind, x0, 13, precision=prec, **kw)
+                    plan = engine.vi_tile_plan(kind, prec)
+                    assert plan["sweeps_per_round"] == int(kh)
+                    outs.append(np.nan_to_num(out))
+                for o in outs[1:]:
+                    assert np.array_equal(outs[0], o), (kind, prec)
+    finally:
+        for k in ("PIQL_TILE_TJ", "PIQL_TILE_NW", "PIQL_TILE_KH", "PIQL_TILE_PLANES_MODE"):
+            os.environ.pop(k, None)

@@ -185,3 +185,19 @@ def test_library_path_override_fails_loudly_when_missing(tmp_path):
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PIQL_B200_LIB=missing), capture_output=True, text=True,
                        timeout=300)
     assert r.returncode == 0 and "IMPORTERROR" in r.stdout and missing in r.stdout, (r.stdout, r.stderr[-300:])
+
+
+def test_grid_key_is_content_based(piql):
+    """solvers.engine_for reloads the device grid iff the tabulated problem changed: the key hashes the wall bytes (tabulate()
+    copies the wall array, so an address would never match; an in-place edit must not leave a stale grid on the device)."""
+    from piql_jl_b200 import gridworld as G
+    gw = piql.make_gridworld((12, 9), density=0.2, rng=np.random.default_rng(4))
+    ctrl = piql.gridworld_ctrl(gw, randomness=0.05, gamma=0.97)
+    k1, k2 = G.tabulate(ctrl).key(), G.tabulate(ctrl).key()
+    assert k1 == k2 and hash(k1) == hash(k2)
+    assert G.tabulate(piql.gridworld_ctrl(gw, randomness=0.06, gamma=0.97)).key() != k1
+    i, j = np.argwhere(~gw.walls)[3]
+    if (i, j) == tuple(gw.goal):
+        i, j = np.argwhere(~gw.walls)[4]
+    gw.walls[i, j] = True                      # in place: same object, same address, other problem
+    assert G.tabulate(ctrl).key() != k1

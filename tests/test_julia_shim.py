@@ -176,3 +176,41 @@ def test_batched_stats_buffers_are_isbits_vectors():
     # the two batched calls hand a Vector{SolveStats} to a `piql_solve_stats*` that the library indexes as an array
     assert len(re.findall(r"Vector\{SolveStats\}\(undef", text)) == 2
     assert "mutable struct SolveStats" not in text and "mutable struct McStats" not in text
+
+
+# The reference's solver signatures (src/value_iteration.jl:42,54,77,107,119,144 -- `function generate_ν(ctrl)`,
+# `generate_logz(ctrl, V; β = 1.0)`, `logz_updateV(ctrl, V; β = 1.0)`, `generate_z(ctrl, V; β = 1.0)`,
+# `z_updateV(ctrl, V; β = 1.0)`, `generate_optimality_gap(ctrl, V; ν = generate_ν(ctrl))`): the shim must extend exactly
+# these functions of PIQL with methods on ControlProblem, so scripts/experiments.jl:10-39 runs unchanged.
+REFERENCE_SIGNATURES = {
+    "generate_ν": ([], []),
+    "generate_logz": (["V"], ["β = 1.0"]),
+    "logz_updateV": (["V"], ["β = 1.0"]),
+    "generate_z": (["V"], ["β = 1.0"]),
+    "z_updateV": (["V"], ["β = 1.0"]),
+    "generate_optimality_gap": (["V"], ["ν = generate_ν(ctrl)"]),
+}
+
+
+def test_reference_signatures_are_extended_on_controlproblem():
+    text = open(JL).read()
+    imp = re.search(r"^import PIQL: (generate_ν.*)$", text, flags=re.M)
+    assert imp, "the solver functions must be imported from PIQL to be extended (not shadowed)"
+    imported = {n.strip() for n in imp.group(1).split(",")}
+    assert set(REFERENCE_SIGNATURES) <= imported, set(REFERENCE_SIGNATURES) - imported
+    for name, (pos, kws) in REFERENCE_SIGNATURES.items():
+        m = re.search(r"^function %s\(ctrl::ControlProblem(.*?)\)\s*$" % re.escape(name), text, flags=re.M)
+        assert m, "no method %s(ctrl::ControlProblem, ...)" % name
+        rest = m.group(1)
+        positional, _, keywords = rest.partition(";")
+        got_pos = [a.strip() for a in positional.split(",") if a.strip()]
+        assert got_pos == pos, (name, got_pos)
+        got_kw = [k.strip() for k in split_top(keywords) if k.strip()]
+        for k in kws:      # the reference's keywords with the reference's defaults; extra solver options ride in kw...
+            assert k in got_kw, (name, k, got_kw)
+        assert got_kw[-1] == "kw..."
+    # the registry recognises gridworld_ctrl problems from the closures' captured variables and reloads on change
+    assert "function gridworld_of(ctrl::ControlProblem)" in text and "function context_for(ctrl::ControlProblem)" in text
+    assert re.search(r"key = \(:grid, hash\(gw\.walls\)", text), "the loaded-problem key must hash the wall contents"
+    # scripts/experiments.jl:20 spells run_experiment(gw; ...): no context argument
+    assert re.search(r"^run_experiment\(gw; kw\.\.\.\) =", text, flags=re.M)

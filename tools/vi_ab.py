@@ -4,9 +4,9 @@
     time  (GPU box):  python tools/vi_ab.py time [grid1024|grid4096 ...]          -> us/sweep of every variant + the product build
 Each timing runs in its own process with PIQL_B200_LIB pointing at the variant.
 Switches the sources honour: PIQL_TILE_UNROLL (columns a warp interleaves, default 1), PIQL_TILE_PACKED (FADD2/FFMA2 nu cell, 1),
-PIQL_LOGZ_OWN_SHIFT (6-MUFU log Z cell, 1), PIQL_TILE_KH (sweeps per launch = ghost depth, a multiple of 4, default 4 -- deeper
-blocking for the 10^6-cell grids has been built but not timed yet; run the tiled tests against the variant first:
-PIQL_B200_LIB=tools/probe/variants/libpiql_kh8.so pytest tests/test_gpu_tiled.py -m gpu)."""
+PIQL_LOGZ_ZDOM (linear-domain fast log Z, 1), PIQL_TILE_PLANES (constant planes in shared memory, 1).  The depth of the temporal
+blocking (4 or 8 sweeps per round) and planes-in-shared-memory are plan variants the library times itself; PIQL_TILE_KH and
+PIQL_TILE_PLANES_MODE pin them."""
 import glob
 import json
 import os
@@ -34,7 +34,7 @@ for kind, prec, kw in (("nu", "f32fast", {}), ("nu", "f32", {}), ("nu", "f64", {
         t0 = time.perf_counter(); eng.vi_sweeps(400); eng.vi_fetch(want_x=False)
         best = min(best, (time.perf_counter() - t0) / 400 * 1e6)
     p = eng.vi_tile_plan(kind, prec)
-    out[kind + "_" + prec] = (round(best, 2), p["TJ"], p["warps"], p["ctas_per_sm"], p["persistent"])
+    out[kind + "_" + prec] = (round(best, 2), p["TJ"], p["warps"], p["ctas_per_sm"], p["persistent"], p["sweeps_per_round"], p["planes_in_smem"])
 print(json.dumps(out))
 """ % ROOT
 
