@@ -607,19 +607,27 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end through the public call, host buffers in pinned memory --------------------
     e2e = None
     if not args.no_e2e:
+        fdt, cdt, ob = (np.float32, np.uint32, 4) if args.e2e_f32 else (np.float64, np.uint64, 8)
         Vp, _k1 = pinned((H, W), np.float64, order="F")
         Vp[...] = V
-        sa, _k2 = pinned((n, 4), np.float64)
-        cn, _k3 = pinned((n, 4), np.uint64)
-        ls, _k4 = pinned((H, W), np.float64, order="F")
-        reps = max(1, min(args.steps, 3))
+        bufs, keep = [], []
+        for _ in range(2):      # two sets of pinned result buffers alternate: iteration k is read while k + 1 is produced
+            sa, k2 = pinned((n, 4), fdt)
+            cn, k3 = pinned((n, 4), cdt)
+            ls, k4 = pinned((H, W), fdt, order="F")
+            bufs.append((sa, cn, ls)); keep += [k2, k3, k4]
+        est = pd.ShardedEstimator(eng, rank, world, P, mode=args.exchange, root_only=True, out_dtype=fdt, buffers=bufs)
+        reps = max(2, min(args.steps, 4))
         tot = 0.0
-        pd.mc_logz_sharded(eng, Vp, BETA, P, rank, world, seed=MC_SEED + 1, out=(sa, cn, ls), mode=args.exchange, root_only=True)   # warm-up
+        est.step(Vp, BETA, seed=MC_SEED + 1)   # warm-up
+        est.finish()
         barrier()
         t0 = time.perf_counter()
         for i in range(reps):
-            _sa, _cn, _ls, st = pd.mc_logz_sharded(eng, Vp, BETA, P, rank, world, seed=MC_SEED + 2 + i, out=(sa, cn, ls), mode=args.exchange, root_only=True)
-            tot += float(st.transitions)
+            prev = est.step(Vp, BETA, seed=MC_SEED + 2 + i)       # returns iteration i - 1, downloaded under iteration i's rollout
+            if prev is not None:
+                tot += float(prev[1].transitions)
+        tot += float(est.finish()[1].transitions)
         barrier()
         dt = time.perf_counter() - t0
         stat = torch.tensor([dt, tot], dtype=torch.float64, device="cuda:%d" % local_rank)
@@ -627,10 +635,12 @@ def run_ours(args, rank, world, local_rank):
             mx = stat.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             sm = stat.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
             dt, tot = float(mx[0]), float(sm[1])
-        e2e = {"value": tot / dt, "unit": "transitions/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 72 * n,
-               "steps": reps, "ms_per_step": 1e3 * dt / reps,
-               "call": "piql_policy_table + piql_mc_reset_dev + piql_mc_rollout_dev (+ all-reduce) + piql_mc_finalize "
-                       "with pinned host V in on every rank, logz_sa / count_sa / logz_s out on rank 0 (results are replicated)"}
+        e2e = {"value": tot / dt, "unit": "transitions/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 9 * ob * n,
+               "steps": reps, "ms_per_step": 1e3 * dt / reps, "output_dtype": "f32/u32" if args.e2e_f32 else "f64/u64",
+               "call": "per iteration: piql_policy_table (pinned host V in, every rank) + piql_mc_reset_dev + piql_mc_rollout_dev "
+                       "(+ exchange) + piql_mc_finalize_async; logz_sa / count_sa / logz_s land in pinned host buffers on rank 0 "
+                       "(results are replicated) through the library's copy stream while the next iteration rolls out; the timed "
+                       "region ends when the last iteration's results are on the host (piql_mc_finalize_wait)"}
 
     # ---- soft-VI sweeps on the same grid (rank 0) ----------------------------------------------
     # algorithmic bytes per state per sweep: nu 2 x sizeof(T), logz 3 x, gap 4 x
@@ -742,6 +752,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: fused log-sum-exp all-reduce kernel over NVLink peer memory, or three NCCL all-reduces")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-f32", action="store_true", help="end-to-end leg downloads float32 / uint32 results (36 B per cell instead of 72)")
     ap.add_argument("--no-vi", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed launch's records and accumulators")

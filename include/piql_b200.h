@@ -255,6 +255,15 @@ int32_t piql_mc_stats_dev(piql_ctx* ctx, void** lse_max_dev, void** lse_sum_dev,
 int32_t piql_mc_rescale_dev(piql_ctx* ctx, const void* global_max_dev);
 int32_t piql_mc_finalize(piql_ctx* ctx, double* logz_sa_out, uint64_t* count_sa_out, double* logz_s_out,
                          piql_mc_stats* stats_out);
+/* Asynchronous finalisation, for iterating callers: the accumulators are snapshot on the context's stream (a device copy),
+ * then finalised and copied to the caller's host buffers on a second stream while the context's stream goes on with the
+ * next iteration (piql_policy_table / piql_mc_reset_dev / piql_mc_rollout_dev ...).  The host buffers (pinned memory makes
+ * the copy truly asynchronous) must stay valid and unread until piql_mc_finalize_wait returns; at most one finalisation is
+ * in flight (a second call waits for the first on the device).  f32_outputs = 0: double / uint64 outputs as piql_mc_finalize;
+ * 1: float / uint32 outputs of the same shapes (36 instead of 72 bytes per cell over PCIe).  Any output may be null.
+ * Replaces the master collecting the workers' results (scripts/distributed_experiments.jl:49-58). */
+int32_t piql_mc_finalize_async(piql_ctx* ctx, void* logz_sa_out, void* count_sa_out, void* logz_s_out, int32_t f32_outputs);
+int32_t piql_mc_finalize_wait(piql_ctx* ctx, piql_mc_stats* stats_out);
 /* The exchange step as ONE kernel over NVLink peer memory (one process per GPU, all on one box): rank r pulls
  * slice r of every rank's three accumulator arrays through CUDA-IPC peer mappings, combines the triples and
  * pushes the result into every rank's arrays (replaces the three all-reduces + rescale above).
@@ -309,6 +318,9 @@ typedef struct {
 int32_t piql_vi_shard_begin(piql_ctx* ctx, int32_t rank, int32_t world, piql_vi_shard_handles* out);
 int32_t piql_vi_shard_connect(piql_ctx* ctx, const piql_vi_shard_handles* all);
 int32_t piql_vi_shard_end(piql_ctx* ctx);
+/* Diagnostics of the halo exchange since the last call (or piql_vi_shard_begin): microseconds this rank's edge CTAs spent
+ * waiting for a neighbour's counter, summed over the waiting CTAs, and the number of such waits (edge CTAs x rounds). */
+int32_t piql_vi_shard_wait_stats(piql_ctx* ctx, double* wait_us_out, int64_t* waits_out);
 
 /* Kernels launched by this context since creation (for the bench's gpu_launches count). */
 int32_t piql_launch_count(piql_ctx* ctx, int64_t* n_out);

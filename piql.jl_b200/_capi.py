@@ -100,6 +100,8 @@ SYMBOLS = {
     "piql_peer_close": (C.c_int32, [_P]),
     "piql_mc_timing": (C.c_int32, [_P, _D, _D, C.POINTER(C.c_int64)]),
     "piql_mc_transitions_total": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
+    "piql_mc_finalize_async": (C.c_int32, [_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "piql_mc_finalize_wait": (C.c_int32, [_P, C.POINTER(McStats)]),
     "piql_mc_records": (C.c_int32, [_P, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_int64]),
     "piql_vi_prepare_dev": (C.c_int32, [_P, C.c_int32, _D, _D, _D, C.c_double, C.c_double, C.c_int32]),
     "piql_learning_traj": (C.c_int32, [_P, _D, _D, C.c_int32, C.c_int32, C.POINTER(SolveOpts), _D, C.POINTER(SolveStats)]),
@@ -112,6 +114,7 @@ SYMBOLS = {
     "piql_vi_shard_begin": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(ViShardHandles)]),
     "piql_vi_shard_connect": (C.c_int32, [_P, C.POINTER(ViShardHandles)]),
     "piql_vi_shard_end": (C.c_int32, [_P]),
+    "piql_vi_shard_wait_stats": (C.c_int32, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "piql_vi_set_iterate": (C.c_int32, [_P, C.POINTER(C.c_double)]),
     "piql_vi_tile_plan": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "piql_vi_sweeps_dev": (C.c_int32, [_P, C.c_int64]),

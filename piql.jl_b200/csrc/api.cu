@@ -77,6 +77,18 @@ struct piql_ctx {
   float* d_inj = nullptr;
   size_t inj_cap = 0;
   unsigned long long paths_done = 0;
+  // asynchronous finalisation (piql_mc_finalize_async): a snapshot of the accumulators is finalised and copied to the
+  // host on a second stream while the context's stream goes on with the next iteration
+  cudaStream_t cstream = nullptr;
+  cudaEvent_t ev_snap = nullptr, ev_done = nullptr;
+  float *snap_max = nullptr, *snap_sum = nullptr;
+  uint32_t* snap_cnt = nullptr;
+  long long snap_cap = 0;
+  unsigned char* fin_out = nullptr;   // device staging of the outputs
+  size_t fin_cap = 0;
+  unsigned long long* h_fin_transitions = nullptr;  // pinned
+  unsigned long long fin_paths = 0;
+  bool fin_pending = false;
   // per-launch timing: triples (before rollout, after rollout, after reduce) since the last reset
   std::vector<cudaEvent_t> tev;
   size_t tev_used = 0;
@@ -488,6 +500,72 @@ int mc_finalize(piql_ctx* ctx, double* logz_sa, uint64_t* count_sa, double* logz
   return PIQL_OK;
 }
 
+// Snapshot + second-stream finalisation.  f32: outputs are float / uint32 instead of double / uint64.
+int mc_finalize_async(piql_ctx* ctx, void* logz_sa, void* count_sa, void* logz_s, bool f32) {
+  cudaStream_t st = ctx->stream;
+  const long long n = ctx->g.n, na = ctx->nstarts * NA;
+  NEED(ctx->nstarts > 0, PIQL_ERR_STATE, "no Monte-Carlo run to finalise");
+  if (!ctx->cstream) {
+    CK(cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_snap, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
+    CK(cudaMallocHost((void**)&ctx->h_fin_transitions, 16));
+  }
+  // the previous snapshot must have been consumed before it is overwritten (and before its host buffers are reused)
+  if (ctx->fin_pending) CK(cudaStreamWaitEvent(st, ctx->ev_done, 0));
+  if (na > ctx->snap_cap) {
+    CK(cudaStreamSynchronize(ctx->cstream));
+    for (void* p : {(void*)ctx->snap_max, (void*)ctx->snap_sum, (void*)ctx->snap_cnt}) if (p) cudaFree(p);
+    ctx->snap_max = ctx->snap_sum = nullptr; ctx->snap_cnt = nullptr; ctx->snap_cap = 0;
+    CK(cudaMalloc((void**)&ctx->snap_max, 4 * (size_t)na));
+    CK(cudaMalloc((void**)&ctx->snap_sum, 4 * (size_t)na));
+    CK(cudaMalloc((void**)&ctx->snap_cnt, 4 * (size_t)na));
+    ctx->snap_cap = na;
+  }
+  const size_t ef = f32 ? 4 : 8;   // bytes per output element (values and counts alike)
+  const size_t need = ef * 9 * (size_t)n + 64;
+  if (need > ctx->fin_cap) {
+    CK(cudaStreamSynchronize(ctx->cstream));
+    if (ctx->fin_out) cudaFree(ctx->fin_out);
+    ctx->fin_out = nullptr; ctx->fin_cap = 0;
+    CK(cudaMalloc((void**)&ctx->fin_out, need));
+    ctx->fin_cap = need;
+  }
+  CK(cudaMemcpyAsync(ctx->snap_max, ctx->acc_max, 4 * (size_t)na, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(ctx->snap_sum, ctx->acc_sum, 4 * (size_t)na, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(ctx->snap_cnt, ctx->acc_cnt, 4 * (size_t)na, cudaMemcpyDeviceToDevice, st));
+  unsigned long long* d_tr = reinterpret_cast<unsigned long long*>(ctx->fin_out + ef * 9 * (size_t)n);
+  CK(cudaMemcpyAsync(d_tr, ctx->d_transitions, 8, cudaMemcpyDeviceToDevice, st));
+  CK(cudaEventRecord(ctx->ev_snap, st));
+  cudaStream_t cs = ctx->cstream;
+  CK(cudaStreamWaitEvent(cs, ctx->ev_snap, 0));
+  unsigned char* d_sa = ctx->fin_out;                      // [n][4] values
+  unsigned char* d_cnt = d_sa + ef * 4 * (size_t)n;        // [n][4] counts
+  unsigned char* d_s = d_cnt + ef * 4 * (size_t)n;         // [n] values
+  if (f32) {
+    if (logz_sa) launch_fill_f32((float*)d_sa, NAN, 4 * n, cs);
+    if (logz_s) launch_fill_f32((float*)d_s, NAN, n, cs);
+    if (count_sa) CK(cudaMemsetAsync(d_cnt, 0, 16 * (size_t)n, cs));
+    launch_mc_finalize_f32(ctx->snap_max, ctx->snap_sum, ctx->snap_cnt, ctx->d_starts, ctx->nstarts, logz_sa ? (float*)d_sa : nullptr,
+                           count_sa ? (uint32_t*)d_cnt : nullptr, logz_s ? (float*)d_s : nullptr, cs);
+  } else {
+    if (logz_sa) launch_fill_f64((double*)d_sa, NAN, 4 * n, cs);
+    if (logz_s) launch_fill_f64((double*)d_s, NAN, n, cs);
+    if (count_sa) CK(cudaMemsetAsync(d_cnt, 0, 32 * (size_t)n, cs));
+    launch_mc_finalize(ctx->snap_max, ctx->snap_sum, ctx->snap_cnt, ctx->d_starts, ctx->nstarts, logz_sa ? (double*)d_sa : nullptr,
+                       count_sa ? (unsigned long long*)d_cnt : nullptr, logz_s ? (double*)d_s : nullptr, cs);
+  }
+  CK_LAST();
+  if (logz_sa) CK(cudaMemcpyAsync(logz_sa, d_sa, ef * 4 * (size_t)n, cudaMemcpyDeviceToHost, cs));
+  if (count_sa) CK(cudaMemcpyAsync(count_sa, d_cnt, ef * 4 * (size_t)n, cudaMemcpyDeviceToHost, cs));
+  if (logz_s) CK(cudaMemcpyAsync(logz_s, d_s, ef * (size_t)n, cudaMemcpyDeviceToHost, cs));
+  CK(cudaMemcpyAsync(ctx->h_fin_transitions, d_tr, 8, cudaMemcpyDeviceToHost, cs));
+  CK(cudaEventRecord(ctx->ev_done, cs));
+  ctx->fin_pending = true;
+  ctx->fin_paths = ctx->paths_done;
+  return PIQL_OK;
+}
+
 int build_table(piql_ctx* ctx, const double* V, const double* Q, double beta, float* kl_dev = nullptr) {
   NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded (call piql_grid_load first)");
   NEED(V != nullptr, PIQL_ERR_ARG, "V is null");
@@ -561,6 +639,7 @@ int32_t piql_destroy(piql_ctx* ctx) {
   peer_close(ctx);
   vpeer_close(ctx);
   if (ctx->vpeer.own_flags) cudaFree(ctx->vpeer.own_flags);
+  if (ctx->vpeer.wait_stats) cudaFree(ctx->vpeer.wait_stats);
   free_table(ctx);
   if (ctx->peer.own_flags) cudaFree(ctx->peer.own_flags);
   if (ctx->peer.done) cudaFree(ctx->peer.done);
@@ -569,8 +648,12 @@ int32_t piql_destroy(piql_ctx* ctx) {
   for (void* p : {(void*)ctx->d_walls, (void*)ctx->d_cell, (void*)ctx->d_free, (void*)ctx->d_table, (void*)ctx->d_rec, (void*)ctx->d_logw,
                   (void*)ctx->d_meta, (void*)ctx->d_starts_own, (void*)ctx->acc_max, (void*)ctx->acc_sum,
                   (void*)ctx->acc_cnt, (void*)ctx->d_scratch, (void*)ctx->d_transitions, (void*)ctx->d_inj,
-                  (void*)ctx->d_scalars})
+                  (void*)ctx->d_scalars, (void*)ctx->snap_max, (void*)ctx->snap_sum, (void*)ctx->snap_cnt, (void*)ctx->fin_out})
     if (p) cudaFree(p);
+  if (ctx->h_fin_transitions) cudaFreeHost(ctx->h_fin_transitions);
+  if (ctx->ev_snap) cudaEventDestroy(ctx->ev_snap);
+  if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+  if (ctx->cstream) cudaStreamDestroy(ctx->cstream);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
   if (ctx->h_transitions) cudaFreeHost(ctx->h_transitions);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1153,8 +1236,10 @@ int32_t piql_vi_shard_begin(piql_ctx* ctx, int32_t rank, int32_t world, piql_vi_
   ctx->tb.tj1 = (int)((long long)pl.tiles_j * (rank + 1) / world);
   CK(tile_begin(ctx->g, ctx->d_cell, ctx->vs, ctx->tb, ctx->num_sms, st));  // packs the iterate in the shared shape
   if (!vp.own_flags) CK(cudaMalloc((void**)&vp.own_flags, 4 * sizeof(unsigned)));
+  if (!vp.wait_stats) CK(cudaMalloc((void**)&vp.wait_stats, 2 * sizeof(unsigned long long)));
   CK(cudaStreamSynchronize(st));
   CK(cudaMemset(vp.own_flags, 0, 4 * sizeof(unsigned)));
+  CK(cudaMemset(vp.wait_stats, 0, 2 * sizeof(unsigned long long)));
   vp.done = vp.own_flags + 2;
   vp.round = 0; vp.rank = rank; vp.world = world;
   CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->x0, ctx->tb.x[0]));
@@ -1191,6 +1276,19 @@ int32_t piql_vi_shard_connect(piql_ctx* ctx, const piql_vi_shard_handles* all) {
     vp.x[0][r] = p[0]; vp.x[1][r] = p[1]; vp.flags[r] = (unsigned*)p[2];
   }
   vp.valid = true;
+  return PIQL_OK;
+}
+int32_t piql_vi_shard_wait_stats(piql_ctx* ctx, double* wait_us_out, int64_t* waits_out) {
+  if (!ctx) return PIQL_ERR_ARG;
+  ViPeer& vp = ctx->vpeer;
+  NEED(vp.wait_stats != nullptr, PIQL_ERR_STATE, "call piql_vi_shard_begin first");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  unsigned long long h[2] = {0, 0};
+  CK(cudaMemcpy(h, vp.wait_stats, sizeof(h), cudaMemcpyDeviceToHost));
+  CK(cudaMemset(vp.wait_stats, 0, sizeof(h)));
+  if (wait_us_out) *wait_us_out = 1e-3 * (double)h[0];
+  if (waits_out) *waits_out = (int64_t)h[1];
   return PIQL_OK;
 }
 int32_t piql_vi_shard_end(piql_ctx* ctx) {
@@ -1510,6 +1608,29 @@ int32_t piql_mc_finalize(piql_ctx* ctx, double* logz_sa_out, uint64_t* count_sa_
   CK(cudaSetDevice(ctx->device));
   NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded");
   return mc_finalize(ctx, logz_sa_out, count_sa_out, logz_s_out, stats);
+}
+int32_t piql_mc_finalize_async(piql_ctx* ctx, void* logz_sa_out, void* count_sa_out, void* logz_s_out, int32_t f32_outputs) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded");
+  return mc_finalize_async(ctx, logz_sa_out, count_sa_out, logz_s_out, f32_outputs != 0);
+}
+int32_t piql_mc_finalize_wait(piql_ctx* ctx, piql_mc_stats* stats_out) {
+  if (!ctx) return PIQL_ERR_ARG;
+  NEED(ctx->fin_pending, PIQL_ERR_STATE, "no asynchronous finalisation in flight (call piql_mc_finalize_async first)");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->ev_done));
+  ctx->fin_pending = false;
+  if (ctx->peer.err && *ctx->peer.err)
+    return fail(ctx, PIQL_ERR_CUDA, "the peer exchange timed out waiting for another rank (did every rank call it?)");
+  if (stats_out) {
+    stats_out->transitions = *ctx->h_fin_transitions;
+    stats_out->paths = ctx->fin_paths;
+    stats_out->rollout_seconds = 0.0;   // the per-launch event timers belong to the stream that may still be running
+    stats_out->device_seconds = 0.0;
+  }
+  return PIQL_OK;
 }
 int32_t piql_mc_timing(piql_ctx* ctx, double* rollout_seconds, double* reduce_seconds, int64_t* launches) {
   if (!ctx) return PIQL_ERR_ARG;

@@ -57,6 +57,7 @@ struct TileHalo {
   unsigned post_epoch = 0;
   int tj_first = -1, tj_last = -1;
   int* err = nullptr;
+  unsigned long long* wait_stats = nullptr;  // [0] nanoseconds edge CTAs spent waiting for a neighbour's counter, [1] waits
 };
 struct TileBuffers {
   void* x[2] = {nullptr, nullptr};  // padded ping-pong iterate
@@ -186,7 +187,10 @@ void launch_mc_rescale(float* acc_max, float* acc_sum, const float* gmax, long l
 void launch_mc_finalize(const float* acc_max, const float* acc_sum, const uint32_t* acc_cnt, const int* starts,
                         long long nstarts, double* logz_sa, unsigned long long* count_sa, double* logz_s,
                         cudaStream_t st);
+void launch_mc_finalize_f32(const float* acc_max, const float* acc_sum, const uint32_t* acc_cnt, const int* starts,
+                            long long nstarts, float* logz_sa, uint32_t* count_sa, float* logz_s, cudaStream_t st);
 void launch_fill_f64(double* dst, double v, long long n, cudaStream_t st);
+void launch_fill_f32(float* dst, float v, long long n, cudaStream_t st);
 void launch_mc_apply_update(const float* acc_max, const float* acc_sum, const uint32_t* acc_cnt, const int* starts,
                             long long nstarts, double beta, double* V, cudaStream_t st);
 
@@ -246,6 +250,7 @@ struct ViPeer {
   unsigned* flags[PEER_MAX] = {};      // flags[r] on rank r: [0] rounds delivered by its left neighbour, [1] by its right one
   unsigned* own_flags = nullptr;       // [0], [1]: counters the neighbours raise; [2]: blocks of my push kernel that are done
   unsigned* done = nullptr;
+  unsigned long long* wait_stats = nullptr;  // device: [0] ns waited for halos, [1] number of waits (piql_vi_shard_wait_stats)
   long long round = 0;                 // rounds completed since the iterate was (re)packed
   bool valid = false;
   void* opened[3 * PEER_MAX] = {};

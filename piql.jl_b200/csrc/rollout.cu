@@ -544,9 +544,11 @@ void launch_mc_rescale(float* acc_max, float* acc_sum, const float* gmax, long l
   mc_rescale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc_max, acc_sum, gmax, n);
   g_launches++;
 }
+// TF / TC: output types -- double / uint64 (the ABI's default) or float / uint32 (half the device-to-host bytes)
+template <typename TF, typename TC>
 __global__ void mc_finalize_kernel(const float* __restrict__ m, const float* __restrict__ s, const uint32_t* __restrict__ c,
-                                   const int* __restrict__ starts, long long nstarts, double* __restrict__ logz_sa,
-                                   unsigned long long* __restrict__ count_sa, double* __restrict__ logz_s) {
+                                   const int* __restrict__ starts, long long nstarts, TF* __restrict__ logz_sa,
+                                   TC* __restrict__ count_sa, TF* __restrict__ logz_s) {
   const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= nstarts) return;
   const size_t cellidx = (size_t)starts[slot];
@@ -556,8 +558,8 @@ __global__ void mc_finalize_kernel(const float* __restrict__ m, const float* __r
   for (int a = 0; a < NA; a++) {
     const size_t i = (size_t)slot * NA + a;
     const uint32_t cnt = c[i];
-    if (logz_sa) logz_sa[cellidx * NA + a] = cnt ? (double)m[i] + log((double)s[i]) - log((double)cnt) : CUDART_NAN;
-    if (count_sa) count_sa[cellidx * NA + a] = cnt;
+    if (logz_sa) logz_sa[cellidx * NA + a] = (TF)(cnt ? (double)m[i] + log((double)s[i]) - log((double)cnt) : CUDART_NAN);
+    if (count_sa) count_sa[cellidx * NA + a] = (TC)cnt;
     if (cnt && (double)m[i] > mm) mm = (double)m[i];
     ctot += cnt;
   }
@@ -568,14 +570,28 @@ __global__ void mc_finalize_kernel(const float* __restrict__ m, const float* __r
       const size_t i = (size_t)slot * NA + a;
       if (c[i]) tot += (double)s[i] * exp((double)m[i] - mm);
     }
-    logz_s[cellidx] = ctot ? mm + log(tot) - log((double)ctot) : CUDART_NAN;
+    logz_s[cellidx] = (TF)(ctot ? mm + log(tot) - log((double)ctot) : CUDART_NAN);
   }
 }
 void launch_mc_finalize(const float* acc_max, const float* acc_sum, const uint32_t* acc_cnt, const int* starts,
                         long long nstarts, double* logz_sa, unsigned long long* count_sa, double* logz_s,
                         cudaStream_t st) {
-  mc_finalize_kernel<<<(unsigned)((nstarts + 255) / 256), 256, 0, st>>>(acc_max, acc_sum, acc_cnt, starts, nstarts, logz_sa,
-                                                                        count_sa, logz_s);
+  mc_finalize_kernel<double, unsigned long long><<<(unsigned)((nstarts + 255) / 256), 256, 0, st>>>(
+      acc_max, acc_sum, acc_cnt, starts, nstarts, logz_sa, count_sa, logz_s);
+  g_launches++;
+}
+void launch_mc_finalize_f32(const float* acc_max, const float* acc_sum, const uint32_t* acc_cnt, const int* starts,
+                            long long nstarts, float* logz_sa, uint32_t* count_sa, float* logz_s, cudaStream_t st) {
+  mc_finalize_kernel<float, uint32_t><<<(unsigned)((nstarts + 255) / 256), 256, 0, st>>>(acc_max, acc_sum, acc_cnt, starts,
+                                                                                         nstarts, logz_sa, count_sa, logz_s);
+  g_launches++;
+}
+__global__ void fill_f32_kernel(float* dst, float v, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
+}
+void launch_fill_f32(float* dst, float v, long long n, cudaStream_t st) {
+  fill_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, v, n);
   g_launches++;
 }
 // The Monte-Carlo form of logz_updateV (value_iteration.jl:119-124): V(s) += log Z^(s) / beta for every start slot that

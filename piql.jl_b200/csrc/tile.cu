@@ -95,6 +95,17 @@ template <> __device__ __forceinline__ void ldg4<double>(const double* p, double
   o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
 }
 
+// L2-only loads (ld.global.cg): data another SM wrote during this kernel must not be served from a stale L1 line
+template <typename T> __device__ __forceinline__ void ldcg4(const T* p, T (&o)[4]);
+template <> __device__ __forceinline__ void ldcg4<float>(const float* p, float (&o)[4]) {
+  const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <> __device__ __forceinline__ void ldcg4<double>(const double* p, double (&o)[4]) {
+  const double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p + 2));
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+
 // ---- TMA (cp.async.bulk.tensor) staging of a tile: one thread issues, an mbarrier (common.cuh) counts the bytes ----
 __device__ __forceinline__ unsigned long long globaltimer_ns_tile() {
   unsigned long long t;
@@ -446,6 +457,10 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
           __nanosleep(100);
         }
       }
+      if (halo.wait_stats) {
+        atomicAdd(halo.wait_stats, globaltimer_ns_tile() - t0);
+        atomicAdd(halo.wait_stats + 1, 1ull);
+      }
       __threadfence_system();
       asm volatile("fence.proxy.async;" ::: "memory");  // the peer's stores, just acquired, before this thread's TMA reads
     }
@@ -561,9 +576,12 @@ tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, con
 // For grids whose tiles are all resident at once (<= CTAs per SM x SMs: the 10^6-cell problems), a launch per
 // TILE_KH sweeps pays a grid-wide barrier, a tail and a pipeline refill every few microseconds.  Here every CTA keeps
 // its tile for the whole batch and synchronises with its (up to 8) neighbouring tiles only: round r waits until they
-// have published round r-1 (a counter per tile, release/acquire at gpu scope), re-stages the tile from the ping-pong
-// global arrays with TMA, sweeps, writes its interior back and publishes r.  Waiting for "neighbours finished r-1"
-// before round r also makes the write-back of round r safe: it overwrites the copy they staged in round r-1.
+// have published round r-1 (a counter per tile, release/acquire at gpu scope).  The tile's interior STAYS in shared memory
+// from round to round: only the halo ring (kh cells deep) is re-read from the ping-pong global arrays, and only the ring of
+// interior cells the neighbours need (kh deep) is written back -- the whole interior just once, after the last round.  (The
+// first version re-staged the whole tile with TMA and wrote the whole interior back every round: it never beat one launch
+// per round.)  Waiting for "neighbours finished r-1" before round r also makes the write-back of round r safe: it
+// overwrites the copy they read in round r-1.
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -624,26 +642,38 @@ tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, c
     if (threadIdx.x == 0) s_abort = *(volatile int*)err;
     __syncthreads();
     if (s_abort) break;  // block-uniform: somebody timed out; the host reports it
-    if (threadIdx.x == 0) {
-      // order this CTA's earlier generic-proxy accesses of the buffers, and the neighbours' global writes just
-      // acquired, before the TMA engine (async proxy) overwrites / reads them
-      asm volatile("fence.proxy.async;" ::: "memory");
-      mbar_expect_tx(&mbar, (unsigned)(EJ * TEI * sizeof(T) + (r == 0 ? EJ * (TMB + NP * TEI * sizeof(T)) : 0)));
-      tma_load_2d(bufA, (r & 1) ? &tmB : &tmA, ti * k.tti, tj * k.TJ, &mbar);
-      if (r == 0) {  // the cell bytes and the constant planes stay for all rounds
+    const int hl = k.kh / 4;  // halo lanes at the top / bottom of a column (a lane holds 4 rows)
+    if (r == 0) {
+      // the whole tile, its cell bytes and the constant planes: TMA boxes, once per launch
+      if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_expect_tx(&mbar, (unsigned)(EJ * (TEI * sizeof(T) + TMB + NP * TEI * sizeof(T))));
+        tma_load_2d(bufA, &tmA, ti * k.tti, tj * k.TJ, &mbar);
         tma_load_2d(msk0, &tmM, ti * k.tti - moff, tj * k.TJ, &mbar);
 #pragma unroll
         for (int q = 0; q < NP; q++) tma_load_3d(planes + q * EJ * TEI, &tmP, ti * k.tti, tj * k.TJ, q, &mbar);
       }
+      mbar_wait(&mbar, 0);
+      if (warp < 2) {  // the outermost columns are never recomputed: keep both ping-pong copies defined
+        const int jj = warp == 0 ? 0 : EJ - 1;
+        T v[4];
+        lds4(bufA + jj * TEI + 4 * lane, v);
+        sts4(bufB + jj * TEI + 4 * lane, v);
+      }
+    } else {
+      // the interior is already here (bufA: every round but the last has an even number of sweeps); refresh the halo ring
+      // from what the neighbours published: whole columns at the left / right edge, the top / bottom strips elsewhere
+      for (int jj = warp; jj < EJ; jj += NW) {
+        const bool edge = jj < k.kh || jj >= EJ - k.kh;
+        if (edge || lane < hl || lane >= 32 - hl) {
+          T v[4];
+          ldcg4(Xin + org + jj * ld + 4 * lane, v);
+          sts4(bufA + jj * TEI + 4 * lane, v);
+          if (jj == 0 || jj == EJ - 1) sts4(bufB + jj * TEI + 4 * lane, v);
+        }
+      }
     }
-    mbar_wait(&mbar, r & 1);
-    if (warp < 2) {  // the outermost columns are never recomputed: keep both ping-pong copies defined
-      const int jj = warp == 0 ? 0 : EJ - 1;
-      T v[4];
-      lds4(bufA + jj * TEI + 4 * lane, v);
-      sts4(bufB + jj * TEI + 4 * lane, v);
-    }
-      __syncthreads();
+    __syncthreads();
     src = bufA; dst = bufB;
     for (int sub = 0; sub < nsub; sub++) {
       tile_subsweep<T, KIND, FAST, PL>(k, src, dst, msk, aux, org, lane, warp, NW, sub);
@@ -654,9 +684,13 @@ tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, c
       }
       T* t = src; src = dst; dst = t;
     }
-    (void)Xin;
-    if (lane >= k.kh / 4 && lane < 32 - k.kh / 4) {
+    // publish: after the last round the whole interior, before that only the ring of interior cells within kh of its
+    // boundary -- what the eight neighbours read as their halo
+    const bool last_round = r == nrounds - 1;
+    if (lane >= hl && lane < 32 - hl) {
       for (int jj = k.kh + warp; jj < k.kh + k.TJ; jj += NW) {
+        const bool ring = jj < 2 * k.kh || jj >= k.TJ || lane < 2 * hl || lane >= 32 - 2 * hl;
+        if (!last_round && !ring) continue;
         T f[4];
         lds4(src + jj * TEI + 4 * lane, f);
         if constexpr (kZDom<T, KIND, FAST>) { if (strip_not_normal(f, msk[jj * TMP + lane])) *err = TILE_ERR_RANGE; }
@@ -1314,6 +1348,7 @@ cudaError_t tile_sweeps_sharded(const GridDev& g, const ViState& vs, TileBuffers
     h.post_epoch = (unsigned)(vp.round + 1);
     h.tj_first = tb.tj0; h.tj_last = tb.tj1 - 1;
     h.err = tb.d_err;
+    h.wait_stats = vp.wait_stats;
     tb.halo = h;
     cudaError_t e;
     if (vs.precision == 0) e = launch_tile_k<double, false>(g, vs, tb, nsub, res, st);

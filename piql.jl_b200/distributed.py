@@ -103,6 +103,51 @@ def mc_logz_sharded(eng, V, beta, npaths, rank, world, seed=0, estimator="A", ho
     return eng.mc_finalize(want=want, out=out)
 
 
+class ShardedEstimator:
+    """Pipelined form of mc_logz_sharded for callers that iterate (one estimate per V): step(V) enqueues upload, policy
+    table, rollout and exchange of this iteration on the engine's stream and hands the accumulators to the library's
+    asynchronous finalisation, so the device-to-host copy of iteration k runs under the rollout of iteration k + 1.
+    step() returns the result of the PREVIOUS iteration (None at first); finish() returns the last one.  Two sets of host
+    buffers alternate; with root_only only rank 0 downloads (the reference's master collects its workers' results)."""
+
+    def __init__(self, eng, rank, world, npaths, mode="peer", group=None, root_only=False, out_dtype=np.float64, buffers=None,
+                 estimator="A", horizon=1 << 20):
+        self.eng, self.rank, self.world, self.npaths = eng, rank, world, int(npaths)
+        self.mode, self.group, self.estimator, self.horizon = mode, group, estimator, horizon
+        self.download = not (root_only and rank != 0)
+        n = eng.H * eng.W
+        cdt = np.uint64 if np.dtype(out_dtype).itemsize == 8 else np.uint32
+
+        def alloc():
+            return (np.empty((n, 4), dtype=out_dtype), np.empty((n, 4), dtype=cdt), np.empty((eng.H, eng.W), dtype=out_dtype, order="F"))
+        self.bufs = list(buffers) if buffers is not None else [alloc(), alloc()]
+        self.k, self.pending = 0, None
+
+    def step(self, V, beta, seed=0):
+        import torch
+        eng = self.eng
+        path0, n = shard_range(self.npaths, self.rank, self.world)
+        eng.policy_table(V, beta=beta, download=False)
+        eng.mc_reset()
+        eng.mc_rollout(n, path0=path0, seed=seed, estimator=self.estimator, horizon=self.horizon)
+        if self.world > 1:
+            with torch.cuda.stream(torch.cuda.ExternalStream(eng.stream, device="cuda:%d" % eng.device)):
+                allreduce_engine_stats(eng, group=self.group, mode=self.mode, rank=self.rank, world=self.world)
+        prev = self.finish()
+        eng.mc_finalize_async(self.bufs[self.k & 1] if self.download else (None, None, None))   # all None: statistics only
+        self.pending = self.k
+        self.k += 1
+        return prev
+
+    def finish(self):
+        """Waits for the iteration in flight: ((sa, count, s) or None, stats), or None if nothing is pending."""
+        if self.pending is None:
+            return None
+        out, st = self.eng.mc_finalize_wait()
+        self.pending = None
+        return (out if self.download else None), st
+
+
 def solve_sharded(eng, kind, rank, world, V=None, nu=None, beta=1.0, reward_scale=1.0, precision="f64", tol=1e-12,
                   max_sweeps=10 ** 7, check_every=64, x0=None, group=None):
     """Soft value iteration of one grid on `world` GPUs: column slabs, halo columns pushed over NVLink peer memory after every
@@ -139,6 +184,67 @@ def solve_sharded(eng, kind, rank, world, V=None, nu=None, beta=1.0, reward_scal
     dist.barrier(group=group)     # nobody unmaps while a neighbour may still push
     eng.vi_shard_end()
     return out, sweeps, res
+
+
+_SHARD_ENV = ("PIQL_TILE_TJ", "PIQL_TILE_NW", "PIQL_TILE_KH", "PIQL_TILE_PLANES_MODE")
+
+
+def _pin_shape(env):
+    import os
+    for k in _SHARD_ENV:
+        os.environ.pop(k, None)
+    for k, v in (env or {}).items():
+        os.environ[k] = str(v)
+
+
+def tune_sharded(eng, kind, rank, world, precision="f32fast", candidates=None, sweeps=32, group=None, prepare=None, keep=True):
+    """Times the sharded sweeps for a few tile shapes on the devices (every rank must run the same shape, so the library
+    cannot tune this by itself: the ranks agree here) and pins the fastest through PIQL_TILE_TJ / _NW / _KH for the solves
+    that follow.  candidates: list of dicts of those variables (default: the model's shape and a few shapes sized for a
+    rank's share of the tiles, at 4 and 8 sweeps per round).  prepare: callable that (re)does eng.vi_prepare(...) -- needed
+    before every piql_vi_shard_begin.  Returns (best env dict, {candidate: us per sweep})."""
+    import time
+    import torch
+    import torch.distributed as dist
+    if candidates is None:
+        candidates = [{}] + [dict(PIQL_TILE_KH=kh, PIQL_TILE_TJ=tj, PIQL_TILE_NW=nw)
+                             for kh in (4, 8) for tj, nw in ((27, 12), (38, 12), (54, 12), (54, 16), (76, 16))]
+    prepare = prepare or (lambda: eng.vi_prepare(kind, precision=precision))
+    dev = "cuda:%d" % eng.device if dist.get_backend(group) == "nccl" else "cpu"
+    results = {}
+    for env in candidates:
+        _pin_shape(env)
+        ok, us = 1.0, float("inf")
+        try:
+            prepare()
+            blob, _cols = eng.vi_shard_begin(rank, world)
+        except Exception:
+            ok, blob = 0.0, None
+        t = torch.tensor([ok], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        if float(t[0]) < 0.5:        # infeasible on some rank (e.g. fewer tile columns than ranks): skipped by everybody
+            if blob is not None:
+                eng.vi_shard_end()
+            continue
+        blobs = [None] * world
+        dist.all_gather_object(blobs, blob, group=group)
+        eng.vi_shard_connect(blobs)
+        dist.barrier(group=group)
+        if sharded_sweeps_ok(eng, sweeps=8, group=group):
+            dist.barrier(group=group)
+            t0 = time.perf_counter()
+            eng.vi_sweeps(sweeps)
+            eng.vi_fetch(want_x=False)
+            us = (time.perf_counter() - t0) / sweeps * 1e6
+        t = torch.tensor([us], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        results[tuple(sorted(env.items()))] = float(t[0])
+        dist.barrier(group=group)
+        eng.vi_shard_end()
+    best = min(results, key=results.get) if results else ()
+    env = dict(best)
+    _pin_shape(env if keep else None)
+    return env, results
 
 
 def sharded_sweeps_ok(eng, sweeps=8, group=None):

@@ -274,6 +274,12 @@ class Engine:
     def vi_shard_end(self):
         self._ck(self._lib.piql_vi_shard_end(self._ctx))
 
+    def vi_shard_wait_stats(self):
+        """(microseconds edge CTAs waited for halos, number of waits) since the last call."""
+        us, n = C.c_double(), C.c_int64()
+        self._ck(self._lib.piql_vi_shard_wait_stats(self._ctx, C.byref(us), C.byref(n)))
+        return us.value, n.value
+
     def vi_sweeps(self, sweeps):
         self._ck(self._lib.piql_vi_sweeps_dev(self._ctx, int(sweeps)))
 
@@ -416,6 +422,25 @@ class Engine:
                                             None if cnt is None else cnt.ctypes.data_as(C.POINTER(C.c_uint64)), _pd(s),
                                             C.byref(st)))
         return sa, cnt, s, st
+
+    def mc_finalize_async(self, out):
+        """Snapshot the accumulators and finalise + download them on the library's copy stream while this context's stream
+        goes on.  out = (sa (n,4), count (n,4), s (H,W) F-order), each None or preallocated (pinned for a truly asynchronous
+        copy): float64 / uint64 arrays, or float32 / uint32 for half the PCIe bytes.  Call mc_finalize_wait() before reading."""
+        sa, cnt, s = out
+        kinds = {a.dtype.itemsize for a in (sa, cnt, s) if a is not None}
+        if len(kinds) > 1 or (kinds and next(iter(kinds)) not in (4, 8)):
+            raise ValueError("outputs must be all float64/uint64 or all float32/uint32")
+        f32 = bool(kinds) and next(iter(kinds)) == 4          # all None: only the statistics come back
+        ptr = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+        self._async_keep = out
+        self._ck(self._lib.piql_mc_finalize_async(self._ctx, ptr(sa), ptr(cnt), ptr(s), 1 if f32 else 0))
+
+    def mc_finalize_wait(self):
+        st = K.McStats()
+        self._ck(self._lib.piql_mc_finalize_wait(self._ctx, C.byref(st)))
+        out, self._async_keep = getattr(self, "_async_keep", None), None
+        return out, st
 
     def mc_timing(self):
         ro, re, n = C.c_double(), C.c_double(), C.c_int64()

@@ -184,3 +184,39 @@ def test_argument_errors_around_the_sampler(piql, golden01):
     sa, cnt, ls, st = eng.mc_logz(V, beta=1.0, npaths=64, starts=[g.s0_idx])
     assert int(cnt.sum()) == 64
     eng.close()
+
+
+def test_async_finalize_matches_the_blocking_call(engine, golden01):
+    """piql_mc_finalize_async: the snapshot is finalised on the copy stream while the context's stream already runs the next
+    iteration (whose reset clears the live accumulators); float64/uint64 and float32/uint32 outputs, and the pipelined
+    ShardedEstimator, must reproduce piql_mc_finalize of the same rollouts."""
+    from piql_jl_b200 import distributed as pd
+    g = golden01
+    engine.load_grid(g.walls, g.goal, **g.params)
+    V = np.nan_to_num(g.V(7, 0))
+    n = g.H * g.W
+    ref = []
+    for seed in (5, 6, 7):
+        engine.policy_table(V, beta=1.0, download=False)
+        engine.mc_reset()
+        engine.mc_rollout(1 << 16, seed=seed)
+        sa, cnt, ls, st = engine.mc_finalize()
+        ref.append((sa.copy(), cnt.copy(), ls.copy(), int(st.transitions)))
+    for fdt, cdt in ((np.float64, np.uint64), (np.float32, np.uint32)):
+        est = pd.ShardedEstimator(engine, 0, 1, 1 << 16, out_dtype=fdt)
+        got = []
+        for seed in (5, 6, 7):
+            prev = est.step(V, 1.0, seed=seed)
+            if prev is not None:
+                got.append((tuple(a.copy() for a in prev[0]), prev[1]))     # the two buffer sets alternate: copy before reuse
+        got.append(est.finish())
+        assert est.finish() is None
+        for (sa, cnt, ls), st in got:
+            assert sa.dtype == fdt and cnt.dtype == cdt and sa.shape == (n, 4)
+        for ((sa, cnt, ls), st), (rsa, rcnt, rls, rtr) in zip(got, ref):
+            assert int(st.transitions) == rtr and np.array_equal(cnt.astype(np.uint64), rcnt)
+            ok = rcnt > 0
+            tol = 0 if fdt == np.float64 else 1e-6
+            assert np.allclose(sa[ok], rsa[ok], rtol=tol, atol=tol) and np.all(np.isnan(sa[~ok]))
+            free = ~np.isnan(rls)
+            assert np.allclose(ls[free], rls[free], rtol=tol, atol=tol)

@@ -168,8 +168,20 @@ def test_values_do_not_depend_on_depth_or_plane_staging(engine):
                     plan = engine.vi_tile_plan(kind, prec)
                     assert plan["sweeps_per_round"] == int(kh)
                     outs.append(np.nan_to_num(out))
+                    assert plan["persistent"] == 1        # 14 tiles: all resident, interiors stay in shared memory, rings exchanged
+                # one launch per round (no persistence) computes the same bits ...
+                os.environ["PIQL_TILE_NO_PERSIST"] = "1"
+                os.environ["PIQL_TILE_KH"], os.environ["PIQL_TILE_PLANES_MODE"] = "4", "0"
+                out, _ = gpu_sweeps(engine, kind, x0, 13, precision=prec, **kw)
+                assert engine.vi_tile_plan(kind, prec)["persistent"] == 0
+                os.environ.pop("PIQL_TILE_NO_PERSIST")
+                outs.append(np.nan_to_num(out))
                 for o in outs[1:]:
                     assert np.array_equal(outs[0], o), (kind, prec)
+                # ... and they are the oracle's 13 Jacobi sweeps
+                if prec == "f64":
+                    ref, _ = oracle_sweeps(oracle.Grid(walls, goal, **PARAMS), kind, x0, 13, **kw)
+                    assert nmax(out, ref) < 1e-12, (kind, nmax(out, ref))
     finally:
-        for k in ("PIQL_TILE_TJ", "PIQL_TILE_NW", "PIQL_TILE_KH", "PIQL_TILE_PLANES_MODE"):
+        for k in ("PIQL_TILE_TJ", "PIQL_TILE_NW", "PIQL_TILE_KH", "PIQL_TILE_PLANES_MODE", "PIQL_TILE_NO_PERSIST"):
             os.environ.pop(k, None)
