@@ -617,7 +617,7 @@ def run_ours(args, rank, world, local_rank):
             ls, k4 = pinned((H, W), fdt, order="F")
             bufs.append((sa, cn, ls)); keep += [k2, k3, k4]
         est = pd.ShardedEstimator(eng, rank, world, P, mode=args.exchange, root_only=True, out_dtype=fdt, buffers=bufs)
-        reps = max(2, min(args.steps, 4))
+        reps = max(2, min(args.steps, 12))     # the last iteration's download is not hidden by a next rollout: enough iterations to amortise that tail
         tot = 0.0
         est.step(Vp, BETA, seed=MC_SEED + 1)   # warm-up
         est.finish()
@@ -675,6 +675,11 @@ def run_ours(args, rank, world, local_rank):
             if parity is not None:
                 parity["vi_sharded"] = vb
         for prec, nbytes in (("f32fast", 8), ("f64", 16)):
+            # the ranks agree on the tile shape by timing a few candidates together (a library call cannot: every rank must
+            # run the same shape); the winner stays pinned for this precision
+            cands = None if prec == "f32fast" else [{}] + [dict(PIQL_TILE_KH=kh, PIQL_TILE_TJ=tj, PIQL_TILE_NW=16)
+                                                           for kh in (4, 8) for tj in (27, 41, 54, 76)]
+            pinned_env, tuning = pd.tune_sharded(eng, "nu", rank, world, precision=prec, candidates=cands)
             eng.vi_prepare("nu", precision=prec)
             blob, cols = eng.vi_shard_begin(rank, world)
             blobs = [None] * world
@@ -687,25 +692,35 @@ def run_ours(args, rank, world, local_rank):
                 vi_sharded[prec] = {"error": "a halo wait timed out on some rank; timed run skipped"}
                 barrier()
                 eng.vi_shard_end()
+                pd._pin_shape(None)
                 continue
             with torch.cuda.stream(stream):
                 eng.vi_sweeps(40)
                 barrier()
+                eng.vi_shard_wait_stats()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream)
                 eng.vi_sweeps(args.vi_sweeps)
                 b.record(stream)
                 barrier()
-            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda:%d" % local_rank)
+            wait_us, waits = eng.vi_shard_wait_stats()
+            plan = eng.vi_tile_plan("nu", prec)
+            t = torch.tensor([a.elapsed_time(b), -wait_us / max(waits, 1)], dtype=torch.float64, device="cuda:%d" % local_rank)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sec = float(t[0]) * 1e-3
             sps = args.vi_sweeps / sec
             gbs = nbytes * eng.nfree * sps / 1e9
+            one = (vi or {}).get(prec, {}).get("us_per_sweep") if isinstance(vi, dict) else None
             vi_sharded[prec] = {"sweeps_per_s": sps, "us_per_sweep": 1e6 / sps, "state_backups_per_s": sps * eng.nfree,
+                                "one_gpu_us_per_sweep": one, "efficiency_vs_one_gpu": (one / (world * 1e6 / sps)) if one else None,
+                                "tile_plan": plan, "pinned": pinned_env,
+                                "min_over_ranks_mean_halo_wait_us": -float(t[1]),
+                                "tuning_us_per_sweep": {json.dumps(dict(k)): round(v, 2) for k, v in sorted(tuning.items(), key=lambda kv: kv[1])[:6]},
                                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak * world, "unit": "GB/s",
                                              "frac": gbs / (peak * world), "bytes_per_state": nbytes}}
             barrier()
             eng.vi_shard_end()
+            pd._pin_shape(None)
         vi_sharded["note"] = ("nu sweeps of the one %s grid split into %d column slabs; 4 sweeps per round, edge columns pushed to "
                               "the neighbours over NVLink after every round; values bit-identical to the 1-GPU solve" % (name, world))
 

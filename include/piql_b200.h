@@ -194,6 +194,12 @@ int32_t piql_sweep_once(piql_ctx* ctx, int32_t kind, const double* V, const doub
                         double beta, double reward_scale, int32_t precision, const double* x_in,
                         double* x_out, double* residual_out);
 
+/* piql_policy_table without blocking and without serialising behind work already enqueued: V (and Q) are uploaded and the
+ * table is built on the library's upload stream into a spare buffer while rollouts enqueued earlier still read the current
+ * table; calls enqueued after this one use the new table (the context's stream waits for it on the device).  For callers
+ * that iterate: the upload of iteration k + 1 runs under the rollout of iteration k.  V / Q should be pinned host memory and
+ * must stay unchanged until a later blocking call on this context returns (e.g. piql_mc_finalize_wait of that iteration). */
+int32_t piql_policy_table_async(piql_ctx* ctx, const double* V, const double* Q, double beta);
 /* ---- Monte-Carlo path sampling --------------------------------------------------------------
  * Replaces choose_action / path_transitions / fitness_reward_estimate   src/path_functions.jl:12-41
  * and the propagator closure src/Problems/GridWorld.jl:113-115.

@@ -100,6 +100,7 @@ SYMBOLS = {
     "piql_peer_close": (C.c_int32, [_P]),
     "piql_mc_timing": (C.c_int32, [_P, _D, _D, C.POINTER(C.c_int64)]),
     "piql_mc_transitions_total": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
+    "piql_policy_table_async": (C.c_int32, [_P, _D, _D, C.c_double]),
     "piql_mc_finalize_async": (C.c_int32, [_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "piql_mc_finalize_wait": (C.c_int32, [_P, C.POINTER(McStats)]),
     "piql_mc_records": (C.c_int32, [_P, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_int64]),

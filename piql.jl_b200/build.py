@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", f) for f in ("backup.cu", "tile.cu", "table.cu", "rollout.cu", "peer.cu", "api.cu")]
-HDR = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "algebra.cuh", "internal.h")] + \
+HDR = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "algebra.cuh", "dtables.cuh", "internal.h")] + \
       [os.path.join(HERE, "..", "include", "piql_b200.h")]
 OUT = os.path.join(HERE, "lib", "libpiql_b200.so")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -77,6 +77,16 @@ struct piql_ctx {
   float* d_inj = nullptr;
   size_t inj_cap = 0;
   unsigned long long paths_done = 0;
+  // asynchronous policy table (piql_policy_table_async): the next table is uploaded and built on an upload stream into a
+  // spare buffer while rollouts enqueued earlier still read the current one
+  cudaStream_t ustream = nullptr;
+  float4* d_table_spare = nullptr;
+  double *d_upV = nullptr, *d_upQ = nullptr;   // upload staging of V (n) and Q (4n)
+  long long up_cap = 0, upq_cap = 0;
+  cudaEvent_t ev_retire_cur = nullptr;    // recorded on the stream when the CURRENT table's buffer was last made current ... see below
+  cudaEvent_t ev_retire_spare = nullptr;  // everything that may read the SPARE buffer had been enqueued before this event
+  cudaEvent_t ev_table_ready = nullptr;
+  bool spare_retired = false;
   // asynchronous finalisation (piql_mc_finalize_async): a snapshot of the accumulators is finalised and copied to the
   // host on a second stream while the context's stream goes on with the next iteration
   cudaStream_t cstream = nullptr;
@@ -650,6 +660,9 @@ int32_t piql_destroy(piql_ctx* ctx) {
                   (void*)ctx->acc_cnt, (void*)ctx->d_scratch, (void*)ctx->d_transitions, (void*)ctx->d_inj,
                   (void*)ctx->d_scalars, (void*)ctx->snap_max, (void*)ctx->snap_sum, (void*)ctx->snap_cnt, (void*)ctx->fin_out})
     if (p) cudaFree(p);
+  for (void* p : {(void*)ctx->d_table_spare, (void*)ctx->d_upV, (void*)ctx->d_upQ}) if (p) cudaFree(p);
+  for (cudaEvent_t e : {ctx->ev_retire_cur, ctx->ev_retire_spare, ctx->ev_table_ready}) if (e) cudaEventDestroy(e);
+  if (ctx->ustream) cudaStreamDestroy(ctx->ustream);
   if (ctx->h_fin_transitions) cudaFreeHost(ctx->h_fin_transitions);
   if (ctx->ev_snap) cudaEventDestroy(ctx->ev_snap);
   if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
@@ -695,9 +708,11 @@ int32_t piql_grid_load(piql_ctx* ctx, const uint8_t* walls, int64_t H, int64_t W
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   CK(cudaStreamSynchronize(st));
-  for (void* q : {(void*)ctx->d_walls, (void*)ctx->d_cell, (void*)ctx->d_free, (void*)ctx->d_table})
+  if (ctx->ustream) CK(cudaStreamSynchronize(ctx->ustream));
+  for (void* q : {(void*)ctx->d_walls, (void*)ctx->d_cell, (void*)ctx->d_free, (void*)ctx->d_table, (void*)ctx->d_table_spare})
     if (q) cudaFree(q);
-  ctx->d_walls = ctx->d_cell = nullptr; ctx->d_free = nullptr; ctx->d_table = nullptr;
+  ctx->d_walls = ctx->d_cell = nullptr; ctx->d_free = nullptr; ctx->d_table = nullptr; ctx->d_table_spare = nullptr;
+  ctx->spare_retired = false;
   ctx->has_grid = ctx->has_table = false; ctx->vs_ready = false;
   // free-cell list, in index order (host: it is the tabulation step of the boundary)
   long long nfree = 0;
@@ -1307,6 +1322,46 @@ int32_t piql_policy_table(piql_ctx* ctx, const double* V, const double* Q, doubl
   if (rc) return rc;
   if (table_out) CK(cudaMemcpyAsync(table_out, ctx->d_table, 32 * (size_t)ctx->g.n, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return PIQL_OK;
+}
+
+int32_t piql_policy_table_async(piql_ctx* ctx, const double* V, const double* Q, double beta) {
+  if (!ctx) return PIQL_ERR_ARG;
+  LaunchScope ls(ctx);
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->has_grid, PIQL_ERR_STATE, "no grid loaded (call piql_grid_load first)");
+  NEED(V != nullptr, PIQL_ERR_ARG, "V is null");
+  NEED(beta == beta, PIQL_ERR_ARG, "beta is NaN");
+  const long long n = ctx->g.n;
+  const double vg = V[ctx->g.goal];
+  NEED(vg == vg, PIQL_ERR_ARG, "V(goal) is NaN");
+  cudaStream_t st = ctx->stream;
+  if (!ctx->ustream) {
+    CK(cudaStreamCreateWithFlags(&ctx->ustream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_retire_cur, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_retire_spare, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_table_ready, cudaEventDisableTiming));
+  }
+  if (!ctx->d_table_spare) CK(cudaMalloc((void**)&ctx->d_table_spare, 32 * (size_t)n));
+  CK(grow(ctx->d_upV, ctx->up_cap, n));
+  if (Q) CK(grow(ctx->d_upQ, ctx->upq_cap, 4 * n));
+  cudaStream_t us = ctx->ustream;
+  // the spare buffer was the current table until the previous call: every launch that may read it was enqueued before the
+  // event recorded then; the upload staging is free once the previous build has run (stream order on the upload stream)
+  if (ctx->spare_retired) CK(cudaStreamWaitEvent(us, ctx->ev_retire_spare, 0));
+  CK(cudaMemcpyAsync(ctx->d_upV, V, 8 * (size_t)n, cudaMemcpyHostToDevice, us));
+  if (Q) CK(cudaMemcpyAsync(ctx->d_upQ, Q, 32 * (size_t)n, cudaMemcpyHostToDevice, us));
+  launch_policy_table(ctx->g, ctx->d_cell, ctx->d_upV, Q ? ctx->d_upQ : nullptr, beta, 1.0, ctx->d_table_spare, us, nullptr);
+  CK_LAST();
+  CK(cudaEventRecord(ctx->ev_table_ready, us));
+  // retire the current table: whatever is enqueued on the context's stream so far may still read it
+  CK(cudaEventRecord(ctx->ev_retire_cur, st));
+  CK(cudaStreamWaitEvent(st, ctx->ev_table_ready, 0));
+  std::swap(ctx->d_table, ctx->d_table_spare);
+  std::swap(ctx->ev_retire_cur, ctx->ev_retire_spare);
+  ctx->spare_retired = true;
+  ctx->v_goal = vg;
+  ctx->has_table = true;
   return PIQL_OK;
 }
 

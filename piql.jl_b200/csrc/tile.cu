@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "algebra.cuh"
+#include "dtables.cuh"
 #include "internal.h"
 
 namespace piql {
@@ -67,6 +68,59 @@ __device__ __forceinline__ float lg2_approx(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// ---- table-driven Float64 exp / log for the tiled sweeps --------------------------------------------------------------
+// The Float64 sweeps are bound by the FP64 pipe, and two thirds of their DFMA are the library's exp / log (~21 each, plus the
+// special-case branches).  Here the arguments are known: exponents are <= 0 (everything is shifted by a maximum), logarithms
+// take sums of such terms.  exp: x = k ln2/256 + r, e^x = 2^(k >> 8) * T[k & 255] * P5(r), |r| <= ln2/512 (Cody-Waite
+// reduction, degree-5 Taylor: truncation 8e-21).  log: s = 2^e m, m in [1,2) looked up in 128 intervals, u = m / c_i - 1,
+// log s = e ln2 + log c_i + (u - u^2/2 + ... + u^7/7), |u| <= 1/256 (truncation 7e-21).  About 10 FP64 operations each and no
+// branches at all; absolute error ~3e-16 (tables: tools/gen_dtables.py, 64-bit-mantissa arithmetic).  Special values (NaN,
+// -inf exponent, zero / subnormal / infinite / negative sum) are patched in with selects so that they propagate as the
+// library's would.
+__device__ __forceinline__ double tile_dexp_np(double x) {
+  // branch-free (a branch per call would fence the scheduler: the 16 calls of a strip are independent and must interleave).
+  // Domain: x <= 0, -inf included, or NaN (propagated); e^-708 is the smallest normal result, below it terms are ~0 anyway.
+  const double xc = fmax(x, -708.0);                    // also maps NaN to a finite value: the result is patched below
+  const double magic = 6755399441055744.0;              // 1.5 * 2^52: the sum's low word is round-to-nearest(x * 256/ln2)
+  const double t = fma(xc, DEXP_INVL, magic);
+  const int k = __double2loint(t);
+  const double kd = t - magic;
+  double r = fma(-kd, DEXP_LHI, xc);
+  r = fma(-kd, DEXP_LLO, r);
+  double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double y = __ldg(&DEXP_TAB[k & 255]) * p;       // in [1, 2 + eps): adding k >> 8 (negative) to the exponent keeps it normal
+  const double e = __hiloint2double(__double2hiint(y) + ((k >> 8) << 20), __double2loint(y));
+  return x != x ? x : e;
+}
+__device__ __forceinline__ double tile_dlog(double s) {
+  const int hi = __double2hiint(s), lo = __double2loint(s);
+  const int i = (hi >> 13) & 127;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const double e = (double)((hi >> 20) - 1023);
+  const double inv = __ldg(&DLOG_TAB[2 * i]), lc = __ldg(&DLOG_TAB[2 * i + 1]);
+  const double u = fma(m, inv, -1.0);
+  double p = fma(u, 1.0 / 7.0, -1.0 / 6.0);
+  p = fma(p, u, 0.2);
+  p = fma(p, u, -0.25);
+  p = fma(p, u, 1.0 / 3.0);
+  p = fma(p, u, -0.5);
+  const double r = fma(e, DLOG_LN2HI, lc) + fma(u * u, p, fma(e, DLOG_LN2LO, u));
+  // anything but a positive normal number (integer tests on the high word, selects only): zero and subnormals (sums whose
+  // every term underflowed) -> -inf, negative -> NaN, +inf and NaN -> themselves
+  const bool normal = (unsigned)(hi - 0x00100000) < 0x7fe00000u;
+  const double special = (unsigned)hi < 0x00100000u ? -CUDART_INF : hi < 0 ? CUDART_NAN : s + s;
+  return normal ? r : special;
+}
+// exp of a non-positive argument / log of a positive sum in the sweep's precision
+__device__ __forceinline__ float texp(float x) { return expf(x); }
+__device__ __forceinline__ double texp(double x) { return tile_dexp_np(x); }
+__device__ __forceinline__ float tlog(float x) { return logf(x); }
+__device__ __forceinline__ double tlog(double x) { return tile_dlog(x); }
 
 template <typename T> __device__ __forceinline__ void lds4(const T* p, T (&o)[4]);
 template <> __device__ __forceinline__ void lds4<float>(const float* p, float (&o)[4]) {
@@ -138,9 +192,9 @@ __device__ __forceinline__ T nu_cell(const TileK<T>& k, T n0, T n1, T n2, T n3) 
     const float hi = fmaf(0.693147180559945f, lg2_approx(sum), fmaf(k.b1, S, fmaf(k.a1, m, k.kc)));
     return hi + fmaf(k.a1_lo, m, k.kc_lo);
   } else {
-    const T sum = ((T)1 + xexp(k.a1 * (mid - m))) + (xexp(k.a1 * (l1 - m)) + xexp(k.a1 * (l2 - m)));
-    if (sizeof(T) == 4) return (k.kc + k.b1 * S + k.a1 * m + xlog(sum)) + (k.kc_lo + k.a1_lo * m);
-    return k.kc + k.b1 * S + k.a1 * m + xlog(sum);
+    const T sum = ((T)1 + texp(k.a1 * (mid - m))) + (texp(k.a1 * (l1 - m)) + texp(k.a1 * (l2 - m)));
+    if (sizeof(T) == 4) return (k.kc + k.b1 * S + k.a1 * m + tlog(sum)) + (k.kc_lo + k.a1_lo * m);
+    return k.kc + k.b1 * S + k.a1 * m + tlog(sum);
   }
 }
 // Two cells at once with the packed fp32 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: two IEEE operations per lane and
@@ -178,7 +232,7 @@ constexpr int TILE_ERR_RANGE = 4;  // *err: a fast fp32 linear-domain sweep left
 template <typename T, bool FAST> __device__ __forceinline__ T damp_half(T nw, T c) {
   const T d = fabs(nw - c), mx = fmax(nw, c);
   if constexpr (FAST) return fmaf(0.693147180559945f, lg2_approx(fmaf(0.5f, ex2_approx(-1.44269504088896f * d), 0.5f)), mx);
-  else return mx + xlog((T)0.5 + (T)0.5 * xexp(-d));
+  else return mx + tlog((T)0.5 + (T)0.5 * texp(-d));
 }
 // logz: with Z = exp(logz), Z_new = sum_a exp(A_a) * (gamma * sum_a' P(a'|a) Z(n_a') + 1 - gamma), evaluated
 // with the neighbour maximum m and M = max(m, 0) factored out (both exponents stay <= 0); ea_a = exp(A_a - amax).
@@ -192,8 +246,8 @@ __device__ __forceinline__ T logz_cell(const TileK<T>& k, T c, T n0, T n1, T n2,
     e2 = ex2_approx(fmaf(n2, l2e, t)); e3 = ex2_approx(fmaf(n3, l2e, t));
     em = ex2_approx(-fabsf(m) * l2e);
   } else {
-    e0 = xexp(n0 - m); e1 = xexp(n1 - m); e2 = xexp(n2 - m); e3 = xexp(n3 - m);
-    em = xexp(-fabs(m));
+    e0 = texp(n0 - m); e1 = texp(n1 - m); e2 = texp(n2 - m); e3 = texp(n3 - m);
+    em = texp(-fabs(m));
   }
   const T wE = k.w_off * ((e0 + e1) + (e2 + e3));
   const bool pos = m >= (T)0;
@@ -206,7 +260,7 @@ __device__ __forceinline__ T logz_cell(const TileK<T>& k, T c, T n0, T n1, T n2,
     const float r = sum * ex2_approx(fminf((fmaxf(m, 0.f) + amax - c) * 1.44269504088896f, 100.f));
     return fmaf(0.693147180559945f, lg2_approx(fmaf(0.5f, r, 0.5f)), c);
   } else {
-    const T nw = fmax(m, (T)0) + amax + xlog(sum);
+    const T nw = fmax(m, (T)0) + amax + tlog(sum);
     return damp_half<T, FAST>(nw, c);
   }
 }
@@ -846,11 +900,10 @@ static std::vector<PlanCand> enumerate_plans(int H, int W, int precision, int ki
   const int tiles_i = (H + TTI - 1) / TTI;
   const char* env_tj = getenv("PIQL_TILE_TJ");
   const char* env_nw = getenv("PIQL_TILE_NW");
-  // registers per thread of the instantiation that will run (48 .. 64 in fp32, 110 .. 128 in Float64): they, the shared
-  // memory of a tile and the 2048-thread limit decide how many CTAs share an SM
-  // (Float64 is ranked at its __launch_bounds__ cap of 128: two resident CTAs of 8-9 warps, which 110 registers would
-  // allow, measured 40 % slower at 4098^2 than one CTA of 16 warps -- and the sharded solve runs the model's first choice untimed)
-  const int regs = precision == 0 ? 128 : tile_kernel_regs(precision, kind, fast, persistent);
+  // registers per thread of the instantiation that will run (48 .. 64 in fp32; Float64: 66 for nu with the table-driven
+  // exp / log, ~110 for log Z and gap): they, the shared memory of a tile and the 2048-thread limit decide how many CTAs share
+  // an SM.  The candidates are timed on the device, so the model only has to offer the right ones.
+  const int regs = tile_kernel_regs(precision, kind, fast, persistent);
   const double strip_issue = 61.0, strip_latency = 1700.0, wave_fixed = 8000.0;
   for (int nw = 4; nw <= 16; nw++) {
     if (env_nw && atoi(env_nw) != nw) continue;

@@ -127,7 +127,7 @@ class ShardedEstimator:
         import torch
         eng = self.eng
         path0, n = shard_range(self.npaths, self.rank, self.world)
-        eng.policy_table(V, beta=beta, download=False)
+        eng.policy_table_async(V, beta=beta)     # uploaded and built under the previous iteration's rollout
         eng.mc_reset()
         eng.mc_rollout(n, path0=path0, seed=seed, estimator=self.estimator, horizon=self.horizon)
         if self.world > 1:
@@ -197,7 +197,8 @@ def _pin_shape(env):
         os.environ[k] = str(v)
 
 
-def tune_sharded(eng, kind, rank, world, precision="f32fast", candidates=None, sweeps=32, group=None, prepare=None, keep=True):
+def tune_sharded(eng, kind, rank, world, precision="f32fast", candidates=None, sweeps=32, group=None, prepare=None, keep=True,
+                 refine=True, _refining=False):
     """Times the sharded sweeps for a few tile shapes on the devices (every rank must run the same shape, so the library
     cannot tune this by itself: the ranks agree here) and pins the fastest through PIQL_TILE_TJ / _NW / _KH for the solves
     that follow.  candidates: list of dicts of those variables (default: the model's shape and a few shapes sized for a
@@ -243,6 +244,16 @@ def tune_sharded(eng, kind, rank, world, precision="f32fast", candidates=None, s
         eng.vi_shard_end()
     best = min(results, key=results.get) if results else ()
     env = dict(best)
+    if refine and env.get("PIQL_TILE_TJ") and not _refining:
+        # second pass around the winner: neighbouring widths and warp counts at the same depth
+        tj, nw, kh = int(env["PIQL_TILE_TJ"]), int(env["PIQL_TILE_NW"]), int(env["PIQL_TILE_KH"])
+        near = [dict(PIQL_TILE_KH=kh, PIQL_TILE_TJ=t, PIQL_TILE_NW=w) for t in (tj - 8, tj - 4, tj + 4, tj + 8) for w in (nw - 2, nw, nw + 2)
+                if t >= 12 and 4 <= w <= 16]
+        env2, res2 = tune_sharded(eng, kind, rank, world, precision=precision, candidates=near, sweeps=sweeps, group=group,
+                                  prepare=prepare, keep=False, refine=False, _refining=True)
+        results.update(res2)
+        best = min(results, key=results.get)
+        env = dict(best)
     _pin_shape(env if keep else None)
     return env, results
 

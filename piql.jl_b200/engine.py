@@ -296,6 +296,13 @@ class Engine:
                                              None if tab is None else tab.ctypes.data_as(C.POINTER(C.c_float))))
         return tab
 
+    def policy_table_async(self, V, beta=1.0, Q=None):
+        """piql_policy_table_async: upload + build on the library's upload stream, overlapping work already enqueued.  V (and
+        Q) must not be modified until a later blocking call returns; they are kept alive here until the next call."""
+        V, Q = _cell(V, self.H, self.W, "V"), _sa(Q, self.H, self.W, "Q")
+        self._table_keep = (V, Q)
+        self._ck(self._lib.piql_policy_table_async(self._ctx, _pd(V), _pd(Q), float(beta)))
+
     def policy_table_set(self, table, v_goal):
         table = np.ascontiguousarray(table, dtype=np.float32)
         assert table.size == self.H * self.W * 8
