@@ -277,8 +277,10 @@ def vi_section(args, eng, stream, V, peak, vst, name=None):
                                 "bytes_per_state": nbytes, "sweeps_per_launch": kh,
                                 "algorithmic_bytes_per_launch": nbytes * eng.nfree * kh,
                                 "avg_launch_us": kh * 1e6 / sps,
-                                "traffic": None if tr is None else tr.get("bytes"),
-                                "traffic_note": None if tr is None else tr.get("note")},
+                                # ncu DRAM bytes of the captured launch, scaled to a round of kh sweeps like the algorithmic figure
+                                "traffic": None if tr is None else tr["bytes"] * kh / max(tr.get("sweeps_in_launch", kh), 1),
+                                "traffic_note": None if tr is None else "%s; kernel %s, %d sweeps in the captured launch" % (
+                                    tr.get("note"), tr.get("kernel"), tr.get("sweeps_in_launch", kh))},
                    "tile_plan": plan}
     # the ground-truth solve itself (config 4: "soft VI ground truth on 1 B200"), host buffers in and out
     solves = {}
@@ -304,6 +306,11 @@ class OracleSide:
         self.org = oracle.Grid(walls, goal, **params)
         self.threads = threads or oracle.num_threads()
         self.table = eng.policy_table(V, beta=BETA) if table is None else table   # the fp32 table the GPU read
+        self.record_bytes = 32
+        if table is None:
+            t16, in_use = eng.policy_table16()
+            if in_use:                       # 4096^2: the production kernel reads the 16-byte form of the same records
+                self.table, self.record_bytes = t16, 16
         self.free = self.org.free_cells()
         self.vgoal = float(V[goal])
 
@@ -354,8 +361,8 @@ def parity_section(args, eng, osd, last_path0, last_count, step_id0, step_id1, w
     with np.errstate(divide="ignore", invalid="ignore"):
         glsa = gm + np.log(gs) - np.log(gc.astype(np.float64))
     err = float(np.max(np.abs(glsa[ok] - lsa[ok]))) if ok.any() else 0.0
-    return {"records_bit_exact": rec_ok, "paths": n,
-            "records_of": "first %d records of the last timed launch of rollout_kernel<0,false,false,STAGED=false> (path ids from %d) "
+    return {"records_bit_exact": rec_ok, "paths": n, "policy_record_bytes": osd.record_bytes,
+            "records_of": "first %d records of the last timed launch of the production rollout_kernel<0,false,false,STAGED=false> (path ids from %d) "
                           "against oracle.rollout on the GPU's table: log-weight bits, first action, length" % (n, last_path0),
             "accumulator_counts_exact": cnt_ok, "accumulator_logz_max_abs_err": err, "accumulator_logz_ok": bool(err < 1e-5),
             "accumulator_slots": int(len(slots)), "accumulator_paths": int(npaths),
@@ -418,10 +425,11 @@ def grid4096_section(args, eng, stream):
     tr = eng.mc_transitions_total() - tr0
     roll_s, red_s, nl = eng.mc_timing()
     peak, _src = measured_peak()
+    rec_bytes = 16 if eng.policy_table16(download=False)[1] else 32
     alg = 32.0 * tr + 8.0 * P * steps
     return {"value": tr / (ms * 1e-3), "unit": "transitions/s", "steps": steps, "warmup": 3, "ms_per_step": ms / steps,
             "config": workload_config(name, args, 1),
-            "roofline": rollout_roofline(name, alg / roll_s / 1e9 if roll_s > 0 else 0.0, peak, nl, roll_s, red_s, tr),
+            "roofline": rollout_roofline(name, alg / roll_s / 1e9 if roll_s > 0 else 0.0, peak, nl, roll_s, red_s, tr, rec_bytes=rec_bytes),
             "note": "same workload as the N > 1 lines (BASELINE config 5) on one GPU, no exchange: divide an N-GPU `value` by "
                     "N x this for the same-config weak-scaling efficiency"}
 
@@ -435,7 +443,7 @@ ROLL_LIMITER = {
 }
 
 
-def rollout_roofline(name, achieved, peak, nl, roll_s, red_s, tr_local, peak_src=None, paths_per_launch=None):
+def rollout_roofline(name, achieved, peak, nl, roll_s, red_s, tr_local, peak_src=None, paths_per_launch=None, rec_bytes=32):
     traffic = prof = None
     tpath = os.path.join(ROOT, "profiles", "rollout_traffic.json")
     # the ncu capture is one launch of the workload's own size: it says nothing about other launch sizes
@@ -447,8 +455,9 @@ def rollout_roofline(name, achieved, peak, nl, roll_s, red_s, tr_local, peak_src
             traffic = None
     bound, why = ROLL_LIMITER.get(name, ("hbm", ""))
     launch_ms = 1e3 * roll_s / max(nl, 1)
-    out = {"bound": bound, "kernel": "rollout_kernel<0,false,false,STAGED=false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    out = {"bound": bound, "kernel": "rollout_kernel<0,false,false,STAGED=false,REC16=%s>" % ("true" if rec_bytes == 16 else "false"), "achieved": achieved, "peak": peak, "unit": "GB/s",
            "frac": achieved / peak, "traffic": traffic, "bytes_per_transition": 32, "bytes_per_path": 8, "launches": nl,
+           "record_bytes_read_by_kernel": rec_bytes,
            "avg_launch_ms": launch_ms, "reduce_share": red_s / max(roll_s + red_s, 1e-12),
            "transitions_per_s_kernel": tr_local / roll_s if roll_s > 0 else 0.0, "limiter": why}
     if traffic and launch_ms > 0:
@@ -471,7 +480,8 @@ def workload_config(name, args, world):
             "paths_per_step": int(args.paths or w["paths"]) * world,
             "sharding": "path ids split in %d contiguous blocks of %d (weak scaling)" % (world, int(args.paths or w["paths"])),
             "l2": "each step writes 8 B x paths of records (> L2) between reads of the policy table; the table is "
-                  "%.0f MB" % (32 * (w["size"] + 2) ** 2 / 1e6)}
+                  "%.0f MB (%d-byte records)" % ((16 if (w["size"] + 2) ** 2 >= 1 << 22 else 32) * (w["size"] + 2) ** 2 / 1e6,
+                                              16 if (w["size"] + 2) ** 2 >= 1 << 22 else 32)}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -553,9 +563,12 @@ def run_ours(args, rank, world, local_rank):
     # + 8 B record per finished path, over the CUDA-event time of the rollout launches
     peak, peak_src = measured_peak()
     p0, cnt = pd.shard_range(P, rank, world)
+    # algorithmic bytes: SURVEY 8(d)'s per-unit figure, 32 B per sampled transition (one policy record {cdf[3], mask, beta fit[4]})
+    # + 8 B per finished path -- whatever the kernel actually moves (on grids beyond L2 it reads a 16-byte form of the record)
+    rec_bytes = 16 if eng.policy_table16(download=False)[1] else 32
     alg_bytes = 32.0 * tr_local + 8.0 * cnt * args.steps
     achieved = alg_bytes / roll_s / 1e9 if roll_s > 0 else 0.0
-    roofline = rollout_roofline(name, achieved, peak, nl, roll_s, red_s, tr_local, peak_src, paths_per_launch=cnt)
+    roofline = rollout_roofline(name, achieved, peak, nl, roll_s, red_s, tr_local, peak_src, paths_per_launch=cnt, rec_bytes=rec_bytes)
 
     # ---- parity of the launch just timed, against the oracle (every rank checks its own shard) -------------------
     parity = None

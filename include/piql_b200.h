@@ -170,6 +170,12 @@ typedef struct {
   double gamma;
 } piql_table_problem;
 int32_t piql_table_load(piql_ctx* ctx, const piql_table_problem* problem);
+/* A tabulated Q for the loaded table problem: Q[s * nactions + a] (any Q callable of src/PIQL.jl:72-89 evaluated on the
+ * tabulated states), used by the log Z / gap solves, piql_table_update_v and piql_table_mc_logz that follow -- Qnormalization,
+ * controlQ, action_probability and fitness are taken from it, controlV still from V.  NULL returns to the V-determined Q
+ * (s, a) -> controlV(ctrl, V, s, a) of value_iteration.jl:97,157.  Copied: the caller keeps ownership.  piql_table_load
+ * clears it. */
+int32_t piql_table_set_q(piql_ctx* ctx, const double* Q);
 /* kind 0: generate_ν (reward_function scaled by reward_scale); 1: generate_logz(ctrl, V; β); 2: generate_optimality_gap(ctrl, V; ν) */
 int32_t piql_table_solve(piql_ctx* ctx, int32_t kind, const double* V, const double* nu, double beta, double reward_scale,
                          const piql_solve_opts* opts, double* x_out, piql_solve_stats* stats_out);
@@ -194,6 +200,12 @@ int32_t piql_sweep_once(piql_ctx* ctx, int32_t kind, const double* V, const doub
                         double beta, double reward_scale, int32_t precision, const double* x_in,
                         double* x_out, double* residual_out);
 
+/* The 16-byte form of the current policy records, which the production rollout kernel reads on grids whose 32-byte table
+ * does not stay in L2 (>= 2^22 cells; V-determined Q only, where beta * fitness does not depend on the action):
+ * per cell four 32-bit words {c0 | (mask & 3) << 30, c1 | (mask >> 2) << 30, c2, bits of beta * fitness(s, action 0)} --
+ * exactly the 32-byte record's c0, c1, c2, mask and first fitness entry.  *in_use_out = 1 when the rollouts use it (then
+ * table16_out, if non-null, receives H*W*4 words), 0 when they read the 32-byte records. */
+int32_t piql_policy_table16(piql_ctx* ctx, uint32_t* table16_out, int32_t* in_use_out);
 /* piql_policy_table without blocking and without serialising behind work already enqueued: V (and Q) are uploaded and the
  * table is built on the library's upload stream into a spare buffer while rollouts enqueued earlier still read the current
  * table; calls enqueued after this one use the new table (the context's stream waits for it on the device).  For callers

@@ -352,6 +352,15 @@ function table_solve(ctx::Context, states, kind; V = nothing, ν = nothing, β =
     Growable(Dict(s => out[i] for (i, s) in enumerate(states)), x -> 0.0)
 end
 
+# a tabulated Q for the table solves / sampler that follow (any Q callable of src/PIQL.jl:72-89); nothing: the V-determined Q
+function table_set_q!(ctx::Context, states, actions, Q)
+    if Q === nothing
+        return check(ctx, ccall((:piql_table_set_q, LIB), Int32, (Ptr{Cvoid}, Ptr{Cdouble}), ctx.ptr, C_NULL))
+    end
+    Qd = Float64[Q(s, a) for a in actions, s in states]          # action fastest, as the ABI lays it out
+    GC.@preserve Qd check(ctx, ccall((:piql_table_set_q, LIB), Int32, (Ptr{Cvoid}, Ptr{Cdouble}), ctx.ptr, Qd))
+end
+
 # logz_updateV / Monte-Carlo log Z on the tabulated problem (states as returned by load_table!)
 function table_logz_updateV(ctx::Context, states, V; β = 1.0, kw...)
     Vd = Float64[V(s) for s in states]; out = similar(Vd); st = Ref(SolveStats())
@@ -391,6 +400,23 @@ function mc_finalize(ctx::Context)
     GC.@preserve logz_sa count logz_s check(ctx, ccall((:piql_mc_finalize, LIB), Int32,
         (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{UInt64}, Ptr{Cdouble}, Ref{McStats}), ctx.ptr, logz_sa, count, logz_s, st))
     (logz = growable(ctx, logz_s), logz_sa = logz_sa, count = count, transitions = st[].transitions)
+end
+
+# ---- pipelined iterations: upload / table of iteration k + 1 and download of iteration k overlap the rollouts ----------
+# V must stay alive and unchanged until the matching mc_finalize_wait returns (keep a reference; pin it for a truly
+# asynchronous copy).  Outputs: Float64 / UInt64 (f32 = false) or Float32 / UInt32 arrays of the shapes of mc_finalize.
+function policy_table_async!(ctx::Context, Vd::Matrix{Float64}; β = 1.0)
+    check(ctx, ccall((:piql_policy_table_async, LIB), Int32, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble), ctx.ptr, Vd, C_NULL, β))
+end
+function mc_finalize_async!(ctx::Context, logz_sa::Array, count::Array, logz_s::Array)
+    f32 = eltype(logz_sa) == Float32
+    check(ctx, ccall((:piql_mc_finalize_async, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32),
+        ctx.ptr, logz_sa, count, logz_s, f32 ? 1 : 0))
+end
+function mc_finalize_wait(ctx::Context)
+    st = Ref(McStats())
+    check(ctx, ccall((:piql_mc_finalize_wait, LIB), Int32, (Ptr{Cvoid}, Ref{McStats}), ctx.ptr, st))
+    st[]
 end
 
 # ---- multi-GPU exchange over NVLink peer memory: one worker process per GPU (replaces addprocs/pmap/@spawn,

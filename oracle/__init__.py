@@ -143,8 +143,10 @@ class Grid:
 
     def rollout(self, table, Vgoal, starts, npaths, path0=0, seed=0, estimator="A", horizon=1 << 20,
                 injected=None, trace_steps=0, nthreads=1):
+        """table: the (H*W, 8) float32 policy records, or the (H*W, 4) uint32 16-byte records of large grids."""
         starts = np.ascontiguousarray(starts, dtype=np.int32)
-        table = np.ascontiguousarray(table, dtype=np.float32)
+        rec_bytes = 16 if table.dtype == np.uint32 else 32
+        table = np.ascontiguousarray(table).view(np.float32) if rec_bytes == 16 else np.ascontiguousarray(table, dtype=np.float32)
         logw = np.empty(npaths, dtype=np.float32)
         meta = np.empty(npaths, dtype=np.uint32)
         inj_steps = 0
@@ -158,7 +160,8 @@ class Grid:
                           C.c_int({"A": 0, "B": 1}[estimator]), C.c_int64(horizon), C.c_int64(path0),
                           C.c_int64(npaths), _p(starts, C.c_int32), C.c_int64(len(starts)), C.c_uint64(seed),
                           _p(injected, C.c_float), C.c_int64(inj_steps), _p(logw, C.c_float),
-                          _p(meta, C.c_uint32), _p(trace, C.c_int32), C.c_int64(trace_steps), C.c_int(nthreads))
+                          _p(meta, C.c_uint32), _p(trace, C.c_int32), C.c_int64(trace_steps), C.c_int(nthreads),
+                          C.c_int(rec_bytes))
         return (logw, meta, trace) if trace_steps else (logw, meta)
 
     def kl_table(self, V, Q=None):
@@ -257,7 +260,7 @@ def num_threads():
         return max(1, os.cpu_count() or int(lib().orc_num_threads()))
 
 
-def table_solve(tab, kind, V=None, nu=None, beta=1.0, reward_scale=1.0, tol=1e-12, max_sweeps=10 ** 7, x0=None):
+def table_solve(tab, kind, V=None, nu=None, beta=1.0, reward_scale=1.0, tol=1e-12, max_sweeps=10 ** 7, x0=None, Q=None):
     """Soft VI on a tabulated ControlProblem (piql_jl_b200.tables.ProblemTable): the restatement in piql_oracle.c
     (orc_table_solve) of PIQL.jl:55-130 / value_iteration.jl:62-169 over CSR rows.  Returns (x, sweeps, residual)."""
     ns = len(tab.terminal)
@@ -266,6 +269,7 @@ def table_solve(tab, kind, V=None, nu=None, beta=1.0, reward_scale=1.0, tol=1e-1
     V = None if V is None else np.ascontiguousarray(V, dtype=np.float64)
     nu = None if nu is None else np.ascontiguousarray(nu, dtype=np.float64)
     x0 = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+    Q = None if Q is None else np.ascontiguousarray(Q, dtype=np.float64).reshape(ns, len(tab.actions))
     a = [np.ascontiguousarray(tab.row_ptr, dtype=np.int64), np.ascontiguousarray(tab.succ, dtype=np.int32),
          np.ascontiguousarray(tab.prob, dtype=np.float64), np.ascontiguousarray(tab.reward, dtype=np.float64),
          np.ascontiguousarray(tab.log_prior, dtype=np.float64), np.ascontiguousarray(tab.terminal, dtype=np.uint8)]
@@ -273,7 +277,7 @@ def table_solve(tab, kind, V=None, nu=None, beta=1.0, reward_scale=1.0, tol=1e-1
                                _p(a[1], C.c_int32), _p(a[2], C.c_double), _p(a[3], C.c_double), _p(a[4], C.c_double),
                                _p(a[5], C.c_uint8), C.c_double(tab.gamma), C.c_double(reward_scale), _p(V, C.c_double),
                                _p(nu, C.c_double), C.c_double(beta), _p(x0, C.c_double), C.c_double(tol),
-                               C.c_int64(max_sweeps), _p(out, C.c_double), C.byref(sweeps), C.byref(res))
+                               C.c_int64(max_sweeps), _p(out, C.c_double), C.byref(sweeps), C.byref(res), _p(Q, C.c_double))
     assert rc == 0
     return out, sweeps.value, res.value
 

@@ -483,7 +483,7 @@ int orc_rollout(int64_t H, int64_t goal, const float *table, double gamma, doubl
                 double Vgoal, int estimator, int64_t horizon, int64_t path0, int64_t npaths,
                 const int32_t *starts, int64_t nstarts, uint64_t seed, const float *inj,
                 int64_t inj_steps, float *logw_out, uint32_t *meta_out, int32_t *trace,
-                int64_t trace_steps, int nthreads) {
+                int64_t trace_steps, int nthreads, int rec_bytes) {
   /* the stop and slip tests compare the (float) uniform with the Float64 gamma / randomness of the problem, as the
    * reference's rand() < randomness does (GridWorld.jl:114): for u = k 2^-24 that is k >= ceil(gamma 2^24) exactly */
   const double gam = gamma, rho = randomness;
@@ -517,7 +517,17 @@ int orc_rollout(int64_t H, int64_t goal, const float *table, double gamma, doubl
         orc_philox4x32_10(ctr, key, r);
         for (int i = 0; i < 4; i++) u[i] = u01(r[i]);
       }
+      float rec16[8];
       const float *rec = table + 8 * s;
+      if (rec_bytes == 16) {
+        /* the 16-byte record of large grids (V-determined Q: fitness does not depend on the action, PIQL.jl:87-89):
+         * {c0 | (mask & 3) << 30, c1 | (mask >> 2) << 30, c2, beta*fitness}; probabilities are < 2, so bits 30-31 are free */
+        uint32_t w[4]; memcpy(w, table + 4 * s, 16);
+        uint32_t c0 = w[0] & 0x3fffffffu, c1 = w[1] & 0x3fffffffu, m = (w[0] >> 30) | ((w[1] >> 30) << 2);
+        memcpy(&rec16[0], &c0, 4); memcpy(&rec16[1], &c1, 4); memcpy(&rec16[2], &w[2], 4); memcpy(&rec16[3], &m, 4);
+        for (int a = 0; a < 4; a++) memcpy(&rec16[4 + a], &w[3], 4);
+        rec = rec16;
+      }
       uint32_t mask; memcpy(&mask, rec + 3, 4);
       int a = 0;
       while (rec[a] < u[0] && a < 3) a++;
@@ -788,25 +798,31 @@ static double t_log_pa(const orc_table *t, int64_t s, int a, const double *f) { 
   for (int64_t e = e0; e < e1; e++) acc += exp(log(t->prob[e]) + f[t->succ[e]] - m);
   return m + log(acc);
 }
-static double t_backup(int kind, const orc_table *t, const double *V, const double *nu, double beta, const double *X, int64_t s) {
-  double x[64] = {0}, cv[64] = {0};
+/* Q: optional table Q[s*na + a] (any Q callable of PIQL.jl:72-89, tabulated); NULL is the V-determined Q (s,a) -> controlV */
+static double t_backup(int kind, const orc_table *t, const double *V, const double *Q, const double *nu, double beta, const double *X,
+                       int64_t s) {
+  double x[64] = {0}, cv[64] = {0}, q[64] = {0};
   const int na = t->na;
   if (t->term[s]) return kind == 1 ? 0.0 - V[s] : 0.0; /* value_iteration.jl:66-67,93-94,133-134 */
   if (kind == 0) { /* truevalue_recursion  PIQL.jl:95-101 */
     for (int a = 0; a < na; a++) x[a] = t->lprior[s * na + a] + t->gamma * t_pa(t, s, a, X) + t_rbar(t, s, a);
     return lse_n(x, na);
   }
-  for (int a = 0; a < na; a++) { cv[a] = t_cV(t, V, s, a); x[a] = t->lprior[s * na + a] + cv[a]; }
-  const double norm = lse_n(x, na); /* Qnormalization of (s,a) -> controlV(ctrl,V,s,a)  PIQL.jl:72-75 */
+  for (int a = 0; a < na; a++) {
+    cv[a] = t_cV(t, V, s, a);
+    q[a] = Q ? Q[s * na + a] : cv[a];
+    x[a] = t->lprior[s * na + a] + q[a];
+  }
+  const double norm = lse_n(x, na); /* Qnormalization  PIQL.jl:72-75 */
   if (kind == 1) { /* logz_recursion  PIQL.jl:125-130 */
     for (int a = 0; a < na; a++)
-      x[a] = t->lprior[s * na + a] + beta * cv[a] + (1.0 - beta) * (cv[a] - norm) +
+      x[a] = t->lprior[s * na + a] + beta * cv[a] + (1.0 - beta) * (q[a] - norm) +
              logaddexp_(log(t->gamma) + t_log_pa(t, s, a, X), log(1.0 - t->gamma));
     return lse_n(x, na);
   }
   double out = 0.0; /* optimality_gap_recursion  value_iteration.jl:160-169 */
   for (int a = 0; a < na; a++) {
-    const double cq = cv[a] - norm;
+    const double cq = q[a] - norm;
     out += exp(t->lprior[s * na + a] + cq) * (cq - t_cV(t, nu, s, a) + t_pa(t, s, a, X));
   }
   return out;
@@ -814,7 +830,7 @@ static double t_backup(int kind, const orc_table *t, const double *V, const doub
 int orc_table_solve(int kind, int64_t ns, int na, const int64_t *ptr, const int32_t *succ, const double *prob,
                     const double *rew, const double *lprior, const uint8_t *term, double gamma, double scale,
                     const double *V, const double *nu, double beta, const double *x0, double tol, int64_t max_sweeps,
-                    double *out, int64_t *sweeps_out, double *residual_out) {
+                    double *out, int64_t *sweeps_out, double *residual_out, const double *Q) {
   if (na > 64) return 1;
   const orc_table t = {ns, na, ptr, succ, prob, rew, lprior, term, gamma, scale};
   double *X = (double *)malloc(sizeof(double) * (size_t)ns), *Y = (double *)malloc(sizeof(double) * (size_t)ns);
@@ -824,7 +840,7 @@ int orc_table_solve(int kind, int64_t ns, int na, const int64_t *ptr, const int3
   while (sweeps < max_sweeps) {
     double d = 0.0;
     for (int64_t s = 0; s < ns; s++) {
-      const double nw = t_backup(kind, &t, V, nu, beta, X, s);
+      const double nw = t_backup(kind, &t, V, Q, nu, beta, X, s);
       d += fabs(nw - X[s]);
       Y[s] = kind == 1 ? logaddexp_(log(0.5) + nw, log(0.5) + X[s]) : nw; /* eta = 0.5  value_iteration.jl:101-102 */
     }

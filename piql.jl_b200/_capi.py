@@ -100,6 +100,7 @@ SYMBOLS = {
     "piql_peer_close": (C.c_int32, [_P]),
     "piql_mc_timing": (C.c_int32, [_P, _D, _D, C.POINTER(C.c_int64)]),
     "piql_mc_transitions_total": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
+    "piql_policy_table16": (C.c_int32, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
     "piql_policy_table_async": (C.c_int32, [_P, _D, _D, C.c_double]),
     "piql_mc_finalize_async": (C.c_int32, [_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "piql_mc_finalize_wait": (C.c_int32, [_P, C.POINTER(McStats)]),
@@ -108,6 +109,7 @@ SYMBOLS = {
     "piql_learning_traj": (C.c_int32, [_P, _D, _D, C.c_int32, C.c_int32, C.POINTER(SolveOpts), _D, C.POINTER(SolveStats)]),
     "piql_solve_gap_batch": (C.c_int32, [_P, _D, C.c_int32, _D, C.POINTER(SolveOpts), _D, C.POINTER(SolveStats)]),
     "piql_table_load": (C.c_int32, [_P, C.POINTER(TableProblem)]),
+    "piql_table_set_q": (C.c_int32, [_P, _D]),
     "piql_table_solve": (C.c_int32, [_P, C.c_int32, _D, _D, C.c_double, C.c_double, C.POINTER(SolveOpts), _D, C.POINTER(SolveStats)]),
     "piql_table_update_v": (C.c_int32, [_P, _D, C.c_double, C.POINTER(SolveOpts), _D, _D, C.POINTER(SolveStats)]),
     "piql_table_mc_logz": (C.c_int32, [_P, _D, C.c_double, C.POINTER(McOpts), _D, C.POINTER(C.c_uint64), _D, C.POINTER(McStats),

@@ -50,11 +50,16 @@ struct piql_ctx {
   TableDev tab{};
   long long tab_nnz = 0;
   std::vector<void*> tab_bufs;  // every device allocation of the table path
+  double* tb_Q = nullptr;        // optional tabulated Q [ns * na] (piql_table_set_q); nullptr: the V-determined Q
+  bool tb_has_q = false;
   double *tb_V = nullptr, *tb_nu = nullptr, *tb_x[2] = {nullptr, nullptr}, *tb_aux = nullptr, *tb_aux1 = nullptr,
          *tb_partial = nullptr, *tb_out = nullptr;
 
   // Monte-Carlo
   float4* d_table = nullptr;
+  uint4* d_table16 = nullptr;        // the same policy as 16-byte records (large grids, V-determined Q), read by the production rollout
+  uint4* d_table16_spare = nullptr;
+  bool t16_valid = false, t16_valid_spare = false;
   bool has_table = false;
   double v_goal = 0.0;
   uint2* d_rec = nullptr;        // per-path records of the last rollout launch {log-weight bits, a0 | len << 2}
@@ -396,6 +401,7 @@ int mc_reset(piql_ctx* ctx, const piql_mc_opts* o) {
 RolloutArgs make_rollout_args(piql_ctx* ctx, const piql_mc_opts* o) {
   RolloutArgs a{};
   a.table = ctx->d_table;
+  a.table16 = ctx->t16_valid ? ctx->d_table16 : nullptr;
   a.table_bytes = 32LL * ctx->g.n;
   a.goal = ctx->g.goal; a.H = ctx->g.H;
   a.gamma = ctx->g.gamma; a.rho = ctx->g.randomness; a.vgoal = (float)ctx->v_goal;
@@ -588,7 +594,9 @@ int build_table(piql_ctx* ctx, const double* V, const double* Q, double beta, fl
   NEED(vg == vg, PIQL_ERR_ARG, "V(goal) is NaN");
   CK(cudaMemcpyAsync(ctx->d_in0, V, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
   if (Q) CK(cudaMemcpyAsync(ctx->d_in4, Q, 32 * (size_t)n, cudaMemcpyHostToDevice, st));
-  launch_policy_table(ctx->g, ctx->d_cell, ctx->d_in0, Q ? ctx->d_in4 : nullptr, beta, 1.0, ctx->d_table, st, kl_dev);
+  ctx->t16_valid = ctx->d_table16 != nullptr && Q == nullptr;
+  launch_policy_table(ctx->g, ctx->d_cell, ctx->d_in0, Q ? ctx->d_in4 : nullptr, beta, 1.0, ctx->d_table, st, kl_dev,
+                      ctx->t16_valid ? ctx->d_table16 : nullptr);
   CK_LAST();
   ctx->v_goal = vg;
   ctx->has_table = true;
@@ -660,7 +668,8 @@ int32_t piql_destroy(piql_ctx* ctx) {
                   (void*)ctx->acc_cnt, (void*)ctx->d_scratch, (void*)ctx->d_transitions, (void*)ctx->d_inj,
                   (void*)ctx->d_scalars, (void*)ctx->snap_max, (void*)ctx->snap_sum, (void*)ctx->snap_cnt, (void*)ctx->fin_out})
     if (p) cudaFree(p);
-  for (void* p : {(void*)ctx->d_table_spare, (void*)ctx->d_upV, (void*)ctx->d_upQ}) if (p) cudaFree(p);
+  for (void* p : {(void*)ctx->d_table_spare, (void*)ctx->d_upV, (void*)ctx->d_upQ, (void*)ctx->d_table16, (void*)ctx->d_table16_spare})
+    if (p) cudaFree(p);
   for (cudaEvent_t e : {ctx->ev_retire_cur, ctx->ev_retire_spare, ctx->ev_table_ready}) if (e) cudaEventDestroy(e);
   if (ctx->ustream) cudaStreamDestroy(ctx->ustream);
   if (ctx->h_fin_transitions) cudaFreeHost(ctx->h_fin_transitions);
@@ -709,9 +718,11 @@ int32_t piql_grid_load(piql_ctx* ctx, const uint8_t* walls, int64_t H, int64_t W
   cudaStream_t st = ctx->stream;
   CK(cudaStreamSynchronize(st));
   if (ctx->ustream) CK(cudaStreamSynchronize(ctx->ustream));
-  for (void* q : {(void*)ctx->d_walls, (void*)ctx->d_cell, (void*)ctx->d_free, (void*)ctx->d_table, (void*)ctx->d_table_spare})
+  for (void* q : {(void*)ctx->d_walls, (void*)ctx->d_cell, (void*)ctx->d_free, (void*)ctx->d_table, (void*)ctx->d_table_spare,
+                  (void*)ctx->d_table16, (void*)ctx->d_table16_spare})
     if (q) cudaFree(q);
   ctx->d_walls = ctx->d_cell = nullptr; ctx->d_free = nullptr; ctx->d_table = nullptr; ctx->d_table_spare = nullptr;
+  ctx->d_table16 = ctx->d_table16_spare = nullptr; ctx->t16_valid = ctx->t16_valid_spare = false;
   ctx->spare_retired = false;
   ctx->has_grid = ctx->has_table = false; ctx->vs_ready = false;
   // free-cell list, in index order (host: it is the tabulation step of the boundary)
@@ -725,6 +736,12 @@ int32_t piql_grid_load(piql_ctx* ctx, const uint8_t* walls, int64_t H, int64_t W
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_cell, (size_t)n);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_free, sizeof(int) * (size_t)(nfree ? nfree : 1));
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_table, 32 * (size_t)n);
+  {
+    // 16-byte records beside the 32-byte table on grids whose table does not stay in L2 (PIQL_ROLL_REC16 = 0 / 1 overrides)
+    const char* env16 = getenv("PIQL_ROLL_REC16");
+    const bool rec16 = env16 ? atoi(env16) != 0 : n >= ROLL_REC16_MIN_CELLS;
+    if (e == cudaSuccess && rec16) e = cudaMalloc((void**)&ctx->d_table16, 16 * (size_t)n);
+  }
   if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_walls, walls, (size_t)n, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_free, h_free, sizeof(int) * (size_t)nfree, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) {
@@ -953,6 +970,8 @@ int32_t piql_table_load(piql_ctx* ctx, const piql_table_problem* p) {
   CK(up(nullptr, 8 * ns, (void**)&ctx->tb_x[0]));
   CK(up(nullptr, 8 * ns, (void**)&ctx->tb_x[1]));
   CK(up(nullptr, 8 * (size_t)rows, (void**)&ctx->tb_aux));
+  CK(up(nullptr, 8 * (size_t)rows, (void**)&ctx->tb_Q));
+  ctx->tb_has_q = false;
   CK(up(nullptr, 8 * ns, (void**)&ctx->tb_aux1));
   CK(up(nullptr, 8 * (size_t)table_blocks(p->nstates), (void**)&ctx->tb_partial));
   CK(up(nullptr, 8 * ns, (void**)&ctx->tb_out));
@@ -964,6 +983,20 @@ int32_t piql_table_load(piql_ctx* ctx, const piql_table_problem* p) {
   t.gamma = p->gamma; t.lgamma = std::log(p->gamma); t.l1mgamma = std::log(1.0 - p->gamma);  // -inf at gamma = 1
   ctx->tab_nnz = nnz;
   ctx->has_table_problem = true;
+  return PIQL_OK;
+}
+
+int32_t piql_table_set_q(piql_ctx* ctx, const double* Q) {
+  if (!ctx) return PIQL_ERR_ARG;
+  NEED(ctx->has_table_problem, PIQL_ERR_STATE, "no tabulated problem loaded (call piql_table_load first)");
+  CK(cudaSetDevice(ctx->device));
+  if (Q) {
+    const size_t rows = (size_t)ctx->tab.ns * (size_t)ctx->tab.na;
+    for (size_t i = 0; i < rows; i++) NEED(Q[i] == Q[i], PIQL_ERR_ARG, "Q holds a NaN");
+    CK(cudaMemcpyAsync(ctx->tb_Q, Q, 8 * rows, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->tb_has_q = Q != nullptr;
   return PIQL_OK;
 }
 
@@ -980,7 +1013,8 @@ static int table_solve(piql_ctx* ctx, int kind, const double* V, const double* n
   if (V) CK(cudaMemcpyAsync(ctx->tb_V, V, nb, cudaMemcpyHostToDevice, st));
   if (nu) CK(cudaMemcpyAsync(ctx->tb_nu, nu, nb, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(ctx->tb_x[0], 0, nb, st));  // Growable default x -> 0.0
-  if (kind != KIND_NU) launch_table_prep(t, kind, reward_scale, beta, ctx->tb_V, ctx->tb_nu, ctx->tb_aux, ctx->tb_aux1, st);
+  if (kind != KIND_NU)
+    launch_table_prep(t, kind, reward_scale, beta, ctx->tb_V, ctx->tb_nu, ctx->tb_aux, ctx->tb_aux1, st, ctx->tb_has_q ? ctx->tb_Q : nullptr);
   CK_LAST();
   const long long every = opts->check_every > 0 ? opts->check_every : 16;
   long long sweeps = 0;
@@ -1097,7 +1131,7 @@ int32_t piql_table_mc_logz(piql_ctx* ctx, const double* V, double beta, const pi
   float ms_roll = 0.f, ms_all = 0.f;
   if (e == cudaSuccess) {
     launch_fold_counter(ctx->d_transitions, st);
-    launch_table_policy(t, 1.0, beta, ctx->tb_V, d_cdf, d_bf, d_cum, d_vt, st);
+    launch_table_policy(t, 1.0, beta, ctx->tb_V, ctx->tb_has_q ? ctx->tb_Q : nullptr, d_cdf, d_bf, d_cum, d_vt, st);
     launch_fill_f64(d_lsa, NAN, rows, st);
     launch_fill_f64(d_ls, NAN, t.ns, st);
     e = cudaMemsetAsync(d_csa, 0, 8 * (size_t)rows, st);
@@ -1343,6 +1377,7 @@ int32_t piql_policy_table_async(piql_ctx* ctx, const double* V, const double* Q,
     CK(cudaEventCreateWithFlags(&ctx->ev_table_ready, cudaEventDisableTiming));
   }
   if (!ctx->d_table_spare) CK(cudaMalloc((void**)&ctx->d_table_spare, 32 * (size_t)n));
+  if (ctx->d_table16 && !ctx->d_table16_spare) CK(cudaMalloc((void**)&ctx->d_table16_spare, 16 * (size_t)n));
   CK(grow(ctx->d_upV, ctx->up_cap, n));
   if (Q) CK(grow(ctx->d_upQ, ctx->upq_cap, 4 * n));
   cudaStream_t us = ctx->ustream;
@@ -1351,17 +1386,32 @@ int32_t piql_policy_table_async(piql_ctx* ctx, const double* V, const double* Q,
   if (ctx->spare_retired) CK(cudaStreamWaitEvent(us, ctx->ev_retire_spare, 0));
   CK(cudaMemcpyAsync(ctx->d_upV, V, 8 * (size_t)n, cudaMemcpyHostToDevice, us));
   if (Q) CK(cudaMemcpyAsync(ctx->d_upQ, Q, 32 * (size_t)n, cudaMemcpyHostToDevice, us));
-  launch_policy_table(ctx->g, ctx->d_cell, ctx->d_upV, Q ? ctx->d_upQ : nullptr, beta, 1.0, ctx->d_table_spare, us, nullptr);
+  ctx->t16_valid_spare = ctx->d_table16_spare != nullptr && Q == nullptr;
+  launch_policy_table(ctx->g, ctx->d_cell, ctx->d_upV, Q ? ctx->d_upQ : nullptr, beta, 1.0, ctx->d_table_spare, us, nullptr,
+                      ctx->t16_valid_spare ? ctx->d_table16_spare : nullptr);
   CK_LAST();
   CK(cudaEventRecord(ctx->ev_table_ready, us));
   // retire the current table: whatever is enqueued on the context's stream so far may still read it
   CK(cudaEventRecord(ctx->ev_retire_cur, st));
   CK(cudaStreamWaitEvent(st, ctx->ev_table_ready, 0));
   std::swap(ctx->d_table, ctx->d_table_spare);
+  std::swap(ctx->d_table16, ctx->d_table16_spare);
+  std::swap(ctx->t16_valid, ctx->t16_valid_spare);
   std::swap(ctx->ev_retire_cur, ctx->ev_retire_spare);
   ctx->spare_retired = true;
   ctx->v_goal = vg;
   ctx->has_table = true;
+  return PIQL_OK;
+}
+
+int32_t piql_policy_table16(piql_ctx* ctx, uint32_t* table16_out, int32_t* in_use_out) {
+  if (!ctx) return PIQL_ERR_ARG;
+  NEED(ctx->has_table, PIQL_ERR_STATE, "no policy table (call piql_policy_table first)");
+  CK(cudaSetDevice(ctx->device));
+  if (in_use_out) *in_use_out = ctx->t16_valid ? 1 : 0;
+  if (table16_out && ctx->t16_valid)
+    CK(cudaMemcpyAsync(table16_out, ctx->d_table16, 16 * (size_t)ctx->g.n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return PIQL_OK;
 }
 
@@ -1372,6 +1422,7 @@ int32_t piql_policy_table_set(piql_ctx* ctx, const float* table, double v_goal) 
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(ctx->d_table, table, 32 * (size_t)ctx->g.n, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->t16_valid = false;  // a caller's table need not have action-independent fitness entries
   ctx->v_goal = v_goal;
   ctx->has_table = true;
   return PIQL_OK;
@@ -1423,7 +1474,8 @@ int32_t piql_mc_update_v(piql_ctx* ctx, const double* V, double beta, const piql
     CK(cudaMemcpyAsync(ctx->h_scalars + 4, ctx->d_in1 + ctx->g.goal, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     ctx->v_goal = ctx->h_scalars[4];
-    launch_policy_table(ctx->g, ctx->d_cell, ctx->d_in1, nullptr, beta, 1.0, ctx->d_table, st);
+    ctx->t16_valid = ctx->d_table16 != nullptr;
+    launch_policy_table(ctx->g, ctx->d_cell, ctx->d_in1, nullptr, beta, 1.0, ctx->d_table, st, nullptr, ctx->d_table16);
     ctx->has_table = true;
     rc = mc_reset(ctx, &o);
     if (rc) return rc;

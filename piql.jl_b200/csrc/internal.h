@@ -132,6 +132,7 @@ void launch_residual_final(const double* partial, int nblocks, double* out, cuda
 // rollout.cu --------------------------------------------------------------------------------
 struct RolloutArgs {
   const float4* table;   // 2 x float4 per cell
+  const uint4* table16;  // nullptr, or the 16-byte records (V-determined Q on grids beyond L2): the production kernel reads these
   long long table_bytes; // 32 * cells
   int goal;
   int H;
@@ -152,7 +153,10 @@ struct RolloutArgs {
 };
 // kl_out (optional): kl_cost(ctrl, s, Q) per cell, path_functions.jl:17-20
 void launch_policy_table(const GridDev& g, const uint8_t* cell, const double* V, const double* Q, double beta,
-                         double reward_scale, float4* table, cudaStream_t st, float* kl_out = nullptr);
+                         double reward_scale, float4* table, cudaStream_t st, float* kl_out = nullptr, uint4* table16 = nullptr);
+// Grids from this many cells on get the 16-byte records as well (their 32-byte table, >= 128 MB, does not stay in L2);
+// PIQL_ROLL_REC16 = 0 / 1 overrides (tests, A/B timing).
+constexpr long long ROLL_REC16_MIN_CELLS = 4LL << 20;
 struct PathEstArgs {
   const float4* table;   // policy records built with beta = 1 (bf = fitness)
   const float* kl;       // kl_cost per cell
@@ -207,15 +211,15 @@ struct TableDev {
   double gamma, lgamma, l1mgamma;
 };
 void launch_table_prep(const TableDev& t, int kind, double scale, double beta, const double* V, const double* nu, double* aux,
-                       double* aux1, cudaStream_t st);
+                       double* aux1, cudaStream_t st, const double* Q = nullptr);
 // One Jacobi sweep X -> Y; partial != nullptr: also the residual sum |new - old| into *residual.
 void launch_table_sweep(const TableDev& t, int kind, double scale, const double* X, double* Y, const double* V, const double* aux,
                         const double* aux1, double* partial, double* residual, cudaStream_t st);
 void launch_table_update_v(long long ns, const double* V, const double* logz, double beta, double* out, cudaStream_t st);
 int table_blocks(long long ns);
 // Monte-Carlo sampling on the table: sampler tables from V, rollout (estimator A), reduction + finalisation
-void launch_table_policy(const TableDev& t, double scale, double beta, const double* V, float* cdf, float* bf, float* cum,
-                         float* vterm, cudaStream_t st);
+void launch_table_policy(const TableDev& t, double scale, double beta, const double* V, const double* Q, float* cdf, float* bf,
+                         float* cum, float* vterm, cudaStream_t st);
 void launch_table_rollout(const TableDev& t, const float* cdf, const float* bf, const float* cum, const float* vterm, double gamma,
                           long long horizon, long long path0, long long npaths, const int* starts, long long nstarts,
                           uint64_t seed, float* logw, uint32_t* meta, int num_sms, cudaStream_t st);

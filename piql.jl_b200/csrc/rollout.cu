@@ -22,7 +22,7 @@ namespace piql {
 __global__ void __launch_bounds__(256)
 policy_table_kernel(GridDev g, double reward_scale, double beta, const uint8_t* __restrict__ cell,
                     const double* __restrict__ V, const double* __restrict__ Q, float4* __restrict__ table,
-                    float* __restrict__ kl_out) {
+                    float* __restrict__ kl_out, uint4* __restrict__ table16) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= g.n) return;
   const unsigned ci = cell[s];
@@ -79,11 +79,20 @@ policy_table_kernel(GridDev g, double reward_scale, double beta, const uint8_t* 
   table[2 * (size_t)s] = r0;
   table[2 * (size_t)s + 1] = r1;
   if (kl_out) kl_out[s] = kl;
+  // 16-byte record (large grids, V-determined Q): with Q = controlV the fitness is -(Q - Qnormalization) + controlV = the
+  // normalisation, the same for every action (PIQL.jl:87-89), so one float carries it (bf0, the 32-byte record's first
+  // entry); the running sums are probabilities, < 2, so bits 30 and 31 of their floats are free and carry the four
+  // blocked-move bits: {c0 | m01 << 30, c1 | m23 << 30, c2, bf0}.  Decoding gives back exactly c0, c1, c2, mask, bf0.
+  if (table16) {
+    const unsigned m = __float_as_uint(r0.w);
+    table16[s] = make_uint4(__float_as_uint(r0.x) | ((m & 3u) << 30), __float_as_uint(r0.y) | (((m >> 2) & 3u) << 30),
+                            __float_as_uint(r0.z), __float_as_uint(r1.x));
+  }
 }
 
 void launch_policy_table(const GridDev& g, const uint8_t* cell, const double* V, const double* Q, double beta,
-                         double reward_scale, float4* table, cudaStream_t st, float* kl_out) {
-  policy_table_kernel<<<(g.n + 255) / 256, 256, 0, st>>>(g, reward_scale, beta, cell, V, Q, table, kl_out);
+                         double reward_scale, float4* table, cudaStream_t st, float* kl_out, uint4* table16) {
+  policy_table_kernel<<<(g.n + 255) / 256, 256, 0, st>>>(g, reward_scale, beta, cell, V, Q, table, kl_out, table16);
   g_launches++;
 }
 
@@ -165,7 +174,9 @@ constexpr size_t ROLL_STAGE_MAX_BYTES = 24 * 1024;  // x 8 resident CTAs per SM
 // Tried and dropped (measured on B200, profiles/r2_roll_tiled_check.txt): a second copy of the records in 8 x 8 blocks of
 // cells so that a horizontal step stays within a DRAM page -- bit-identical records, 12 % slower at 4098^2 (1.51e11 against
 // 1.71e11 transitions/s): the extra address arithmetic costs issue slots and the sector traffic does not change.
-template <int EST, bool INJ, bool TRACE, bool STAGED>
+// REC16: the 16-byte records of policy_table_kernel (grids whose 32-byte table does not fit L2: half the footprint, two
+// cells per DRAM sector, eight per line); decoded with five extra integer operations per step.
+template <int EST, bool INJ, bool TRACE, bool STAGED, bool REC16 = false>
 __global__ void __launch_bounds__(ROLL_THREADS)
 rollout_kernel(const RolloutArgs p) {
   extern __shared__ __align__(128) unsigned char roll_smem[];
@@ -245,7 +256,15 @@ rollout_kernel(const RolloutArgs p) {
         // two passes over the same sector; issued first (volatile keeps it there) so that the ~45 instructions of Philox
         // run under the load's latency -- at 4096^2 half of these loads miss L2
         float4 r0, r1;
-        if (STAGED) {
+        if (REC16) {
+          uint4 q16;
+          asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q16.x), "=r"(q16.y), "=r"(q16.z), "=r"(q16.w)
+                       : "l"(p.table16 + s));
+          r0 = make_float4(__uint_as_float(q16.x & 0x3fffffffu), __uint_as_float(q16.y & 0x3fffffffu), __uint_as_float(q16.z),
+                           __uint_as_float((q16.x >> 30) | ((q16.y >> 30) << 2)));
+          const float bf0 = __uint_as_float(q16.w);
+          r1 = make_float4(bf0, bf0, bf0, bf0);
+        } else if (STAGED) {
           r0 = stab[2 * s];
           r1 = stab[2 * s + 1];
         } else {
@@ -325,6 +344,9 @@ void launch_rollout(const RolloutArgs& a, int num_sms, cudaStream_t st) {
     // reference-scale tables: staged in shared memory
     if (a.estimator == 0) rollout_kernel<0, false, false, true><<<grid, ROLL_THREADS, (size_t)a.table_bytes, st>>>(a);
     else rollout_kernel<1, false, false, true><<<grid, ROLL_THREADS, (size_t)a.table_bytes, st>>>(a);
+  } else if (a.table16 && !inj && !tr) {
+    if (a.estimator == 0) rollout_kernel<0, false, false, false, true><<<grid, ROLL_THREADS, 0, st>>>(a);
+    else rollout_kernel<1, false, false, false, true><<<grid, ROLL_THREADS, 0, st>>>(a);
   } else if (a.estimator == 0) {
     if (inj) { if (tr) PIQL_ROLL(0, true, true); else PIQL_ROLL(0, true, false); }
     else { if (tr) PIQL_ROLL(0, false, true); else PIQL_ROLL(0, false, false); }

@@ -43,19 +43,20 @@ __device__ __forceinline__ double tab_lse(const double* x, int n) {
 // Per-(state, action) constants of a logz / gap solve: logz A = log prior + beta cV + (1-beta) cQ; gap pi (and D per state).
 __global__ void __launch_bounds__(TAB_THREADS)
 table_prep_kernel(TableDev t, int kind, double scale, double beta, const double* __restrict__ V, const double* __restrict__ nu,
-                  double* __restrict__ aux, double* __restrict__ aux1) {
+                  const double* __restrict__ Q, double* __restrict__ aux, double* __restrict__ aux1) {
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= t.ns) return;
   const int na = t.na;
-  double cv[TAB_MAX_ACTIONS], x[TAB_MAX_ACTIONS];
+  double cv[TAB_MAX_ACTIONS], q[TAB_MAX_ACTIONS], x[TAB_MAX_ACTIONS];
   for (int a = 0; a < na; a++) {
     cv[a] = t.gamma * tab_pa(t, s * na + a, V) - V[s] + tab_rbar(t, s * na + a, scale);  // controlV  PIQL.jl:63-66
-    x[a] = t.lprior[s * na + a] + cv[a];
+    q[a] = Q ? Q[s * na + a] : cv[a];       // a tabulated Q, or (s,a) -> controlV(ctrl,V,s,a)   value_iteration.jl:97,157
+    x[a] = t.lprior[s * na + a] + q[a];
   }
   const double norm = tab_lse(x, na);  // Qnormalization  PIQL.jl:72-75
   double D = 0.0;
   for (int a = 0; a < na; a++) {
-    const double cq = cv[a] - norm;  // controlQ  PIQL.jl:79-81
+    const double cq = q[a] - norm;  // controlQ  PIQL.jl:79-81
     if (kind == KIND_LOGZ) {
       aux[s * na + a] = t.lprior[s * na + a] + beta * cv[a] + (1.0 - beta) * cq;
     } else {
@@ -113,8 +114,8 @@ __global__ void table_update_v_kernel(long long ns, const double* __restrict__ V
 static inline unsigned tblk(long long n) { return (unsigned)((n + TAB_THREADS - 1) / TAB_THREADS); }
 
 void launch_table_prep(const TableDev& t, int kind, double scale, double beta, const double* V, const double* nu, double* aux,
-                       double* aux1, cudaStream_t st) {
-  table_prep_kernel<<<tblk(t.ns), TAB_THREADS, 0, st>>>(t, kind, scale, beta, V, nu, aux, aux1);
+                       double* aux1, cudaStream_t st, const double* Q) {
+  table_prep_kernel<<<tblk(t.ns), TAB_THREADS, 0, st>>>(t, kind, scale, beta, V, nu, Q, aux, aux1);
   g_launches++;
 }
 void launch_table_sweep(const TableDev& t, int kind, double scale, const double* X, double* Y, const double* V, const double* aux,
@@ -147,24 +148,25 @@ namespace piql {
 
 // per-(state, action) sampler tables from V: running normalised action probabilities and beta * fitness (PIQL.jl:83-89)
 __global__ void __launch_bounds__(TAB_THREADS)
-table_policy_kernel(TableDev t, double scale, double beta, const double* __restrict__ V, float* __restrict__ cdf,
-                    float* __restrict__ bf, float* __restrict__ vterm) {
+table_policy_kernel(TableDev t, double scale, double beta, const double* __restrict__ V, const double* __restrict__ Q,
+                    float* __restrict__ cdf, float* __restrict__ bf, float* __restrict__ vterm) {
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= t.ns) return;
   const int na = t.na;
   vterm[s] = (float)V[s];
-  double cv[TAB_MAX_ACTIONS], x[TAB_MAX_ACTIONS], w[TAB_MAX_ACTIONS];
+  double cv[TAB_MAX_ACTIONS], q[TAB_MAX_ACTIONS], x[TAB_MAX_ACTIONS], w[TAB_MAX_ACTIONS];
   for (int a = 0; a < na; a++) {
     cv[a] = t.term[s] ? 0.0 : t.gamma * tab_pa(t, s * na + a, V) - V[s] + tab_rbar(t, s * na + a, scale);
-    x[a] = t.lprior[s * na + a] + cv[a];
+    q[a] = (Q && !t.term[s]) ? Q[s * na + a] : cv[a];
+    x[a] = t.lprior[s * na + a] + q[a];
   }
   const double norm = tab_lse(x, na);
   double sum = 0.0, cw = 0.0;
-  for (int a = 0; a < na; a++) { w[a] = exp(t.lprior[s * na + a] + cv[a] - norm); sum += w[a]; }
+  for (int a = 0; a < na; a++) { w[a] = exp(t.lprior[s * na + a] + q[a] - norm); sum += w[a]; }
   for (int a = 0; a < na; a++) {
     cw += w[a];
     cdf[s * na + a] = (float)(cw / sum);
-    bf[s * na + a] = (float)(beta * (cv[a] - (cv[a] - norm)));
+    bf[s * na + a] = (float)(beta * (cv[a] - (q[a] - norm)));      // beta * fitness   PIQL.jl:87-89
   }
 }
 // running transition probabilities within each (state, action) row
@@ -323,9 +325,9 @@ __global__ void table_finalize_kernel(const int* __restrict__ omax, const double
   }
 }
 
-void launch_table_policy(const TableDev& t, double scale, double beta, const double* V, float* cdf, float* bf, float* cum,
-                         float* vterm, cudaStream_t st) {
-  table_policy_kernel<<<tblk(t.ns), TAB_THREADS, 0, st>>>(t, scale, beta, V, cdf, bf, vterm);
+void launch_table_policy(const TableDev& t, double scale, double beta, const double* V, const double* Q, float* cdf, float* bf,
+                         float* cum, float* vterm, cudaStream_t st) {
+  table_policy_kernel<<<tblk(t.ns), TAB_THREADS, 0, st>>>(t, scale, beta, V, Q, cdf, bf, vterm);
   table_cum_kernel<<<tblk(t.ns * t.na), TAB_THREADS, 0, st>>>(t, cum);
   g_launches += 2;
 }

@@ -193,6 +193,11 @@ class Engine:
         self.table_na = len(tab.actions)
         self.table_key = tab.key()
 
+    def table_set_q(self, Q=None):
+        """Tabulated Q[(state, action)] for the table solves / sampler that follow; None: the V-determined Q."""
+        q = None if Q is None else np.ascontiguousarray(Q, dtype=np.float64).reshape(self.table_n, self.table_na)
+        self._ck(self._lib.piql_table_set_q(self._ctx, _pd(q)))
+
     def table_solve(self, kind, V=None, nu=None, beta=1.0, reward_scale=1.0, tol=1e-12, max_sweeps=10 ** 7, check_every=0,
                     allow_unconverged=False):
         kind = {"nu": K.KIND_NU, "logz": K.KIND_LOGZ, "gap": K.KIND_GAP}[kind]
@@ -295,6 +300,16 @@ class Engine:
         self._ck(self._lib.piql_policy_table(self._ctx, _pd(V), _pd(Q), float(beta),
                                              None if tab is None else tab.ctypes.data_as(C.POINTER(C.c_float))))
         return tab
+
+    def policy_table16(self, download=True):
+        """The 16-byte policy records the production rollout reads on large grids: (table (H*W, 4) uint32 or None, in_use)."""
+        use = C.c_int32()
+        self._ck(self._lib.piql_policy_table16(self._ctx, None, C.byref(use)))
+        if not use.value or not download:
+            return None, bool(use.value)
+        tab = np.empty((self.H * self.W, 4), dtype=np.uint32)
+        self._ck(self._lib.piql_policy_table16(self._ctx, tab.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(use)))
+        return tab, True
 
     def policy_table_async(self, V, beta=1.0, Q=None):
         """piql_policy_table_async: upload + build on the library's upload stream, overlapping work already enqueued.  V (and

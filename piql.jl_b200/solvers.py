@@ -211,6 +211,15 @@ def _table_values(tab, V):
     return tab.values(V) if callable(V) else np.asarray(V, dtype=np.float64)
 
 
+def _table_q(tab, Q):
+    """Q over the tabulated (state, action) pairs: a callable Q(s, a) as in the reference (PIQL.jl:72-89), or an array."""
+    if Q is None:
+        return None
+    if callable(Q):
+        return np.array([[float(Q(s, a)) for a in tab.actions] for s in tab.states], dtype=np.float64)
+    return np.asarray(Q, dtype=np.float64).reshape(len(tab.states), len(tab.actions))
+
+
 # ---- solvers on the GPU -----------------------------------------------------------------------------
 def generate_nu(ctrl, tol=1e-12, max_sweeps=10 ** 7, precision="f64", device=0, return_stats=False):
     if ctrl.grid is None:
@@ -232,7 +241,11 @@ def generate_logz(ctrl, V, beta=1.0, β=None, Q=None, tol=1e-12, max_sweeps=10 *
     beta = beta if β is None else β
     if ctrl.grid is None:
         eng, tab = table_for(ctrl, device)
-        out, st = eng.table_solve("logz", V=_table_values(tab, V), beta=beta, tol=tol, max_sweeps=max_sweeps)
+        eng.table_set_q(_table_q(tab, Q))
+        try:
+            out, st = eng.table_solve("logz", V=_table_values(tab, V), beta=beta, tol=tol, max_sweeps=max_sweeps)
+        finally:
+            eng.table_set_q(None)
         g = Growable.from_table(tab, out)
         return (g, st) if return_stats else g
     eng = engine_for(ctrl, device)
@@ -286,7 +299,11 @@ def generate_optimality_gap(ctrl, V, nu=None, ν=None, Q=None, tol=1e-12, max_sw
         nu = generate_nu(ctrl, device=device)
     if ctrl.grid is None:
         eng, tab = table_for(ctrl, device)
-        out, st = eng.table_solve("gap", V=_table_values(tab, V), nu=_table_values(tab, nu), tol=tol, max_sweeps=max_sweeps)
+        eng.table_set_q(_table_q(tab, Q))
+        try:
+            out, st = eng.table_solve("gap", V=_table_values(tab, V), nu=_table_values(tab, nu), tol=tol, max_sweeps=max_sweeps)
+        finally:
+            eng.table_set_q(None)
         g = Growable.from_table(tab, out)
         return (g, st) if return_stats else g
     eng = engine_for(ctrl, device)
@@ -328,11 +345,15 @@ def mc_logz(ctrl, V, beta=1.0, β=None, Q=None, npaths=1 << 20, seed=0, estimato
     """
     beta = beta if β is None else β
     if ctrl.grid is None:
-        if Q is not None or estimator != "A":
-            raise NotImplementedError("tabulated problems: V-determined Q and the sampled-stop estimator only")
+        if estimator != "A":
+            raise NotImplementedError("tabulated problems: the sampled-stop estimator only")
         eng, tab = table_for(ctrl, device)
         idx = None if starts is None else [tab.index[s] for s in starts]
-        sa, cnt, ls, st = eng.table_mc_logz(_table_values(tab, V), beta=beta, npaths=npaths, seed=seed, horizon=horizon, starts=idx)
+        eng.table_set_q(_table_q(tab, Q))
+        try:
+            sa, cnt, ls, st = eng.table_mc_logz(_table_values(tab, V), beta=beta, npaths=npaths, seed=seed, horizon=horizon, starts=idx)
+        finally:
+            eng.table_set_q(None)
         return TableMcResult(tab, sa, cnt, ls, st)
     eng = engine_for(ctrl, device)
     cells = None if starts is None else [int(s[0]) + eng.H * int(s[1]) for s in starts]

@@ -39,11 +39,14 @@ class World:
         V, _ = engine.solve_nu(reward_scale=0.1, tol=0.0, max_sweeps=sweeps, precision="f64")   # the bench's V_lo recipe
         self.V = np.nan_to_num(V)
         self.table = engine.policy_table(self.V, beta=1.0)
+        # grids of 2^22 cells and more: the production kernel reads the 16-byte form of the same records
+        self.table16, self.rec16 = engine.policy_table16()
         self.vgoal = float(self.V[self.goal])
         self.threads = oracle.num_threads()
 
     def oracle_records(self, path0, n):
-        return self.org.rollout(self.table, self.vgoal, self.free, n, path0=path0, seed=SEED, nthreads=self.threads)
+        table = self.table16 if self.rec16 else self.table
+        return self.org.rollout(table, self.vgoal, self.free, n, path0=path0, seed=SEED, nthreads=self.threads)
 
 
 @pytest.fixture(scope="module", params=["grid1024", "grid4096"])
@@ -52,9 +55,32 @@ def world(request, engine):
 
 
 def test_policy_table_bits(engine, world):
-    """The 32-byte records the production kernel reads are the oracle's, bit for bit, at 1026^2 and 4098^2."""
+    """The 32-byte records are the oracle's, bit for bit, at 1026^2 and 4098^2; the 16-byte records the production kernel reads
+    at 4098^2 decode to exactly their running sums, blocked-move bits and first fitness entry."""
     ref = world.org.policy_table(world.V, beta=1.0, nthreads=world.threads)
     assert np.array_equal(world.table.view(np.uint32), ref.view(np.uint32))
+    assert world.rec16 == (world.walls.size >= 1 << 22)
+    if world.rec16:
+        t32, t16 = world.table.view(np.uint32), world.table16
+        free = world.free
+        assert np.array_equal(t16[free, 0] & 0x3fffffff, t32[free, 0]) and np.array_equal(t16[free, 1] & 0x3fffffff, t32[free, 1])
+        assert np.array_equal(t16[free, 2], t32[free, 2]) and np.array_equal(t16[free, 3], t32[free, 4])
+        assert np.array_equal((t16[free, 0] >> 30) | ((t16[free, 1] >> 30) << 2), t32[free, 3])
+        # with the V-determined Q the four fitness entries agree to the last bits of the double they were rounded from
+        bf = world.table[free, 4:8]
+        assert float(np.max(np.abs(bf - bf[:, :1]))) <= 1e-6 * max(1.0, float(np.max(np.abs(bf))))
+
+
+def test_record_forms_sample_the_same_trajectories(engine, world):
+    """16- and 32-byte records carry the same running sums and blocked-move bits: first actions and path lengths are
+    identical, the log-weights agree to float rounding (the one fitness float against four that agree to ~1 ulp)."""
+    if not world.rec16:
+        pytest.skip("the 32-byte records are the only form at this size")
+    n = 1 << 18
+    a = world.org.rollout(world.table16, world.vgoal, world.free, n, path0=11, seed=SEED, nthreads=world.threads)
+    b = world.org.rollout(world.table, world.vgoal, world.free, n, path0=11, seed=SEED, nthreads=world.threads)
+    assert np.array_equal(a[1], b[1])
+    assert np.allclose(a[0], b[0], rtol=1e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("path0", [0, 3 * (1 << 27) + 5, (1 << 33) + 12345])

@@ -126,3 +126,45 @@ def test_bandit_mc_through_the_reference_interface(piql):
     res = piql.mc_logz(bb, v, beta=1.0, npaths=1 << 20, seed=4, starts=[s0])
     assert abs(res.logz(s0) - exact(s0)) < 0.01 and res.transitions > 1 << 20
     assert res.count_sa.sum() == 1 << 20
+
+
+def test_table_solves_and_sampler_with_a_q_table(engine, piql):
+    """piql_table_set_q: a tabulated Q enters Qnormalization / controlQ / action_probability / fitness of the table path --
+    log Z and gap solves equal the table oracle (1e-12) and the GPU grid path with the same Q (1e-10); the sampler's records
+    stay bit-exact against the oracle on the tables built from that Q; clearing Q restores the V-determined solve."""
+    g = Golden("r0_01g0_99")
+    gw = piql.Gridworld(g.walls != 0, g.goal)
+    ctrl = piql.modify(piql.gridworld_ctrl(gw, **g.params), grid=None)
+    tab = piql.tabulate_problem(ctrl, roots=[g.goal] + piql.state_iterator(gw))
+    rng = np.random.default_rng(3)
+    Qd = rng.normal(size=(g.H * g.W, 4)) * 0.2
+    idx = np.array([s[0] + g.H * s[1] for s in tab.states])
+    Qt, V = Qd[idx], np.nan_to_num(g.V(5, 2))
+    Vt = V.ravel(order="F")[idx]
+    engine.load_table(tab)
+    base, _ = engine.table_solve("logz", V=Vt, beta=0.6)
+    engine.table_set_q(Qt)
+    out, _ = engine.table_solve("logz", V=Vt, beta=0.6)
+    ref, _, _ = oracle.table_solve(tab, "logz", V=Vt, beta=0.6, Q=Qt)
+    assert np.abs(out - ref).max() < 1e-12 and np.abs(out - base).max() > 1e-3
+    nut = np.nan_to_num(g.nu).ravel(order="F")[idx]
+    gap, _ = engine.table_solve("gap", V=Vt, nu=nut)
+    refg, _, _ = oracle.table_solve(tab, "gap", V=Vt, nu=nut, Q=Qt)
+    assert np.abs(gap - refg).max() < 1e-11
+    n = 1 << 18
+    sa, cnt, ls, st, (cdf, bf, cum) = engine.table_mc_logz(Vt, beta=0.6, npaths=n, seed=5, starts=[3], nnz=len(tab.succ), want_tables=True)
+    logw, meta = engine.mc_records(n)
+    lw_ref, meta_ref = oracle.table_rollout(tab, cdf, bf, cum, Vt.astype(np.float32), n, starts=[3], seed=5)
+    assert np.array_equal(meta, meta_ref) and np.array_equal(logw.view(np.uint32), lw_ref.view(np.uint32))
+    w = np.exp(logw.astype(np.float64) - logw.max())
+    assert abs(ls[3] - out[3]) < 5 * w.std() / np.sqrt(n) / w.mean() + 1e-5       # the estimate targets the Q solve's fixed point
+    engine.table_set_q(None)
+    again, _ = engine.table_solve("logz", V=Vt, beta=0.6)
+    assert np.array_equal(again, base)
+    # the grid path with the same Q
+    engine.load_grid(g.walls, g.goal, **g.params)
+    grid, _ = engine.solve_logz(V, beta=0.6, Q=Qd)
+    assert np.abs(grid.ravel(order="F")[idx] - out).max() < 1e-10
+    # through the reference interface: Q as a callable (s, a) -> value
+    lz = piql.generate_logz(ctrl, lambda s: float(V[s]), beta=0.6, Q=lambda s, a: float(Qd[s[0] + g.H * s[1], a]))
+    assert max(abs(lz(s) - o) for s, o in zip(tab.states, out)) < 1e-12

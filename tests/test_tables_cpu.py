@@ -80,3 +80,27 @@ def test_table_oracle_equals_grid_oracle_on_a_tabulated_gridworld(piql):
     assert np.abs(lz - pick(ref)).max() < 1e-11
     gp, _, _ = oracle.table_solve(tab, "gap", V=pick(np.nan_to_num(g.V(7, 2))), nu=pick(np.nan_to_num(g.nu)))
     assert np.abs(gp - pick(g.G(7, 2))).max() < 1e-9                  # the reference's stored gap
+
+
+def test_table_oracle_with_a_q_table_equals_the_grid_oracle(golden01):
+    """A tabulated Q (any Q callable of PIQL.jl:72-89) through the table restatement against the grid restatement, which
+    is pinned to data/*.jld2: log Z and gap solves with a random Q agree on the tabulated reference gridworld."""
+    import piql_jl_b200 as piql
+    g = golden01
+    gw = piql.Gridworld(g.walls != 0, g.goal)
+    ctrl = piql.modify(piql.gridworld_ctrl(gw, **g.params), grid=None)
+    tab = piql.tabulate_problem(ctrl, roots=[g.goal] + piql.state_iterator(gw))
+    org = g.oracle()
+    rng = np.random.default_rng(3)
+    Qd = rng.normal(size=(g.H * g.W, 4)) * 0.2
+    idx = np.array([s[0] + g.H * s[1] for s in tab.states])
+    Qt = Qd[idx]
+    V = np.nan_to_num(g.V(5, 2))
+    Vt = V.ravel(order="F")[idx]
+    ref, _ = org.solve("logz", V=V, Q=Qd, beta=0.6)
+    out, sweeps, res = oracle.table_solve(tab, "logz", V=Vt, beta=0.6, Q=Qt)
+    assert np.abs(out - ref.ravel(order="F")[idx]).max() < 1e-10
+    nu = np.nan_to_num(g.nu)
+    refg, _ = org.solve("gap", V=V, Q=Qd, nu=nu)
+    outg, _, _ = oracle.table_solve(tab, "gap", V=Vt, nu=nu.ravel(order="F")[idx], Q=Qt)
+    assert np.abs(outg - refg.ravel(order="F")[idx]).max() < 1e-9
