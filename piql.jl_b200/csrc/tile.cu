@@ -1170,7 +1170,7 @@ cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs,
   const long long probe = 32;
   // Short probes (small grids: 0.1 ms) are noisy and are repeated; once a probe lasts more than half a millisecond one
   // measurement per shape is enough, and all a first solve should pay (tuning stays near a tenth of a solve to tolerance).
-  int reps = 2;
+  int reps = 3;
   for (const Try& t : tries) {
     if ((err = tile_setup(g, cell, vs, tb, t.plan, t.persist, st)) != cudaSuccess) break;
     if ((err = tile_sweeps(g, vs, tb, 2 * t.plan.kh, false, st)) != cudaSuccess) break;
