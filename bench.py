@@ -70,7 +70,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("PIQL_BENCH_SMI_MS", "100")],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -532,7 +532,7 @@ def run_ours(args, rank, world, local_rank):
 
     with torch.cuda.stream(stream):
         sampler = ClockSampler(local_rank)
-        if rank == 0:
+        if rank == 0 and os.environ.get("PIQL_BENCH_NO_SMI") is None:
             sampler.start()        # nvidia-smi needs ~0.1 s to come up: it also sees the warm-up steps
         for _ in range(args.warmup):
             step()
@@ -638,21 +638,36 @@ def run_ours(args, rank, world, local_rank):
         est.step(Vp, BETA, seed=MC_SEED + 1)   # warm-up
         est.finish()
         barrier()
+        eng.mc_timing()
         t0 = time.perf_counter()
         for i in range(reps):
             prev = est.step(Vp, BETA, seed=MC_SEED + 2 + i)       # returns iteration i - 1, downloaded under iteration i's rollout
             if prev is not None:
                 tot += float(prev[1].transitions)
-        tot += float(est.finish()[1].transitions)
+        last_out, last_st = est.finish()
+        tot += float(last_st.transitions)
         barrier()
         dt = time.perf_counter() - t0
+        e_roll_s, e_red_s, e_nl = eng.mc_timing()
+        # the pipelined calls against the blocking ones: the last iteration again through piql_policy_table / piql_mc_finalize
+        same = None
+        if not args.no_parity:
+            ref = pd.mc_logz_sharded(eng, Vp, BETA, P, rank, world, seed=MC_SEED + 2 + reps - 1, mode=args.exchange, root_only=True)
+            if rank == 0:
+                rsa, rcn, rls, rst = ref
+                ok = rcn > 0
+                same = bool(np.array_equal(last_out[1].astype(np.uint64), rcn) and
+                            np.allclose(last_out[0][ok], rsa[ok], rtol=0, atol=1e-6 if args.e2e_f32 else 0) and
+                            np.allclose(last_out[2][~np.isnan(rls)], rls[~np.isnan(rls)], rtol=0, atol=1e-6 if args.e2e_f32 else 0))
         stat = torch.tensor([dt, tot], dtype=torch.float64, device="cuda:%d" % local_rank)
         if world > 1:
             mx = stat.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             sm = stat.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
             dt, tot = float(mx[0]), float(sm[1])
         e2e = {"value": tot / dt, "unit": "transitions/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 9 * ob * n,
-               "steps": reps, "ms_per_step": 1e3 * dt / reps, "output_dtype": "f32/u32" if args.e2e_f32 else "f64/u64",
+               "steps": reps, "ms_per_step": 1e3 * dt / reps,
+               "rollout_ms_per_launch": 1e3 * e_roll_s / max(e_nl, 1), "reduce_ms_per_launch": 1e3 * e_red_s / max(e_nl, 1),
+               "matches_blocking_calls": same, "output_dtype": "f32/u32" if args.e2e_f32 else "f64/u64",
                "call": "per iteration: piql_policy_table (pinned host V in, every rank) + piql_mc_reset_dev + piql_mc_rollout_dev "
                        "(+ exchange) + piql_mc_finalize_async; logz_sa / count_sa / logz_s land in pinned host buffers on rank 0 "
                        "(results are replicated) through the library's copy stream while the next iteration rolls out; the timed "
