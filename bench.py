@@ -271,6 +271,8 @@ def vi_section(args, eng, stream, V, peak, vst, name=None):
             vi["tile_plan"] = eng.vi_tile_plan("nu", "f32fast")   # the shape the library timed fastest on this device
         plan = eng.vi_tile_plan(kind, prec)
         kh = max(int(plan.get("sweeps_per_round", 4)), 1)
+        if plan.get("column_resident"):
+            kh = args.vi_sweeps          # the column-resident schedule runs the whole batch of sweeps in one launch
         tr = vi_traffic(name, key)
         vi[key] = {"sweeps_per_s": sps, "state_backups_per_s": sps * eng.nfree, "us_per_sweep": 1e6 / sps,
                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
@@ -290,8 +292,11 @@ def vi_section(args, eng, stream, V, peak, vst, name=None):
         solves[prec] = {"tol_sum_abs_delta": tol, "sweeps": int(sst.sweeps), "converged": bool(sst.converged),
                         "seconds": time.perf_counter() - t0, "device_seconds": float(sst.device_seconds)}
     vi["solve_nu"] = solves
-    vi["kernel"] = ("tile_sweep_kernel<T,KIND,FAST>: 4 Jacobi sweeps per launch on 128 x (TJ+8) shared-memory tiles "
-                    "(includes the residual reduction on the last launch); f32fast = MUFU ex2/lg2; keys without a kind are nu")
+    vi["kernel"] = ("per (kind, precision) the schedule the library timed fastest on this device (tile_plan): tile_sweep_kernel<T,KIND,FAST> "
+                    "= 4 or 8 Jacobi sweeps per launch on 128 x (TJ + 2 kh) shared-memory tiles; col_resident_kernel<T,KIND,FAST> "
+                    "(tile_plan.column_resident = 1) = one CTA per SM keeps a slab of whole columns in shared memory for the whole batch of "
+                    "sweeps and exchanges one column per sweep with each neighbour through L2 mailboxes, every cell computed once per sweep; "
+                    "timings include the residual reduction of the last sweep; f32fast = MUFU ex2/lg2; keys without a kind are nu")
     vi["setup_vlo"] = {"sweeps": int(vst.sweeps), "device_seconds": float(vst.device_seconds)}
     return vi
 

@@ -747,6 +747,12 @@ int32_t piql_grid_load(piql_ctx* ctx, const uint8_t* walls, int64_t H, int64_t W
   if (e == cudaSuccess) {
     ctx->g.H = (int)H; ctx->g.W = (int)W; ctx->g.n = (int)n; ctx->g.goal = (int)(goal_i + H * goal_j);
     ctx->g.randomness = p->randomness; ctx->g.step_cost = p->step_cost; ctx->g.reward = p->reward; ctx->g.gamma = p->gamma;
+    ctx->g.bi0 = (int)H; ctx->g.bi1 = -1; ctx->g.bj0 = (int)W; ctx->g.bj1 = -1;
+    for (long long q = 0; q < nfree; q++) {
+      const int i = h_free[q] % (int)H, j = h_free[q] / (int)H;
+      ctx->g.bi0 = i < ctx->g.bi0 ? i : ctx->g.bi0; ctx->g.bi1 = i > ctx->g.bi1 ? i : ctx->g.bi1;
+      ctx->g.bj0 = j < ctx->g.bj0 ? j : ctx->g.bj0; ctx->g.bj1 = j > ctx->g.bj1 ? j : ctx->g.bj1;
+    }
     launch_cellinfo(ctx->d_walls, ctx->g, ctx->d_cell, st);
     e = cudaGetLastError();
   }
@@ -1208,7 +1214,7 @@ int32_t piql_vi_tile_plan(piql_ctx* ctx, int32_t kind, int32_t precision, int32_
     persistent = ctx->tb.persistent;
   }
   plan_out[0] = pl.TJ; plan_out[1] = pl.nw; plan_out[2] = pl.tiles_i; plan_out[3] = pl.tiles_j;
-  plan_out[4] = pl.ctas_per_sm; plan_out[5] = (int32_t)pl.smem; plan_out[6] = pl.kh; plan_out[7] = (persistent ? 1 : 0) | (pl.planes << 1);
+  plan_out[4] = pl.ctas_per_sm; plan_out[5] = (int32_t)pl.smem; plan_out[6] = pl.kh; plan_out[7] = (persistent ? 1 : 0) | (pl.planes << 1) | (pl.colres << 4);
   return PIQL_OK;
 }
 int32_t piql_vi_set_iterate(piql_ctx* ctx, const double* x) {

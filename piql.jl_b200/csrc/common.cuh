@@ -18,6 +18,7 @@ struct GridDev {
   int n;       // H*W
   int goal;    // linear index of the goal cell
   double randomness, step_cost, reward, gamma;
+  int bi0, bi1, bj0, bj1;  // bounding box of the free cells (rows bi0..bi1, columns bj0..bj1; the border is wall)
 };
 
 // ---- precision-generic math ------------------------------------------------------------------

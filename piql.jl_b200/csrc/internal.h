@@ -41,6 +41,14 @@ struct TilePlan {
   long long np;          // ld * Wp
   size_t smem;           // dynamic shared memory per CTA
   int ctas_per_sm;
+  int gi;                // ghost rows of the padded layout (= kh for the tiled plans)
+  // column-resident schedule (col_resident_kernel: one CTA per SM keeps a slab of whole columns in shared memory for a whole
+  // batch of sweeps and exchanges one column per sweep with each neighbour): geometry in padded coordinates
+  int colres;            // 1: this plan
+  int r0, NS;            // first resident row (multiple of 4), 128-row strips per column
+  int c0, ncta;          // first column of CTA 0, CTAs
+  int wbase, wrem, wmax; // CTA c owns wbase + (c < wrem) columns; wmax = the widest slab
+  int nwc, G;            // compute warps (nw less the mail warps), groups per warp of the work list
 };
 // Halo exchange of the multi-GPU soft VI, carried by the tile kernel itself: the CTAs of the slab's first / last tile column
 // wait for the neighbour's counter before they stage their tile, and after the write-back also store their edge columns
@@ -80,6 +88,12 @@ struct TileBuffers {
   long long cap_flags = 0;
   int* err = nullptr;          // pinned host word: set when a neighbour wait timed out (copied from d_err after a launch)
   int* d_err = nullptr;        // device word the kernel polls and sets
+  // column-resident schedule: L2 mailboxes of the per-sweep column exchange ({word, sequence} pairs) and the sequence counter
+  unsigned long long* mail = nullptr;
+  size_t cap_mail = 0;
+  unsigned col_seq = 0;
+  void* sched = nullptr;       // work list of a sweep (uint2 [2 shapes][nwc][G]), built by tile_setup
+  size_t cap_sched = 0;
   // multi-GPU column slabs: this rank sweeps tile columns [tj0, tj1) (piql_vi_shard_*)
   bool sharded = false;
   int tj0 = 0, tj1 = 0;

@@ -22,6 +22,7 @@
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -337,29 +338,14 @@ template <int KIND> __device__ __forceinline__ double sweep_diff(double stored, 
   return x > -1.0 ? fabs(log1p(x)) : CUDART_INF;
 }
 
-// One column of one Jacobi sweep of the staged tile: lane l recomputes rows 4l .. 4l+3 of column jj from src into dst,
-// every cell by the generic formula (the goal and its neighbours are redone by tile_goal_fixup).
-template <typename T, int KIND, bool FAST, bool PL>
-__device__ __forceinline__ void tile_strip(const TileK<T>& k, const T* __restrict__ src, T* __restrict__ dst,
-                                           const uint32_t* __restrict__ msk, const T* __restrict__ aux, int org, int lane, int jj) {
-  T v[4], L[4], R[4], out[4];
-  lds4(src + jj * TEI + 4 * lane, v);
-  lds4(src + (jj - 1) * TEI + 4 * lane, L);
-  lds4(src + (jj + 1) * TEI + 4 * lane, R);
-  const uint32_t mk = msk[jj * TMP + lane];
-  // rows 0 and 127 have no vertical neighbour in the tile: they are halo, any value will do
-  const T up = __shfl_up_sync(FULL, v[3], 1), dn = __shfl_down_sync(FULL, v[0], 1);
-  T ax[5][4];
-  if constexpr (kPlanes<T, KIND, FAST, PL> > 0) {
-    // the tile's planes sit behind the ping-pong pair in shared memory (aux points at them)
-#pragma unroll
-    for (int pl = 0; pl < kPlanes<T, KIND, FAST, PL>; pl++) lds4(aux + (pl * k.EJ + jj) * TEI + 4 * lane, ax[pl]);
-  } else if (KIND != KIND_NU) {
-    const int sidx = org + jj * k.ld + 4 * lane;
-#pragma unroll
-    for (int pl = 0; pl < ((kZDom<T, KIND, FAST> || (PIQL_LOGZ_OWN_SHIFT && KIND == KIND_LOGZ && FAST)) ? 4 : 5); pl++)
-      ldg4(aux + (size_t)pl * k.np + sidx, ax[pl]);
-  }
+// The per-cell work of one 128-cell strip, on registers: lane l holds rows 4l .. 4l+3 of the column (v), of its left and right
+// neighbours (L, R), the cells above row 4l and below row 4l+3 (up, dn), the four cell bytes (mk) and the strip's constants
+// (ax: planes of the linear sweeps / A_a / pi_a, D).  Every cell by the generic formula (the goal and its neighbours are
+// redone by the callers).  Shared by every schedule of the sweeps -- one launch per round, persistent tiles, resident
+// columns -- so that their values agree bit for bit.
+template <typename T, int KIND, bool FAST>
+__device__ __forceinline__ void strip_compute(const TileK<T>& k, const T (&v)[4], const T (&L)[4], const T (&R)[4], T up, T dn,
+                                              uint32_t mk, const T (&ax)[5][4], T (&out)[4]) {
   if constexpr (kZDom<T, KIND, FAST>) {
     float nb[4][4];  // [action][row]
 #pragma unroll
@@ -414,6 +400,34 @@ __device__ __forceinline__ void tile_strip(const TileK<T>& k, const T* __restric
       out[r] = o;
     }
   }
+}
+// planes a sweep reads per cell when they come from global memory (0 for nu)
+template <typename T, int KIND, bool FAST>
+constexpr int kPlanesGlobal = KIND == KIND_NU ? 0 : (kZDom<T, KIND, FAST> || (PIQL_LOGZ_OWN_SHIFT && KIND == KIND_LOGZ && FAST)) ? 4 : 5;
+
+// One column of one Jacobi sweep of the staged tile: lane l recomputes rows 4l .. 4l+3 of column jj from src into dst,
+// every cell by the generic formula (the goal and its neighbours are redone by tile_goal_fixup).
+template <typename T, int KIND, bool FAST, bool PL>
+__device__ __forceinline__ void tile_strip(const TileK<T>& k, const T* __restrict__ src, T* __restrict__ dst,
+                                           const uint32_t* __restrict__ msk, const T* __restrict__ aux, int org, int lane, int jj) {
+  T v[4], L[4], R[4], out[4];
+  lds4(src + jj * TEI + 4 * lane, v);
+  lds4(src + (jj - 1) * TEI + 4 * lane, L);
+  lds4(src + (jj + 1) * TEI + 4 * lane, R);
+  const uint32_t mk = msk[jj * TMP + lane];
+  // rows 0 and 127 have no vertical neighbour in the tile: they are halo, any value will do
+  const T up = __shfl_up_sync(FULL, v[3], 1), dn = __shfl_down_sync(FULL, v[0], 1);
+  T ax[5][4];
+  if constexpr (kPlanes<T, KIND, FAST, PL> > 0) {
+    // the tile's planes sit behind the ping-pong pair in shared memory (aux points at them)
+#pragma unroll
+    for (int pl = 0; pl < kPlanes<T, KIND, FAST, PL>; pl++) lds4(aux + (pl * k.EJ + jj) * TEI + 4 * lane, ax[pl]);
+  } else if (KIND != KIND_NU) {
+    const int sidx = org + jj * k.ld + 4 * lane;
+#pragma unroll
+    for (int pl = 0; pl < kPlanesGlobal<T, KIND, FAST>; pl++) ldg4(aux + (size_t)pl * k.np + sidx, ax[pl]);
+  }
+  strip_compute<T, KIND, FAST>(k, v, L, R, up, dn, mk, ax, out);
   sts4(dst + jj * TEI + 4 * lane, out);
 }
 
@@ -781,17 +795,343 @@ tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, c
   }
 }
 
+// ---- the column-resident variant: every cell computed exactly once per sweep ---------------------------------------------
+// Temporal blocking pays for its few launches with halo recomputation: at 1026^2 (8 sweeps per round, 128 x 40 tiles) a CTA
+// computes 1.9 cells per cell it keeps.  When a sweep is at most two 128-row strips per warp (28 warps x 148 SMs: ~10^6 cells, the
+// config-4 grid) there is a schedule with no redundancy at all: one CTA per SM owns a slab of whole columns (all rows of the
+// free cells' bounding box: 8 strips of 128 rows at 1026^2, so no vertical halo either -- the border is wall, grid_load checks
+// it), keeps it in shared memory for the whole batch of sweeps, and exchanges ONE column with each neighbour per sweep through an
+// L2 mailbox:
+//   * every 32-bit word travels as a 64-bit {word, sequence number} pair written and polled with single 64-bit accesses
+//     (single-copy atomic), so there is no fence, no flag round trip and no grid barrier: a reader spins on the data itself
+//     (one way: 0.3 us between two otherwise idle SMs, 0.65 us with every SM pair talking; tools/probe/mail_latency.cu);
+//   * a warp owns its (at most two) strips for the whole launch, so what does not change lives in its registers: the strip's own
+//     values (stored for the neighbours, never reloaded), the cell bytes and, for the linear fast sweeps, the constant planes --
+//     a strip of those is four shared-memory accesses instead of nine, and the shared-memory pipe is what bounds them;
+//   * a warp's first strip is an edge-column strip while they last: it is posted the moment it is stored, and the neighbour's
+//     strip of the same sweep is collected (into the halo column of the buffer the next sweep reads) after the warp's second strip;
+//   * mailboxes are double-buffered by sweep parity (a neighbour can be at most one sweep ahead);
+//   * the goal cell and (nu) its neighbours are patched, one lane per cell, by the warp that owns them before anything is posted.
+// Per sweep and CTA: one __syncthreads.  The per-cell arithmetic is strip_compute, shared with the other schedules: same bits.
+// What bounds it (clock64 stamps, PIQL_TILE_COLRES_TRACE): the period of a sweep is first strip + post-to-collect latency
+// (~2300 + ~2900 cycles for nu at 1026^2: an L2 round trip costs ~1000 cycles under this kernel's shared-memory load), not the
+// warps' work (~4000 cycles): 2.8 us per sweep against 3.05 for the tiled kernel (nu), 2.1 against 2.8 (log Z), 2.6 against 2.95 (gap).
+struct ColGeom {
+  int r0;           // first padded row of the resident columns (a multiple of 4: vector accesses stay aligned)
+  int NS, RS;       // 128-row strips per column, RS = 128 * NS rows
+  int c0;           // first padded column of CTA 0
+  int wbase, wrem;  // CTA c owns wbase + (c < wrem) columns
+  int wmax;         // widest slab (shared-memory layout)
+  int ncta;
+  int nwc;          // warps per CTA
+  int G;            // strips per warp in the work list (2)
+  int diag;         // timing experiments only (PIQL_TILE_COLRES_DIAG): 1 = no exchange at all (wrong values at the slab seams)
+  int diag_cta;     // the CTA PIQL_TILE_COLRES_TRACE follows
+  int diag_sw;      // first of the four sweeps it stamps (PIQL_TILE_COLRES_TRACE_SW, default 10)
+};
+constexpr int COL_ERR_TIMEOUT = 1;
+// 28 warps of 72 registers in fp32 (the planes of the linear sweeps live in registers), 16 of 128 in Float64
+template <typename T> constexpr int kColMaxThreads = sizeof(T) == 8 ? 512 : 896;
+constexpr uint32_t COL_NONE = 0xffffffffu;  // host work list: no item
+constexpr uint32_t COL_END = 0u;           // shared-memory work list: no item (offset 0 is the halo column, never a strip)
+// work-list item in shared memory: offset of the strip's first row in a buffer (20 bits) and flags
+constexpr uint32_t COL_OFS = 0xfffffu, COL_EDGE_L = 1u << 20, COL_EDGE_R = 1u << 21, COL_HAS_UP = 1u << 22, COL_HAS_DN = 1u << 23,
+                   COL_GOAL = 1u << 24;
+__device__ __forceinline__ void ld_mail(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_mail(unsigned long long* p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+template <typename T> constexpr int kMailWords = (int)(sizeof(T) / 4);  // 64-bit pairs per value
+// posts the lane's four values of a strip with sequence number seq
+__device__ __forceinline__ void mail_post(unsigned long long* p, unsigned seq, const float (&f)[4]) {
+  const unsigned long long hi = (unsigned long long)seq << 32;
+  st_mail(p, hi | __float_as_uint(f[0]), hi | __float_as_uint(f[1]));
+  st_mail(p + 2, hi | __float_as_uint(f[2]), hi | __float_as_uint(f[3]));
+}
+__device__ __forceinline__ void mail_post(unsigned long long* p, unsigned seq, const double (&f)[4]) {
+  const unsigned long long hi = (unsigned long long)seq << 32;
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+    st_mail(p + 2 * r, hi | (unsigned)__double2loint(f[r]), hi | (unsigned)__double2hiint(f[r]));
+}
+__device__ __forceinline__ void mail_unpack(const unsigned long long (&w)[4], float (&f)[4]) {
+#pragma unroll
+  for (int r = 0; r < 4; r++) f[r] = __uint_as_float((unsigned)w[r]);
+}
+__device__ __forceinline__ void mail_unpack(const unsigned long long (&w)[8], double (&f)[4]) {
+#pragma unroll
+  for (int r = 0; r < 4; r++) f[r] = __hiloint2double((int)(unsigned)w[2 * r + 1], (int)(unsigned)w[2 * r]);
+}
+// Waits until the lane's four values of a neighbour's strip carry seq and stores them into the halo column.  false: gave up
+// (somebody reported an error, or two seconds went by).
+template <typename T>
+__device__ __forceinline__ bool mail_take(const unsigned long long* p, unsigned seq, T* halo, int* err) {
+  constexpr int NQ = 2 * kMailWords<T>;  // 16-byte loads per lane
+  unsigned long long w[2 * NQ];
+  unsigned long long t0 = 0;
+  for (unsigned spin = 0;; spin++) {
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) ld_mail(p + 2 * q, w[2 * q], w[2 * q + 1]);
+#pragma unroll
+    for (int q = 0; q < 2 * NQ; q++) ok = ok && (unsigned)(w[q] >> 32) == seq;
+    if (ok) break;
+    if ((spin & 127u) == 127u) {
+      if (*(volatile int*)err) return false;
+      const unsigned long long t = globaltimer_ns_tile();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) { *err = COL_ERR_TIMEOUT; return false; }
+    }
+  }
+  T f[4];
+  mail_unpack(w, f);
+  sts4(halo, f);
+  return true;
+}
+// The goal cell (t = 0) and, for nu, its four neighbours (t = 1..4: (+1,0) (-1,0) (0,+1) (0,-1)) are not what the generic
+// formula gives (tile_goal_fixup).  The warp that has just stored the strip at buffer offset ob redoes those of them that lie in
+// it, one lane per cell, from src; gcell[t] = the cell's offset in a buffer (-1: not in this slab).  A serial version of this
+// cost the goal's CTA -- and, through the exchange, every CTA -- 3000 cycles per sweep.
+template <typename T, int KIND, bool FAST>
+__device__ __forceinline__ void col_goal_patch(const TileK<T>& k, const T* __restrict__ src, T* __restrict__ dst,
+                                               const uint32_t* __restrict__ msk, const int* __restrict__ gcell, int RS, int ob, int t) {
+  if (t < (KIND == KIND_NU ? 5 : 1)) {
+    const int i = gcell[t];
+    if (i >= ob && i < ob + TEI) {
+      const int m = i - RS;  // the cell bytes have no halo column in front
+      const uint32_t b = (msk[m >> 2] >> (8 * (m & 3))) & 0xffu;
+      const T c = src[i];
+      if (t == 0) {
+        // terminal_condition: nu, gap -> 0; logz -> 0 - V(goal), damped like every other state
+        if constexpr (kZDom<T, KIND, FAST>) dst[i] = (T)0.5 * k.term + (T)0.5 * c;
+        else dst[i] = (KIND == KIND_LOGZ) ? damp_half<T, FAST>(k.term, c) : k.term;
+      } else if (!(b & CELL_WALL)) {
+        T nb[NA];
+        nb[0] = (b & 1u) ? c : src[i + 1];
+        nb[1] = (b & 2u) ? c : src[i - 1];
+        nb[2] = (b & 4u) ? c : src[i + RS];
+        nb[3] = (b & 8u) ? c : src[i - RS];
+        const int cidx = k.goal_p + (t == 1) - (t == 2) + k.ld * ((t == 3) - (t == 4));
+        dst[i] = backup_nu(k.k, cidx, b, nb);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// One of a warp's (at most two) strips in sweep sw: level sw-1 in src -> level sw in dst.  The warp owns the strip for the whole
+// launch, so everything that does not change stays in registers: the lane's four values v (its own output of the last sweep;
+// they are stored for the neighbours, never reloaded), the cell bytes mk and, for the linear fast sweeps, the constant planes pl
+// (a strip of those sweeps is four shared-memory accesses instead of nine: they are bound by the shared-memory pipe).
+// item: offset in a buffer | flags; fix: this lane's seam flags (COL_HAS_UP for lane 0, COL_HAS_DN for lane 31, else 0).
+template <typename T, int KIND, bool FAST, bool PL>
+__device__ __forceinline__ void col_slot(const TileK<T>& k, const T* __restrict__ src, T* __restrict__ dst, const uint32_t* __restrict__ msk,
+                                         const T* __restrict__ auxg, unsigned long long* __restrict__ mine, const int* __restrict__ gcell,
+                                         uint32_t item, uint32_t gofs, T (&v)[4], uint32_t mk, T (&pl)[5][4], int wc, int lane4,
+                                         uint32_t fix, int RS, unsigned seq, bool post) {
+  constexpr int NP = kPlanes<T, KIND, FAST, PL>;
+  constexpr int MW = kMailWords<T>;
+  const int ob = (int)(item & COL_OFS), o = ob + lane4;
+  T L[4], R[4], out[4];
+  lds4(src + o - RS, L);
+  lds4(src + o + RS, R);
+  if constexpr (NP == 0 && KIND != KIND_NU) {
+#pragma unroll
+    for (int q = 0; q < kPlanesGlobal<T, KIND, FAST>; q++) ldg4(auxg + (size_t)q * k.np + gofs + lane4, pl[q]);
+  }
+  // the cell above a strip's first row / below its last one lives in the neighbouring strip of the same column; outside the
+  // bounding box (first / last strip) it is wall and the cell byte blocks the move
+  T up = __shfl_up_sync(FULL, v[3], 1), dn = __shfl_down_sync(FULL, v[0], 1);
+  if (item & fix & COL_HAS_UP) up = src[o - 1];
+  if (item & fix & COL_HAS_DN) dn = src[o + 4];
+  strip_compute<T, KIND, FAST>(k, v, L, R, up, dn, mk, pl, out);
+  sts4(dst + o, out);
+#pragma unroll
+  for (int r = 0; r < 4; r++) v[r] = out[r];
+  if (item & COL_GOAL) {  // warp-uniform, at most six strips of the grid
+    col_goal_patch<T, KIND, FAST>(k, src, dst, msk, gcell, RS, ob, lane4 >> 2);
+    lds4(dst + o, v);
+  }
+  if (post) {  // the slab's first column is the left neighbour's halo (box 0), its last one the right neighbour's (box 1)
+    if (item & COL_EDGE_L) mail_post(mine + (size_t)(o - RS) * MW, seq, v);
+    if (item & COL_EDGE_R) mail_post(mine + (size_t)RS * MW + (size_t)(o - wc * RS) * MW, seq, v);
+  }
+}
+
+// grid = ncta CTAs (one per SM, cooperative launch: all resident) of nwc warps; shared memory: col_smem_bytes().
+// sched: the work list [2 shapes: wmax / wmax - 1 columns][nwc warps][G groups] of {item, item or COL_NONE} with item =
+// column | strip << 16 (| 0x8000: phase 1); a warp's phase-1 groups come first, a row ends with an empty group.
+template <typename T, int KIND, bool FAST, bool PL>
+__global__ void __launch_bounds__(kColMaxThreads<T>, 1)
+col_resident_kernel(const TileK<T> k, const ColGeom cg, const uint8_t* __restrict__ maskp, const T* __restrict__ X, T* __restrict__ Y,
+                    const T* __restrict__ auxg, const uint2* __restrict__ sched, int nsweeps, int want_res, double* __restrict__ partial,
+                    unsigned long long* __restrict__ mail, unsigned seq0, int* __restrict__ err, long long* __restrict__ trace) {
+  extern __shared__ __align__(128) unsigned char tile_smem[];
+  __shared__ double red[32];
+  __shared__ int gcell[5];
+  constexpr int NP = kPlanes<T, KIND, FAST, PL>;
+  constexpr int MW = kMailWords<T>;
+  const int RS = cg.RS, NS = cg.NS;
+  // PIQL_TILE_COLRES_TRACE = CTA: lane 0 of every warp of that CTA stamps six points of sweeps 10..13 (timing experiments)
+#define COL_STAMP(i) do { if (trace && blockIdx.x == (unsigned)cg.diag_cta && sw >= cg.diag_sw && sw < cg.diag_sw + 4 && lane == 0) \
+    trace[((sw - cg.diag_sw) * 32 + warp) * 6 + (i)] = clock64(); } while (0)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+  const int c = blockIdx.x;
+  const int wc = cg.wbase + (c < cg.wrem ? 1 : 0);
+  const int j0 = cg.c0 + c * cg.wbase + min(c, cg.wrem);
+  // two buffers of wmax + 2 columns (a halo column on either side of the slab), the cell bytes of the slab, the work list
+  T* bufA = reinterpret_cast<T*>(tile_smem);
+  T* bufB = bufA + (size_t)(cg.wmax + 2) * RS;
+  uint32_t* msk = reinterpret_cast<uint32_t*>(bufB + (size_t)(cg.wmax + 2) * RS);
+  uint4* work = reinterpret_cast<uint4*>(msk + (size_t)cg.wmax * RS / 4);
+  const int gr = k.goal_pi - cg.r0, gcol = k.goal_pj - j0;  // the goal relative to the slab (row, column)
+  if (threadIdx.x < 5) {  // the goal and its four neighbours: offset in a buffer when the cell is this slab's
+    const int t = threadIdx.x, row = gr + (t == 1) - (t == 2), col = gcol + (t == 3) - (t == 4);
+    gcell[t] = (col >= 0 && col < wc && row >= 0 && row < RS) ? (col + 1) * RS + row : -1;
+  }
+  for (int e = threadIdx.x; e < cg.nwc * cg.G; e += blockDim.x) {
+    const uint2 in = sched[(size_t)(wc == cg.wmax ? 0 : 1) * cg.nwc * cg.G + e];
+    uint32_t it[2] = {in.x, in.y}, gofs[2] = {0u, 0u};
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      if (it[q] == COL_NONE) { it[q] = COL_END; continue; }
+      const int col = (int)(it[q] & 0xffffu), s = (int)(it[q] >> 16);
+      uint32_t w = (uint32_t)((col + 1) * RS + 128 * s);
+      if (col == 0 && c > 0) w |= COL_EDGE_L;
+      if (col == wc - 1 && c < cg.ncta - 1) w |= COL_EDGE_R;
+      if (s > 0) w |= COL_HAS_UP;
+      if (s < NS - 1) w |= COL_HAS_DN;
+      if (col - gcol >= -1 && col - gcol <= 1 && gr - 128 * s >= -1 && gr - 128 * s <= 128) w |= COL_GOAL;
+      it[q] = w;
+      gofs[q] = (uint32_t)((cg.r0 + 128 * s) + k.ld * (j0 + col));
+    }
+    work[e] = make_uint4(it[0], it[1], gofs[0], gofs[1]);
+  }
+  // stage the slab: iterate (with the neighbours' columns of level 0 as halo), cell bytes, constant planes -- once per launch
+  const int nitems = wc * NS;
+  for (int it = warp; it < (wc + 2) * NS; it += NW) {
+    const int col = it / NS - 1, s = it - (col + 1) * NS;
+    const int row = 128 * s + 4 * lane, o = (col + 1) * RS + row;
+    const size_t g = (size_t)(cg.r0 + row) + (size_t)k.ld * (j0 + col);
+    T v[4];
+    ldg4(X + g, v);
+    sts4(bufA + o, v);
+    if (col < 0 || col >= wc) { sts4(bufB + o, v); continue; }  // (both halo copies defined: the first / last slab never receives one)
+    msk[(o - RS) >> 2] = __ldg(reinterpret_cast<const uint32_t*>(maskp + g));
+  }
+  __syncthreads();
+
+  // the warp's two strips (edge-column strips first: they are what the neighbours wait for) and their register state
+  const uint4 e0 = work[warp * cg.G], e1 = work[warp * cg.G + 1];
+  const uint32_t it0 = e0.x, it1 = e1.x;
+  const int lane4 = 4 * lane;
+  const uint32_t fix = lane == 0 ? COL_HAS_UP : lane == 31 ? COL_HAS_DN : 0u;
+  T v0[4], v1[4], pl0[5][4], pl1[5][4];
+  uint32_t mk0 = 0, mk1 = 0;
+  if (it0 != COL_END) {
+    const int o = (int)(it0 & COL_OFS) + lane4;
+    lds4(bufA + o, v0);
+    mk0 = msk[(o - RS) >> 2];
+#pragma unroll
+    for (int q = 0; q < NP; q++) ldg4(auxg + (size_t)q * k.np + e0.z + lane4, pl0[q]);
+  }
+  if (it1 != COL_END) {
+    const int o = (int)(it1 & COL_OFS) + lane4;
+    lds4(bufA + o, v1);
+    mk1 = msk[(o - RS) >> 2];
+#pragma unroll
+    for (int q = 0; q < NP; q++) ldg4(auxg + (size_t)q * k.np + e1.z + lane4, pl1[q]);
+  }
+  T* src = bufA;
+  T* dst = bufB;
+  const size_t box = (size_t)RS * MW;
+  for (int sw = 1; sw <= nsweeps; sw++) {
+    int bad = 0;
+    const bool exchange = sw < nsweeps && !(cg.diag & 1);  // the last sweep's columns are not needed by anybody
+    const unsigned seq = seq0 + (unsigned)sw;
+    unsigned long long* mine = mail + (size_t)((sw & 1) * cg.ncta + c) * 2 * box;
+    COL_STAMP(0);
+    if (it0 != COL_END) col_slot<T, KIND, FAST, PL>(k, src, dst, msk, auxg, mine, gcell, it0, e0.z, v0, mk0, pl0, wc, lane4, fix, RS, seq, exchange);
+    COL_STAMP(1);
+    if (it1 != COL_END) col_slot<T, KIND, FAST, PL>(k, src, dst, msk, auxg, mine, gcell, it1, e1.z, v1, mk1, pl1, wc, lane4, fix, RS, seq, exchange);
+    COL_STAMP(2);
+    // the neighbours' strips of this sweep, posted right after they were computed (while this warp did its second strip), into
+    // the halo columns of dst.  Tried and dropped (us per nu sweep at 1026^2 against 2.8): four extra warps that do nothing but
+    // collect mail (4.0: under this kernel's shared-memory load a global round trip costs 1000-2000 cycles -- a MEMBAR.GPU behind
+    // the post takes 2000 -- and their probe-then-fetch needed two); the other warps held back on a named barrier until the
+    // edge strips are posted (3.1: the strips finish 800 cycles earlier, their mail arrives no sooner); a fence or a load
+    // right behind the post (3.4 / 2.9); two phases with the columns next to the edge in the first (3.3).
+    if (exchange) {
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const uint32_t it = q ? it1 : it0;
+        const int ob = (int)(it & COL_OFS);
+        if (it & COL_EDGE_L) {  // my first column's strip: the left neighbour's last column (its box 1), same rows
+          const int row = ob - RS + lane4;
+          if (!mail_take<T>(mail + ((size_t)((sw & 1) * cg.ncta + c - 1) * 2 + 1) * box + (size_t)row * MW, seq, dst + row, err)) bad = 1;
+        }
+        if (it & COL_EDGE_R) {
+          const int row = ob - wc * RS + lane4;
+          if (!mail_take<T>(mail + ((size_t)((sw & 1) * cg.ncta + c + 1) * 2 + 0) * box + (size_t)row * MW, seq,
+                            dst + (size_t)(wc + 1) * RS + row, err)) bad = 1;
+        }
+      }
+    }
+    COL_STAMP(3);
+    T* t = src; src = dst; dst = t;
+    COL_STAMP(4);
+    if (__syncthreads_or(bad)) break;  // block-uniform: a neighbour never answered (the host reports it)
+    COL_STAMP(5);
+  }
+#undef COL_STAMP
+
+  // write the slab back (src: last iterate, dst: the one before); residual of the last sweep
+  double res = 0.0;
+  bool range = false;
+  for (int it = warp; it < nitems; it += NW) {
+    const int col = it / NS, s = it - col * NS;
+    const int row = 128 * s + 4 * lane, o = (col + 1) * RS + row;
+    const size_t g = (size_t)(cg.r0 + row) + (size_t)k.ld * (j0 + col);
+    T f[4];
+    lds4(src + o, f);
+    const uint32_t mk = msk[(o - RS) >> 2];
+    if constexpr (kZDom<T, KIND, FAST>) range |= strip_not_normal(f, mk);
+    if (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(Y + g) = make_float4((float)f[0], (float)f[1], (float)f[2], (float)f[3]);
+    } else {
+      *reinterpret_cast<double2*>(Y + g) = make_double2((double)f[0], (double)f[1]);
+      *reinterpret_cast<double2*>(Y + g + 2) = make_double2((double)f[2], (double)f[3]);
+    }
+    if (want_res) {
+      T p[4];
+      lds4(dst + o, p);
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+        if (!((mk >> (8 * r)) & CELL_WALL))
+          res += kZDom<T, KIND, FAST> ? sweep_diff_z((double)f[r], (double)p[r]) : sweep_diff<KIND>((double)f[r], (double)p[r]);
+    }
+  }
+  if (kZDom<T, KIND, FAST> && range) *err = TILE_ERR_RANGE;
+  if (want_res) {  // uniform
+    const double sum = block_sum(res, red);
+    if (threadIdx.x == 0) partial[c] = sum;
+  }
+}
+
 // ---- packing between the dense H x W arrays of the ABI side and the padded tile layout -------------------
 static bool tile_zdom(int precision, int kind, bool fast) { return PIQL_LOGZ_ZDOM && precision != 0 && fast && kind == KIND_LOGZ; }
 struct PadGeom {
-  int H, W, ld, Wp, kh;
+  int H, W, ld, Wp, kh;  // kh: ghost columns
+  int gi;                // ghost rows (= kh for the tiled plans; the column-resident plans align the bounding box instead)
 };
 // zdom: the padded iterate is kept in the linear domain (fast fp32 log Z): Z = e^(log Z) on the way in, the log on the way out
 template <typename T>
 __global__ void tile_pack_kernel(PadGeom g, const T* __restrict__ dense, T* __restrict__ padded, int zdom) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.ld * g.Wp) return;
-  const int i = p % g.ld - g.kh, j = p / g.ld - g.kh;
+  const int i = p % g.ld - g.gi, j = p / g.ld - g.kh;
   T v = (i >= 0 && i < g.H && j >= 0 && j < g.W) ? dense[i + g.H * j] : (T)0;
   if (zdom) v = (T)exp((double)v);
   padded[p] = v;
@@ -799,7 +1139,7 @@ __global__ void tile_pack_kernel(PadGeom g, const T* __restrict__ dense, T* __re
 __global__ void tile_pack_mask_kernel(PadGeom g, const uint8_t* __restrict__ cell, uint8_t* __restrict__ maskp) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.ld * g.Wp) return;
-  const int i = p % g.ld - g.kh, j = p / g.ld - g.kh;
+  const int i = p % g.ld - g.gi, j = p / g.ld - g.kh;
   maskp[p] = (i >= 0 && i < g.H && j >= 0 && j < g.W) ? cell[i + g.H * j] : (uint8_t)(CELL_WALL | CELL_BLOCK_MASK);
 }
 // aux4 [cell][4] + aux1 [cell] -> five planes.  logz: exp(A_a - max A), max A (as prep_kernel stores them); gap: pi_a, D.
@@ -814,7 +1154,7 @@ __global__ void tile_pack_zplanes_kernel(PadGeom g, ZPlaneK zk, const T* __restr
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int np = g.ld * g.Wp;
   if (p >= np) return;
-  const int i = p % g.ld - g.kh, j = p / g.ld - g.kh;
+  const int i = p % g.ld - g.gi, j = p / g.ld - g.kh;
   double o[5] = {0, 0, 0, 0, 0};
   if (i >= 0 && i < g.H && j >= 0 && j < g.W) {
     const int s = i + g.H * j;
@@ -837,7 +1177,7 @@ __global__ void tile_pack_aux_kernel(PadGeom g, const T* __restrict__ aux4, cons
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int np = g.ld * g.Wp;
   if (p >= np) return;
-  const int i = p % g.ld - g.kh, j = p / g.ld - g.kh;
+  const int i = p % g.ld - g.gi, j = p / g.ld - g.kh;
   T o[5] = {0, 0, 0, 0, 0};
   if (i >= 0 && i < g.H && j >= 0 && j < g.W) {
     const int s = i + g.H * j;
@@ -862,7 +1202,7 @@ __global__ void tile_unpack_kernel(PadGeom g, const T* __restrict__ padded, T* _
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= g.H * g.W) return;
   const int i = s % g.H, j = s / g.H;
-  const T v = padded[(i + g.kh) + g.ld * (j + g.kh)];
+  const T v = padded[(i + g.gi) + g.ld * (j + g.kh)];
   dense[s] = zdom ? (T)log((double)v) : v;
 }
 
@@ -946,13 +1286,84 @@ static std::vector<PlanCand> enumerate_plans(int H, int W, int precision, int ki
       p.ld = ((tiles_i * TTI + 2 * TKH + 31) / 32) * 32;
       p.Wp = tiles_j * TJ + 2 * TKH;
       p.np = (long long)p.ld * p.Wp;
-      p.kh = kh; p.planes = planes;
+      p.kh = kh; p.gi = kh; p.planes = planes;
       out.push_back({cost / kh, p});
     }
   }
   std::stable_sort(out.begin(), out.end(), [](const PlanCand& a, const PlanCand& b) {
     return a.cost < b.cost || (a.cost == b.cost && a.plan.TJ > b.plan.TJ);
   });
+  return out;
+}
+// Column-resident plans (col_resident_kernel): the geometry follows from the grid -- whole columns of the free cells' bounding box,
+// split evenly over at most one CTA per SM -- so the candidates differ in warps per CTA and in where the constant planes of the
+// linear sweeps live.  Empty when a slab does not fit an SM's shared memory.  PIQL_TILE_COLRES = 0 disables the schedule, = 1
+// forces it (tests, tuning sweeps); PIQL_TILE_NW and PIQL_TILE_PLANES_MODE pin a candidate.
+static size_t col_smem_bytes(int wmax, int NS, int precision, int planes, int nwc, int G) {
+  const size_t col = (size_t)128 * NS, e = precision == 0 ? 8 : 4;
+  (void)planes;  // the planes of the linear fast sweeps live in registers
+  return 2 * (wmax + 2) * col * e + wmax * col + (size_t)nwc * G * sizeof(uint4);
+}
+// Work list of a sweep for a slab of wc columns x NS strips on nwc warps: at most two strips per warp (they and their constants
+// stay in the warp's registers for the whole launch; 0 is returned when the slab has more strips than that).  A warp's first strip
+// is an edge-column strip while they last -- the neighbours wait for those -- dealt out round robin; the second round goes the
+// other way, so that the warps with an edge strip (which also collect the neighbours' strips at the end of the sweep) are the last
+// to get a second one.  item = column | strip << 16; returns the items per warp (2).
+static int col_schedule(int wc, int NS, int nwc, std::vector<uint2>& out) {
+  if (wc * NS > 2 * nwc) return 0;
+  std::vector<uint32_t> items;
+  for (int sidx = 0; sidx < NS; sidx++)
+    for (int col : {0, wc - 1})
+      if (col == 0 || wc > 1) items.push_back((uint32_t)col | ((uint32_t)sidx << 16));
+  for (int sidx = 0; sidx < NS; sidx++)
+    for (int col = 1; col < wc - 1; col++) items.push_back((uint32_t)col | ((uint32_t)sidx << 16));
+  const int G = 2;
+  out.assign((size_t)nwc * G, make_uint2(COL_NONE, COL_NONE));
+  for (size_t q = 0; q < items.size(); q++) {
+    const int i = q < (size_t)nwc ? (int)q : 2 * nwc - 1 - (int)q;
+    out[(size_t)i * G + (q < (size_t)nwc ? 0 : 1)] = make_uint2(items[q], COL_NONE);
+  }
+  return G;
+}
+static std::vector<TilePlan> enumerate_colres(const GridDev& g, int precision, int kind, bool fast, int num_sms) {
+  std::vector<TilePlan> out;
+  const char* env = getenv("PIQL_TILE_COLRES");
+  if ((env && atoi(env) == 0) || num_sms < 1 || g.bi1 < g.bi0 || g.bj1 < g.bj0) return out;
+  const int Hb = g.bi1 - g.bi0 + 1, Wb = g.bj1 - g.bj0 + 1;
+  const int NS = (Hb + TEI - 1) / TEI;
+  const int wmax = (Wb + num_sms - 1) / num_sms, ncta = (Wb + wmax - 1) / wmax;
+  if (wmax > 0x7fff || NS > 0xffff) return out;
+  const size_t limit = 227 * 1024 - 1024;  // opt-in maximum less the kernel's static shared memory
+  const int kh = 4;                         // ghost columns of the padded layout (the schedule itself needs none)
+  const int gi = (4 - g.bi0 % 4) % 4, r0 = gi + g.bi0;
+  const char* env_nw = getenv("PIQL_TILE_NW");
+  const char* env_pm = getenv("PIQL_TILE_PLANES_MODE");
+  const int npl = tile_planes(precision, kind, fast);
+  for (int pm = (npl > 0 ? 1 : 0); pm >= 0; pm--) {
+    if (env_pm && atoi(env_pm) != pm && npl > 0) continue;
+    const int planes = pm ? npl : 0;
+    // warps: the sweep is wmax * NS strips; the register file allows 28 warps of 72 registers (fp32) or 16 of 128 (Float64)
+    // (kColMaxThreads: 28 warps of 72 registers in fp32, 16 of 128 in Float64)
+    const int maxw = precision == 0 ? 16 : 28;
+    for (int nw = maxw; nw >= 8; nw -= 4) {
+      if (env_nw && std::min(atoi(env_nw), maxw) != nw) continue;
+      const int nwc = nw;
+      std::vector<uint2> tmp;
+      const int G = col_schedule(wmax, NS, nwc, tmp);
+      if (G == 0) continue;  // more than two strips per warp
+      const size_t smem = col_smem_bytes(wmax, NS, precision, planes, nwc, G);
+      if (smem > limit) continue;
+      TilePlan p{};
+      p.nwc = nwc; p.G = G;
+      p.TJ = wmax; p.EJ = wmax; p.kh = kh; p.gi = gi; p.planes = planes; p.tiles_i = 1; p.tiles_j = ncta; p.nw = nw;
+      p.ld = ((std::max(gi + g.H, r0 + TEI * NS) + 31) / 32) * 32;
+      p.Wp = g.W + 2 * kh;
+      p.np = (long long)p.ld * p.Wp;
+      p.smem = smem; p.ctas_per_sm = 1;
+      p.colres = 1; p.r0 = r0; p.NS = NS; p.c0 = kh + g.bj0; p.ncta = ncta; p.wbase = Wb / ncta; p.wrem = Wb % ncta; p.wmax = wmax;
+      out.push_back(p);
+    }
+  }
   return out;
 }
 // The variant an untimed plan uses: 4 sweeps per round, planes from global memory, unless the environment pins another
@@ -983,7 +1394,7 @@ template <typename T> static TileK<T> make_tile_k(const GridDev& g, const ViStat
   TileK<T> k;
   k.ld = pl.ld; k.np = (int)pl.np; k.TJ = pl.TJ; k.EJ = pl.EJ; k.tiles_i = pl.tiles_i; k.tj0 = 0;
   k.kh = pl.kh; k.tti = TEI - 2 * pl.kh;
-  k.goal_pi = g.goal % g.H + pl.kh; k.goal_pj = g.goal / g.H + pl.kh; k.goal_p = k.goal_pi + pl.ld * k.goal_pj;
+  k.goal_pi = g.goal % g.H + pl.gi; k.goal_pj = g.goal / g.H + pl.kh; k.goal_p = k.goal_pi + pl.ld * k.goal_pj;
   const double w_on = 1.0 * (1.0 - g.randomness) + g.randomness / NA, w_off = 0.0 * (1.0 - g.randomness) + g.randomness / NA;
   const double a1 = g.gamma * (w_on - w_off);
   const double kc = log(1.0 / NA) + vs.reward_scale * -g.step_cost;
@@ -1046,7 +1457,7 @@ static bool encode_plane_map(void* out, void* base, const TilePlan& pl) {
 }
 
 void tile_free(TileBuffers& tb) {
-  for (void* p : {tb.x[0], tb.x[1], tb.aux, (void*)tb.mask, (void*)tb.partial, (void*)tb.flags, (void*)tb.d_err}) if (p) cudaFree(p);
+  for (void* p : {tb.x[0], tb.x[1], tb.aux, (void*)tb.mask, (void*)tb.partial, (void*)tb.flags, (void*)tb.d_err, (void*)tb.mail, (void*)tb.sched}) if (p) cudaFree(p);
   if (tb.err) cudaFreeHost(tb.err);
   const TileBuffers keep = tb;  // the tuning results and the sharded flag survive a re-allocation
   tb = TileBuffers{};
@@ -1059,7 +1470,7 @@ void tile_free(TileBuffers& tb) {
 
 template <typename T>
 static void pack_t(const GridDev& g, const uint8_t* cell, const ViState& vs, TileBuffers& tb, cudaStream_t st) {
-  const PadGeom pg{g.H, g.W, tb.plan.ld, tb.plan.Wp, tb.plan.kh};
+  const PadGeom pg{g.H, g.W, tb.plan.ld, tb.plan.Wp, tb.plan.kh, tb.plan.gi};
   const unsigned nb = nblk(tb.plan.np, 256);
   const int zdom = tile_zdom(vs.precision, vs.kind, vs.fast) ? 1 : 0;
   tile_pack_kernel<T><<<nb, 256, 0, st>>>(pg, (const T*)vs.x[vs.cur], (T*)tb.x[0], zdom);
@@ -1107,6 +1518,41 @@ static cudaError_t tile_setup(const GridDev& g, const uint8_t* cell, const ViSta
     *tb.err = 0;
     tb.cap_x = bx; tb.cap_aux = 5 * bx; tb.cap_mask = bx / 8; tb.cap_partial = nt; tb.cap_flags = nt;
   }
+  if (pl.colres) {
+    // mailboxes of the per-sweep column exchange: [parity][CTA][side][row] pairs of {32-bit word, sequence number}
+    const size_t need_mail = 2 * (size_t)pl.ncta * 2 * TEI * pl.NS * (e / 4) * sizeof(unsigned long long);
+    if (need_mail > tb.cap_mail) {
+      cudaError_t err = cudaStreamSynchronize(st);
+      if (err != cudaSuccess) return err;
+      if (tb.mail) cudaFree(tb.mail);
+      tb.mail = nullptr; tb.cap_mail = 0;
+      if ((err = cudaMalloc((void**)&tb.mail, need_mail)) != cudaSuccess) return err;
+      if ((err = cudaMemset(tb.mail, 0, need_mail)) != cudaSuccess) return err;
+      tb.cap_mail = need_mail;
+      tb.col_seq = 0;
+    }
+  }
+  if (pl.colres) {
+    // the work list of both slab shapes (wmax / wmax - 1 columns)
+    std::vector<uint2> a, b, both;
+    const int Ga = col_schedule(pl.wmax, pl.NS, pl.nwc, a), Gb = pl.wmax > 1 ? col_schedule(pl.wmax - 1, pl.NS, pl.nwc, b) : 1;
+    if (Ga != pl.G || (pl.wmax > 1 && Gb != pl.G)) return cudaErrorInvalidValue;
+    both.assign(2 * (size_t)pl.nwc * pl.G, make_uint2(COL_NONE, COL_NONE));
+    for (int i = 0; i < pl.nwc; i++) {
+      for (int g = 0; g < Ga; g++) both[(size_t)i * pl.G + g] = a[(size_t)i * Ga + g];
+      if (pl.wmax > 1) for (int g = 0; g < Gb; g++) both[((size_t)pl.nwc + i) * pl.G + g] = b[(size_t)i * Gb + g];
+    }
+    const size_t bytes = both.size() * sizeof(uint2);
+    cudaError_t err = cudaStreamSynchronize(st);  // an earlier launch may still read the list
+    if (err != cudaSuccess) return err;
+    if (bytes > tb.cap_sched) {
+      if (tb.sched) cudaFree(tb.sched);
+      tb.sched = nullptr; tb.cap_sched = 0;
+      if ((err = cudaMalloc((void**)&tb.sched, bytes)) != cudaSuccess) return err;
+      tb.cap_sched = bytes;
+    }
+    if ((err = cudaMemcpy(tb.sched, both.data(), bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return err;
+  }
   tb.plan = pl;
   tb.cur = 0;
   // a new solve starts with a clean error word (timed-out waits, exponent-domain range)
@@ -1115,7 +1561,7 @@ static cudaError_t tile_setup(const GridDev& g, const uint8_t* cell, const ViSta
     return cudaGetLastError();
   static_assert(sizeof(CUtensorMap) == 128, "descriptor size");
   const CUtensorMapDataType dt = vs.precision == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  tb.use_tma = getenv("PIQL_TILE_NO_TMA") == nullptr && encode_tile_map(tb.tmx[0], tb.x[0], dt, e, pl) &&
+  tb.use_tma = !pl.colres && getenv("PIQL_TILE_NO_TMA") == nullptr && encode_tile_map(tb.tmx[0], tb.x[0], dt, e, pl) &&
                encode_tile_map(tb.tmx[1], tb.x[1], dt, e, pl) &&
                encode_tile_map(tb.tmm, tb.mask, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, pl, TMB) &&
                (pl.planes == 0 || encode_plane_map(tb.tmp, tb.aux, pl));
@@ -1132,6 +1578,8 @@ cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs,
     const TilePlan pl = make_tile_plan(g.H, g.W, vs.precision, vs.kind, vs.fast, num_sms);
     return tile_setup(g, cell, vs, tb, pl, false, st);
   }
+  const std::vector<TilePlan> cr = enumerate_colres(g, vs.precision, vs.kind, vs.fast, num_sms);
+  if (!cr.empty() && getenv("PIQL_TILE_COLRES") != nullptr) return tile_setup(g, cell, vs, tb, cr[0], false, st);  // forced
   const bool pinned = getenv("PIQL_TILE_TJ") || getenv("PIQL_TILE_NW") || getenv("PIQL_TILE_NO_TUNE");
   if (!pinned)
     for (int i = 0; i < tb.ntuned; i++)
@@ -1161,33 +1609,61 @@ cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs,
       for (size_t i = 0; i < mm.size() && i < TUNE_CANDIDATES; i++) tries.push_back({mm[i].plan, false});
     }
   }
+  for (const TilePlan& p : cr) tries.push_back({p, false});  // every cell once per sweep, slabs resident in shared memory
   cudaEvent_t e0, e1;
   cudaError_t err = cudaEventCreate(&e0);
   if (err != cudaSuccess) return err;
   if ((err = cudaEventCreate(&e1)) != cudaSuccess) { cudaEventDestroy(e0); return err; }
-  double best = 1e300;
   Try chosen{model, persist};
-  const long long probe = 32;
   // Short probes (small grids: 0.1 ms) are noisy and are repeated; once a probe lasts more than half a millisecond one
   // measurement per shape is enough, and all a first solve should pay (tuning stays near a tenth of a solve to tolerance).
   int reps = 3;
-  for (const Try& t : tries) {
-    if ((err = tile_setup(g, cell, vs, tb, t.plan, t.persist, st)) != cudaSuccess) break;
-    if ((err = tile_sweeps(g, vs, tb, 2 * t.plan.kh, false, st)) != cudaSuccess) break;
-    float ms = 1e30f;
-    for (int rep = 0; rep < reps && err == cudaSuccess; rep++) {
+  auto time_try = [&](const Try& t, long long probe, float& ms, bool& persisted) -> cudaError_t {
+    cudaError_t e = tile_setup(g, cell, vs, tb, t.plan, t.persist, st);
+    if (e != cudaSuccess) return e;
+    if ((e = tile_sweeps(g, vs, tb, 2 * t.plan.kh, false, st)) != cudaSuccess) return e;
+    ms = 1e30f;
+    for (int rep = 0; rep < reps; rep++) {
       cudaEventRecord(e0, st);
-      if ((err = tile_sweeps(g, vs, tb, probe, false, st)) != cudaSuccess) break;
+      if ((e = tile_sweeps(g, vs, tb, probe, false, st)) != cudaSuccess) return e;
       cudaEventRecord(e1, st);
-      if ((err = cudaStreamSynchronize(st)) != cudaSuccess) break;
+      if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
       float m1 = 0.f;
       cudaEventElapsedTime(&m1, e0, e1);
       ms = std::min(ms, m1);
       if (m1 > 0.5f) reps = 1;
     }
-    if (err != cudaSuccess) break;
-    if (tb.err && *tb.err) { err = cudaErrorLaunchTimeout; break; }
-    if (ms < best) { best = ms; chosen = t; chosen.persist = tb.persistent; }
+    persisted = tb.persistent;
+    return (tb.err && *tb.err) ? cudaErrorLaunchTimeout : cudaSuccess;
+  };
+  // first every candidate with a short probe, then the three fastest and the fastest column-resident one again with a probe
+  // of 128 sweeps -- the length of a solver's batches: a whole batch in one launch (column-resident) and one launch per round
+  // differ by a few per cent, which 32 sweeps do not resolve
+  std::vector<std::pair<float, size_t>> rank;
+  for (size_t i = 0; i < tries.size() && err == cudaSuccess; i++) {
+    float ms = 0.f;
+    bool p = false;
+    if ((err = time_try(tries[i], 32, ms, p)) == cudaSuccess) { tries[i].persist = p; rank.push_back({ms, i}); }
+  }
+  if (err == cudaSuccess && !rank.empty()) {
+    std::stable_sort(rank.begin(), rank.end());
+    std::vector<size_t> finals;
+    for (size_t q = 0; q < rank.size() && q < 3; q++) finals.push_back(rank[q].second);
+    for (size_t q = 0; q < rank.size(); q++)
+      if (tries[rank[q].second].plan.colres) {
+        if (std::find(finals.begin(), finals.end(), rank[q].second) == finals.end()) finals.push_back(rank[q].second);
+        break;
+      }
+    chosen = tries[finals[0]];
+    if (finals.size() > 1 && rank[0].first < 2.0f) {  // (a long probe of a slow grid would cost more than it can gain)
+      float best = 1e30f;
+      for (size_t i : finals) {
+        float ms = 0.f;
+        bool p = false;
+        if ((err = time_try(tries[i], 128, ms, p)) != cudaSuccess) break;
+        if (ms < best) { best = ms; chosen = tries[i]; chosen.persist = p; }
+      }
+    }
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
@@ -1270,6 +1746,75 @@ static cudaError_t launch_persist_t(const GridDev& g, const ViState& vs, TileBuf
   tb.cur = (tb.cur + nrounds) & 1;
   return cudaSuccess;
 }
+// The column-resident schedule: all nsweeps sweeps of the batch in one cooperative launch of one CTA per slab.
+template <typename T, int KIND, bool FAST, bool PL>
+static cudaError_t launch_colres_t(const GridDev& g, const ViState& vs, TileBuffers& tb, int nsweeps, bool want_res, cudaStream_t st) {
+  static size_t configured[64] = {};  // shared-memory opt-in per instantiation and device (grows with the plan)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || configured[dev] < tb.plan.smem) {
+    cudaError_t e = cudaFuncSetAttribute(col_resident_kernel<T, KIND, FAST, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb.plan.smem);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = tb.plan.smem;
+  }
+  const TilePlan& pl = tb.plan;
+  const TileK<T> k = make_tile_k<T>(g, vs, pl);
+  const char* env_diag = getenv("PIQL_TILE_COLRES_DIAG");
+  const char* env_trace = getenv("PIQL_TILE_COLRES_TRACE");
+  const ColGeom cg{pl.r0, pl.NS, TEI * pl.NS, pl.c0, pl.wbase, pl.wrem, pl.wmax, pl.ncta, pl.nwc, pl.G, env_diag ? atoi(env_diag) : 0,
+                   env_trace ? atoi(env_trace) : 0, getenv("PIQL_TILE_COLRES_TRACE_SW") ? atoi(getenv("PIQL_TILE_COLRES_TRACE_SW")) : 10};
+  long long* d_trace = nullptr;
+  if (env_trace && nsweeps >= cg.diag_sw + 4) {
+    if (cudaMalloc((void**)&d_trace, sizeof(long long) * 4 * 32 * 6) != cudaSuccess) return cudaGetLastError();
+    cudaMemsetAsync(d_trace, 0, sizeof(long long) * 4 * 32 * 6, st);
+  }
+  cudaError_t e;
+  if (tb.col_seq > 0xC0000000u) {  // sequence numbers wrap: start over on clean mailboxes
+    if ((e = cudaMemsetAsync(tb.mail, 0, tb.cap_mail, st)) != cudaSuccess) return e;
+    tb.col_seq = 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)pl.ncta); cfg.blockDim = dim3(32 * pl.nw); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, col_resident_kernel<T, KIND, FAST, PL>, k, cg, (const uint8_t*)tb.mask, (const T*)tb.x[tb.cur],
+                         (T*)tb.x[tb.cur ^ 1], (const T*)tb.aux, (const uint2*)tb.sched, nsweeps, want_res ? 1 : 0, tb.partial, tb.mail,
+                         tb.col_seq, tb.d_err, d_trace);
+  if (e != cudaSuccess) return e;
+  if (d_trace) {  // timing experiment: print the stamps of sweeps 10..13 relative to the first one (cycles)
+    std::vector<long long> h(4 * 32 * 6);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), d_trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+    cudaFree(d_trace);
+    long long t0 = 0;
+    for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+    for (int q = 0; q < 4; q++)
+      for (int w = 0; w < pl.nw; w++) {
+        fprintf(stderr, "trace sweep %d warp %2d:", cg.diag_sw + q, w);
+        for (int i = 0; i < 6; i++) fprintf(stderr, " %7lld", h[(q * 32 + w) * 6 + i] ? h[(q * 32 + w) * 6 + i] - t0 : -1);
+        fprintf(stderr, "\n");
+      }
+  }
+  g_launches++;
+  tb.col_seq += (unsigned)nsweeps;
+  tb.cur ^= 1;
+  return cudaSuccess;
+}
+template <typename T, bool FAST>
+static cudaError_t launch_colres_k(const GridDev& g, const ViState& vs, TileBuffers& tb, int nsweeps, bool want_res, cudaStream_t st) {
+  const bool pl = tb.plan.planes > 0;
+  switch (vs.kind) {
+    case KIND_NU: return launch_colres_t<T, KIND_NU, FAST, false>(g, vs, tb, nsweeps, want_res, st);
+    case KIND_LOGZ:
+      if constexpr (FAST) { if (pl) return launch_colres_t<T, KIND_LOGZ, FAST, true>(g, vs, tb, nsweeps, want_res, st); }
+      return launch_colres_t<T, KIND_LOGZ, FAST, false>(g, vs, tb, nsweeps, want_res, st);
+    default:
+      if constexpr (FAST) { if (pl) return launch_colres_t<T, KIND_GAP, FAST, true>(g, vs, tb, nsweeps, want_res, st); }
+      return launch_colres_t<T, KIND_GAP, FAST, false>(g, vs, tb, nsweeps, want_res, st);
+  }
+}
 // PL = true exists for the two linear fast fp32 sweeps only (the plan asks for it through TilePlan::planes)
 template <typename T, bool FAST>
 static cudaError_t launch_persist_k(const GridDev& g, const ViState& vs, TileBuffers& tb, long long nsweeps, bool want_res,
@@ -1329,6 +1874,22 @@ static int tile_kernel_regs(int precision, int kind, bool fast, bool persistent)
 // nsweeps Jacobi sweeps in ceil(nsweeps / TILE_KH) launches; the residual of the last sweep lands in vs.residual.
 cudaError_t tile_sweeps(const GridDev& g, const ViState& vs, TileBuffers& tb, long long nsweeps, bool want_res, cudaStream_t st) {
   const int TKH = tb.plan.kh;
+  if (tb.plan.colres) {
+    if (tb.err && *tb.err == COL_ERR_TIMEOUT) return cudaErrorLaunchTimeout;  // an earlier launch gave up waiting for a neighbour
+    while (nsweeps > 0) {
+      const int batch = (int)std::min<long long>(nsweeps, 1 << 24);
+      nsweeps -= batch;
+      const bool res = want_res && nsweeps == 0;
+      cudaError_t e;
+      if (vs.precision == 0) e = launch_colres_k<double, false>(g, vs, tb, batch, res, st);
+      else if (vs.fast) e = launch_colres_k<float, true>(g, vs, tb, batch, res, st);
+      else e = launch_colres_k<float, false>(g, vs, tb, batch, res, st);
+      if (e != cudaSuccess) return e;
+      if (res) launch_residual_final(tb.partial, tb.plan.ncta, vs.residual, st);
+    }
+    cudaError_t e = cudaMemcpyAsync(tb.err, tb.d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
+    return e != cudaSuccess ? e : cudaGetLastError();
+  }
   if (tb.persistent && nsweeps > TKH) {
     if (tb.err && *tb.err) return cudaErrorLaunchTimeout;  // an earlier persistent launch gave up waiting for a neighbour
     cudaError_t e;
@@ -1363,7 +1924,7 @@ cudaError_t tile_sweeps(const GridDev& g, const ViState& vs, TileBuffers& tb, lo
 
 // Copies the current iterate back into the dense array vs.x[vs.cur].
 void tile_unpack(const GridDev& g, const ViState& vs, const TileBuffers& tb, cudaStream_t st) {
-  const PadGeom pg{g.H, g.W, tb.plan.ld, tb.plan.Wp, tb.plan.kh};
+  const PadGeom pg{g.H, g.W, tb.plan.ld, tb.plan.Wp, tb.plan.kh, tb.plan.gi};
   const int zdom = tile_zdom(vs.precision, vs.kind, vs.fast) ? 1 : 0;
   if (vs.precision == 0) tile_unpack_kernel<double><<<nblk(g.n, 256), 256, 0, st>>>(pg, (const double*)tb.x[tb.cur], (double*)vs.x[vs.cur], 0);
   else tile_unpack_kernel<float><<<nblk(g.n, 256), 256, 0, st>>>(pg, (const float*)tb.x[tb.cur], (float*)vs.x[vs.cur], zdom);

@@ -257,7 +257,8 @@ class Engine:
         self._ck(self._lib.piql_vi_tile_plan(self._ctx, {"nu": K.KIND_NU, "logz": K.KIND_LOGZ, "gap": K.KIND_GAP}[kind],
                                              K.PRECISIONS[precision], out))
         d = dict(zip(("TJ", "warps", "tiles_i", "tiles_j", "ctas_per_sm", "smem", "sweeps_per_round", "persistent"), list(out)))
-        d["planes_in_smem"], d["persistent"] = d["persistent"] >> 1, d["persistent"] & 1
+        flags = d["persistent"]
+        d["persistent"], d["planes_in_smem"], d["column_resident"] = flags & 1, (flags >> 1) & 7, (flags >> 4) & 1
         return d
 
     def vi_set_iterate(self, x):
