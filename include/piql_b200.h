@@ -313,8 +313,11 @@ int32_t piql_vi_prepare_dev(piql_ctx* ctx, int32_t kind, const double* V, const 
 /* Shape of the tiled soft-VI kernel for the loaded grid (grids above 8192 cells): plan_out[8] =
  * {interior columns per tile, warps per CTA, tile rows, tile columns, CTAs per SM, shared bytes per CTA,
  *  sweeps per round (4 or 8: the temporal-blocking depth the library timed fastest), flags: bit 0 = all tiles are
- *  resident at once (persistent kernel: one cooperative launch per batch), bits 1.. = constant planes the linear fast fp32
- *  sweeps keep in shared memory (log Z: 4, gap: 5; 0 = read from global memory)}. */
+ *  resident at once (persistent kernel: one cooperative launch per batch), bits 1..3 = constant planes the linear fast fp32
+ *  sweeps keep on chip (log Z: 4, gap: 5; 0 = read from global memory), bit 4 = the column-resident schedule (grids of at
+ *  most two 128-row strips per warp: one CTA per SM keeps a slab of whole columns in shared memory for the whole batch of
+ *  sweeps -- a cooperative launch per batch -- and the fields read {columns per slab, warps per CTA, 1, slabs, 1, shared
+ *  bytes, -, flags})}. */
 int32_t piql_vi_tile_plan(piql_ctx* ctx, int32_t kind, int32_t precision, int32_t* plan_out);
 /* Replaces the current iterate (warm start / resume from a caller-kept array; wall cells ignored). */
 int32_t piql_vi_set_iterate(piql_ctx* ctx, const double* x);
