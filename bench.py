@@ -247,6 +247,52 @@ def vi_traffic(name, key):
         return None
 
 
+def table_section(device, with_cpu=True):
+    """The tabulated-problem path on the reference's BinaryBandit (30 rounds, 2 coins: 46,376 belief states, 163,680 transitions):
+    Float64 solves of nu and of one logz_updateV, then Monte-Carlo path sampling on the tables.  Functional numbers: the table
+    kernels are one thread per state in Float64 (table.cu), not tuned like the gridworld path."""
+    import piql_jl_b200 as piql
+    bb = piql.binary_bandit_problem(rounds=30, ncoins=2, payoff=0.8, gamma=0.98)
+    t0 = time.perf_counter()
+    tab = piql.tabulate_problem(bb)
+    t_tab = time.perf_counter() - t0
+    eng = piql.Engine(device)
+    try:
+        eng.load_table(tab)
+        eng.table_solve("nu", max_sweeps=8, allow_unconverged=True)          # warm-up
+        t0 = time.perf_counter()
+        nu, st = eng.table_solve("nu", tol=1e-9)
+        t_nu = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        v1, logz, st1 = eng.table_update_v(0.5 * nu, beta=1.0, tol=1e-9)   # (46,376 states: the rounding floor of sum |delta| is ~1e-11)
+        t_up = time.perf_counter() - t0
+        npaths = 1 << 22
+        s0 = tab.index[bb.initial_state()]
+        eng.table_mc_logz(0.5 * nu, beta=1.0, npaths=1 << 16, seed=3, starts=[s0])       # warm-up
+        t0 = time.perf_counter()
+        sa, cnt, ls, mst = eng.table_mc_logz(0.5 * nu, beta=1.0, npaths=npaths, seed=4, starts=[s0])
+        t_mc = time.perf_counter() - t0
+        out = {"problem": "binary_bandit_problem(rounds=30, ncoins=2, payoff=0.8, gamma=0.98) tabulated through its closures",
+               "states": len(tab.states), "transitions_nnz": int(len(tab.succ)), "tabulation_seconds_host": t_tab,
+               "tol_sum_abs_delta": 1e-9, "solve_nu": {"sweeps": int(st.sweeps), "converged": bool(st.converged), "seconds": t_nu,
+                            "state_backups_per_s": st.sweeps * len(tab.states) / t_nu},
+               "logz_update_v": {"sweeps": int(st1.sweeps), "converged": bool(st1.converged), "seconds": t_up},
+               "mc_logz": {"paths": npaths, "starts": "the initial belief state", "transitions": float(mst.transitions), "seconds": t_mc,
+                           "transitions_per_s": float(mst.transitions) / t_mc,
+                           "logz_s0_mc": float(ls[s0]), "logz_s0_exact": float(logz[s0])},
+               "call": "piql_table_load + piql_table_solve + piql_table_update_v + piql_table_mc_logz (host buffers in and out)"}
+        if with_cpu:
+            import oracle
+            t0 = time.perf_counter()
+            ref, sw, _ = oracle.table_solve(tab, "nu", tol=1e-9)
+            t_ref = time.perf_counter() - t0
+            out["cpu_baseline"] = {"kind": "port", "cores": 1, "solve_nu_seconds": t_ref, "sweeps": int(sw),
+                                   "max_abs_diff_vs_gpu": float(np.abs(nu - ref).max())}
+        return out
+    finally:
+        eng.close()
+
+
 def vi_section(args, eng, stream, V, peak, vst, name=None):
     """Soft-VI sweep rates on the loaded grid (rank 0): nu in three precisions, log Z and gap in fast fp32, the ground-truth solve."""
     import torch
@@ -772,6 +818,11 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_exp:
         experiment = run_extra("experiment", lambda: run_golden_experiment(local_rank, with_cpu=not args.no_cpu))
 
+    # ---- the sparse-table path (any ControlProblem through its closures): the reference's binary bandit ----
+    table = None
+    if rank == 0 and world == 1 and not args.no_exp:
+        table = run_extra("table", lambda: table_section(local_rank, with_cpu=not args.no_cpu))
+
     # ---- the config-5 workload on this one GPU: same-config anchor of the scaling curve (last: it reloads the grid) ----
     g4096 = None
     if rank == 0 and world == 1 and name == "grid1024" and not args.no_4096:
@@ -783,7 +834,7 @@ def run_ours(args, rank, world, local_rank):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(name, args, world), "clocks": clocks, "exchange": exchange, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "vi": vi, "vi_sharded": vi_sharded, "experiment": experiment,
-                "rollout_grid4096": g4096,
+                "rollout_grid4096": g4096, "table": table,
                 "transitions_per_step": transitions / args.steps}
         print(json.dumps(line), flush=True)
     eng.close()

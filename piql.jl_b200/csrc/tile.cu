@@ -1651,6 +1651,11 @@ cudaError_t tile_begin(const GridDev& g, const uint8_t* cell, const ViState& vs,
     float ms = 0.f;
     bool p = false;
     if ((err = time_try(tries[i], 32, ms, p)) == cudaSuccess) { tries[i].persist = p; rank.push_back({ms, i}); }
+    else if (err == cudaErrorCooperativeLaunchTooLarge && tries[i].plan.colres) {
+      // the slabs cannot all be resident (SMs taken by another context): the schedule is simply not a candidate here
+      cudaGetLastError();
+      err = cudaSuccess;
+    }
   }
   if (err == cudaSuccess && !rank.empty()) {
     std::stable_sort(rank.begin(), rank.end());
