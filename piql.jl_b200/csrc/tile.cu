@@ -831,7 +831,7 @@ struct ColGeom {
   int wmax;         // widest slab (shared-memory layout)
   int ncta;
   int nwc;          // warps per CTA
-  int G;            // strips per warp in the work list (2)
+  int G;            // strips per warp in the work list (kColSlots: 2 in fp32, 4 in Float64)
   int diag;         // timing experiments only (PIQL_TILE_COLRES_DIAG): 1 = no exchange at all (wrong values at the slab seams)
   int diag_cta;     // the CTA PIQL_TILE_COLRES_TRACE follows
   int diag_sw;      // first of the four sweeps it stamps (PIQL_TILE_COLRES_TRACE_SW, default 10)
@@ -928,11 +928,14 @@ __device__ __forceinline__ void col_goal_patch(const TileK<T>& k, const T* __res
   __syncwarp();
 }
 
-// One of a warp's (at most two) strips in sweep sw: level sw-1 in src -> level sw in dst.  The warp owns the strip for the whole
-// launch, so everything that does not change stays in registers: the lane's four values v (its own output of the last sweep;
-// they are stored for the neighbours, never reloaded), the cell bytes mk and, for the linear fast sweeps, the constant planes pl
-// (a strip of those sweeps is four shared-memory accesses instead of nine: they are bound by the shared-memory pipe).
+// One of a warp's strips (at most two in fp32, four in Float64) in sweep sw: level sw-1 in src -> level sw in dst.  The warp owns
+// the strip for the whole launch, so in fp32 everything that does not change stays in registers: the lane's four values v (its own
+// output of the last sweep; they are stored for the neighbours, never reloaded), the cell bytes mk and, for the linear fast
+// sweeps, the constant planes pl (a strip of those sweeps is four shared-memory accesses instead of nine: they are bound by the
+// shared-memory pipe).  Float64 (KEEPV = false: a strip's arithmetic needs the 128 registers) reloads v and keeps only mk.
 // item: offset in a buffer | flags; fix: this lane's seam flags (COL_HAS_UP for lane 0, COL_HAS_DN for lane 31, else 0).
+template <typename T> constexpr int kColSlots = sizeof(T) == 8 ? 4 : 2;
+template <typename T> constexpr bool kColKeepV = sizeof(T) == 4;
 template <typename T, int KIND, bool FAST, bool PL>
 __device__ __forceinline__ void col_slot(const TileK<T>& k, const T* __restrict__ src, T* __restrict__ dst, const uint32_t* __restrict__ msk,
                                          const T* __restrict__ auxg, unsigned long long* __restrict__ mine, const int* __restrict__ gcell,
@@ -942,6 +945,7 @@ __device__ __forceinline__ void col_slot(const TileK<T>& k, const T* __restrict_
   constexpr int MW = kMailWords<T>;
   const int ob = (int)(item & COL_OFS), o = ob + lane4;
   T L[4], R[4], out[4];
+  if constexpr (!kColKeepV<T>) lds4(src + o, v);
   lds4(src + o - RS, L);
   lds4(src + o + RS, R);
   if constexpr (NP == 0 && KIND != KIND_NU) {
@@ -956,7 +960,7 @@ __device__ __forceinline__ void col_slot(const TileK<T>& k, const T* __restrict_
   strip_compute<T, KIND, FAST>(k, v, L, R, up, dn, mk, pl, out);
   sts4(dst + o, out);
 #pragma unroll
-  for (int r = 0; r < 4; r++) v[r] = out[r];
+  for (int r = 0; r < 4; r++) v[r] = out[r];  // (also what is posted below)
   if (item & COL_GOAL) {  // warp-uniform, at most six strips of the grid
     col_goal_patch<T, KIND, FAST>(k, src, dst, msk, gcell, RS, ob, lane4 >> 2);
     lds4(dst + o, v);
@@ -968,8 +972,8 @@ __device__ __forceinline__ void col_slot(const TileK<T>& k, const T* __restrict_
 }
 
 // grid = ncta CTAs (one per SM, cooperative launch: all resident) of nwc warps; shared memory: col_smem_bytes().
-// sched: the work list [2 shapes: wmax / wmax - 1 columns][nwc warps][G groups] of {item, item or COL_NONE} with item =
-// column | strip << 16 (| 0x8000: phase 1); a warp's phase-1 groups come first, a row ends with an empty group.
+// sched: the work list [2 shapes: wmax / wmax - 1 columns][nwc warps][G = kColSlots strips] of {item or COL_NONE, -} with item =
+// column | strip << 16; a warp's edge-column strip comes first.
 template <typename T, int KIND, bool FAST, bool PL>
 __global__ void __launch_bounds__(kColMaxThreads<T>, 1)
 col_resident_kernel(const TileK<T> k, const ColGeom cg, const uint8_t* __restrict__ maskp, const T* __restrict__ X, T* __restrict__ Y,
@@ -1030,26 +1034,25 @@ col_resident_kernel(const TileK<T> k, const ColGeom cg, const uint8_t* __restric
   }
   __syncthreads();
 
-  // the warp's two strips (edge-column strips first: they are what the neighbours wait for) and their register state
-  const uint4 e0 = work[warp * cg.G], e1 = work[warp * cg.G + 1];
-  const uint32_t it0 = e0.x, it1 = e1.x;
+  // the warp's strips (edge-column strips first: they are what the neighbours wait for) and their register state
+  constexpr int NSL = kColSlots<T>, NKV = kColKeepV<T> ? NSL : 1;
+  uint32_t it[NSL], gofs[NSL], mk[NSL];
+  T v[NKV][4], pl[NKV][5][4];
   const int lane4 = 4 * lane;
   const uint32_t fix = lane == 0 ? COL_HAS_UP : lane == 31 ? COL_HAS_DN : 0u;
-  T v0[4], v1[4], pl0[5][4], pl1[5][4];
-  uint32_t mk0 = 0, mk1 = 0;
-  if (it0 != COL_END) {
-    const int o = (int)(it0 & COL_OFS) + lane4;
-    lds4(bufA + o, v0);
-    mk0 = msk[(o - RS) >> 2];
 #pragma unroll
-    for (int q = 0; q < NP; q++) ldg4(auxg + (size_t)q * k.np + e0.z + lane4, pl0[q]);
-  }
-  if (it1 != COL_END) {
-    const int o = (int)(it1 & COL_OFS) + lane4;
-    lds4(bufA + o, v1);
-    mk1 = msk[(o - RS) >> 2];
+  for (int q = 0; q < NSL; q++) {
+    const uint4 e = work[warp * cg.G + q];
+    it[q] = e.x; gofs[q] = e.z; mk[q] = 0u;
+    if (e.x != COL_END) {
+      const int o = (int)(e.x & COL_OFS) + lane4;
+      mk[q] = msk[(o - RS) >> 2];
+      if constexpr (kColKeepV<T>) {
+        lds4(bufA + o, v[q]);
 #pragma unroll
-    for (int q = 0; q < NP; q++) ldg4(auxg + (size_t)q * k.np + e1.z + lane4, pl1[q]);
+        for (int r = 0; r < NP; r++) ldg4(auxg + (size_t)r * k.np + e.z + lane4, pl[q][r]);
+      }
+    }
   }
   T* src = bufA;
   T* dst = bufB;
@@ -1060,9 +1063,13 @@ col_resident_kernel(const TileK<T> k, const ColGeom cg, const uint8_t* __restric
     const unsigned seq = seq0 + (unsigned)sw;
     unsigned long long* mine = mail + (size_t)((sw & 1) * cg.ncta + c) * 2 * box;
     COL_STAMP(0);
-    if (it0 != COL_END) col_slot<T, KIND, FAST, PL>(k, src, dst, msk, auxg, mine, gcell, it0, e0.z, v0, mk0, pl0, wc, lane4, fix, RS, seq, exchange);
-    COL_STAMP(1);
-    if (it1 != COL_END) col_slot<T, KIND, FAST, PL>(k, src, dst, msk, auxg, mine, gcell, it1, e1.z, v1, mk1, pl1, wc, lane4, fix, RS, seq, exchange);
+#pragma unroll
+    for (int q = 0; q < NSL; q++) {
+      if (it[q] != COL_END)
+        col_slot<T, KIND, FAST, PL>(k, src, dst, msk, auxg, mine, gcell, it[q], gofs[q], v[kColKeepV<T> ? q : 0], mk[q],
+                                    pl[kColKeepV<T> ? q : 0], wc, lane4, fix, RS, seq, exchange);
+      if (q == 0) COL_STAMP(1);
+    }
     COL_STAMP(2);
     // the neighbours' strips of this sweep, posted right after they were computed (while this warp did its second strip), into
     // the halo columns of dst.  Tried and dropped (us per nu sweep at 1026^2 against 2.8): four extra warps that do nothing but
@@ -1072,14 +1079,13 @@ col_resident_kernel(const TileK<T> k, const ColGeom cg, const uint8_t* __restric
     // right behind the post (3.4 / 2.9); two phases with the columns next to the edge in the first (3.3).
     if (exchange) {
 #pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const uint32_t it = q ? it1 : it0;
-        const int ob = (int)(it & COL_OFS);
-        if (it & COL_EDGE_L) {  // my first column's strip: the left neighbour's last column (its box 1), same rows
+      for (int q = 0; q < NSL; q++) {
+        const int ob = (int)(it[q] & COL_OFS);
+        if (it[q] & COL_EDGE_L) {  // my first column's strip: the left neighbour's last column (its box 1), same rows
           const int row = ob - RS + lane4;
           if (!mail_take<T>(mail + ((size_t)((sw & 1) * cg.ncta + c - 1) * 2 + 1) * box + (size_t)row * MW, seq, dst + row, err)) bad = 1;
         }
-        if (it & COL_EDGE_R) {
+        if (it[q] & COL_EDGE_R) {
           const int row = ob - wc * RS + lane4;
           if (!mail_take<T>(mail + ((size_t)((sw & 1) * cg.ncta + c + 1) * 2 + 0) * box + (size_t)row * MW, seq,
                             dst + (size_t)(wc + 1) * RS + row, err)) bad = 1;
@@ -1311,24 +1317,25 @@ static size_t col_smem_bytes(int wmax, int NS, int precision, int planes, int nw
   (void)planes;  // the planes of the linear fast sweeps live in registers
   return 2 * (wmax + 2) * col * e + wmax * col + (size_t)nwc * G * sizeof(uint4);
 }
-// Work list of a sweep for a slab of wc columns x NS strips on nwc warps: at most two strips per warp (they and their constants
-// stay in the warp's registers for the whole launch; 0 is returned when the slab has more strips than that).  A warp's first strip
-// is an edge-column strip while they last -- the neighbours wait for those -- dealt out round robin; the second round goes the
-// other way, so that the warps with an edge strip (which also collect the neighbours' strips at the end of the sweep) are the last
-// to get a second one.  item = column | strip << 16; returns the items per warp (2).
-static int col_schedule(int wc, int NS, int nwc, std::vector<uint2>& out) {
-  if (wc * NS > 2 * nwc) return 0;
+// Work list of a sweep for a slab of wc columns x NS strips on nwc warps: at most nslots strips per warp (two in fp32: they and
+// their constants stay in the warp's registers for the whole launch; four in Float64; 0 is returned when the slab has more strips
+// than that).  A warp's first strip is an edge-column strip while they last -- the neighbours wait for those -- dealt out round
+// robin; every other round goes the other way, so that the warps with an edge strip (which also collect the neighbours' strips at
+// the end of the sweep) are the last to get a second one.  item = column | strip << 16; returns the items per warp (nslots).
+static int col_schedule(int wc, int NS, int nwc, int nslots, std::vector<uint2>& out) {
+  if (wc * NS > nslots * nwc) return 0;
   std::vector<uint32_t> items;
   for (int sidx = 0; sidx < NS; sidx++)
     for (int col : {0, wc - 1})
       if (col == 0 || wc > 1) items.push_back((uint32_t)col | ((uint32_t)sidx << 16));
   for (int sidx = 0; sidx < NS; sidx++)
     for (int col = 1; col < wc - 1; col++) items.push_back((uint32_t)col | ((uint32_t)sidx << 16));
-  const int G = 2;
+  const int G = nslots;
   out.assign((size_t)nwc * G, make_uint2(COL_NONE, COL_NONE));
   for (size_t q = 0; q < items.size(); q++) {
-    const int i = q < (size_t)nwc ? (int)q : 2 * nwc - 1 - (int)q;
-    out[(size_t)i * G + (q < (size_t)nwc ? 0 : 1)] = make_uint2(items[q], COL_NONE);
+    const int round = (int)(q / (size_t)nwc), pos = (int)(q % (size_t)nwc);
+    const int i = (round & 1) ? nwc - 1 - pos : pos;
+    out[(size_t)i * G + round] = make_uint2(items[q], COL_NONE);
   }
   return G;
 }
@@ -1356,8 +1363,9 @@ static std::vector<TilePlan> enumerate_colres(const GridDev& g, int precision, i
       if (env_nw && std::min(atoi(env_nw), maxw) != nw) continue;
       const int nwc = nw;
       std::vector<uint2> tmp;
-      const int G = col_schedule(wmax, NS, nwc, tmp);
-      if (G == 0) continue;  // more than two strips per warp
+      const int nslots = precision == 0 ? 4 : 2;  // kColSlots
+      const int G = col_schedule(wmax, NS, nwc, nslots, tmp);
+      if (G == 0) continue;  // more strips per warp than that
       const size_t smem = col_smem_bytes(wmax, NS, precision, planes, nwc, G);
       if (smem > limit) continue;
       TilePlan p{};
@@ -1542,7 +1550,7 @@ static cudaError_t tile_setup(const GridDev& g, const uint8_t* cell, const ViSta
   if (pl.colres) {
     // the work list of both slab shapes (wmax / wmax - 1 columns)
     std::vector<uint2> a, b, both;
-    const int Ga = col_schedule(pl.wmax, pl.NS, pl.nwc, a), Gb = pl.wmax > 1 ? col_schedule(pl.wmax - 1, pl.NS, pl.nwc, b) : 1;
+    const int Ga = col_schedule(pl.wmax, pl.NS, pl.nwc, pl.G, a), Gb = pl.wmax > 1 ? col_schedule(pl.wmax - 1, pl.NS, pl.nwc, pl.G, b) : 1;
     if (Ga != pl.G || (pl.wmax > 1 && Gb != pl.G)) return cudaErrorInvalidValue;
     both.assign(2 * (size_t)pl.nwc * pl.G, make_uint2(COL_NONE, COL_NONE));
     for (int i = 0; i < pl.nwc; i++) {
