@@ -38,7 +38,13 @@ namespace piql {
 #define PIQL_TILE_UNROLL 1  // columns of a sub-sweep a warp interleaves; measured on B200: 1 beats 2, 3 and 4 by 3-6 % on every kind and precision
 #endif
 constexpr int TILE_UNROLL = PIQL_TILE_UNROLL;
-// launch bounds of the Float64 instantiations: threads per CTA, CTAs per SM (registers per thread <= 65536 / their product)
+// launch bounds of the tiled kernels: threads per CTA, CTAs per SM (registers per thread <= 65536 / their product)
+#ifndef PIQL_TILE_F32_MAXT
+#define PIQL_TILE_F32_MAXT 512
+#endif
+#ifndef PIQL_TILE_F32_MINB
+#define PIQL_TILE_F32_MINB 2
+#endif
 #ifndef PIQL_TILE_F64_MAXT
 #define PIQL_TILE_F64_MAXT 512
 #endif
@@ -491,7 +497,7 @@ template <typename T> __device__ __forceinline__ bool strip_not_normal(const T (
 // ---- the kernel ------------------------------------------------------------------------------------------
 // grid = tiles_i * tiles_j CTAs of NW warps; dynamic shared memory = EJ * (2 * 128 * sizeof(T) + 144) bytes.
 template <typename T, int KIND, bool FAST, bool PL>
-__global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : PIQL_TILE_F64_MAXT, sizeof(T) == 4 ? 2 : PIQL_TILE_F64_MINB)
+__global__ void __launch_bounds__(sizeof(T) == 4 ? PIQL_TILE_F32_MAXT : PIQL_TILE_F64_MAXT, sizeof(T) == 4 ? PIQL_TILE_F32_MINB : PIQL_TILE_F64_MINB)
 tile_sweep_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmM,
                   const __grid_constant__ CUtensorMap tmP, int use_tma, const uint8_t* __restrict__ maskp, const T* __restrict__ X,
                   T* __restrict__ Y, const T* __restrict__ auxg, int nsub, int want_res, double* __restrict__ partial,
@@ -667,7 +673,7 @@ __device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
 }
 
 template <typename T, int KIND, bool FAST, bool PL>
-__global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : PIQL_TILE_F64_MAXT, sizeof(T) == 4 ? 2 : PIQL_TILE_F64_MINB)
+__global__ void __launch_bounds__(sizeof(T) == 4 ? PIQL_TILE_F32_MAXT : PIQL_TILE_F64_MAXT, sizeof(T) == 4 ? PIQL_TILE_F32_MINB : PIQL_TILE_F64_MINB)
 tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmP, T* __restrict__ XA,
                     T* __restrict__ XB, const T* __restrict__ auxg,
@@ -1258,7 +1264,7 @@ static std::vector<PlanCand> enumerate_plans(int H, int W, int precision, int ki
   // an SM.  The candidates are timed on the device, so the model only has to offer the right ones.
   const int regs = tile_kernel_regs(precision, kind, fast, persistent);
   const double strip_issue = 61.0, strip_latency = 1700.0, wave_fixed = 8000.0;
-  for (int nw = 4; nw <= (precision == 0 ? PIQL_TILE_F64_MAXT / 32 : 16); nw++) {
+  for (int nw = 4; nw <= (precision == 0 ? PIQL_TILE_F64_MAXT : PIQL_TILE_F32_MAXT) / 32; nw++) {
     if (env_nw && atoi(env_nw) != nw) continue;
     for (int TJ = 8; TJ <= 120; TJ++) {
       if (env_tj && atoi(env_tj) != TJ) continue;
