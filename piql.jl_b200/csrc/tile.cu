@@ -903,6 +903,42 @@ __device__ __forceinline__ bool mail_take(const unsigned long long* p, unsigned 
   sts4(halo, f);
   return true;
 }
+// two strips at once: all loads of both are in flight together
+template <typename T>
+__device__ __forceinline__ bool mail_take2(const unsigned long long* p0, const unsigned long long* p1, unsigned seq, T* halo0, T* halo1,
+                                           int* err) {
+  constexpr int NQ = 2 * kMailWords<T>;
+  unsigned long long w0[2 * NQ], w1[2 * NQ];
+  unsigned long long t0 = 0;
+  bool ok0 = false, ok1 = false;
+  for (unsigned spin = 0;; spin++) {
+    if (!ok0) {
+#pragma unroll
+      for (int q = 0; q < NQ; q++) ld_mail(p0 + 2 * q, w0[2 * q], w0[2 * q + 1]);
+    }
+    if (!ok1) {
+#pragma unroll
+      for (int q = 0; q < NQ; q++) ld_mail(p1 + 2 * q, w1[2 * q], w1[2 * q + 1]);
+    }
+    bool a = true, b = true;
+#pragma unroll
+    for (int q = 0; q < 2 * NQ; q++) { a = a && (unsigned)(w0[q] >> 32) == seq; b = b && (unsigned)(w1[q] >> 32) == seq; }
+    ok0 = a; ok1 = b;
+    if (ok0 && ok1) break;
+    if ((spin & 127u) == 127u) {
+      if (*(volatile int*)err) return false;
+      const unsigned long long t = globaltimer_ns_tile();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) { *err = COL_ERR_TIMEOUT; return false; }
+    }
+  }
+  T f[4];
+  mail_unpack(w0, f);
+  sts4(halo0, f);
+  mail_unpack(w1, f);
+  sts4(halo1, f);
+  return true;
+}
 // The goal cell (t = 0) and, for nu, its four neighbours (t = 1..4: (+1,0) (-1,0) (0,+1) (0,-1)) are not what the generic
 // formula gives (tile_goal_fixup).  The warp that has just stored the strip at buffer offset ob redoes those of them that lie in
 // it, one lane per cell, from src; gcell[t] = the cell's offset in a buffer (-1: not in this slab).  A serial version of this
@@ -1077,24 +1113,49 @@ col_resident_kernel(const TileK<T> k, const ColGeom cg, const uint8_t* __restric
       if (q == 0) COL_STAMP(1);
     }
     COL_STAMP(2);
-    // the neighbours' strips of this sweep, posted right after they were computed (while this warp did its second strip), into
-    // the halo columns of dst.  Tried and dropped (us per nu sweep at 1026^2 against 2.8): four extra warps that do nothing but
+    // the neighbours' strips of this sweep, posted right after they were computed, into the halo columns of dst: by the warps the
+    // work list names (all-interior warps first: they finish ~1000 cycles before the warps that own edge strips).  Tried and dropped (us per nu sweep at 1026^2 against 2.8): four extra warps that do nothing but
     // collect mail (4.0: under this kernel's shared-memory load a global round trip costs 1000-2000 cycles -- a MEMBAR.GPU behind
     // the post takes 2000 -- and their probe-then-fetch needed two); the other warps held back on a named barrier until the
     // edge strips are posted (3.1: the strips finish 800 cycles earlier, their mail arrives no sooner); a fence or a load
     // right behind the post (3.4 / 2.9); two phases with the columns next to the edge in the first (3.3).
     if (exchange) {
+      // (the duties -- work list .y: the edge strip whose halo twin this warp fetches -- are read here, not kept in registers)
+      const unsigned long long* fromL = mail + ((size_t)((sw & 1) * cg.ncta + c - 1) * 2 + 1) * box;  // left neighbour's last column
+      const unsigned long long* fromR = mail + ((size_t)((sw & 1) * cg.ncta + c + 1) * 2 + 0) * box;  // right neighbour's first one
+      T* const haloR = dst + (size_t)(wc + 1) * RS;
+      if constexpr (NP == 0 && sizeof(T) == 4 && NSL == 2) {
+        // two strips' loads in flight together where the registers allow it (a round trip is ~1000 cycles)
+        const uint32_t d0 = work[warp * cg.G].y, d1 = work[warp * cg.G + 1].y;
+        const int ob0 = (int)(d0 & COL_OFS), ob1 = (int)(d1 & COL_OFS);
+        const bool l0 = (d0 & COL_EDGE_L) != 0u, l1 = (d1 & COL_EDGE_L) != 0u;
+        const int r0 = (l0 ? ob0 - RS : ob0 - wc * RS) + lane4, r1 = (l1 ? ob1 - RS : ob1 - wc * RS) + lane4;
+        const bool has0 = (d0 & (COL_EDGE_L | COL_EDGE_R)) != 0u, has1 = (d1 & (COL_EDGE_L | COL_EDGE_R)) != 0u;
+        const unsigned long long* p0 = (l0 ? fromL : fromR) + (size_t)r0 * MW;
+        const unsigned long long* p1 = (l1 ? fromL : fromR) + (size_t)r1 * MW;
+        T* const h0 = (l0 ? dst : haloR) + r0;
+        T* const h1 = (l1 ? dst : haloR) + r1;
+        if (has0 && has1) { if (!mail_take2<T>(p0, p1, seq, h0, h1, err)) bad = 1; }
+        else if (has0) { if (!mail_take<T>(p0, seq, h0, err)) bad = 1; }
+        else if (has1) { if (!mail_take<T>(p1, seq, h1, err)) bad = 1; }
+        // (a slab of one column: the same strip faces both neighbours)
+        if ((d0 & COL_EDGE_L) && (d0 & COL_EDGE_R)) { if (!mail_take<T>(fromR + (size_t)(ob0 - wc * RS + lane4) * MW, seq, haloR + ob0 - wc * RS + lane4, err)) bad = 1; }
+        if ((d1 & COL_EDGE_L) && (d1 & COL_EDGE_R)) { if (!mail_take<T>(fromR + (size_t)(ob1 - wc * RS + lane4) * MW, seq, haloR + ob1 - wc * RS + lane4, err)) bad = 1; }
+      } else {
+        // (with the constant planes in registers there is none to spare: the owner of an edge strip fetches its halo twin --
+        // the strip's own flags -- and nothing is read from the work list here; Float64 follows the list, one strip at a time)
 #pragma unroll
-      for (int q = 0; q < NSL; q++) {
-        const int ob = (int)(it[q] & COL_OFS);
-        if (it[q] & COL_EDGE_L) {  // my first column's strip: the left neighbour's last column (its box 1), same rows
-          const int row = ob - RS + lane4;
-          if (!mail_take<T>(mail + ((size_t)((sw & 1) * cg.ncta + c - 1) * 2 + 1) * box + (size_t)row * MW, seq, dst + row, err)) bad = 1;
-        }
-        if (it[q] & COL_EDGE_R) {
-          const int row = ob - wc * RS + lane4;
-          if (!mail_take<T>(mail + ((size_t)((sw & 1) * cg.ncta + c + 1) * 2 + 0) * box + (size_t)row * MW, seq,
-                            dst + (size_t)(wc + 1) * RS + row, err)) bad = 1;
+        for (int q = 0; q < NSL; q++) {
+          const uint32_t d = NP > 0 ? it[q] : work[warp * cg.G + q].y;
+          const int ob = (int)(d & COL_OFS);
+          if (d & COL_EDGE_L) {
+            const int row = ob - RS + lane4;
+            if (!mail_take<T>(fromL + (size_t)row * MW, seq, dst + row, err)) bad = 1;
+          }
+          if (d & COL_EDGE_R) {
+            const int row = ob - wc * RS + lane4;
+            if (!mail_take<T>(fromR + (size_t)row * MW, seq, haloR + row, err)) bad = 1;
+          }
         }
       }
     }
@@ -1328,7 +1389,7 @@ static size_t col_smem_bytes(int wmax, int NS, int precision, int planes, int nw
 // than that).  A warp's first strip is an edge-column strip while they last -- the neighbours wait for those -- dealt out round
 // robin; every other round goes the other way, so that the warps with an edge strip (which also collect the neighbours' strips at
 // the end of the sweep) are the last to get a second one.  item = column | strip << 16; returns the items per warp (nslots).
-static int col_schedule(int wc, int NS, int nwc, int nslots, std::vector<uint2>& out) {
+static int col_schedule(int wc, int NS, int nwc, int nslots, int duties_per_idle, std::vector<uint2>& out) {
   if (wc * NS > nslots * nwc) return 0;
   std::vector<uint32_t> items;
   for (int sidx = 0; sidx < NS; sidx++)
@@ -1343,6 +1404,37 @@ static int col_schedule(int wc, int NS, int nwc, int nslots, std::vector<uint2>&
     const int i = (round & 1) ? nwc - 1 - pos : pos;
     out[(size_t)i * G + round] = make_uint2(items[q], COL_NONE);
   }
+  // Who collects the neighbours' strips (.y: the edge strip whose halo twin a warp fetches at the end of the sweep): a warp
+  // whose strips are all interior, one each while they last -- the warps that own edge strips are the last to finish (an edge
+  // strip also packs and posts) and a fetch is another ~1000 cycles -- and the owner itself for the rest.
+  std::vector<int> idle;
+  for (int i = nwc - 1; i >= 0; i--) {
+    bool edge = false, any = false;
+    for (int g = 0; g < G; g++) {
+      const uint32_t it = out[(size_t)i * G + g].x;
+      if (it == COL_NONE) continue;
+      any = true;
+      const int col = (int)(it & 0xffffu);
+      edge = edge || col == 0 || col == wc - 1;
+    }
+    if (any && !edge) idle.push_back(i);
+  }
+  // (duties_per_idle of them per all-interior warp: two where the kernel fetches two strips at once)
+  size_t next = 0;
+  const size_t room = idle.size() * (size_t)std::min(duties_per_idle, G);
+  for (int i = 0; i < nwc; i++)
+    for (int g = 0; g < G; g++) {
+      const uint32_t it = out[(size_t)i * G + g].x;
+      if (it == COL_NONE) continue;
+      const int col = (int)(it & 0xffffu);
+      if (col != 0 && col != wc - 1) continue;
+      if (next < room) { out[(size_t)idle[next % idle.size()] * G + next / idle.size()].y = it; next++; }
+      else {
+        int slot = g;  // the owner collects: its first free duty slot
+        for (int h = 0; h < G; h++) if (out[(size_t)i * G + h].y == COL_NONE) { slot = h; break; }
+        out[(size_t)i * G + slot].y = it;
+      }
+    }
   return G;
 }
 static std::vector<TilePlan> enumerate_colres(const GridDev& g, int precision, int kind, bool fast, int num_sms) {
@@ -1370,7 +1462,7 @@ static std::vector<TilePlan> enumerate_colres(const GridDev& g, int precision, i
       const int nwc = nw;
       std::vector<uint2> tmp;
       const int nslots = precision == 0 ? 4 : 2;  // kColSlots
-      const int G = col_schedule(wmax, NS, nwc, nslots, tmp);
+      const int G = col_schedule(wmax, NS, nwc, nslots, 1, tmp);
       if (G == 0) continue;  // more strips per warp than that
       const size_t smem = col_smem_bytes(wmax, NS, precision, planes, nwc, G);
       if (smem > limit) continue;
@@ -1556,7 +1648,10 @@ static cudaError_t tile_setup(const GridDev& g, const uint8_t* cell, const ViSta
   if (pl.colres) {
     // the work list of both slab shapes (wmax / wmax - 1 columns)
     std::vector<uint2> a, b, both;
-    const int Ga = col_schedule(pl.wmax, pl.NS, pl.nwc, pl.G, a), Gb = pl.wmax > 1 ? col_schedule(pl.wmax - 1, pl.NS, pl.nwc, pl.G, b) : 1;
+    // (two duties per all-interior warp where the kernel fetches two strips at once: fp32 without planes in registers)
+    const char* env_dp = getenv("PIQL_TILE_COLRES_DUTIES");
+    const int dp = env_dp ? atoi(env_dp) : (vs.precision != 0 && pl.planes == 0) ? 2 : 1;
+    const int Ga = col_schedule(pl.wmax, pl.NS, pl.nwc, pl.G, dp, a), Gb = pl.wmax > 1 ? col_schedule(pl.wmax - 1, pl.NS, pl.nwc, pl.G, dp, b) : 1;
     if (Ga != pl.G || (pl.wmax > 1 && Gb != pl.G)) return cudaErrorInvalidValue;
     both.assign(2 * (size_t)pl.nwc * pl.G, make_uint2(COL_NONE, COL_NONE));
     for (int i = 0; i < pl.nwc; i++) {
