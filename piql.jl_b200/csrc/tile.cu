@@ -821,14 +821,17 @@ tile_persist_kernel(const TileK<T> k, const __grid_constant__ CUtensorMap tmA, c
 //   * a warp owns its (at most two) strips for the whole launch, so what does not change lives in its registers: the strip's own
 //     values (stored for the neighbours, never reloaded), the cell bytes and, for the linear fast sweeps, the constant planes --
 //     a strip of those is four shared-memory accesses instead of nine, and the shared-memory pipe is what bounds them;
-//   * a warp's first strip is an edge-column strip while they last: it is posted the moment it is stored, and the neighbour's
-//     strip of the same sweep is collected (into the halo column of the buffer the next sweep reads) after the warp's second strip;
+//   * a warp's first strip is an edge-column strip while they last: it is posted the moment it is stored; the neighbours' strips
+//     of the same sweep are collected at its end (into the halo columns of the buffer the next sweep reads) by the warps the work
+//     list names: those whose strips are all interior first -- they finish ~1000 cycles before the owners of edge strips, and a
+//     fetch is another ~1000 -- two strips' loads in flight at once;
 //   * mailboxes are double-buffered by sweep parity (a neighbour can be at most one sweep ahead);
 //   * the goal cell and (nu) its neighbours are patched, one lane per cell, by the warp that owns them before anything is posted.
 // Per sweep and CTA: one __syncthreads.  The per-cell arithmetic is strip_compute, shared with the other schedules: same bits.
-// What bounds it (clock64 stamps, PIQL_TILE_COLRES_TRACE): the period of a sweep is first strip + post-to-collect latency
-// (~2300 + ~2900 cycles for nu at 1026^2: an L2 round trip costs ~1000 cycles under this kernel's shared-memory load), not the
-// warps' work (~4000 cycles): 2.8 us per sweep against 3.05 for the tiled kernel (nu), 2.1 against 2.8 (log Z), 2.6 against 2.95 (gap).
+// What bounds it (clock64 stamps, PIQL_TILE_COLRES_TRACE; nu at 1026^2): two strips per warp take 3400-3900 cycles, a fetch of
+// the neighbours' strips ~1000 (a global round trip under this kernel's shared-memory load), barrier and loop head ~600: 2.7 us
+// per sweep against 3.05 for the tiled kernel (nu), 2.2 against 2.8 (log Z), 2.65 against 2.95 (gap); 2.3 / 1.4 / 1.8 without
+// the exchange.  DESIGN.md 5.4 lists what was tried against that latency.
 struct ColGeom {
   int r0;           // first padded row of the resident columns (a multiple of 4: vector accesses stay aligned)
   int NS, RS;       // 128-row strips per column, RS = 128 * NS rows
